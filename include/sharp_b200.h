@@ -1,0 +1,196 @@
+/*
+ * sharp_b200.h -- C ABI of libsharpb200.so: the B200-native (sm_100a) implementation of SHARP's
+ * ensemble random-projection clustering hot path.
+ *
+ * The reference (shibiaowan/SHARP v1.1.0) is a pure-R package with NO native code and NO FFI
+ * (no src/, no useDynLib in NAMESPACE): its operator API is the set of exported R closures.  Each
+ * entry point below is therefore what an R `.Call` glue for this path binds (INTEGRATION.md shows the
+ * glue), and cites the R closure / lines whose body it replaces.  Everything is plain C: raw pointers,
+ * sizes, int status.  No torch types, no C++ types.
+ *
+ * Conventions
+ *  - All functions return 0 on success, a negative SHARP_E_* code otherwise; sharp_last_error() gives
+ *    the message (per calling thread).  SHARP_E_RSTOP marks conditions where the reference itself
+ *    would stop() (the message quotes the R error).
+ *  - Host pointers unless a parameter is documented as "device".  Inputs are never written.
+ *  - fp64 everywhere (R's numeric); int32 labels, 1-based like R.
+ *  - Matrices: the expression matrix is genes x cells exactly as R stores it (dense column-major, or
+ *    dgCMatrix slots i / p / x).  Cell-by-feature matrices (projections, viE, x0) are ROW-major
+ *    ncells x ncol, i.e. the memory image of R's t(matrix).
+ *  - There is NO CPU fallback: every call needs a CUDA device and fails with SHARP_E_CUDA without one.
+ */
+#ifndef SHARP_B200_H
+#define SHARP_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SHARP_B200_ABI_VERSION 1
+
+enum {
+    SHARP_OK = 0,
+    SHARP_E_ARG = -1,    /* bad argument */
+    SHARP_E_CUDA = -2,   /* CUDA runtime failure / no device */
+    SHARP_E_NOMEM = -3,  /* output buffer too small or device memory exhausted */
+    SHARP_E_RSTOP = -4,  /* the reference would stop() here (message quotes it) */
+    SHARP_E_LIMIT = -5   /* a documented size limit of this implementation */
+};
+
+/* stats::hclust method codes (index into hclust's METHODS vector = hclust.f iOpt) */
+enum { SHARP_WARD_D = 1, SHARP_SINGLE = 2, SHARP_COMPLETE = 3, SHARP_AVERAGE = 4, SHARP_MCQUITTY = 5,
+       SHARP_MEDIAN = 6, SHARP_CENTROID = 7, SHARP_WARD_D2 = 8 };
+
+/* Arguments shared by get_opt_hclust / getrowColor / wMetaC / sMetaC   (R/get_opt_hclust.R:33-62) */
+typedef struct {
+    int hmethod;          /* SHARP_WARD_D ... ; 0 = default "ward.D" */
+    int n_cluster;        /* N.cluster: 0 = NULL (choose automatically) */
+    int min_n;            /* minN.cluster (0 = default 2) */
+    int max_n;            /* maxN.cluster (0 = default 40) */
+    double sil_thre;      /* sil.thre */
+    double height_ntimes; /* height.Ntimes */
+} sharp_hc_params;
+
+typedef struct sharp_ctx sharp_ctx;       /* one CUDA device + stream + workspace */
+typedef struct sharp_rm_dev sharp_rm_dev; /* K ranM matrices prepared on the device */
+
+/* ---- library / device -------------------------------------------------------------------------
+ * Replaces: registerDoParallel(n.cores) / detectCores()  (R/SHARP.R:162-167): `n.cores` is accepted by the
+ * R wrappers and ignored; the unit of parallelism is the GPU. */
+int sharp_abi_version(void);
+const char *sharp_last_error(void);
+int sharp_device_count(void);
+int sharp_device_info(int device, char *name, int name_len, int *sm_count, int *cc_major, int *cc_minor,
+                      size_t *total_mem);
+int sharp_ctx_create(int device, sharp_ctx **ctx);
+void sharp_ctx_destroy(sharp_ctx *ctx);
+/* CUDA stream of the context as a void* (cudaStream_t), for callers that time with CUDA events. */
+void *sharp_ctx_stream(sharp_ctx *ctx);
+int sharp_ctx_sync(sharp_ctx *ctx);
+/* device-time helpers on the context's stream (CUDA events): start/stop a region, elapsed in ms. */
+int sharp_timer_start(sharp_ctx *ctx);
+int sharp_timer_stop_ms(sharp_ctx *ctx, double *ms);
+/* number of kernels this library launched on the context since creation (bench.py's gpu_launches). */
+int64_t sharp_ctx_launch_count(sharp_ctx *ctx);
+
+/* ---- ranM matrices ----------------------------------------------------------------------------
+ * Replaces nothing: ranM()/ranM2() stay in R (R/ranM.R:11-33, R/ranM2.R:11-35) and their dgCMatrix slots
+ * are handed in.  K matrices, each m x p: colptr K x (p+1) (slot `p`), rowidx (slot `i`, ascending inside a
+ * column) and x (slot `x`) concatenated, nnz_off[K+1] offsets of each matrix in rowidx/x.
+ * All non-zero entries must have the same magnitude (they do: +-sqrt(sqrt(m))); otherwise SHARP_E_LIMIT. */
+int sharp_rm_upload(sharp_ctx *ctx, int m, int p, int K, const int32_t *colptr, const int32_t *rowidx,
+                    const double *x, const int64_t *nnz_off, sharp_rm_dev **out);
+void sharp_rm_free(sharp_rm_dev *rm);
+
+/* ---- a2/a3/a4: random projection with the normalisation fused into the load ---------------------
+ * Replaces: RPmat()'s `1/sqrt(p) * t(x) %*% scdata` (R/RPmat.R:32), the inline projection of SHARP_large /
+ * SHARP_fpart / testlog (R/SHARP.R:567-585, 899-905; R/SHARP_unlimited2.R:388-410), log2(x+1)
+ * (R/SHARP.R:344,570) and the CPM normalisation t(t(x)/colSums(x))*1e6 (R/SHARP.R:113).
+ *
+ * E (m genes x n cells): dense column-major (`dense`) or CSC (`colptr` int64[n+1], `rowidx`, `val`).
+ * cells: optional 0-based source column of every output row (E[, tind]); NULL = all n columns in order.
+ * normalize: 0 = none; 1 = value / colsum[c] * norm_mul with colsum given (per SOURCE column, length n);
+ *            2 = same with the column sums computed on the device.
+ * logkind: 0 none, 2 = log2(x+1), 10 = log10(x+1).  round_digits: <0 none, else round(., digits).
+ * out: K matrices, each row-major ncell x p, concatenated (out[k][cell][j]). */
+int sharp_rp_project(sharp_ctx *ctx, int m, int64_t n, const double *dense, const int64_t *colptr,
+                     const int32_t *rowidx, const double *val, const int64_t *cells, int64_t ncell, int normalize,
+                     const double *colsum, double norm_mul, int logkind, int round_digits, const sharp_rm_dev *rm,
+                     double *out);
+
+/* ---- a6: distance   as.dist(1 - cor(t(scale-rows(mat))))   (R/get_opt_hclust.R:71-72) -------------
+ * mat row-major n x p -> dist full symmetric n x n (diag 0).  Stage-level entry used by the parity tests. */
+int sharp_corrdist(sharp_ctx *ctx, int n, int p, const double *mat, double *dist);
+
+/* ---- a7: stats::hclust(d, method)   (R/get_opt_hclust.R:77) ---------------------------------------
+ * dist: full symmetric n x n (what as.matrix(d) holds).  ia/ib[n-1]: 1-based representatives (min index of
+ * each cluster) merged at every step, in hclust.f order; height[n-1]. */
+int sharp_hclust(sharp_ctx *ctx, int n, const double *dist, int method, int32_t *ia, int32_t *ib, double *height);
+
+/* ---- a6-a10: get_opt_hclust   (R/get_opt_hclust.R:33-244) -----------------------------------------
+ * mat row-major nrow x ncol.  symmetric: 1 = similarity matrix (d = 1 - mat), 0 = feature matrix.
+ * (isSymmetric(mat) is evaluated by the caller: it is a property of the R object.)
+ * exact: 1 = every level swept with the reference's summation order (bit-compatible, O(levels n^2));
+ *        0 = the nested one-pass sweep used for the 2000-cell blocks (same ties, last-bit differences).
+ * Outputs (any may be NULL): f[nrow]; v row-major nrow x *nlev (room for nrow x (max_n-min_n+1));
+ * msil/chind[*nlev]; height[nrow-1]; *optn = optN.cluster; *maxsil; *oind (1-based column of v). */
+int sharp_opt_hclust(sharp_ctx *ctx, int nrow, int ncol, const double *mat, int symmetric, int exact,
+                     const sharp_hc_params *prm, int32_t *f, int32_t *v, int *nlev, double *msil, double *chind,
+                     double *height, int *optn, double *maxsil, int *oind);
+
+/* ---- a5: getrowColor   (R/getrowColor.R:17-121) ---------------------------------------------------
+ * emat row-major n x p.  color[n]: index (1..40) into the reference's colour vector (cluster ids in order of
+ * first appearance, wrapping modulo 40 exactly like R/getrowColor.R:59-68). */
+int sharp_getrowcolor(sharp_ctx *ctx, int n, int p, const double *emat, const sharp_hc_params *prm, int32_t *color,
+                      double *maxsil);
+
+/* ---- a11-a14: wMetaC   (R/wMetaC.R:15-226 incl. getA :242-283, getss/getnewk :299-320) -------------
+ * labels: column-major N x C integer codes (the R glue passes match(nC[,c], unique(nC[,c]))).
+ * finalc[N]: the meta-cluster id R returns as a string in finalC; *ncluster = length(unique(finalC));
+ * x0 (may be NULL): row-major N x *ncluster, columns in unique(finalC) order, room for N x max_x0_cols;
+ * w1 (may be NULL): the adjusted point weights (R/wMetaC.R:44). */
+int sharp_wmetac(sharp_ctx *ctx, int N, int C, const int32_t *labels, const sharp_hc_params *prm, int32_t *finalc,
+                 int *ncluster, double *x0, int max_x0_cols, double *w1);
+
+/* ---- a15: sMetaC   (R/sMetaC.R:17-210) ------------------------------------------------------------
+ * labels[ncells]: integer codes of rerowColor (any codes; unique() order = first appearance);
+ * se1 row-major ncells x p.  finalcolor[ncells]; tf[nC] (may be NULL); *nc = nC. */
+int sharp_smetac(sharp_ctx *ctx, int64_t ncells, int p, const int32_t *labels, const double *se1,
+                 const sharp_hc_params *prm, int32_t *finalcolor, int32_t *tf, int *nc);
+
+/* ---- a16: SHARP_small / SHARP_large compute, fused on the device -----------------------------------
+ * Replaces the bodies of SHARP_small (R/SHARP.R:343-416) and SHARP_large (R/SHARP.R:502-783) (and SHARP_fpart,
+ * R/SHARP_unlimited2.R:316-520, through logkind/round_digits): projection of every (member, block), per-block
+ * getrowColor, gather of enrp / enE, per-block wMetaC, sMetaC across blocks, un-shuffle.  What stays in R:
+ * argument defaults, prep, seeds / ranM / sample(), the small-cluster merge and the final relabel
+ * (R/SHARP.R:816-843), the result list. */
+typedef struct {
+    int large;            /* 0 = SHARP_small (one block, no sMetaC), 1 = SHARP_large */
+    int logflag;          /* `flag` */
+    int logkind;          /* 2 or 10 (0 = 2) */
+    int round_digits;     /* <0 none */
+    int partition_ncells; /* ng */
+    int n_cluster;        /* N.cluster      (0 = NULL) */
+    int enp_n_cluster;    /* enpN.cluster   (0 = NULL) */
+    int ind_n_cluster;    /* indN.cluster   (0 = NULL) */
+    sharp_hc_params hc;   /* hmethod, minN, maxN, sil.thre, height.Ntimes (n_cluster ignored) */
+    int normalize;        /* as in sharp_rp_project */
+    double norm_mul;
+} sharp_run_params;
+
+/* reind: 1-based permutation from `set.seed(50); sample(ncells)` or NULL; applied iff ncells < 1e5
+ * (R/SHARP.R:504).  labels[n]: SrowColor after the un-shuffle, as integers (R/SHARP.R:775-778) -- for
+ * large=1 with one block, the position of the cluster in unique(fColor).  vie (may be NULL): row-major n x p =
+ * enE/K.  x0 (may be NULL): row-major n x *x0_cols, room for n x max_x0_cols. */
+int sharp_run(sharp_ctx *ctx, int m, int64_t n, const double *dense, const int64_t *colptr, const int32_t *rowidx,
+              const double *val, const double *colsum, const sharp_rm_dev *rm, const int64_t *reind,
+              const sharp_run_params *prm, int32_t *labels, double *vie, double *x0, int *x0_cols, int max_x0_cols);
+
+/* ---- device-resident variant (bench `value`, SHARP_unlimited parts) ---------------------------------
+ * sharp_expr_upload copies one expression matrix (or part) to the device (asynchronously on the context's
+ * stream when the host buffers are pinned); sharp_run_dev is sharp_run on it and additionally keeps viE on
+ * the device to feed sharp_centroids (the colMeans of R/sMetaC.R:58-63 for SHARP_unlimited's global sMetaC). */
+typedef struct sharp_expr_dev sharp_expr_dev;
+int sharp_expr_upload(sharp_ctx *ctx, int m, int64_t n, const double *dense, const int64_t *colptr,
+                      const int32_t *rowidx, const double *val, sharp_expr_dev **out);
+void sharp_expr_free(sharp_expr_dev *e);
+int sharp_run_dev(sharp_ctx *ctx, const sharp_expr_dev *e, const double *colsum, const sharp_rm_dev *rm,
+                  const int64_t *reind, const sharp_run_params *prm, int32_t *labels, double *vie, double *x0,
+                  int *x0_cols, int max_x0_cols);
+/* centroids of the LAST sharp_run/sharp_run_dev on this context: for cluster ids 1..nclust (values of `labels`,
+ * e.g. pred_clusters after the host relabel), cen row-major nclust x p = colMeans(viE[labels == c, ]). */
+int sharp_centroids(sharp_ctx *ctx, int64_t n, const int32_t *labels, int nclust, double *cen, int64_t *counts);
+
+/* sMetaC given precomputed centroids (what SHARP_unlimited's global step needs when parts live on several
+ * GPUs): cen row-major nC x p in unique(fColor) order; ncells_total drives the k-range tweak (R/sMetaC.R:101-119).
+ * tf[nC]. */
+int sharp_smetac_centroids(sharp_ctx *ctx, int nC, int p, const double *cen, int64_t ncells_total,
+                           const sharp_hc_params *prm, int32_t *tf);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

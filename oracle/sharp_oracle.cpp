@@ -403,7 +403,8 @@ int opt_hclust_core(int nrow, int ncol, const double *mat, int symmetric, const 
     int myp = ncol;
     if (sym) {
         for (int i = 0; i < n; i++)
-            for (int j = 0; j < n; j++) dist[(size_t)i * n + j] = (i == j) ? 0.0 : 1.0 - mat[(size_t)i * n + j];
+            for (int j = 0; j < n; j++) /* as.dist() keeps the lower triangle (row > col) */
+                dist[(size_t)i * n + j] = (i == j) ? 0.0 : 1.0 - mat[(size_t)std::max(i, j) * n + std::min(i, j)];
     } else {
         zmat.resize((size_t)n * ncol);
         zscore_rows(n, ncol, mat, zmat.data());

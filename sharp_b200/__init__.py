@@ -1,0 +1,13 @@
+"""sharp_b200 -- B200-native (sm_100a) implementation of SHARP's ensemble random-projection clustering path.
+
+Host side: a Python mirror of the reference's R operator API (SHARP(), SHARP_unlimited*, RPmat, ranM,
+get_opt_hclust, getrowColor, wMetaC, sMetaC ...) over the C ABI of ``libsharpb200.so`` (include/sharp_b200.h).
+R is not available in this image; INTEGRATION.md shows the `.Call` glue a maintainer of the reference adds.
+Importing the package does not need a GPU; every compute call does (there is no CPU fallback).
+"""
+from . import _lib
+from ._lib import Context, HcParams, RStop, RunParams, SharpError, device_count, device_info, hc_params
+from .rrng import ranM, ranM2, r_sample_perm
+
+__all__ = ["_lib", "Context", "HcParams", "RunParams", "SharpError", "RStop", "device_count", "device_info",
+           "hc_params", "ranM", "ranM2", "r_sample_perm"]

@@ -1,0 +1,157 @@
+// internal.cuh -- shared declarations of libsharpb200 (not part of the public ABI).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include "../../include/sharp_b200.h"
+
+namespace sharp {
+
+// ---- errors ------------------------------------------------------------------------------------
+int set_error(int code, const char *fmt, ...);
+#define SHARP_CUDA(expr)                                                                                 \
+    do {                                                                                                 \
+        cudaError_t _e = (expr);                                                                         \
+        if (_e != cudaSuccess)                                                                           \
+            return ::sharp::set_error(SHARP_E_CUDA, "%s failed at %s:%d: %s", #expr, __FILE__, __LINE__, \
+                                      cudaGetErrorString(_e));                                           \
+    } while (0)
+#define SHARP_TRY(expr)           \
+    do {                          \
+        int _rc = (expr);         \
+        if (_rc != 0) return _rc; \
+    } while (0)
+
+// ---- device buffer that grows and never shrinks (workspace slot) -------------------------------------
+struct DevBuf {
+    void *ptr = nullptr;
+    size_t cap = 0;
+    int reserve(size_t bytes);
+    void release();
+    template <class T> T *as() const { return reinterpret_cast<T *>(ptr); }
+};
+
+// A problem for the hierarchical clustering kernels (lives in DEVICE memory; n may be written by a kernel).
+struct HcProb {
+    int n;            // number of objects (0 = skip)
+    int ld;           // leading dimension of the distance matrices
+    double *D;        // full symmetric n x ld, read-only after it is built (silhouettes)
+    double *Dw;       // working copy, destroyed by the agglomeration
+    int *ia;          // [n-1] 1-based representative kept      (hclust.f IA)
+    int *ib;          // [n-1] 1-based representative absorbed  (hclust.f IB)
+    double *crit;     // [n-1] heights
+    const double *Y;  // data for the CH index: feature problems: unit rows (n x p); similarity problems: S
+    int p;            // columns of Y
+    int ldy;          // leading dimension of Y
+    int status;       // 0 ok, else a SWEEP_E_* / WM_E_* code
+};
+
+// results of the cluster-number sweep for one problem (device pointers)
+struct SweepOut {
+    int *f;          // [n] chosen labels (cutree ids, first-appearance numbering, 1-based)
+    int *v;          // optional [n x nlev] row-major
+    double *msil;    // [maxlev]
+    double *chind;   // [maxlev]
+    int *meta;       // [8]: 0 nlev, 1 optn, 2 oind, 3 status, 4 kmin, 5 kmax
+    double *maxsil;  // [1]
+};
+
+struct HcParamsDev {
+    int hmethod, n_cluster, min_n, max_n;
+    double sil_thre, height_ntimes;
+};
+
+inline HcParamsDev to_dev(const sharp_hc_params &p) {
+    HcParamsDev d;
+    d.hmethod = p.hmethod ? p.hmethod : SHARP_WARD_D;
+    d.n_cluster = p.n_cluster;
+    d.min_n = p.min_n > 0 ? p.min_n : 2;
+    d.max_n = p.max_n > 0 ? p.max_n : 40;
+    d.sil_thre = p.sil_thre;
+    d.height_ntimes = p.height_ntimes;
+    return d;
+}
+
+enum { SWEEP_E_HCLUST_NA = 12, SWEEP_E_KRANGE = 15, SWEEP_E_NAN = 17, SWEEP_E_CHNAN = 18, SWEEP_E_UNSORTED = 19,
+       WM_E_ONECLUSTER = 20, SWEEP_E_FEWPOINTS = 21, SWEEP_E_OIND = 22, WM_E_FEWCLUSTERS = 23, SM_E_FEWCLUSTERS = 24,
+       WM_E_TOOMANY = 30 };
+
+const char *status_message(int st);
+
+}  // namespace sharp
+
+struct sharp_ctx {
+    int device = 0;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    int64_t launches = 0;
+    sharp::DevBuf ws[48];  // grow-only workspaces (slots named in pipeline.cu)
+    void *pinned = nullptr; // pinned staging for descriptor uploads / small downloads
+    size_t pinned_cap = 0;
+    int64_t last_n = 0;     // state of the last run (for sharp_centroids)
+    int last_p = 0;
+    int reserve_pinned(size_t bytes);
+};
+
+struct sharp_rm_dev {
+    int device = 0;
+    int m = 0, p = 0, K = 0;
+    double mag = 0.0;            // common |x| of all entries
+    int tile_genes = 0, ntiles = 0, max_tile_entries = 0;
+    int64_t nnz = 0;
+    uint32_t *rowptr = nullptr;  // [m+1] offsets into ent (gene-major)
+    uint16_t *ent16 = nullptr;   // [nnz] (col | sign<<15) when K*p <= 32768
+    uint32_t *ent32 = nullptr;   // [nnz] (col | sign<<31) otherwise
+};
+
+struct sharp_expr_dev {
+    int device = 0;
+    int m = 0;
+    int64_t n = 0;
+    double *dense = nullptr;
+    int64_t *colptr = nullptr;
+    int32_t *rowidx = nullptr;
+    double *val = nullptr;
+    int64_t nnz = 0;
+    bool owned = true;
+};
+
+namespace sharp {
+
+constexpr int RP_TILE_GENES_HOST = 512;
+
+// ---- kernel launchers (each returns after enqueueing on ctx->stream) ---------------------------------
+// rp_project.cu
+int launch_colsum(sharp_ctx *c, const sharp_expr_dev &e, double *colsum);
+int launch_rp_project(sharp_ctx *c, const sharp_expr_dev &e, const int64_t *cells_dev, int64_t ncell,
+                      const double *colsum_dev, int normalize, double norm_mul, int logkind, int round_digits,
+                      const sharp_rm_dev &rm, double *out /* [K][ncell][p] */);
+// corrdist.cu
+int launch_unit_rows(sharp_ctx *c, const double *X, int64_t rows, int p, int ldu, double *U);
+struct GemmProb {
+    const double *U;  // first unit row of the problem (row stride ldu)
+    int n;
+    int ld;
+    double *D;
+    double *Dw;       // may be null
+};
+int corrdist_tiles(int n);
+int launch_corrdist_batched(sharp_ctx *c, const GemmProb *probs_dev, const int *tile_prefix_dev, int nprob,
+                            int total_tiles, int ldu);
+// ward.cu
+int launch_hclust(sharp_ctx *c, HcProb *probs_dev, int nprob, int max_n, int method);
+// sweep.cu
+size_t sweep_nested_scratch_bytes(int max_n, int max_p, HcParamsDev prm);
+int launch_sweep_nested(sharp_ctx *c, HcProb *probs_dev, SweepOut *outs_dev, int nprob, int max_n, int max_p,
+                        HcParamsDev prm, double *scratch, size_t scratch_per_prob);
+size_t sweep_exact_scratch_bytes(int max_n, int max_p);
+int launch_sweep_exact(sharp_ctx *c, HcProb *probs_dev, SweepOut *outs_dev, int nprob, int max_n, int max_p,
+                       const HcParamsDev *prm_dev, int max_levels, int kcap, double *scratch, size_t scratch_per_prob);
+constexpr int NESTED_MAXK_HOST = 64;
+
+}  // namespace sharp

@@ -1,0 +1,1314 @@
+// pipeline.cu -- host side of libsharpb200: contexts, workspaces, the C ABI of include/sharp_b200.h and the
+// fused SHARP_small / SHARP_large device pipeline.  No CPU fallback anywhere: every entry point enqueues CUDA
+// kernels of this library on the context's stream and fails with SHARP_E_CUDA when there is no device.
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstring>
+#include <numeric>
+
+#include "internal.cuh"
+#include "metac.cuh"
+
+namespace sharp {
+
+// ---- errors ------------------------------------------------------------------------------------
+static thread_local char g_err[1024] = "";
+
+int set_error(int code, const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+const char *status_message(int st) {
+    switch (st) {
+    case SWEEP_E_HCLUST_NA: return "hclust: NA/NaN/Inf in foreign function call (dissimilarities are not finite; a cell with a constant projection?)";
+    case SWEEP_E_KRANGE: return "cutree: elements of 'k' must be between 1 and n";
+    case SWEEP_E_NAN: return "get_opt_hclust: the median silhouette is NaN";
+    case SWEEP_E_CHNAN: return "get_opt_hclust: which.max(CHind) is empty (all CH indices are NaN)";
+    case SWEEP_E_UNSORTED: return "cutree: the 'height' component of 'tree' is not sorted (increasingly)";
+    case WM_E_ONECLUSTER: return "wMetaC: missing value where TRUE/FALSE needed (one-cluster fallback, R/wMetaC.R:152)";
+    case SWEEP_E_FEWPOINTS: return "get_opt_hclust: fewer than minN.cluster+1 objects (silhouette() returns NA; R: incorrect number of dimensions)";
+    case SWEEP_E_OIND: return "get_opt_hclust: subscript out of bounds (v[, oind], R/get_opt_hclust.R:228)";
+    case WM_E_FEWCLUSTERS: return "wMetaC: combn(allC, 2) needs at least two clusters";
+    case SM_E_FEWCLUSTERS: return "sMetaC: combn(nC, 2) needs at least two clusters";
+    case WM_E_TOOMANY: return "more clusters than this implementation's capacity";
+    default: return "unknown status";
+    }
+}
+
+static int rstop(int st, const char *where) {
+    int code = (st == WM_E_TOOMANY) ? SHARP_E_LIMIT : SHARP_E_RSTOP;
+    return set_error(code, "%s: %s", where, status_message(st));
+}
+
+// ---- buffers -------------------------------------------------------------------------------------
+int DevBuf::reserve(size_t bytes) {
+    if (bytes <= cap) return 0;
+    if (ptr) {
+        cudaError_t e = cudaFree(ptr);
+        ptr = nullptr;
+        cap = 0;
+        if (e != cudaSuccess) return set_error(SHARP_E_CUDA, "cudaFree: %s", cudaGetErrorString(e));
+    }
+    size_t want = (bytes + (1 << 20) - 1) & ~(size_t)((1 << 20) - 1);
+    cudaError_t e = cudaMalloc(&ptr, want);
+    if (e != cudaSuccess) {
+        ptr = nullptr;
+        return set_error(SHARP_E_NOMEM, "cudaMalloc(%zu bytes) failed: %s", want, cudaGetErrorString(e));
+    }
+    cap = want;
+    return 0;
+}
+
+void DevBuf::release() {
+    if (ptr) cudaFree(ptr);
+    ptr = nullptr;
+    cap = 0;
+}
+
+}  // namespace sharp
+
+int sharp_ctx::reserve_pinned(size_t bytes) {
+    if (bytes <= pinned_cap) return 0;
+    if (pinned) cudaFreeHost(pinned);
+    pinned = nullptr;
+    pinned_cap = 0;
+    size_t want = (bytes + (1 << 16) - 1) & ~(size_t)((1 << 16) - 1);
+    cudaError_t e = cudaMallocHost(&pinned, want);
+    if (e != cudaSuccess) return sharp::set_error(SHARP_E_NOMEM, "cudaMallocHost(%zu) failed: %s", want, cudaGetErrorString(e));
+    pinned_cap = want;
+    return 0;
+}
+
+namespace sharp {
+
+// workspace slots
+enum Slot {
+    WS_SRC = 0, WS_COLSUM, WS_PROJ, WS_U, WS_D, WS_DW, WS_HC_INT, WS_HC_DBL, WS_DESC, WS_SWEEP_SCRATCH, WS_ENRP, WS_E1,
+    WS_WM_INT, WS_WM_DBL, WS_WM_S, WS_WM_DESC, WS_WM_SCRATCH, WS_SM_INT, WS_SM_DBL, WS_SM_S, WS_SM_SCRATCH, WS_VIEU,
+    WS_LABELS, WS_X0, WS_TMP0, WS_TMP1, WS_TMP2, WS_TMP3, WS_START, WS_CEN, WS_COUNT
+};
+
+// bump allocator over a byte region
+struct Bump {
+    unsigned char *base;
+    size_t off = 0, cap;
+    Bump(void *b, size_t c) : base(reinterpret_cast<unsigned char *>(b)), cap(c) {}
+    template <class T> T *take(size_t count) {
+        off = (off + 255) & ~(size_t)255;
+        T *r = reinterpret_cast<T *>(base + off);
+        off += count * sizeof(T);
+        return r;
+    }
+};
+static size_t bump_size(std::initializer_list<size_t> bytes) {
+    size_t t = 256;
+    for (size_t b : bytes) t += b + 256;
+    return t;
+}
+
+static int ld_of(int n) { return (n + 3) & ~3; }
+static int ldu_of(int p) { return (p + 15) & ~15; }
+
+// ---- small utility kernels ---------------------------------------------------------------------------
+__global__ void sym_to_dist_kernel(int n, const double *__restrict__ S, int lds, double *D, double *Dw, int ld) {
+    /* d = as.dist(1 - mat): as.dist keeps the lower triangle (row > col) of the R matrix */
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (size_t)n * n) return;
+    const int i = (int)(idx / n), j = (int)(idx % n);
+    const int hi = i > j ? i : j, lo = i > j ? j : i;
+    const double d = (i == j) ? 0.0 : __dsub_rn(1.0, S[(size_t)hi * lds + lo]);
+    D[(size_t)i * ld + j] = d;
+    if (Dw) Dw[(size_t)i * ld + j] = d;
+}
+
+__global__ void pad_copy_kernel(int n, int ncol, const double *__restrict__ src, int lds, double *dst, int ldd) {
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (size_t)n * ncol) return;
+    const int i = (int)(idx / ncol), j = (int)(idx % ncol);
+    dst[(size_t)i * ldd + j] = src[(size_t)i * lds + j];
+}
+
+// enE/K in member order: E1[i][j] = (((0 + P_1) + P_2) + ...)/K   (R/SHARP.R:629-635, 750)
+__global__ void ene_kernel(const double *__restrict__ proj, int64_t np, int K, double *__restrict__ E1) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= np) return;
+    double s = 0.0;
+    for (int k = 0; k < K; k++) s = __dadd_rn(s, proj[(size_t)k * np + idx]);
+    E1[idx] = __ddiv_rn(s, (double)K);
+}
+
+// colour index: cluster ids above 40 wrap (R/getrowColor.R:59-68)
+__global__ void colour_wrap_kernel(int32_t *lab, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int c = lab[i];
+    if (c > 40) { c = c % 40; if (c == 0) c = 40; lab[i] = c; }
+}
+
+// scatter rows: dst[row_of[i]] = src[i]  (viE[reind, ] = viE)
+__global__ void scatter_rows_kernel(const double *__restrict__ src, int64_t n, int p, const int64_t *__restrict__ row_of,
+                                    double *__restrict__ dst) {
+    const int64_t i = blockIdx.x;
+    if (i >= n) return;
+    const int64_t r = row_of ? row_of[i] : i;
+    for (int j = threadIdx.x; j < p; j += blockDim.x) dst[(size_t)r * p + j] = src[(size_t)i * p + j];
+}
+
+static int grid1d(size_t n, int threads) { return (int)((n + threads - 1) / threads); }
+
+// ---- upload helpers -------------------------------------------------------------------------------
+static int upload_expr(sharp_ctx *c, int m, int64_t n, const double *dense, const int64_t *colptr, const int32_t *rowidx,
+                       const double *val, sharp_expr_dev *e) {
+    e->device = c->device;
+    e->m = m;
+    e->n = n;
+    if (m <= 0 || n < 0) return set_error(SHARP_E_ARG, "expression matrix: bad dimensions %d x %lld", m, (long long)n);
+    if (dense) {
+        size_t bytes = (size_t)m * n * sizeof(double);
+        SHARP_CUDA(cudaMalloc((void **)&e->dense, std::max<size_t>(bytes, 8)));
+        SHARP_CUDA(cudaMemcpyAsync(e->dense, dense, bytes, cudaMemcpyHostToDevice, c->stream));
+    } else {
+        if (!colptr || (!rowidx && colptr[n] > 0) || (!val && colptr[n] > 0))
+            return set_error(SHARP_E_ARG, "expression matrix: neither dense nor complete CSC slots given");
+        e->nnz = colptr[n];
+        SHARP_CUDA(cudaMalloc((void **)&e->colptr, (size_t)(n + 1) * 8));
+        SHARP_CUDA(cudaMalloc((void **)&e->rowidx, std::max<size_t>((size_t)e->nnz * 4, 8)));
+        SHARP_CUDA(cudaMalloc((void **)&e->val, std::max<size_t>((size_t)e->nnz * 8, 8)));
+        SHARP_CUDA(cudaMemcpyAsync(e->colptr, colptr, (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, c->stream));
+        SHARP_CUDA(cudaMemcpyAsync(e->rowidx, rowidx, (size_t)e->nnz * 4, cudaMemcpyHostToDevice, c->stream));
+        SHARP_CUDA(cudaMemcpyAsync(e->val, val, (size_t)e->nnz * 8, cudaMemcpyHostToDevice, c->stream));
+    }
+    return 0;
+}
+
+static void free_expr(sharp_expr_dev *e) {
+    if (!e) return;
+    if (e->dense) cudaFree(e->dense);
+    if (e->colptr) cudaFree(e->colptr);
+    if (e->rowidx) cudaFree(e->rowidx);
+    if (e->val) cudaFree(e->val);
+    e->dense = nullptr;
+    e->colptr = nullptr;
+    e->rowidx = nullptr;
+    e->val = nullptr;
+}
+
+static int h2d(sharp_ctx *c, void *dst, const void *src, size_t bytes) {
+    if (bytes == 0) return 0;
+    SHARP_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, c->stream));
+    return 0;
+}
+static int d2h(sharp_ctx *c, void *dst, const void *src, size_t bytes) {
+    if (bytes == 0) return 0;
+    SHARP_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, c->stream));
+    return 0;
+}
+static int sync(sharp_ctx *c) {
+    SHARP_CUDA(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+static int use(sharp_ctx *c) {
+    if (!c) return set_error(SHARP_E_ARG, "null context");
+    SHARP_CUDA(cudaSetDevice(c->device));
+    return 0;
+}
+
+// =====================================================================================================
+// get_opt_hclust on one matrix already on the device
+// =====================================================================================================
+struct OptResult {  // device pointers into workspaces, valid until the next call on the context
+    int *f;
+    int *v;
+    double *msil, *chind, *crit;
+    int *meta;
+    double *maxsil;
+    int maxlev;
+};
+
+// mat_dev: row-major nrow x ncol on the device.  exact: 1 exact sweep, 0 nested (feature only).
+static int opt_hclust_dev(sharp_ctx *c, int nrow, int ncol, const double *mat_dev, int symmetric, int exact,
+                          const sharp_hc_params &prm_in, bool want_v, OptResult *R) {
+    HcParamsDev prm = to_dev(prm_in);
+    const int n = nrow;
+    if (n < 2) return set_error(SHARP_E_RSTOP, "hclust: must have n >= 2 objects to cluster");
+    if (symmetric && nrow != ncol) return set_error(SHARP_E_ARG, "a similarity matrix must be square");
+    if (prm.n_cluster != 0 && prm.n_cluster < 2)
+        return set_error(SHARP_E_RSTOP, "The given N.cluster is less than 2, which is not suitable for clustering!");
+    const int ld = ld_of(n);
+    int maxlev = prm.n_cluster ? 1 : std::max(1, prm.max_n - prm.min_n + 1);
+    int kcap = prm.n_cluster ? prm.n_cluster : prm.max_n;
+    if (!symmetric && !exact && std::min(kcap, n - 1) > NESTED_MAXK_HOST) exact = 1;
+    if (symmetric) exact = 1;
+    SHARP_TRY(c->ws[WS_D].reserve((size_t)n * ld * 8));
+    SHARP_TRY(c->ws[WS_DW].reserve((size_t)n * ld * 8));
+    double *D = c->ws[WS_D].as<double>(), *Dw = c->ws[WS_DW].as<double>();
+    const double *Y;
+    int yp, ldy;
+    if (symmetric) {
+        sym_to_dist_kernel<<<grid1d((size_t)n * n, 256), 256, 0, c->stream>>>(n, mat_dev, ncol, D, Dw, ld);
+        c->launches++;
+        Y = mat_dev;
+        yp = n;
+        ldy = ncol;
+    } else {
+        const int ldu = ldu_of(ncol);
+        SHARP_TRY(c->ws[WS_U].reserve((size_t)n * ldu * 8));
+        double *U = c->ws[WS_U].as<double>();
+        SHARP_TRY(launch_unit_rows(c, mat_dev, n, ncol, ldu, U));
+        SHARP_TRY(c->reserve_pinned(4096));
+        SHARP_TRY(c->ws[WS_DESC].reserve(4096));
+        Bump hb(c->pinned, 4096), db(c->ws[WS_DESC].ptr, 4096);
+        GemmProb *gp = hb.take<GemmProb>(1);
+        int *tp = hb.take<int>(2);
+        gp->U = U; gp->n = n; gp->ld = ld; gp->D = D; gp->Dw = Dw;
+        tp[0] = 0; tp[1] = corrdist_tiles(n);
+        GemmProb *gpd = db.take<GemmProb>(1);
+        int *tpd = db.take<int>(2);
+        SHARP_TRY(h2d(c, c->ws[WS_DESC].ptr, c->pinned, hb.off));
+        SHARP_TRY(launch_corrdist_batched(c, gpd, tpd, 1, tp[1], ldu));
+        SHARP_TRY(sync(c)); /* pinned staging is reused below */
+        Y = U;
+        yp = ncol;
+        ldy = ldu;
+    }
+    // hc problem + outputs
+    size_t ibytes = bump_size({(size_t)n * 4, (size_t)n * 4, (size_t)n * 4, (size_t)n * maxlev * 4, 64});
+    size_t dbytes = bump_size({(size_t)n * 8, (size_t)maxlev * 8, (size_t)maxlev * 8, 64});
+    SHARP_TRY(c->ws[WS_HC_INT].reserve(ibytes));
+    SHARP_TRY(c->ws[WS_HC_DBL].reserve(dbytes));
+    Bump bi(c->ws[WS_HC_INT].ptr, ibytes), bd(c->ws[WS_HC_DBL].ptr, dbytes);
+    int *ia = bi.take<int>(n), *ib = bi.take<int>(n);
+    R->f = bi.take<int>(n);
+    R->v = want_v ? bi.take<int>((size_t)n * maxlev) : nullptr;
+    R->meta = bi.take<int>(8);
+    R->crit = bd.take<double>(n);
+    R->msil = bd.take<double>(maxlev);
+    R->chind = bd.take<double>(maxlev);
+    R->maxsil = bd.take<double>(1);
+    R->maxlev = maxlev;
+    SHARP_CUDA(cudaMemsetAsync(R->meta, 0, 8 * 4, c->stream));
+    SHARP_CUDA(cudaMemsetAsync(R->msil, 0, (size_t)maxlev * 8, c->stream));
+    SHARP_CUDA(cudaMemsetAsync(R->chind, 0, (size_t)maxlev * 8, c->stream));
+    SHARP_TRY(c->reserve_pinned(4096));
+    SHARP_TRY(c->ws[WS_DESC].reserve(4096));
+    Bump hb(c->pinned, 4096), db(c->ws[WS_DESC].ptr, 4096);
+    HcProb *hp = hb.take<HcProb>(1);
+    SweepOut *so = hb.take<SweepOut>(1);
+    HcParamsDev *pp = hb.take<HcParamsDev>(1);
+    hp->n = n; hp->ld = ld; hp->D = D; hp->Dw = Dw; hp->ia = ia; hp->ib = ib; hp->crit = R->crit;
+    hp->Y = Y; hp->p = yp; hp->ldy = ldy; hp->status = 0;
+    so->f = R->f; so->v = R->v; so->msil = R->msil; so->chind = R->chind; so->meta = R->meta; so->maxsil = R->maxsil;
+    *pp = prm;
+    HcProb *hpd = db.take<HcProb>(1);
+    SweepOut *sod = db.take<SweepOut>(1);
+    HcParamsDev *ppd = db.take<HcParamsDev>(1);
+    SHARP_TRY(h2d(c, c->ws[WS_DESC].ptr, c->pinned, hb.off));
+    SHARP_TRY(launch_hclust(c, hpd, 1, n, prm.hmethod));
+    if (exact) {
+        size_t sb = sweep_exact_scratch_bytes(n, yp);
+        SHARP_TRY(c->ws[WS_SWEEP_SCRATCH].reserve(sb));
+        SHARP_TRY(launch_sweep_exact(c, hpd, sod, 1, n, yp, ppd, maxlev, std::max(kcap, 2), c->ws[WS_SWEEP_SCRATCH].as<double>(), sb));
+    } else {
+        size_t sb = sweep_nested_scratch_bytes(n, yp, prm);
+        SHARP_TRY(c->ws[WS_SWEEP_SCRATCH].reserve(sb));
+        SHARP_TRY(launch_sweep_nested(c, hpd, sod, 1, n, yp, prm, c->ws[WS_SWEEP_SCRATCH].as<double>(), sb));
+    }
+    return 0;
+}
+
+// =====================================================================================================
+// wMetaC on labels already on the device: [K][ncells] codes, T blocks given by start (host copy too)
+// =====================================================================================================
+struct WmBuffers {
+    WmArgs A;
+    SweepOut *outs_dev;
+    HcParamsDev *prm_dev;
+    int T, max_block_n;
+};
+
+static int wmetac_dev(sharp_ctx *c, const int32_t *labels_dev, int64_t ncells, int K, int T, const int64_t *start_host,
+                      const int64_t *start_dev, int max_label, const sharp_hc_params &prm_in, WmBuffers *W) {
+    HcParamsDev prm = to_dev(prm_in);
+    if (prm.n_cluster != 0 && prm.n_cluster < 2)
+        return set_error(SHARP_E_RSTOP, "The given N.cluster is less than 2, which is not suitable for clustering!");
+    if (K > WM_MAXK) return set_error(SHARP_E_LIMIT, "wMetaC: at most %d clustering solutions (got %d)", WM_MAXK, K);
+    if (max_label > WM_MAXL) return set_error(SHARP_E_LIMIT, "wMetaC: at most %d clusters per solution (got %d)", WM_MAXL, max_label);
+    int max_block_n = 0;
+    for (int t = 0; t < T; t++) max_block_n = std::max<int>(max_block_n, (int)(start_host[t + 1] - start_host[t]));
+    const int capC = std::max(2, K * std::min(max_label, max_block_n));
+    const int kcap = prm.n_cluster ? prm.n_cluster : prm.max_n;
+    const int capU = std::max(2, std::min(std::max(kcap, 2), capC));
+    if (capU > WM_MAXU) return set_error(SHARP_E_LIMIT, "wMetaC: at most %d meta-clusters (got %d)", WM_MAXU, capU);
+    const int maxlev = prm.n_cluster ? 1 : std::max(1, prm.max_n - prm.min_n + 1);
+    WmArgs &A = W->A;
+    A.labels = labels_dev;
+    A.ncells = ncells;
+    A.K = K;
+    A.start = start_dev;
+    A.capC = capC;
+    A.capU = capU;
+    size_t ibytes = bump_size({(size_t)K * ncells * 4, (size_t)K * ncells * 4, (size_t)T * (capC + 1) * 4, (size_t)T * capC * 4,
+                               (size_t)T * 4, (size_t)T * capC * 4, (size_t)T * capC * 4, (size_t)ncells * 4,
+                               (size_t)ncells * 4, (size_t)T * 4, (size_t)T * capU * 4, (size_t)T * 4,
+                               (size_t)T * capC * 4, (size_t)T * 8 * 4});
+    size_t dbytes = bump_size({(size_t)ncells * 8, (size_t)T * capC * 8, (size_t)T * maxlev * 8, (size_t)T * maxlev * 8, (size_t)T * 8});
+    SHARP_TRY(c->ws[WS_WM_INT].reserve(ibytes));
+    SHARP_TRY(c->ws[WS_WM_DBL].reserve(dbytes));
+    SHARP_TRY(c->ws[WS_WM_S].reserve((size_t)3 * T * capC * capC * 8));
+    Bump bi(c->ws[WS_WM_INT].ptr, ibytes), bd(c->ws[WS_WM_DBL].ptr, dbytes);
+    A.gid = bi.take<int>((size_t)K * ncells);
+    A.members = bi.take<int>((size_t)K * ncells);
+    A.moff = bi.take<int>((size_t)T * (capC + 1));
+    A.col_of = bi.take<int>((size_t)T * capC);
+    A.allc = bi.take<int>(T);
+    A.ia = bi.take<int>((size_t)T * capC);
+    A.ib = bi.take<int>((size_t)T * capC);
+    A.finalc = bi.take<int>(ncells);
+    A.fcode = bi.take<int>(ncells);
+    A.ucount = bi.take<int>(T);
+    A.ulist = bi.take<int>((size_t)T * capU);
+    A.status = bi.take<int>(T);
+    int *meta_f = bi.take<int>((size_t)T * capC);
+    int *meta_meta = bi.take<int>((size_t)T * 8);
+    A.w1 = bd.take<double>(ncells);
+    A.crit = bd.take<double>((size_t)T * capC);
+    double *msil = bd.take<double>((size_t)T * maxlev);
+    double *chind = bd.take<double>((size_t)T * maxlev);
+    double *maxsil = bd.take<double>(T);
+    A.S = c->ws[WS_WM_S].as<double>();
+    A.D = A.S + (size_t)T * capC * capC;
+    A.Dw = A.D + (size_t)T * capC * capC;
+    SHARP_CUDA(cudaMemsetAsync(meta_meta, 0, (size_t)T * 8 * 4, c->stream));
+    SHARP_CUDA(cudaMemsetAsync(A.status, 0, (size_t)T * 4, c->stream));
+    SHARP_CUDA(cudaMemsetAsync(A.ucount, 0, (size_t)T * 4, c->stream));
+    // descriptors
+    size_t desc = bump_size({(size_t)T * sizeof(HcProb), (size_t)T * sizeof(SweepOut), (size_t)T * sizeof(HcParamsDev)});
+    SHARP_TRY(c->reserve_pinned(desc));
+    SHARP_TRY(c->ws[WS_WM_DESC].reserve(desc));
+    Bump hb(c->pinned, desc), db(c->ws[WS_WM_DESC].ptr, desc);
+    (void)hb.take<HcProb>(T); /* filled on the device by wm_similarity */
+    SweepOut *so = hb.take<SweepOut>(T);
+    HcParamsDev *pp = hb.take<HcParamsDev>(T);
+    for (int t = 0; t < T; t++) {
+        so[t].f = meta_f + (size_t)t * capC;
+        so[t].v = nullptr;
+        so[t].msil = msil + (size_t)t * maxlev;
+        so[t].chind = chind + (size_t)t * maxlev;
+        so[t].meta = meta_meta + (size_t)t * 8;
+        so[t].maxsil = maxsil + t;
+        pp[t] = prm;
+    }
+    A.probs = db.take<HcProb>(T);
+    W->outs_dev = db.take<SweepOut>(T);
+    W->prm_dev = db.take<HcParamsDev>(T);
+    SHARP_TRY(h2d(c, c->ws[WS_WM_DESC].ptr, c->pinned, hb.off));
+    W->T = T;
+    W->max_block_n = max_block_n;
+    SHARP_TRY(launch_wmetac_front(c, A, T, max_block_n));
+    SHARP_TRY(launch_hclust(c, A.probs, T, capC, prm.hmethod));
+    size_t sb = sweep_exact_scratch_bytes(capC, capC);
+    SHARP_TRY(c->ws[WS_WM_SCRATCH].reserve(sb * T));
+    SHARP_TRY(launch_sweep_exact(c, A.probs, W->outs_dev, T, capC, capC, W->prm_dev, maxlev, std::max(kcap, 2),
+                                 c->ws[WS_WM_SCRATCH].as<double>(), sb));
+    SHARP_TRY(launch_wmetac_vote(c, A, W->outs_dev, T));
+    SHARP_TRY(sync(c)); /* the pinned descriptor staging may be reused by the caller */
+    return 0;
+}
+
+// =====================================================================================================
+// sMetaC core on the device: cluster member lists (corder/coff) and E1 given
+// =====================================================================================================
+struct SmBuffers {
+    SmArgs A;
+    SweepOut *out_dev;
+    int *tf;        // [capS]
+    int *status;    // [1]
+    double *cen;    // [capS][p]
+};
+
+// nc_ptr/status_in: device ints.  cen_in: optional precomputed centroids (device) -- else computed from E1.
+static int smetac_dev(sharp_ctx *c, int capS, int p, const int *nc_ptr, const int *status_in, const double *E1,
+                      const int *corder, const int *coff, const double *cen_in, int64_t ncells_total,
+                      const sharp_hc_params &prm_in, SmBuffers *B) {
+    HcParamsDev prm = to_dev(prm_in);
+    if (prm.n_cluster != 0 && prm.n_cluster < 2)
+        return set_error(SHARP_E_RSTOP, "The given N.cluster is less than 2, which is not suitable for clustering!");
+    // host-side upper bounds of the tweaked range (R/sMetaC.R:101-119)
+    int maxN = prm.max_n, minN = prm.min_n;
+    if (ncells_total >= 1000000) {
+        maxN = std::max(maxN, (int)(ncells_total / 5000));
+        minN = std::max(minN, (int)(ncells_total / 50000));
+    }
+    const int maxlev = prm.n_cluster ? 1 : std::max(1, maxN - std::min(minN, prm.min_n) + 1);
+    const int kcap = std::max(2, prm.n_cluster ? prm.n_cluster : maxN);
+    const int ld = ld_of(capS);
+    size_t ibytes = bump_size({(size_t)ld * 4, (size_t)ld * 4, (size_t)ld * 4, (size_t)ld * 4, 64, 64});
+    size_t dbytes = bump_size({(size_t)ld * 8, (size_t)maxlev * 8, (size_t)maxlev * 8, 64, (size_t)capS * 8, (size_t)capS * 8,
+                               (size_t)capS * p * 8});
+    SHARP_TRY(c->ws[WS_SM_INT].reserve(ibytes));
+    SHARP_TRY(c->ws[WS_SM_DBL].reserve(dbytes));
+    SHARP_TRY(c->ws[WS_SM_S].reserve((size_t)3 * ld * ld * 8));
+    Bump bi(c->ws[WS_SM_INT].ptr, ibytes), bd(c->ws[WS_SM_DBL].ptr, dbytes);
+    SmArgs &A = B->A;
+    A.ia = bi.take<int>(ld);
+    A.ib = bi.take<int>(ld);
+    int *f = bi.take<int>(ld);
+    B->tf = bi.take<int>(ld);
+    int *meta = bi.take<int>(8);
+    B->status = bi.take<int>(1);
+    A.crit = bd.take<double>(ld);
+    double *msil = bd.take<double>(maxlev);
+    double *chind = bd.take<double>(maxlev);
+    double *maxsil = bd.take<double>(1);
+    double *mean = bd.take<double>(capS);
+    double *sdev = bd.take<double>(capS);
+    B->cen = bd.take<double>((size_t)capS * p);
+    A.S = c->ws[WS_SM_S].as<double>();
+    A.D = A.S + (size_t)ld * ld;
+    A.Dw = A.D + (size_t)ld * ld;
+    A.ld = ld;
+    A.nc_ptr = nc_ptr;
+    A.status_in = status_in;
+    A.prm = prm;
+    A.ncells_total = ncells_total;
+    A.tf = B->tf;
+    A.status_out = B->status;
+    SHARP_CUDA(cudaMemsetAsync(meta, 0, 8 * 4, c->stream));
+    size_t desc = bump_size({sizeof(HcProb), sizeof(SweepOut), sizeof(HcParamsDev)});
+    SHARP_TRY(c->reserve_pinned(desc));
+    SHARP_TRY(c->ws[WS_DESC].reserve(desc));
+    Bump hb(c->pinned, desc), db(c->ws[WS_DESC].ptr, desc);
+    (void)hb.take<HcProb>(1);
+    SweepOut *so = hb.take<SweepOut>(1);
+    (void)hb.take<HcParamsDev>(1);
+    so->f = f; so->v = nullptr; so->msil = msil; so->chind = chind; so->meta = meta; so->maxsil = maxsil;
+    A.prob = db.take<HcProb>(1);
+    B->out_dev = db.take<SweepOut>(1);
+    A.prm_out = db.take<HcParamsDev>(1);
+    SHARP_TRY(h2d(c, c->ws[WS_DESC].ptr, c->pinned, hb.off));
+    const double *cen = cen_in;
+    if (!cen) {
+        SHARP_TRY(launch_sm_centroids(c, E1, p, corder, coff, nc_ptr, capS, B->cen, nullptr));
+        cen = B->cen;
+    }
+    SHARP_TRY(launch_sm_similarity(c, A, cen, p, capS, mean, sdev));
+    SHARP_TRY(launch_hclust(c, A.prob, 1, ld, prm.hmethod));
+    size_t sb = sweep_exact_scratch_bytes(ld, ld);
+    SHARP_TRY(c->ws[WS_SM_SCRATCH].reserve(sb));
+    SHARP_TRY(launch_sweep_exact(c, A.prob, B->out_dev, 1, ld, ld, A.prm_out, maxlev, kcap, c->ws[WS_SM_SCRATCH].as<double>(), sb));
+    SHARP_TRY(launch_sm_finish(c, A, B->out_dev));
+    SHARP_TRY(sync(c));
+    return 0;
+}
+
+// R/SHARP.R:513-536: block boundaries in the (shuffled) cell order
+static void make_blocks(int64_t n, int large, int ng, std::vector<int64_t> &start) {
+    start.clear();
+    if (!large || ng <= 0 || n <= ng) {
+        start = {0, n};
+        return;
+    }
+    int64_t T = (n + ng - 1) / ng;
+    int64_t nt = n - (T - 2) * ng;
+    start.push_back(0);
+    for (int64_t t = 0; t < T - 2; t++) start.push_back(start.back() + ng);
+    start.push_back(start.back() + nt / 2);
+    start.push_back(n);
+}
+
+// =====================================================================================================
+// the fused SHARP_small / SHARP_large pipeline
+// =====================================================================================================
+static int run_core(sharp_ctx *c, const sharp_expr_dev &e, const double *colsum_host, const sharp_rm_dev &rm,
+                    const int64_t *reind, const sharp_run_params &Q, int32_t *labels_out, double *vie_out, double *x0_out,
+                    int *x0_cols, int max_x0_cols) {
+    const int64_t n = e.n;
+    const int p = rm.p, K = rm.K;
+    if (n < 2) return set_error(SHARP_E_ARG, "need at least 2 cells");
+    if (n > 2000000000LL / std::max(1, K)) return set_error(SHARP_E_LIMIT, "too many cells for one call (%lld); split into parts", (long long)n);
+    std::vector<int64_t> start;
+    make_blocks(n, Q.large, Q.partition_ncells, start);
+    const int T = (int)start.size() - 1;
+    int max_bn = 0;
+    for (int t = 0; t < T; t++) max_bn = std::max<int>(max_bn, (int)(start[t + 1] - start[t]));
+    const bool shuffle = Q.large && reind && n < 100000;
+
+    // ---- inputs: source column per position, column sums ----
+    int64_t *src_dev = nullptr;
+    if (shuffle) {
+        SHARP_TRY(c->ws[WS_SRC].reserve((size_t)n * 8));
+        src_dev = c->ws[WS_SRC].as<int64_t>();
+        SHARP_TRY(c->reserve_pinned((size_t)n * 8));
+        int64_t *hp = reinterpret_cast<int64_t *>(c->pinned);
+        for (int64_t i = 0; i < n; i++) {
+            if (reind[i] < 1 || reind[i] > n) return set_error(SHARP_E_ARG, "reind is not a permutation of 1..n");
+            hp[i] = reind[i] - 1;
+        }
+        SHARP_TRY(h2d(c, src_dev, hp, (size_t)n * 8));
+        SHARP_TRY(sync(c));
+    }
+    SHARP_TRY(c->ws[WS_START].reserve((size_t)(T + 1) * 8));
+    int64_t *start_dev = c->ws[WS_START].as<int64_t>();
+    SHARP_TRY(c->reserve_pinned((size_t)(T + 1) * 8));
+    memcpy(c->pinned, start.data(), (size_t)(T + 1) * 8);
+    SHARP_TRY(h2d(c, start_dev, c->pinned, (size_t)(T + 1) * 8));
+    SHARP_TRY(sync(c));
+    double *colsum_dev = nullptr;
+    if (Q.normalize) {
+        SHARP_TRY(c->ws[WS_COLSUM].reserve((size_t)n * 8));
+        colsum_dev = c->ws[WS_COLSUM].as<double>();
+        if (Q.normalize == 1) {
+            if (!colsum_host) return set_error(SHARP_E_ARG, "normalize = 1 needs the column sums");
+            SHARP_TRY(h2d(c, colsum_dev, colsum_host, (size_t)n * 8));
+        } else SHARP_TRY(launch_colsum(c, e, colsum_dev));
+    }
+    const int logkind = Q.logflag ? (Q.logkind ? Q.logkind : 2) : 0;
+
+    // ---- K1: projection of every cell for all K members ----
+    const size_t np = (size_t)n * p;
+    SHARP_TRY(c->ws[WS_PROJ].reserve((size_t)K * np * 8));
+    double *proj = c->ws[WS_PROJ].as<double>();
+    SHARP_TRY(launch_rp_project(c, e, src_dev, n, colsum_dev, Q.normalize, Q.norm_mul, logkind, Q.round_digits, rm, proj));
+
+    // ---- K2 input: unit rows ----
+    const int ldu = ldu_of(p);
+    SHARP_TRY(c->ws[WS_U].reserve((size_t)K * n * ldu * 8));
+    double *U = c->ws[WS_U].as<double>();
+    SHARP_TRY(launch_unit_rows(c, proj, (int64_t)K * n, p, ldu, U));
+
+    // ---- per-(member, block) clustering in waves ----
+    sharp_hc_params indp = Q.hc;
+    indp.n_cluster = Q.ind_n_cluster;
+    HcParamsDev ind = to_dev(indp);
+    if (ind.n_cluster != 0 && ind.n_cluster < 2)
+        return set_error(SHARP_E_RSTOP, "The given N.cluster is less than 2, which is not suitable for clustering!");
+    const int kcap_ind = ind.n_cluster ? ind.n_cluster : ind.max_n;
+    const bool nested = std::min(kcap_ind, max_bn - 1) <= NESTED_MAXK_HOST;
+    const int maxlev = ind.n_cluster ? 1 : std::max(1, ind.max_n - ind.min_n + 1);
+    const int nprob = K * T;
+    SHARP_TRY(c->ws[WS_ENRP].reserve((size_t)K * n * 4));
+    int32_t *enrp = c->ws[WS_ENRP].as<int32_t>();
+    // per-problem small outputs
+    size_t ibytes = bump_size({(size_t)K * n * 4, (size_t)K * n * 4, (size_t)nprob * 8 * 4});
+    size_t dbytes = bump_size({(size_t)K * n * 8, (size_t)nprob * maxlev * 8, (size_t)nprob * maxlev * 8, (size_t)nprob * 8});
+    SHARP_TRY(c->ws[WS_HC_INT].reserve(ibytes));
+    SHARP_TRY(c->ws[WS_HC_DBL].reserve(dbytes));
+    Bump bi(c->ws[WS_HC_INT].ptr, ibytes), bd(c->ws[WS_HC_DBL].ptr, dbytes);
+    int *ia_all = bi.take<int>((size_t)K * n), *ib_all = bi.take<int>((size_t)K * n);
+    int *meta_all = bi.take<int>((size_t)nprob * 8);
+    double *crit_all = bd.take<double>((size_t)K * n);
+    double *msil_all = bd.take<double>((size_t)nprob * maxlev);
+    double *chind_all = bd.take<double>((size_t)nprob * maxlev);
+    double *maxsil_all = bd.take<double>(nprob);
+    SHARP_CUDA(cudaMemsetAsync(meta_all, 0, (size_t)nprob * 8 * 4, c->stream));
+    // wave size from the distance-matrix budget
+    size_t free_b = 0, total_b = 0;
+    SHARP_CUDA(cudaMemGetInfo(&free_b, &total_b));
+    size_t have = c->ws[WS_D].cap + c->ws[WS_DW].cap;
+    size_t budget = std::min<size_t>((size_t)48 << 30, (size_t)((free_b + have) * 0.6));
+    const size_t per_prob = (size_t)max_bn * ld_of(max_bn) * 8;
+    int wave_blocks = (int)std::max<size_t>(1, (budget / 2 / per_prob) / K);
+    wave_blocks = std::min(wave_blocks, T);
+    const int wave_probs = wave_blocks * K;
+    SHARP_TRY(c->ws[WS_D].reserve(per_prob * wave_probs));
+    SHARP_TRY(c->ws[WS_DW].reserve(per_prob * wave_probs));
+    double *Dall = c->ws[WS_D].as<double>(), *Dwall = c->ws[WS_DW].as<double>();
+    size_t sweep_scr = nested ? sweep_nested_scratch_bytes(max_bn, ldu, ind) : sweep_exact_scratch_bytes(max_bn, ldu);
+    SHARP_TRY(c->ws[WS_SWEEP_SCRATCH].reserve(sweep_scr * wave_probs));
+    // descriptors of ALL problems, built once
+    size_t desc = bump_size({(size_t)nprob * sizeof(GemmProb), (size_t)(nprob + T + 2) * 4, (size_t)nprob * sizeof(HcProb),
+                             (size_t)nprob * sizeof(SweepOut), (size_t)nprob * sizeof(HcParamsDev)});
+    SHARP_TRY(c->reserve_pinned(desc));
+    SHARP_TRY(c->ws[WS_DESC].reserve(desc));
+    Bump hb(c->pinned, desc), db(c->ws[WS_DESC].ptr, desc);
+    GemmProb *gp = hb.take<GemmProb>(nprob);
+    int *tp = hb.take<int>(nprob + T + 2);
+    HcProb *hp = hb.take<HcProb>(nprob);
+    SweepOut *so = hb.take<SweepOut>(nprob);
+    HcParamsDev *pp = hb.take<HcParamsDev>(nprob);
+    GemmProb *gpd = db.take<GemmProb>(nprob);
+    int *tpd = db.take<int>(nprob + T + 2);
+    HcProb *hpd = db.take<HcProb>(nprob);
+    SweepOut *sod = db.take<SweepOut>(nprob);
+    HcParamsDev *ppd = db.take<HcParamsDev>(nprob);
+    struct Wave { int q0, nq, tiles, tp_off; };
+    std::vector<Wave> waves;
+    {
+        int q = 0, tpo = 0;
+        for (int t0 = 0; t0 < T; t0 += wave_blocks) {
+            int t1 = std::min(T, t0 + wave_blocks);
+            Wave w;
+            w.q0 = q;
+            w.tp_off = tpo;
+            int tiles = 0, slot = 0;
+            tp[tpo] = 0;
+            for (int t = t0; t < t1; t++)
+                for (int k = 0; k < K; k++) {
+                    int nq = (int)(start[t + 1] - start[t]);
+                    int ld = ld_of(nq);
+                    size_t row0 = (size_t)k * n + start[t];
+                    gp[q].U = U + row0 * ldu;
+                    gp[q].n = nq;
+                    gp[q].ld = ld;
+                    gp[q].D = Dall + (size_t)slot * (per_prob / 8);
+                    gp[q].Dw = Dwall + (size_t)slot * (per_prob / 8);
+                    tiles += corrdist_tiles(nq);
+                    tp[tpo + slot + 1] = tiles;
+                    hp[q].n = nq; hp[q].ld = ld; hp[q].D = gp[q].D; hp[q].Dw = gp[q].Dw;
+                    hp[q].ia = ia_all + row0; hp[q].ib = ib_all + row0; hp[q].crit = crit_all + row0;
+                    hp[q].Y = gp[q].U; hp[q].p = p; hp[q].ldy = ldu; hp[q].status = 0;
+                    so[q].f = enrp + row0; so[q].v = nullptr;
+                    so[q].msil = msil_all + (size_t)q * maxlev; so[q].chind = chind_all + (size_t)q * maxlev;
+                    so[q].meta = meta_all + (size_t)q * 8; so[q].maxsil = maxsil_all + q;
+                    pp[q] = ind;
+                    q++;
+                    slot++;
+                }
+            w.nq = q - w.q0;
+            w.tiles = tiles;
+            tpo += w.nq + 1;
+            waves.push_back(w);
+        }
+    }
+    SHARP_TRY(h2d(c, c->ws[WS_DESC].ptr, c->pinned, hb.off));
+    for (const Wave &w : waves) {
+        SHARP_TRY(launch_corrdist_batched(c, gpd + w.q0, tpd + w.tp_off, w.nq, w.tiles, ldu));
+        SHARP_TRY(launch_hclust(c, hpd + w.q0, w.nq, max_bn, ind.hmethod));
+        if (nested)
+            SHARP_TRY(launch_sweep_nested(c, hpd + w.q0, sod + w.q0, w.nq, max_bn, ldu, ind, c->ws[WS_SWEEP_SCRATCH].as<double>(), sweep_scr));
+        else
+            SHARP_TRY(launch_sweep_exact(c, hpd + w.q0, sod + w.q0, w.nq, max_bn, p, ppd + w.q0, maxlev, std::max(kcap_ind, 2),
+                                         c->ws[WS_SWEEP_SCRATCH].as<double>(), sweep_scr));
+    }
+    colour_wrap_kernel<<<grid1d((size_t)K * n, 256), 256, 0, c->stream>>>(enrp, (int64_t)K * n);
+    c->launches++;
+    // ---- enE / K ----
+    SHARP_TRY(c->ws[WS_E1].reserve(np * 8));
+    double *E1 = c->ws[WS_E1].as<double>();
+    ene_kernel<<<grid1d(np, 256), 256, 0, c->stream>>>(proj, (int64_t)np, K, E1);
+    c->launches++;
+    // status of the block problems (also makes the pinned staging reusable)
+    {
+        std::vector<int> meta((size_t)nprob * 8);
+        SHARP_TRY(d2h(c, meta.data(), meta_all, meta.size() * 4));
+        SHARP_TRY(sync(c));
+        for (int q = 0; q < nprob; q++)
+            if (meta[(size_t)q * 8 + 3] != 0) return rstop(meta[(size_t)q * 8 + 3], "getrowColor (block clustering)");
+    }
+
+    // ---- wMetaC per block ----
+    sharp_hc_params wp = Q.hc;
+    wp.n_cluster = Q.large ? Q.enp_n_cluster : Q.n_cluster;
+    WmBuffers W;
+    SHARP_TRY(wmetac_dev(c, enrp, n, K, T, start.data(), start_dev, 40, wp, &W));
+    {
+        std::vector<int> st(T);
+        SHARP_TRY(d2h(c, st.data(), W.A.status, (size_t)T * 4));
+        SHARP_TRY(sync(c));
+        for (int t = 0; t < T; t++)
+            if (st[t] != 0) return rstop(st[t], "wMetaC");
+    }
+
+    // ---- labels / sMetaC ----
+    SHARP_TRY(c->ws[WS_LABELS].reserve((size_t)n * 4));
+    int *labels_dev = c->ws[WS_LABELS].as<int>();
+    int ncol_x0 = 0;
+    std::vector<int> colmap_host;
+    int *coloff_dev = nullptr, *colmap_dev = nullptr;
+    if (T == 1) {
+        if (!Q.large) SHARP_TRY(launch_sm_relabel(c, n, W.A.finalc, nullptr, 0, src_dev, labels_dev)); /* finalC ids */
+        else SHARP_TRY(launch_sm_relabel(c, n, W.A.fcode, nullptr, 1, src_dev, labels_dev)); /* position in unique(fColor) */
+        int nu = 0;
+        SHARP_TRY(d2h(c, &nu, W.A.ucount, 4));
+        SHARP_TRY(sync(c));
+        ncol_x0 = nu;
+    } else {
+        const int capS = T * W.A.capU;
+        size_t ib2 = bump_size({(size_t)(T + 1) * 4, 64, 64, (size_t)n * 4, (size_t)n * 4, (size_t)(capS + 1) * 4});
+        SHARP_TRY(c->ws[WS_TMP0].reserve(ib2));
+        Bump b2(c->ws[WS_TMP0].ptr, ib2);
+        coloff_dev = b2.take<int>(T + 1);
+        int *nc_dev = b2.take<int>(1);
+        int *st_dev = b2.take<int>(1);
+        int *code = b2.take<int>(n);
+        int *corder = b2.take<int>(n);
+        int *coff = b2.take<int>(capS + 1);
+        SHARP_TRY(launch_sm_codes(c, W.A, T, coloff_dev, nc_dev, st_dev, code, corder, coff));
+        sharp_hc_params sp = Q.hc;
+        sp.n_cluster = Q.n_cluster;
+        SmBuffers B;
+        SHARP_TRY(smetac_dev(c, capS, p, nc_dev, st_dev, E1, corder, coff, nullptr, n, sp, &B));
+        int st = 0;
+        SHARP_TRY(d2h(c, &st, B.status, 4));
+        SHARP_TRY(sync(c));
+        if (st != 0) return rstop(st, "sMetaC");
+        SHARP_TRY(launch_sm_relabel(c, n, code, B.tf, 0, src_dev, labels_dev));
+        colmap_dev = B.tf;
+        if (x0_out || x0_cols) {
+            int nC = 0;
+            SHARP_TRY(d2h(c, &nC, nc_dev, 4));
+            SHARP_TRY(sync(c));
+            colmap_host.resize(nC);
+            SHARP_TRY(d2h(c, colmap_host.data(), B.tf, (size_t)nC * 4));
+            SHARP_TRY(sync(c));
+            for (int v : colmap_host) ncol_x0 = std::max(ncol_x0, v);
+        }
+    }
+    if (x0_cols) *x0_cols = ncol_x0;
+
+    // ---- outputs ----
+    SHARP_TRY(d2h(c, labels_out, labels_dev, (size_t)n * 4));
+    if (x0_out) {
+        if (ncol_x0 > max_x0_cols) return set_error(SHARP_E_NOMEM, "x0 needs %d columns but the buffer has %d", ncol_x0, max_x0_cols);
+        SHARP_TRY(c->ws[WS_X0].reserve((size_t)n * ncol_x0 * 8));
+        double *x0d = c->ws[WS_X0].as<double>();
+        SHARP_CUDA(cudaMemsetAsync(x0d, 0, (size_t)n * ncol_x0 * 8, c->stream));
+        if (T == 1) {
+            SHARP_TRY(launch_wmetac_x0(c, W.A, W.outs_dev, T, W.max_block_n, nullptr, nullptr, src_dev, x0d, ncol_x0));
+        } else {
+            /* colmap = tf - 1 (0-based output column of every block-level cluster) */
+            SHARP_TRY(c->ws[WS_TMP1].reserve(colmap_host.size() * 4 + 64));
+            int *cm = c->ws[WS_TMP1].as<int>();
+            for (int &v : colmap_host) v -= 1;
+            SHARP_TRY(c->reserve_pinned(colmap_host.size() * 4 + 64));
+            memcpy(c->pinned, colmap_host.data(), colmap_host.size() * 4);
+            SHARP_TRY(h2d(c, cm, c->pinned, colmap_host.size() * 4));
+            SHARP_TRY(launch_wmetac_x0(c, W.A, W.outs_dev, T, W.max_block_n, coloff_dev, cm, src_dev, x0d, ncol_x0));
+        }
+        SHARP_TRY(d2h(c, x0_out, x0d, (size_t)n * ncol_x0 * 8));
+    }
+    // viE = enE/K, un-shuffled; kept on the device for sharp_centroids
+    SHARP_TRY(c->ws[WS_VIEU].reserve(np * 8));
+    double *vieu = c->ws[WS_VIEU].as<double>();
+    scatter_rows_kernel<<<(unsigned)n, 128, 0, c->stream>>>(E1, n, p, src_dev, vieu);
+    c->launches++;
+    c->last_n = n;
+    c->last_p = p;
+    if (vie_out) SHARP_TRY(d2h(c, vie_out, vieu, np * 8));
+    SHARP_TRY(sync(c));
+    (void)colmap_dev;
+    return 0;
+}
+
+}  // namespace sharp
+
+using namespace sharp;
+
+// =====================================================================================================
+// C ABI
+// =====================================================================================================
+extern "C" {
+
+int sharp_abi_version(void) { return SHARP_B200_ABI_VERSION; }
+const char *sharp_last_error(void) { return g_err; }
+
+int sharp_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+int sharp_device_info(int device, char *name, int name_len, int *sm_count, int *cc_major, int *cc_minor, size_t *total_mem) {
+    cudaDeviceProp prop;
+    SHARP_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (name && name_len > 0) {
+        strncpy(name, prop.name, name_len - 1);
+        name[name_len - 1] = 0;
+    }
+    if (sm_count) *sm_count = prop.multiProcessorCount;
+    if (cc_major) *cc_major = prop.major;
+    if (cc_minor) *cc_minor = prop.minor;
+    if (total_mem) *total_mem = prop.totalGlobalMem;
+    return 0;
+}
+
+int sharp_ctx_create(int device, sharp_ctx **out) {
+    if (!out) return set_error(SHARP_E_ARG, "null output pointer");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return set_error(SHARP_E_CUDA, "no CUDA device available (%s): libsharpb200 has no CPU fallback",
+                         e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    }
+    if (device < 0 || device >= ndev) return set_error(SHARP_E_ARG, "device %d out of range (0..%d)", device, ndev - 1);
+    SHARP_CUDA(cudaSetDevice(device));
+    sharp_ctx *c = new sharp_ctx();
+    c->device = device;
+    cudaDeviceProp prop;
+    SHARP_CUDA(cudaGetDeviceProperties(&prop, device));
+    c->sm_count = prop.multiProcessorCount;
+    SHARP_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    SHARP_CUDA(cudaEventCreate(&c->ev0));
+    SHARP_CUDA(cudaEventCreate(&c->ev1));
+    *out = c;
+    return 0;
+}
+
+void sharp_ctx_destroy(sharp_ctx *c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    for (auto &b : c->ws) b.release();
+    if (c->pinned) cudaFreeHost(c->pinned);
+    cudaEventDestroy(c->ev0);
+    cudaEventDestroy(c->ev1);
+    cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+void *sharp_ctx_stream(sharp_ctx *c) { return c ? (void *)c->stream : nullptr; }
+int sharp_ctx_sync(sharp_ctx *c) {
+    SHARP_TRY(use(c));
+    return sync(c);
+}
+int sharp_timer_start(sharp_ctx *c) {
+    SHARP_TRY(use(c));
+    SHARP_CUDA(cudaEventRecord(c->ev0, c->stream));
+    return 0;
+}
+int sharp_timer_stop_ms(sharp_ctx *c, double *ms) {
+    SHARP_TRY(use(c));
+    SHARP_CUDA(cudaEventRecord(c->ev1, c->stream));
+    SHARP_CUDA(cudaEventSynchronize(c->ev1));
+    float f = 0;
+    SHARP_CUDA(cudaEventElapsedTime(&f, c->ev0, c->ev1));
+    if (ms) *ms = f;
+    return 0;
+}
+int64_t sharp_ctx_launch_count(sharp_ctx *c) { return c ? c->launches : 0; }
+
+// ---- ranM upload: dgCMatrix slots of K matrices -> gene-major ternary entries -------------------------
+int sharp_rm_upload(sharp_ctx *c, int m, int p, int K, const int32_t *colptr, const int32_t *rowidx, const double *x,
+                    const int64_t *nnz_off, sharp_rm_dev **out) {
+    SHARP_TRY(use(c));
+    if (!out || m <= 0 || p <= 0 || K <= 0 || !colptr || !nnz_off) return set_error(SHARP_E_ARG, "rm_upload: bad arguments");
+    const int64_t nnz = nnz_off[K];
+    if (nnz > 0 && (!rowidx || !x)) return set_error(SHARP_E_ARG, "rm_upload: missing slots");
+    if ((int64_t)K * p > 0x7fffffffLL) return set_error(SHARP_E_LIMIT, "K*p too large");
+    double mag = 0.0;
+    for (int64_t q = 0; q < nnz; q++) {
+        double a = std::fabs(x[q]);
+        if (a == 0.0) continue;
+        if (mag == 0.0) mag = a;
+        else if (a != mag)
+            return set_error(SHARP_E_LIMIT, "rm_upload: the projection matrices are not ternary (|x| = %g and %g); only ranM()-style matrices are supported", mag, a);
+    }
+    const bool e16 = (int64_t)K * p <= 32768;
+    std::vector<uint32_t> rowptr((size_t)m + 1, 0);
+    for (int k = 0; k < K; k++) {
+        const int32_t *cp = colptr + (size_t)k * (p + 1);
+        if (cp[p] != nnz_off[k + 1] - nnz_off[k]) return set_error(SHARP_E_ARG, "rm_upload: colptr/nnz_off mismatch for matrix %d", k);
+        for (int64_t q = nnz_off[k]; q < nnz_off[k + 1]; q++) {
+            if (rowidx[q] < 0 || rowidx[q] >= m) return set_error(SHARP_E_ARG, "rm_upload: row index out of range");
+            if (x[q] != 0.0) rowptr[rowidx[q] + 1]++;
+        }
+    }
+    for (int i = 0; i < m; i++) rowptr[i + 1] += rowptr[i];
+    const int64_t nz = rowptr[m];
+    std::vector<uint32_t> ent((size_t)nz + 8, 0);
+    {
+        std::vector<uint32_t> fill(rowptr.begin(), rowptr.end() - 1);
+        for (int k = 0; k < K; k++) {
+            const int32_t *cp = colptr + (size_t)k * (p + 1);
+            for (int j = 0; j < p; j++)
+                for (int32_t q = cp[j]; q < cp[j + 1]; q++) {
+                    int64_t g = nnz_off[k] + q;
+                    if (x[g] == 0.0) continue;
+                    uint32_t col = (uint32_t)(k * p + j);
+                    uint32_t v = e16 ? (col | (x[g] < 0 ? 0x8000u : 0u)) : (col | (x[g] < 0 ? 0x80000000u : 0u));
+                    ent[fill[rowidx[g]]++] = v;
+                }
+        }
+    }
+    sharp_rm_dev *r = new sharp_rm_dev();
+    r->device = c->device;
+    r->m = m; r->p = p; r->K = K; r->mag = mag; r->nnz = nz;
+    r->tile_genes = RP_TILE_GENES_HOST;
+    r->ntiles = (m + r->tile_genes - 1) / r->tile_genes;
+    for (int t = 0; t < r->ntiles; t++) {
+        int g0 = t * r->tile_genes, g1 = std::min(m, g0 + r->tile_genes);
+        r->max_tile_entries = std::max<int>(r->max_tile_entries, (int)(rowptr[g1] - rowptr[g0]));
+    }
+    cudaError_t e1 = cudaMalloc((void **)&r->rowptr, (size_t)(m + 1) * 4);
+    cudaError_t e2;
+    if (e16) {
+        std::vector<uint16_t> e16v((size_t)nz + 16, 0);
+        for (int64_t q = 0; q < nz; q++) e16v[q] = (uint16_t)ent[q];
+        e2 = cudaMalloc((void **)&r->ent16, e16v.size() * 2);
+        if (e1 == cudaSuccess && e2 == cudaSuccess) e2 = cudaMemcpy(r->ent16, e16v.data(), e16v.size() * 2, cudaMemcpyHostToDevice);
+    } else {
+        e2 = cudaMalloc((void **)&r->ent32, ent.size() * 4);
+        if (e1 == cudaSuccess && e2 == cudaSuccess) e2 = cudaMemcpy(r->ent32, ent.data(), ent.size() * 4, cudaMemcpyHostToDevice);
+    }
+    if (e1 == cudaSuccess) e1 = cudaMemcpy(r->rowptr, rowptr.data(), (size_t)(m + 1) * 4, cudaMemcpyHostToDevice);
+    if (e1 != cudaSuccess || e2 != cudaSuccess) {
+        sharp_rm_free(r);
+        return set_error(SHARP_E_CUDA, "rm_upload: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
+    }
+    *out = r;
+    return 0;
+}
+
+void sharp_rm_free(sharp_rm_dev *r) {
+    if (!r) return;
+    cudaSetDevice(r->device);
+    if (r->rowptr) cudaFree(r->rowptr);
+    if (r->ent16) cudaFree(r->ent16);
+    if (r->ent32) cudaFree(r->ent32);
+    delete r;
+}
+
+int sharp_expr_upload(sharp_ctx *c, int m, int64_t n, const double *dense, const int64_t *colptr, const int32_t *rowidx,
+                      const double *val, sharp_expr_dev **out) {
+    SHARP_TRY(use(c));
+    if (!out) return set_error(SHARP_E_ARG, "null output pointer");
+    sharp_expr_dev *e = new sharp_expr_dev();
+    int rc = upload_expr(c, m, n, dense, colptr, rowidx, val, e);
+    if (rc) {
+        free_expr(e);
+        delete e;
+        return rc;
+    }
+    *out = e;
+    return 0;
+}
+
+void sharp_expr_free(sharp_expr_dev *e) {
+    if (!e) return;
+    cudaSetDevice(e->device);
+    free_expr(e);
+    delete e;
+}
+
+int sharp_rp_project(sharp_ctx *c, int m, int64_t n, const double *dense, const int64_t *colptr, const int32_t *rowidx,
+                     const double *val, const int64_t *cells, int64_t ncell, int normalize, const double *colsum,
+                     double norm_mul, int logkind, int round_digits, const sharp_rm_dev *rm, double *out) {
+    SHARP_TRY(use(c));
+    if (!rm || !out) return set_error(SHARP_E_ARG, "rp_project: null argument");
+    sharp_expr_dev e;
+    int rc = upload_expr(c, m, n, dense, colptr, rowidx, val, &e);
+    auto body = [&]() -> int {
+        if (rc) return rc;
+        int64_t *cells_dev = nullptr;
+        if (cells) {
+            for (int64_t i = 0; i < ncell; i++)
+                if (cells[i] < 0 || cells[i] >= n) return set_error(SHARP_E_ARG, "rp_project: cell index out of range");
+            SHARP_TRY(c->ws[WS_SRC].reserve((size_t)ncell * 8));
+            cells_dev = c->ws[WS_SRC].as<int64_t>();
+            SHARP_TRY(h2d(c, cells_dev, cells, (size_t)ncell * 8));
+        } else ncell = n;
+        double *cs = nullptr;
+        if (normalize) {
+            SHARP_TRY(c->ws[WS_COLSUM].reserve((size_t)n * 8));
+            cs = c->ws[WS_COLSUM].as<double>();
+            if (normalize == 1) {
+                if (!colsum) return set_error(SHARP_E_ARG, "normalize = 1 needs colsum");
+                SHARP_TRY(h2d(c, cs, colsum, (size_t)n * 8));
+            } else SHARP_TRY(launch_colsum(c, e, cs));
+        }
+        size_t ob = (size_t)rm->K * ncell * rm->p * 8;
+        SHARP_TRY(c->ws[WS_PROJ].reserve(ob));
+        SHARP_TRY(launch_rp_project(c, e, cells_dev, ncell, cs, normalize, norm_mul, logkind, round_digits, *rm, c->ws[WS_PROJ].as<double>()));
+        SHARP_TRY(d2h(c, out, c->ws[WS_PROJ].ptr, ob));
+        return sync(c);
+    };
+    rc = body();
+    cudaStreamSynchronize(c->stream);
+    free_expr(&e);
+    return rc;
+}
+
+int sharp_corrdist(sharp_ctx *c, int n, int p, const double *mat, double *dist) {
+    SHARP_TRY(use(c));
+    if (n < 1 || p < 1 || !mat || !dist) return set_error(SHARP_E_ARG, "corrdist: bad arguments");
+    const int ld = ld_of(n), ldu = ldu_of(p);
+    SHARP_TRY(c->ws[WS_TMP0].reserve((size_t)n * p * 8));
+    SHARP_TRY(c->ws[WS_U].reserve((size_t)n * ldu * 8));
+    SHARP_TRY(c->ws[WS_D].reserve((size_t)n * ld * 8));
+    SHARP_TRY(c->ws[WS_TMP1].reserve((size_t)n * n * 8));
+    SHARP_TRY(h2d(c, c->ws[WS_TMP0].ptr, mat, (size_t)n * p * 8));
+    SHARP_TRY(launch_unit_rows(c, c->ws[WS_TMP0].as<double>(), n, p, ldu, c->ws[WS_U].as<double>()));
+    SHARP_TRY(c->reserve_pinned(4096));
+    SHARP_TRY(c->ws[WS_DESC].reserve(4096));
+    Bump hb(c->pinned, 4096), db(c->ws[WS_DESC].ptr, 4096);
+    GemmProb *gp = hb.take<GemmProb>(1);
+    int *tp = hb.take<int>(2);
+    gp->U = c->ws[WS_U].as<double>(); gp->n = n; gp->ld = ld; gp->D = c->ws[WS_D].as<double>(); gp->Dw = nullptr;
+    tp[0] = 0; tp[1] = corrdist_tiles(n);
+    GemmProb *gpd = db.take<GemmProb>(1);
+    int *tpd = db.take<int>(2);
+    SHARP_TRY(h2d(c, c->ws[WS_DESC].ptr, c->pinned, hb.off));
+    SHARP_TRY(launch_corrdist_batched(c, gpd, tpd, 1, tp[1], ldu));
+    pad_copy_kernel<<<grid1d((size_t)n * n, 256), 256, 0, c->stream>>>(n, n, c->ws[WS_D].as<double>(), ld, c->ws[WS_TMP1].as<double>(), n);
+    c->launches++;
+    SHARP_TRY(d2h(c, dist, c->ws[WS_TMP1].ptr, (size_t)n * n * 8));
+    return sync(c);
+}
+
+int sharp_hclust(sharp_ctx *c, int n, const double *dist, int method, int32_t *ia, int32_t *ib, double *height) {
+    SHARP_TRY(use(c));
+    if (n < 2) return set_error(SHARP_E_RSTOP, "hclust: must have n >= 2 objects to cluster");
+    if (!dist || !ia || !ib || !height) return set_error(SHARP_E_ARG, "hclust: null argument");
+    const int ld = ld_of(n);
+    SHARP_TRY(c->ws[WS_TMP1].reserve((size_t)n * n * 8));
+    SHARP_TRY(c->ws[WS_DW].reserve((size_t)n * ld * 8));
+    SHARP_TRY(h2d(c, c->ws[WS_TMP1].ptr, dist, (size_t)n * n * 8));
+    pad_copy_kernel<<<grid1d((size_t)n * n, 256), 256, 0, c->stream>>>(n, n, c->ws[WS_TMP1].as<double>(), n, c->ws[WS_DW].as<double>(), ld);
+    c->launches++;
+    size_t ibytes = bump_size({(size_t)n * 4, (size_t)n * 4}), dbytes = bump_size({(size_t)n * 8});
+    SHARP_TRY(c->ws[WS_HC_INT].reserve(ibytes));
+    SHARP_TRY(c->ws[WS_HC_DBL].reserve(dbytes));
+    Bump bi(c->ws[WS_HC_INT].ptr, ibytes), bd(c->ws[WS_HC_DBL].ptr, dbytes);
+    int *iad = bi.take<int>(n), *ibd = bi.take<int>(n);
+    double *cr = bd.take<double>(n);
+    SHARP_TRY(c->reserve_pinned(4096));
+    SHARP_TRY(c->ws[WS_DESC].reserve(4096));
+    HcProb *hp = reinterpret_cast<HcProb *>(c->pinned);
+    memset(hp, 0, sizeof(HcProb));
+    hp->n = n; hp->ld = ld; hp->D = nullptr; hp->Dw = c->ws[WS_DW].as<double>(); hp->ia = iad; hp->ib = ibd; hp->crit = cr;
+    SHARP_TRY(h2d(c, c->ws[WS_DESC].ptr, hp, sizeof(HcProb)));
+    SHARP_TRY(launch_hclust(c, c->ws[WS_DESC].as<HcProb>(), 1, n, method));
+    int st = 0;
+    SHARP_TRY(d2h(c, ia, iad, (size_t)(n - 1) * 4));
+    SHARP_TRY(d2h(c, ib, ibd, (size_t)(n - 1) * 4));
+    SHARP_TRY(d2h(c, height, cr, (size_t)(n - 1) * 8));
+    SHARP_TRY(d2h(c, &st, &c->ws[WS_DESC].as<HcProb>()->status, 4));
+    SHARP_TRY(sync(c));
+    if (st != 0) return rstop(st, "hclust");
+    return 0;
+}
+
+static int fetch_opt(sharp_ctx *c, int nrow, const OptResult &R, int32_t *f, int32_t *v, int *nlev, double *msil,
+                     double *chind, double *height, int *optn, double *maxsil, int *oind, const char *where) {
+    int meta[8];
+    SHARP_TRY(d2h(c, meta, R.meta, sizeof meta));
+    SHARP_TRY(sync(c));
+    if (meta[3] != 0) return rstop(meta[3], where);
+    const int L = meta[0];
+    if (f) SHARP_TRY(d2h(c, f, R.f, (size_t)nrow * 4));
+    if (v && R.v) SHARP_TRY(d2h(c, v, R.v, (size_t)nrow * L * 4));
+    if (msil) SHARP_TRY(d2h(c, msil, R.msil, (size_t)L * 8));
+    if (chind) SHARP_TRY(d2h(c, chind, R.chind, (size_t)L * 8));
+    if (height) SHARP_TRY(d2h(c, height, R.crit, (size_t)(nrow - 1) * 8));
+    if (maxsil) SHARP_TRY(d2h(c, maxsil, R.maxsil, 8));
+    SHARP_TRY(sync(c));
+    if (nlev) *nlev = L;
+    if (optn) *optn = meta[1];
+    if (oind) *oind = meta[2];
+    return 0;
+}
+
+int sharp_opt_hclust(sharp_ctx *c, int nrow, int ncol, const double *mat, int symmetric, int exact,
+                     const sharp_hc_params *prm, int32_t *f, int32_t *v, int *nlev, double *msil, double *chind,
+                     double *height, int *optn, double *maxsil, int *oind) {
+    SHARP_TRY(use(c));
+    if (!mat || !prm || nrow < 1 || ncol < 1) return set_error(SHARP_E_ARG, "opt_hclust: bad arguments");
+    SHARP_TRY(c->ws[WS_TMP0].reserve((size_t)nrow * ncol * 8));
+    SHARP_TRY(h2d(c, c->ws[WS_TMP0].ptr, mat, (size_t)nrow * ncol * 8));
+    OptResult R;
+    SHARP_TRY(opt_hclust_dev(c, nrow, ncol, c->ws[WS_TMP0].as<double>(), symmetric ? 1 : 0, exact, *prm, v != nullptr, &R));
+    return fetch_opt(c, nrow, R, f, v, nlev, msil, chind, height, optn, maxsil, oind, "get_opt_hclust");
+}
+
+int sharp_getrowcolor(sharp_ctx *c, int n, int p, const double *emat, const sharp_hc_params *prm, int32_t *color, double *maxsil) {
+    SHARP_TRY(use(c));
+    if (!emat || !prm || !color) return set_error(SHARP_E_ARG, "getrowcolor: bad arguments");
+    SHARP_TRY(c->ws[WS_TMP0].reserve((size_t)n * p * 8));
+    SHARP_TRY(h2d(c, c->ws[WS_TMP0].ptr, emat, (size_t)n * p * 8));
+    OptResult R;
+    SHARP_TRY(opt_hclust_dev(c, n, p, c->ws[WS_TMP0].as<double>(), 0, 0, *prm, false, &R));
+    colour_wrap_kernel<<<grid1d(n, 256), 256, 0, c->stream>>>(R.f, n);
+    c->launches++;
+    return fetch_opt(c, n, R, color, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, maxsil, nullptr, "getrowColor");
+}
+
+int sharp_wmetac(sharp_ctx *c, int N, int C, const int32_t *labels, const sharp_hc_params *prm, int32_t *finalc,
+                 int *ncluster, double *x0, int max_x0_cols, double *w1) {
+    SHARP_TRY(use(c));
+    if (N < 1 || C < 1 || !labels || !prm || !finalc) return set_error(SHARP_E_ARG, "wmetac: bad arguments");
+    // the kernels want codes 1..L in first-appearance order per column: remap on the host (R glue passes
+    // match(x, unique(x)) already; this makes any integer coding valid)
+    std::vector<int32_t> lab((size_t)N * C);
+    int max_label = 1;
+    for (int k = 0; k < C; k++) {
+        std::vector<std::pair<int32_t, int>> seen;
+        for (int i = 0; i < N; i++) {
+            int32_t l = labels[(size_t)k * N + i];
+            int code = 0;
+            for (auto &s : seen)
+                if (s.first == l) { code = s.second; break; }
+            if (!code) { code = (int)seen.size() + 1; seen.push_back({l, code}); }
+            lab[(size_t)k * N + i] = code;
+        }
+        max_label = std::max<int>(max_label, (int)seen.size());
+    }
+    SHARP_TRY(c->ws[WS_ENRP].reserve((size_t)N * C * 4));
+    SHARP_TRY(h2d(c, c->ws[WS_ENRP].ptr, lab.data(), (size_t)N * C * 4));
+    int64_t start[2] = {0, N};
+    SHARP_TRY(c->ws[WS_START].reserve(16));
+    SHARP_TRY(h2d(c, c->ws[WS_START].ptr, start, 16));
+    SHARP_TRY(sync(c));
+    WmBuffers W;
+    SHARP_TRY(wmetac_dev(c, c->ws[WS_ENRP].as<int32_t>(), N, C, 1, start, c->ws[WS_START].as<int64_t>(), max_label, *prm, &W));
+    int st = 0, nu = 0;
+    SHARP_TRY(d2h(c, &st, W.A.status, 4));
+    SHARP_TRY(d2h(c, &nu, W.A.ucount, 4));
+    SHARP_TRY(sync(c));
+    if (st != 0) return rstop(st, "wMetaC");
+    SHARP_TRY(d2h(c, finalc, W.A.finalc, (size_t)N * 4));
+    if (w1) SHARP_TRY(d2h(c, w1, W.A.w1, (size_t)N * 8));
+    if (ncluster) *ncluster = nu;
+    if (x0) {
+        if (nu > max_x0_cols) return set_error(SHARP_E_NOMEM, "wmetac: x0 needs %d columns", nu);
+        SHARP_TRY(c->ws[WS_X0].reserve((size_t)N * nu * 8));
+        SHARP_CUDA(cudaMemsetAsync(c->ws[WS_X0].ptr, 0, (size_t)N * nu * 8, c->stream));
+        SHARP_TRY(launch_wmetac_x0(c, W.A, W.outs_dev, 1, N, nullptr, nullptr, nullptr, c->ws[WS_X0].as<double>(), nu));
+        SHARP_TRY(d2h(c, x0, c->ws[WS_X0].ptr, (size_t)N * nu * 8));
+    }
+    return sync(c);
+}
+
+// host helper: first-appearance codes + member lists
+static void codes_and_lists(int64_t n, const int32_t *labels, std::vector<int> &code, std::vector<int> &corder,
+                            std::vector<int> &coff, int *nc) {
+    code.resize(n);
+    std::vector<std::pair<int32_t, int>> sorted;
+    int next = 0;
+    for (int64_t i = 0; i < n; i++) {
+        int32_t l = labels[i];
+        auto it = std::lower_bound(sorted.begin(), sorted.end(), std::make_pair(l, -1));
+        if (it == sorted.end() || it->first != l) it = sorted.insert(it, {l, next++});
+        code[i] = it->second;
+    }
+    *nc = next;
+    coff.assign(next + 1, 0);
+    for (int64_t i = 0; i < n; i++) coff[code[i] + 1]++;
+    for (int q = 0; q < next; q++) coff[q + 1] += coff[q];
+    corder.resize(n);
+    std::vector<int> fill(coff.begin(), coff.end() - 1);
+    for (int64_t i = 0; i < n; i++) corder[fill[code[i]]++] = (int)i;
+}
+
+int sharp_smetac(sharp_ctx *c, int64_t ncells, int p, const int32_t *labels, const double *se1,
+                 const sharp_hc_params *prm, int32_t *finalcolor, int32_t *tf, int *nc) {
+    SHARP_TRY(use(c));
+    if (ncells < 1 || p < 2 || !labels || !se1 || !prm || !finalcolor) return set_error(SHARP_E_ARG, "smetac: bad arguments");
+    if (ncells > 2000000000LL) return set_error(SHARP_E_LIMIT, "smetac: too many cells");
+    std::vector<int> code, corder, coff;
+    int nC = 0;
+    codes_and_lists(ncells, labels, code, corder, coff, &nC);
+    if (nC < 2) return rstop(SM_E_FEWCLUSTERS, "sMetaC");
+    size_t ib = bump_size({(size_t)ncells * 4, (size_t)ncells * 4, (size_t)(nC + 1) * 4, 64, 64, (size_t)ncells * 4});
+    SHARP_TRY(c->ws[WS_TMP0].reserve(ib));
+    Bump b(c->ws[WS_TMP0].ptr, ib);
+    int *code_d = b.take<int>(ncells), *corder_d = b.take<int>(ncells), *coff_d = b.take<int>(nC + 1);
+    int *nc_d = b.take<int>(1), *st_d = b.take<int>(1);
+    int *out_d = b.take<int>(ncells);
+    SHARP_TRY(c->ws[WS_E1].reserve((size_t)ncells * p * 8));
+    SHARP_TRY(h2d(c, c->ws[WS_E1].ptr, se1, (size_t)ncells * p * 8));
+    SHARP_TRY(h2d(c, code_d, code.data(), (size_t)ncells * 4));
+    SHARP_TRY(h2d(c, corder_d, corder.data(), (size_t)ncells * 4));
+    SHARP_TRY(h2d(c, coff_d, coff.data(), (size_t)(nC + 1) * 4));
+    int zero = 0;
+    SHARP_TRY(h2d(c, nc_d, &nC, 4));
+    SHARP_TRY(h2d(c, st_d, &zero, 4));
+    SHARP_TRY(sync(c));
+    SmBuffers B;
+    SHARP_TRY(smetac_dev(c, nC, p, nc_d, st_d, c->ws[WS_E1].as<double>(), corder_d, coff_d, nullptr, ncells, *prm, &B));
+    int st = 0;
+    SHARP_TRY(d2h(c, &st, B.status, 4));
+    SHARP_TRY(sync(c));
+    if (st != 0) return rstop(st, "sMetaC");
+    SHARP_TRY(launch_sm_relabel(c, ncells, code_d, B.tf, 0, nullptr, out_d));
+    SHARP_TRY(d2h(c, finalcolor, out_d, (size_t)ncells * 4));
+    if (tf) SHARP_TRY(d2h(c, tf, B.tf, (size_t)nC * 4));
+    if (nc) *nc = nC;
+    return sync(c);
+}
+
+int sharp_smetac_centroids(sharp_ctx *c, int nC, int p, const double *cen, int64_t ncells_total,
+                           const sharp_hc_params *prm, int32_t *tf) {
+    SHARP_TRY(use(c));
+    if (nC < 1 || p < 2 || !cen || !prm || !tf) return set_error(SHARP_E_ARG, "smetac_centroids: bad arguments");
+    if (nC < 2) return rstop(SM_E_FEWCLUSTERS, "sMetaC");
+    SHARP_TRY(c->ws[WS_CEN].reserve((size_t)nC * p * 8 + 64));
+    SHARP_TRY(c->ws[WS_TMP0].reserve(256));
+    int *nc_d = c->ws[WS_TMP0].as<int>(), *st_d = nc_d + 16;
+    int zero = 0;
+    SHARP_TRY(h2d(c, c->ws[WS_CEN].ptr, cen, (size_t)nC * p * 8));
+    SHARP_TRY(h2d(c, nc_d, &nC, 4));
+    SHARP_TRY(h2d(c, st_d, &zero, 4));
+    SHARP_TRY(sync(c));
+    SmBuffers B;
+    SHARP_TRY(smetac_dev(c, nC, p, nc_d, st_d, nullptr, nullptr, nullptr, c->ws[WS_CEN].as<double>(), ncells_total, *prm, &B));
+    int st = 0;
+    SHARP_TRY(d2h(c, &st, B.status, 4));
+    SHARP_TRY(sync(c));
+    if (st != 0) return rstop(st, "sMetaC");
+    SHARP_TRY(d2h(c, tf, B.tf, (size_t)nC * 4));
+    return sync(c);
+}
+
+int sharp_run_dev(sharp_ctx *c, const sharp_expr_dev *e, const double *colsum, const sharp_rm_dev *rm,
+                  const int64_t *reind, const sharp_run_params *prm, int32_t *labels, double *vie, double *x0,
+                  int *x0_cols, int max_x0_cols) {
+    SHARP_TRY(use(c));
+    if (!e || !rm || !prm || !labels) return set_error(SHARP_E_ARG, "run: null argument");
+    if (e->m != rm->m) return set_error(SHARP_E_ARG, "run: expression has %d genes but ranM has %d rows", e->m, rm->m);
+    return run_core(c, *e, colsum, *rm, reind, *prm, labels, vie, x0, x0_cols, max_x0_cols);
+}
+
+int sharp_run(sharp_ctx *c, int m, int64_t n, const double *dense, const int64_t *colptr, const int32_t *rowidx,
+              const double *val, const double *colsum, const sharp_rm_dev *rm, const int64_t *reind,
+              const sharp_run_params *prm, int32_t *labels, double *vie, double *x0, int *x0_cols, int max_x0_cols) {
+    SHARP_TRY(use(c));
+    if (!rm || !prm || !labels) return set_error(SHARP_E_ARG, "run: null argument");
+    sharp_expr_dev e;
+    int rc = upload_expr(c, m, n, dense, colptr, rowidx, val, &e);
+    if (!rc) rc = sharp_run_dev(c, &e, colsum, rm, reind, prm, labels, vie, x0, x0_cols, max_x0_cols);
+    cudaStreamSynchronize(c->stream);
+    free_expr(&e);
+    return rc;
+}
+
+int sharp_centroids(sharp_ctx *c, int64_t n, const int32_t *labels, int nclust, double *cen, int64_t *counts) {
+    SHARP_TRY(use(c));
+    if (!labels || !cen || nclust < 1) return set_error(SHARP_E_ARG, "centroids: bad arguments");
+    if (n != c->last_n || !c->ws[WS_VIEU].ptr) return set_error(SHARP_E_ARG, "centroids: no matching run on this context");
+    const int p = c->last_p;
+    std::vector<int> coff(nclust + 1, 0), corder(n);
+    for (int64_t i = 0; i < n; i++) {
+        if (labels[i] < 1 || labels[i] > nclust) return set_error(SHARP_E_ARG, "centroids: label out of range");
+        coff[labels[i]]++;
+    }
+    for (int q = 0; q < nclust; q++) coff[q + 1] += coff[q];
+    {
+        std::vector<int> fill(coff.begin(), coff.end() - 1);
+        for (int64_t i = 0; i < n; i++) corder[fill[labels[i] - 1]++] = (int)i;
+    }
+    size_t ib = bump_size({(size_t)n * 4, (size_t)(nclust + 1) * 4, 64, (size_t)nclust * 8});
+    SHARP_TRY(c->ws[WS_TMP0].reserve(ib));
+    Bump b(c->ws[WS_TMP0].ptr, ib);
+    int *corder_d = b.take<int>(n), *coff_d = b.take<int>(nclust + 1), *nc_d = b.take<int>(1);
+    int64_t *cnt_d = b.take<int64_t>(nclust);
+    SHARP_TRY(c->ws[WS_CEN].reserve((size_t)nclust * p * 8));
+    SHARP_TRY(h2d(c, corder_d, corder.data(), (size_t)n * 4));
+    SHARP_TRY(h2d(c, coff_d, coff.data(), (size_t)(nclust + 1) * 4));
+    SHARP_TRY(h2d(c, nc_d, &nclust, 4));
+    SHARP_TRY(sync(c));
+    SHARP_TRY(launch_sm_centroids(c, c->ws[WS_VIEU].as<double>(), p, corder_d, coff_d, nc_d, nclust, c->ws[WS_CEN].as<double>(), cnt_d));
+    SHARP_TRY(d2h(c, cen, c->ws[WS_CEN].ptr, (size_t)nclust * p * 8));
+    if (counts) SHARP_TRY(d2h(c, counts, cnt_d, (size_t)nclust * 8));
+    return sync(c);
+}
+
+}  /* extern "C" */

@@ -1,0 +1,609 @@
+// sweep.cu -- K4/K5/K6 + the selection rule of get_opt_hclust (R/get_opt_hclust.R:111-229).
+//
+// For every candidate number of clusters k in minN..min(maxN, n-1) the reference calls cutree, silhouette
+// (+ median) and clues::get_CH -- 39 passes over the distance matrix per 2000-cell block.  Two kernels:
+//
+//  * sweep_nested_kernel (feature problems, the 2000-cell blocks): the cuts are nested, so the per-point
+//    distance sums diC[x][c] are accumulated ONCE for the finest cut (one coalesced pass over D, summed in
+//    ascending y like cluster::sildist) and every coarser level only adds two columns, following the dendrogram
+//    (so a cluster that is unchanged between two levels keeps bit-identical sums and the reference's exact
+//    ties msil[k] == msil[k+1] survive).  The CH index comes from the Gram matrix of the finest-level cluster
+//    sums.  One CTA per problem.
+//  * sweep_exact_kernel (similarity problems of wMetaC / sMetaC, n <= ~1000, full of exact ties): one CTA per
+//    (problem, level); every sum runs in the reference's order, so msil is bit-identical to the CPU oracle.
+//
+// Both are followed by the selection rule (sil -> CH -> height gap) and the final cutree.
+#include "devutil.cuh"
+#include "internal.cuh"
+
+namespace sharp {
+
+constexpr int SW_THREADS = 256;
+constexpr int NESTED_MAXK = 64;
+
+// ---- dendrogram helpers --------------------------------------------------------------------------
+// hclust.f keeps the merged cluster under the smaller representative I2 and retires J2, so the representative
+// of a cluster is always its minimum index.  step_of[j] = merge step at which j was retired (INT_MAX if never),
+// link[j] = the representative it was merged into.
+__device__ __forceinline__ void build_links(int n, const int *ia, const int *ib, int *step_of, int *link) {
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        step_of[i] = INT_MAX;
+        link[i] = i;
+    }
+    __syncthreads();
+    for (int s = threadIdx.x; s < n - 1; s += blockDim.x) {
+        int j2 = ib[s] - 1;
+        step_of[j2] = s;
+        link[j2] = ia[s] - 1;
+    }
+    __syncthreads();
+}
+
+__device__ __forceinline__ int root_at(int x, int nmerge, const int *step_of, const int *link) {
+    while (step_of[x] < nmerge) x = link[x];
+    return x;
+}
+
+// cutree(h, k): labels numbered by first appearance = rank of the cluster's representative (its minimum index)
+// among the live representatives.  rank[] (shared, n ints) is scratch; lab[] receives 0-based ids.
+template <int THREADS>
+__device__ __forceinline__ void labels_at(int n, int k, const int *step_of, const int *link, int *rank, int *tmp,
+                                          int *lab) {
+    const int nmerge = n - k;
+    for (int i = threadIdx.x; i < n; i += THREADS) rank[i] = (step_of[i] >= nmerge) ? 1 : 0;
+    __syncthreads();
+    block_exclusive_scan<THREADS>(rank, n, tmp);
+    for (int i = threadIdx.x; i < n; i += THREADS) lab[i] = rank[root_at(i, nmerge, step_of, link)];
+    __syncthreads();
+}
+
+// ---- selection rule (R/get_opt_hclust.R:162-217), run by one thread ----------------------------------
+// Returns the 1-based column `oind` of v (level kmin + oind - 1) or a negative status.
+__device__ int select_rule(int n, int nlev, const double *msil, const double *chind, const double *height,
+                           double sil_thre, double height_ntimes, double *maxsil_out) {
+    double mx = msil[0];
+    bool anynan = (msil[0] != msil[0]);
+    for (int i = 1; i < nlev; i++) {
+        if (msil[i] != msil[i]) anynan = true;
+        if (msil[i] > mx) mx = msil[i];
+    }
+    if (anynan) return -SWEEP_E_NAN;
+    int ntie = 0;
+    for (int i = 0; i < nlev; i++) ntie += (msil[i] == mx);
+    int want = (ntie + 1) / 2; /* tmp[ceiling(length(tmp)/2)] */
+    int oind = 0;
+    for (int i = 0, seen = 0; i < nlev; i++)
+        if (msil[i] == mx && ++seen == want) { oind = i + 1; break; }
+    *maxsil_out = mx;
+    if (mx <= sil_thre) {
+        int best = -1; /* which.max(CHind): first maximum, NaN skipped */
+        for (int i = 0; i < nlev; i++)
+            if (chind[i] == chind[i] && (best < 0 || chind[i] > chind[best])) best = i;
+        if (best < 0) return -SWEEP_E_CHNAN;
+        oind = best + 1;
+        if (oind == 1) {
+            const int nh = n - 1;
+            const int nt = nh < 10 ? nh : 10;
+            const double *t = height + (nh - nt); /* tail(h$height, 10) */
+            int pind = -1;
+            for (int i = 0; i + 1 < nt; i++) {
+                double dif = __dsub_rn(t[i + 1], t[i]);
+                if (dif > __dmul_rn(height_ntimes - 1.0, t[i])) { pind = i; break; }
+            }
+            if (pind >= 0) {
+                double opth = __ddiv_rn(__dadd_rn(t[pind], t[pind + 1]), 2.0);
+                for (int i = 0; i + 1 < nh; i++)
+                    if (height[i + 1] < height[i]) return -SWEEP_E_UNSORTED;
+                int idx = nh;
+                for (int i = 0; i < nh; i++)
+                    if (height[i] > opth) { idx = i; break; }
+                int kcut = n + 1 - (idx + 1);
+                oind = kcut - 1; /* used as a COLUMN index by the reference (quirk B2) */
+            }
+        }
+    }
+    if (oind < 1 || oind > nlev) return -SWEEP_E_OIND;
+    return oind;
+}
+
+// =====================================================================================================
+// nested sweep (feature problems)
+// =====================================================================================================
+// dynamic shared memory layout (bytes):
+//   acc      [kcap][SW_THREADS] double   (also: sort buffer P2 doubles; Gram matrix kcap*kcap doubles)
+//   step_of  [n] int, link [n] int, rank [n] int, cidf [n] int
+//   small tables: cnt_lv [nlevcap][kcap] int, own map slot_lv [nlevcap][kcap] uint8, mergeA/B [nlevcap] int
+struct NestedLayout {
+    size_t acc_off, ints_off, cnt_off, slot_off, merge_off, msil_off, total;
+};
+__host__ __device__ inline NestedLayout nested_layout(int n, int kcap, int nlevcap) {
+    NestedLayout L;
+    size_t acc_bytes = (size_t)kcap * SW_THREADS * 8;
+    int p2 = 1;
+    while (p2 < n) p2 <<= 1;
+    size_t sort_bytes = (size_t)p2 * 8;
+    size_t gram_bytes = (size_t)kcap * kcap * 8;
+    size_t a = acc_bytes > sort_bytes ? acc_bytes : sort_bytes;
+    a = a > gram_bytes ? a : gram_bytes;
+    L.acc_off = 0;
+    L.ints_off = (a + 15) & ~(size_t)15;
+    L.cnt_off = L.ints_off + (size_t)4 * n * 4;
+    L.slot_off = L.cnt_off + (size_t)nlevcap * kcap * 4;
+    L.merge_off = (L.slot_off + (size_t)nlevcap * kcap + 15) & ~(size_t)15;
+    L.msil_off = (L.merge_off + (size_t)nlevcap * 2 * 4 + 15) & ~(size_t)15;
+    L.total = L.msil_off + (size_t)nlevcap * 2 * 8;
+    return L;
+}
+
+size_t sweep_nested_scratch_bytes(int max_n, int max_p, HcParamsDev prm) {
+    int nlev = prm.n_cluster ? 1 : (prm.max_n - prm.min_n + 1);
+    if (nlev < 1) nlev = 1;
+    size_t sil = (size_t)nlev * max_n * 8;
+    size_t csum = (size_t)NESTED_MAXK * max_p * 8;
+    return ((sil + csum) + 255) & ~(size_t)255;
+}
+
+__global__ void __launch_bounds__(SW_THREADS)
+sweep_nested_kernel(HcProb *probs, SweepOut *outs, HcParamsDev prm, int n_cap, int kcap, int nlevcap, double *scratch,
+                    size_t scratch_per_prob) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    __shared__ int tmp_scan[SW_THREADS];
+    __shared__ double red[SW_THREADS / 32];
+    __shared__ int s_oind;
+
+    HcProb &P = probs[blockIdx.x];
+    SweepOut &O = outs[blockIdx.x];
+    const int n = P.n;
+    const int tid = threadIdx.x;
+    if (n <= 0) return;
+    if (P.status != 0) { if (tid == 0) O.meta[3] = P.status; return; }
+
+    // levels
+    int kmin, kmax;
+    if (prm.n_cluster) { kmin = kmax = prm.n_cluster; }
+    else { kmin = prm.min_n; kmax = min(prm.max_n, n - 1); }
+    if (kmax < kmin || kmax > n - 1 || kmin < 2) {
+        /* R: silhouette() returns NA when k >= n or nc runs backwards; cutree stops for k > n */
+        if (tid == 0) { O.meta[0] = 0; O.meta[3] = (prm.n_cluster && kmax > n) ? SWEEP_E_KRANGE : SWEEP_E_FEWPOINTS; }
+        return;
+    }
+    const int nlev = kmax - kmin + 1;
+    const int ld = P.ld;
+    const double *__restrict__ D = P.D;
+
+    NestedLayout L = nested_layout(n_cap, kcap, nlevcap);
+    double *acc = reinterpret_cast<double *>(smem + L.acc_off);
+    int *step_of = reinterpret_cast<int *>(smem + L.ints_off);
+    int *link = step_of + n_cap;
+    int *rank = link + n_cap;
+    int *cidf = rank + n_cap;
+    int *cnt_lv = reinterpret_cast<int *>(smem + L.cnt_off);          // [nlev][kcap], level 0 = finest (k = kmax)
+    unsigned char *slot_lv = smem + L.slot_off;                       // [nlev][kcap]: fine id -> slot at level
+    int *mergeA = reinterpret_cast<int *>(smem + L.merge_off);        // [nlev] slot kept when going to level l
+    int *mergeB = mergeA + nlevcap;                                   // [nlev] slot absorbed
+    double *msil = reinterpret_cast<double *>(smem + L.msil_off);     // [nlev] indexed by level (0 = finest)
+    double *chv = msil + nlevcap;
+
+    build_links(n, P.ia, P.ib, step_of, link);
+    // finest cut
+    labels_at<SW_THREADS>(n, kmax, step_of, link, rank, tmp_scan, cidf);
+    for (int i = tid; i < nlevcap * kcap; i += SW_THREADS) cnt_lv[i] = 0;
+    __syncthreads();
+    for (int i = tid; i < n; i += SW_THREADS) atomicAdd(&cnt_lv[cidf[i]], 1);
+    __syncthreads();
+    if (tid == 0) {
+        for (int c = 0; c < kmax; c++) slot_lv[c] = (unsigned char)c;
+        mergeA[0] = mergeB[0] = -1;
+        for (int l = 1; l < nlev; l++) {
+            /* level l has k = kmax - l clusters: apply merge step s = n - (kmax - l) - 1 (0-based) */
+            int s = n - (kmax - l) - 1;
+            int a = cidf[P.ia[s] - 1], b = cidf[P.ib[s] - 1]; /* fine ids of the two representatives */
+            a = slot_lv[(l - 1) * kcap + a];
+            b = slot_lv[(l - 1) * kcap + b];
+            mergeA[l] = a;
+            mergeB[l] = b;
+            for (int c = 0; c < kmax; c++) {
+                unsigned char sl = slot_lv[(l - 1) * kcap + c];
+                slot_lv[l * kcap + c] = (sl == b) ? (unsigned char)a : sl;
+                cnt_lv[l * kcap + c] = cnt_lv[(l - 1) * kcap + c];
+            }
+            cnt_lv[l * kcap + a] += cnt_lv[l * kcap + b];
+            cnt_lv[l * kcap + b] = 0;
+        }
+    }
+    __syncthreads();
+
+    double *silg = scratch + blockIdx.x * (scratch_per_prob / 8);   // [nlev][n]
+    double *csum = silg + (size_t)nlev * n;                          // [kmax][p]
+
+    // ---- silhouettes: one pass over D per chunk of SW_THREADS points ----
+    for (int c0 = 0; c0 < n; c0 += SW_THREADS) {
+        const int x = c0 + tid;
+        const bool valid = x < n;
+        for (int c = 0; c < kmax; c++) acc[c * SW_THREADS + tid] = 0.0;
+        const double *col = D + (valid ? x : 0);
+        int y = 0;
+        for (; y + 4 <= n; y += 4) {
+            double d0 = col[(size_t)(y + 0) * ld], d1 = col[(size_t)(y + 1) * ld];
+            double d2 = col[(size_t)(y + 2) * ld], d3 = col[(size_t)(y + 3) * ld];
+            acc[cidf[y + 0] * SW_THREADS + tid] += d0;
+            acc[cidf[y + 1] * SW_THREADS + tid] += d1;
+            acc[cidf[y + 2] * SW_THREADS + tid] += d2;
+            acc[cidf[y + 3] * SW_THREADS + tid] += d3;
+        }
+        for (; y < n; y++) acc[cidf[y] * SW_THREADS + tid] += col[(size_t)y * ld];
+        const int myfine = valid ? cidf[x] : 0;
+        for (int l = 0; l < nlev; l++) {
+            if (l > 0) acc[mergeA[l] * SW_THREADS + tid] += acc[mergeB[l] * SW_THREADS + tid];
+            const int *cnt = cnt_lv + l * kcap;
+            const int own = slot_lv[l * kcap + myfine];
+            const int n_own = cnt[own];
+            double a_i = 0.0, b_i = SHARP_INF;
+            for (int c = 0; c < kmax; c++) {
+                const int nc = cnt[c];
+                if (nc == 0) continue;
+                double v = acc[c * SW_THREADS + tid];
+                if (c == own) {
+                    if (n_own > 1) a_i = __ddiv_rn(v, (double)(n_own - 1));
+                } else {
+                    v = __ddiv_rn(v, (double)nc);
+                    if (v < b_i) b_i = v;
+                }
+            }
+            double s = (n_own > 1 && b_i != a_i) ? __ddiv_rn(__dsub_rn(b_i, a_i), fmax(a_i, b_i)) : 0.0;
+            if (valid) silg[(size_t)l * n + x] = s;
+        }
+    }
+    __syncthreads();
+
+    // ---- medians ----
+    {
+        const int P2 = next_pow2(n);
+        double *sb = acc;
+        for (int l = 0; l < nlev; l++) {
+            for (int i = tid; i < P2; i += SW_THREADS) sb[i] = (i < n) ? silg[(size_t)l * n + i] : SHARP_INF;
+            __syncthreads();
+            block_bitonic_sort<SW_THREADS>(sb, P2);
+            if (tid == 0) msil[l] = median_sorted(sb, n);
+            __syncthreads();
+        }
+    }
+
+    // ---- CH index from the finest-level cluster sums of the unit rows ----
+    {
+        const double *__restrict__ Y = P.Y;
+        const int p = P.p, ldy = P.ldy;
+        for (int d0 = 0; d0 < p; d0 += SW_THREADS) {
+            const int d = d0 + tid;
+            for (int c = 0; c < kmax; c++) acc[c * SW_THREADS + tid] = 0.0;
+            if (d < p)
+                for (int x = 0; x < n; x++) acc[cidf[x] * SW_THREADS + tid] += Y[(size_t)x * ldy + d];
+            if (d < p)
+                for (int c = 0; c < kmax; c++) csum[(size_t)c * p + d] = acc[c * SW_THREADS + tid];
+        }
+        __syncthreads();
+        double *G = acc; /* [kmax][kmax] Gram matrix of the cluster sums */
+        const int lane = tid & 31, warp = tid >> 5;
+        for (int pr = warp; pr < kmax * kmax; pr += SW_THREADS / 32) {
+            int a = pr / kmax, b = pr % kmax;
+            if (b < a) continue;
+            double s = 0.0;
+            for (int d = lane; d < p; d += 32) s = fma(csum[(size_t)a * p + d], csum[(size_t)b * p + d], s);
+            s = warp_sum(s);
+            if (lane == 0) { G[a * kmax + b] = s; G[b * kmax + a] = s; }
+        }
+        __syncthreads();
+        if (tid == 0) {
+            double gtot = 0.0;
+            for (int a = 0; a < kmax; a++)
+                for (int b = 0; b < kmax; b++) gtot += G[a * kmax + b];
+            /* total sum of squares about the grand mean: sum ||y||^2 - ||sum y||^2 / n */
+            double ssq = 0.0;
+            (void)ssq;
+            double T; /* rows are unit vectors: sum ||y||^2 = n */
+            T = (double)n - gtot / (double)n;
+            for (int l = 0; l < nlev; l++) {
+                if (l > 0) {
+                    int a = mergeA[l], b = mergeB[l];
+                    for (int c = 0; c < kmax; c++) {
+                        if (c == a || c == b) continue;
+                        G[a * kmax + c] += G[b * kmax + c];
+                        G[c * kmax + a] = G[a * kmax + c];
+                    }
+                    G[a * kmax + a] += G[b * kmax + b] + 2.0 * G[a * kmax + b];
+                }
+                const int *cnt = cnt_lv + l * kcap;
+                double B = 0.0;
+                for (int c = 0; c < kmax; c++)
+                    if (cnt[c] > 0) B += G[c * kmax + c] / (double)cnt[c];
+                B -= gtot / (double)n;
+                double W = T - B;
+                int k = kmax - l;
+                chv[l] = (B / (double)(k - 1)) / (W / (double)(n - k));
+            }
+        }
+        __syncthreads();
+    }
+
+    // ---- outputs in ascending-k order + selection ----
+    if (tid == 0) {
+        for (int l = 0; l < nlev; l++) {
+            O.msil[nlev - 1 - l] = msil[l];
+            O.chind[nlev - 1 - l] = chv[l];
+        }
+        int oind;
+        double mx = 0.0;
+        if (prm.n_cluster) { oind = 1; mx = msil[0]; }
+        else oind = select_rule(n, nlev, O.msil, O.chind, P.crit, prm.sil_thre, prm.height_ntimes, &mx);
+        O.meta[0] = nlev;
+        O.meta[4] = kmin;
+        O.meta[5] = kmax;
+        if (oind < 0) { O.meta[3] = -oind; oind = 0; }
+        else O.meta[3] = 0;
+        O.meta[2] = oind;
+        *O.maxsil = mx;
+        s_oind = oind;
+    }
+    __syncthreads();
+    const int oind = s_oind;
+    if (oind <= 0) return;
+    // final cutree at the chosen level (+ every level when v is requested)
+    int *lab = cidf;
+    {
+        const int k = kmin + oind - 1;
+        labels_at<SW_THREADS>(n, k, step_of, link, rank, tmp_scan, lab);
+        for (int i = tid; i < n; i += SW_THREADS) O.f[i] = lab[i] + 1;
+        if (tid == 0) O.meta[1] = k; /* optN.cluster = length(unique(f)) = k */
+        __syncthreads();
+    }
+    if (O.v) {
+        for (int l = 0; l < nlev; l++) {
+            labels_at<SW_THREADS>(n, kmin + l, step_of, link, rank, tmp_scan, lab);
+            for (int i = tid; i < n; i += SW_THREADS) O.v[(size_t)i * nlev + l] = lab[i] + 1;
+            __syncthreads();
+        }
+    }
+    (void)red;
+}
+
+int launch_sweep_nested(sharp_ctx *c, HcProb *probs_dev, SweepOut *outs_dev, int nprob, int max_n, int max_p,
+                        HcParamsDev prm, double *scratch, size_t scratch_per_prob) {
+    if (nprob <= 0) return 0;
+    int kcap = prm.n_cluster ? prm.n_cluster : prm.max_n;
+    if (kcap > max_n - 1) kcap = max_n - 1;
+    if (kcap < 2) kcap = 2;
+    if (kcap > NESTED_MAXK)
+        return set_error(SHARP_E_LIMIT, "nested sweep supports at most %d clusters per level (got %d)", NESTED_MAXK, kcap);
+    int nlevcap = prm.n_cluster ? 1 : (prm.max_n - prm.min_n + 1);
+    if (nlevcap < 1) nlevcap = 1;
+    NestedLayout L = nested_layout(max_n, kcap, nlevcap);
+    if (L.total > 220 * 1024)
+        return set_error(SHARP_E_LIMIT, "nested sweep: %d objects need %zu bytes of shared memory", max_n, L.total);
+    SHARP_CUDA(cudaFuncSetAttribute(sweep_nested_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
+    sweep_nested_kernel<<<nprob, SW_THREADS, L.total, c->stream>>>(probs_dev, outs_dev, prm, max_n, kcap, nlevcap,
+                                                                   scratch, scratch_per_prob);
+    c->launches++;
+    SHARP_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// =====================================================================================================
+// exact sweep (similarity problems; also selectable for feature problems through sharp_opt_hclust(exact=1))
+// =====================================================================================================
+// Pre-pass per problem: row-standardised copy of Y for the CH index (clues::get_CH "1-corr").
+__global__ void __launch_bounds__(SW_THREADS) exact_prep_kernel(HcProb *probs, double *ystd_all, size_t ystd_per_prob) {
+    HcProb &P = probs[blockIdx.y];
+    const int n = P.n, p = P.p, ldy = P.ldy;
+    if (n <= 0) return;
+    double *ys = ystd_all + blockIdx.y * ystd_per_prob;
+    for (int i = blockIdx.x * SW_THREADS + threadIdx.x; i < n; i += gridDim.x * SW_THREADS) {
+        const double *x = P.Y + (size_t)i * ldy;
+        double s = 0.0;
+        for (int j = 0; j < p; j++) s = __dadd_rn(s, x[j]);
+        double mean = __ddiv_rn(s, (double)p);
+        double ss = 0.0;
+        for (int j = 0; j < p; j++) {
+            double d = __dsub_rn(x[j], mean);
+            ss = __dadd_rn(ss, __dmul_rn(d, d));
+        }
+        double sd = sqrt(__ddiv_rn(ss, (double)(p - 1)));
+        for (int j = 0; j < p; j++) ys[(size_t)i * p + j] = (p > 1) ? __ddiv_rn(__dsub_rn(x[j], mean), sd) : x[j];
+    }
+}
+
+// levels of a problem under its own parameters
+__device__ __forceinline__ bool level_range(const HcParamsDev &prm, int n, int *kmin, int *kmax) {
+    if (prm.n_cluster) { *kmin = *kmax = prm.n_cluster; }
+    else { *kmin = prm.min_n; *kmax = min(prm.max_n, n - 1); }
+    return !(*kmax < *kmin || *kmax > n - 1 || *kmin < 2);
+}
+
+// grid: (max_levels, nprob).  dynamic smem: 4 int arrays of n_cap + sort buffer of P2(n_cap) doubles + coff
+__global__ void __launch_bounds__(SW_THREADS)
+sweep_exact_kernel(HcProb *probs, SweepOut *outs, const HcParamsDev *prms, int n_cap, int kcap, const double *ystd_all,
+                   size_t ystd_per_prob) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    __shared__ int tmp_scan[SW_THREADS];
+    __shared__ double red[SW_THREADS / 32];
+
+    HcProb &P = probs[blockIdx.y];
+    SweepOut &O = outs[blockIdx.y];
+    const HcParamsDev prm = prms[blockIdx.y];
+    const int n = P.n;
+    const int tid = threadIdx.x;
+    if (n <= 0 || P.status != 0) return;
+    int kmin, kmax;
+    if (!level_range(prm, n, &kmin, &kmax)) return;
+    const int lev = blockIdx.x;
+    const int k = kmin + lev;
+    if (k > kmax) return;
+    const int ld = P.ld;
+    const double *__restrict__ D = P.D;
+
+    int p2cap = 1;
+    while (p2cap < n_cap) p2cap <<= 1;
+    double *sb = reinterpret_cast<double *>(smem);             // [P2] silhouette widths / sort buffer
+    int *step_of = reinterpret_cast<int *>(sb + p2cap);        // [n]
+    int *link = step_of + n_cap;
+    int *rank = link + n_cap;
+    int *lab = rank + n_cap;
+    int *order = lab + n_cap;                                   // [n] members grouped by cluster, ascending inside
+    int *coff = order + n_cap;                                  // [kcap + 1]
+
+    build_links(n, P.ia, P.ib, step_of, link);
+    labels_at<SW_THREADS>(n, k, step_of, link, rank, tmp_scan, lab);
+    // stable counting sort of the points by label
+    for (int c = tid; c <= k; c += SW_THREADS) coff[c] = 0;
+    __syncthreads();
+    for (int i = tid; i < n; i += SW_THREADS) atomicAdd(&coff[lab[i] + 1], 1);
+    __syncthreads();
+    if (tid == 0)
+        for (int c = 0; c < k; c++) coff[c + 1] += coff[c];
+    __syncthreads();
+    for (int c = tid; c < k; c += SW_THREADS) {
+        int pos = coff[c];
+        for (int i = 0; i < n; i++)
+            if (lab[i] == c) order[pos++] = i;
+    }
+    __syncthreads();
+
+    // ---- silhouette widths: diC[x][c] summed over the members of c in ascending order (cluster::sildist) ----
+    for (int x = tid; x < n; x += SW_THREADS) {
+        const int own = lab[x];
+        const int n_own = coff[own + 1] - coff[own];
+        double a_i = 0.0, b_i = SHARP_INF;
+        for (int c = 0; c < k; c++) {
+            double s = 0.0;
+            const int q1 = coff[c + 1];
+            for (int q = coff[c]; q < q1; q++) s = __dadd_rn(s, D[(size_t)order[q] * ld + x]);
+            if (c == own) {
+                if (n_own > 1) a_i = __ddiv_rn(s, (double)(n_own - 1));
+            } else {
+                s = __ddiv_rn(s, (double)(q1 - coff[c]));
+                if (s < b_i) b_i = s;
+            }
+        }
+        sb[x] = (n_own > 1 && b_i != a_i) ? __ddiv_rn(__dsub_rn(b_i, a_i), fmax(a_i, b_i)) : 0.0;
+    }
+    const int P2 = next_pow2(n);
+    for (int i = n + tid; i < P2; i += SW_THREADS) sb[i] = SHARP_INF;
+    __syncthreads();
+    block_bitonic_sort<SW_THREADS>(sb, P2);
+    if (tid == 0) O.msil[lev] = median_sorted(sb, n);
+    __syncthreads();
+
+    // ---- CH index on the row-standardised data: per-dimension between / within sums, fixed-tree reduction ----
+    {
+        const double *__restrict__ Y = ystd_all ? ystd_all + blockIdx.y * ystd_per_prob : P.Y;
+        const int p = P.p;
+        const int ldy = ystd_all ? p : P.ldy;
+        double Bsum = 0.0, Wsum = 0.0;
+        for (int j = tid; j < p; j += SW_THREADS) {
+            double tot = 0.0;
+            for (int i = 0; i < n; i++) tot += Y[(size_t)i * ldy + j];
+            tot /= (double)n;
+            for (int c = 0; c < k; c++) {
+                const int q0 = coff[c], q1 = coff[c + 1];
+                double s = 0.0;
+                for (int q = q0; q < q1; q++) s += Y[(size_t)order[q] * ldy + j];
+                const double cen = s / (double)(q1 - q0);
+                const double db = cen - tot;
+                Bsum += (double)(q1 - q0) * db * db;
+                for (int q = q0; q < q1; q++) {
+                    double dw = Y[(size_t)order[q] * ldy + j] - cen;
+                    Wsum += dw * dw;
+                }
+            }
+        }
+        double B = block_sum<SW_THREADS>(Bsum, red);
+        double W = block_sum<SW_THREADS>(Wsum, red);
+        if (tid == 0) O.chind[lev] = (B / (double)(k - 1)) / (W / (double)(n - k));
+    }
+}
+
+// selection + final labels for the exact path: one CTA per problem
+__global__ void __launch_bounds__(SW_THREADS)
+sweep_select_kernel(HcProb *probs, SweepOut *outs, const HcParamsDev *prms, int n_cap) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    __shared__ int tmp_scan[SW_THREADS];
+    __shared__ int s_oind;
+    HcProb &P = probs[blockIdx.x];
+    SweepOut &O = outs[blockIdx.x];
+    const HcParamsDev prm = prms[blockIdx.x];
+    const int n = P.n;
+    const int tid = threadIdx.x;
+    if (n <= 0) return;
+    if (P.status != 0) { if (tid == 0) { O.meta[3] = P.status; O.meta[0] = 0; } return; }
+    int kmin, kmax;
+    if (!level_range(prm, n, &kmin, &kmax)) {
+        if (tid == 0) { O.meta[0] = 0; O.meta[3] = (prm.n_cluster && kmax > n) ? SWEEP_E_KRANGE : SWEEP_E_FEWPOINTS; }
+        return;
+    }
+    const int nlev = kmax - kmin + 1;
+    int *step_of = reinterpret_cast<int *>(smem);
+    int *link = step_of + n_cap;
+    int *rank = link + n_cap;
+    int *lab = rank + n_cap;
+    if (tid == 0) {
+        int oind;
+        double mx = 0.0;
+        if (prm.n_cluster) { oind = 1; mx = O.msil[0]; }
+        else oind = select_rule(n, nlev, O.msil, O.chind, P.crit, prm.sil_thre, prm.height_ntimes, &mx);
+        O.meta[0] = nlev;
+        O.meta[4] = kmin;
+        O.meta[5] = kmax;
+        if (oind < 0) { O.meta[3] = -oind; oind = 0; }
+        else O.meta[3] = 0;
+        O.meta[2] = oind;
+        *O.maxsil = mx;
+        s_oind = oind;
+    }
+    __syncthreads();
+    const int oind = s_oind;
+    if (oind <= 0) return;
+    build_links(n, P.ia, P.ib, step_of, link);
+    const int k = kmin + oind - 1;
+    labels_at<SW_THREADS>(n, k, step_of, link, rank, tmp_scan, lab);
+    for (int i = tid; i < n; i += SW_THREADS) O.f[i] = lab[i] + 1;
+    if (tid == 0) O.meta[1] = k;
+    __syncthreads();
+    if (O.v) {
+        for (int l = 0; l < nlev; l++) {
+            labels_at<SW_THREADS>(n, kmin + l, step_of, link, rank, tmp_scan, lab);
+            for (int i = tid; i < n; i += SW_THREADS) O.v[(size_t)i * nlev + l] = lab[i] + 1;
+            __syncthreads();
+        }
+    }
+}
+
+size_t sweep_exact_scratch_bytes(int max_n, int max_p) { return (((size_t)max_n * max_p * 8) + 255) & ~(size_t)255; }
+
+int launch_sweep_exact(sharp_ctx *c, HcProb *probs_dev, SweepOut *outs_dev, int nprob, int max_n, int max_p,
+                       const HcParamsDev *prm_dev, int max_levels, int kcap, double *scratch, size_t scratch_per_prob) {
+    if (nprob <= 0) return 0;
+    if (max_levels < 1) max_levels = 1;
+    int p2 = 1;
+    while (p2 < max_n) p2 <<= 1;
+    size_t smem = (size_t)p2 * 8 + (size_t)5 * max_n * 4 + (size_t)(kcap + 2) * 4;
+    smem = (smem + 15) & ~(size_t)15;
+    if (smem > 220 * 1024)
+        return set_error(SHARP_E_LIMIT, "exact sweep: %d objects need %zu bytes of shared memory", max_n, smem);
+    {
+        dim3 g((max_n + SW_THREADS - 1) / SW_THREADS, nprob);
+        exact_prep_kernel<<<g, SW_THREADS, 0, c->stream>>>(probs_dev, scratch, scratch_per_prob / 8);
+        c->launches++;
+    }
+    SHARP_CUDA(cudaFuncSetAttribute(sweep_exact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid(max_levels, nprob);
+    sweep_exact_kernel<<<grid, SW_THREADS, smem, c->stream>>>(probs_dev, outs_dev, prm_dev, max_n, kcap, scratch,
+                                                              scratch_per_prob / 8);
+    c->launches++;
+    size_t smem2 = (size_t)4 * max_n * 4;
+    SHARP_CUDA(cudaFuncSetAttribute(sweep_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+    sweep_select_kernel<<<nprob, SW_THREADS, smem2, c->stream>>>(probs_dev, outs_dev, prm_dev, max_n);
+    c->launches++;
+    SHARP_CUDA(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace sharp

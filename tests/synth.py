@@ -2,24 +2,31 @@
 import numpy as np
 
 
-def make_expression(m, n, n_types=4, seed=0, zero_frac=0.7, kind="tpm", sep=1.0):
-    """genes x cells matrix (Fortran order) with planted cell types.
+def make_expression(m, n, n_types=4, seed=0, zero_frac=0.7, kind="tpm", sep=1.5, frac=0.3):
+    """genes x cells matrix (Fortran order) with planted cell types and realistic sparsity.
 
-    kind "tpm": columns scaled to 1e6 (TPM-like, dense with ~zero_frac zeros);
-    kind "umi": small integer counts."""
+    Gene means are log-normal, a fraction `frac` of the genes is differentially expressed (log fold change
+    ~ N(0, sep)) per type, counts are Poisson at a sequencing depth chosen so that `zero_frac` of the entries
+    are zero (zeros concentrate in lowly expressed genes, like drop-outs do).
+    kind "umi": the raw counts; kind "tpm": columns scaled to 1e6."""
     rng = np.random.default_rng(seed)
-    base = rng.normal(0.0, 1.0, size=m)
-    types = base[:, None] + sep * rng.normal(0.0, 1.0, size=(m, n_types)) * (rng.random((m, n_types)) < 0.15)
+    base = rng.normal(0.0, 1.5, size=m)
+    types = base[:, None] + sep * rng.normal(0.0, 1.0, size=(m, n_types)) * (rng.random((m, n_types)) < frac)
     lab = rng.integers(0, n_types, size=n)
-    mu = np.exp(types[:, lab] + 0.3 * rng.normal(size=(m, n)))
-    keep = rng.random((m, n)) > zero_frac
-    x = mu * keep
-    if kind == "umi":
-        x = rng.poisson(np.minimum(x * 0.6, 50.0)).astype(np.float64)
-        # every cell needs a few non-zero genes
-        for c in np.flatnonzero(x.sum(0) == 0):
-            x[rng.integers(0, m, 5), c] = 1.0
-    else:
+    mu = np.exp(types)
+    lo, hi = 1e-4, 1e3
+    for _ in range(60):
+        mid = np.sqrt(lo * hi)
+        if np.exp(-mid * mu).mean() > zero_frac:
+            lo = mid
+        else:
+            hi = mid
+    depth = np.sqrt(lo * hi)
+    x = rng.poisson(depth * mu[:, lab] * np.exp(0.2 * rng.normal(size=(1, n)))).astype(np.float64)
+    # every cell needs a few non-zero genes (a constant projection makes scale() produce NaN in the reference)
+    for c in np.flatnonzero((x != 0).sum(0) < 3):
+        x[rng.integers(0, m, 5), c] += 1.0
+    if kind != "umi":
         x = x / x.sum(0, keepdims=True) * 1e6
     return np.asfortranarray(x), lab + 1
 

@@ -1,0 +1,257 @@
+"""GPU parity tests, stage by stage: every C-ABI entry point of libsharpb200 against the CPU oracle on the same
+seeded inputs.  Integer artefacts (merge sequences, labels) must be identical; floating point within the
+tolerance written in each test (the projection's contract is 1e-5 relative, BASELINE.json north_star)."""
+import numpy as np
+import pytest
+
+import orc
+import synth
+from sharp_b200 import Context, RStop, _lib, hc_params
+from sharp_b200.rrng import ranM2
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = Context(0)
+    yield c
+    c.close()
+
+
+def orc_prm(p):
+    return orc.hc_params(p.hmethod, p.n_cluster, p.min_n, p.max_n, p.sil_thre, p.height_ntimes)
+
+
+def relerr(a, b):
+    return float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-300))
+
+
+# --------------------------------------------------------------------------------------------- K1
+@pytest.mark.parametrize("fmt", ["dense", "csc"])
+@pytest.mark.parametrize("normalize,logkind", [(0, 2), (1, 2), (2, 2), (0, 0), (0, 10)])
+def test_rp_project(ctx, fmt, normalize, logkind):
+    m, n, K, p = 3000, 257, 3, 61
+    kind = "umi" if normalize else "tpm"
+    x, _ = synth.make_expression(m, n, seed=3, zero_frac=0.8, kind=kind)
+    rms = [ranM2(m, p, 2154 + k) for k in range(K)]
+    rm = ctx.upload_rm(rms)
+    colsum = x.sum(0)
+    kw = dict(dense=x) if fmt == "dense" else dict(csc=synth.to_csc(x))
+    got = ctx.rp_project(m, n, rm, normalize=normalize, colsum=colsum if normalize == 1 else None, logkind=logkind, **kw)
+    for k in range(K):
+        ref = orc.rp_project(m, n, rms[k], colsum=colsum if normalize else None, logkind=logkind, **kw)
+        assert relerr(got[k], ref) <= 1e-5, (k, relerr(got[k], ref))
+        assert relerr(got[k], ref) <= 1e-11  # what fp64 accumulation should actually deliver
+
+
+def test_rp_project_cells_and_round(ctx):
+    m, n, K, p = 1500, 100, 2, 40
+    x, _ = synth.make_expression(m, n, seed=5)
+    rms = [ranM2(m, p, 77 + k) for k in range(K)]
+    rm = ctx.upload_rm(rms)
+    cells = np.random.default_rng(0).permutation(n)[:63]
+    got = ctx.rp_project(m, n, rm, csc=synth.to_csc(x), cells=cells)
+    for k in range(K):
+        ref = orc.rp_project(m, n, rms[k], csc=synth.to_csc(x), cells=cells)
+        assert relerr(got[k], ref) <= 1e-11
+    got = ctx.rp_project(m, n, rm, dense=x, logkind=10, round_digits=1)
+    ref = orc.rp_project(m, n, rms[0], dense=x, logkind=10, round_digits=1)
+    # rounding to one decimal can flip on a last-bit difference of the unrounded value: allow a few
+    assert np.mean(np.abs(got[0] - ref) > 1e-9) < 1e-3
+
+
+def test_rp_project_rejects_non_ternary(ctx):
+    rm = ranM2(100, 10, 1)
+    rm["x"] = rm["x"].copy()
+    rm["x"][0] *= 2
+    with pytest.raises(_lib.SharpError):
+        ctx.upload_rm([rm])
+
+
+# --------------------------------------------------------------------------------------------- K2
+@pytest.mark.parametrize("n,p", [(50, 7), (300, 61), (517, 333)])
+def test_corrdist(ctx, n, p):
+    X = np.random.default_rng(n).normal(size=(n, p)) + np.arange(p) * 0.01
+    d = ctx.corrdist(X)
+    _, ref = orc.zscore_corrdist(X)
+    assert np.all(np.diag(d) == 0.0)
+    assert np.array_equal(d, d.T)
+    assert np.max(np.abs(d - ref)) <= 1e-12
+
+
+# --------------------------------------------------------------------------------------------- K3
+@pytest.mark.parametrize("method", [1, 2, 3, 4, 5, 6, 7, 8])
+def test_hclust_exact_order(ctx, method):
+    rng = np.random.default_rng(method)
+    X = rng.normal(size=(150, 9))
+    _, d = orc.zscore_corrdist(X)
+    ia, ib, h = ctx.hclust(d, method)
+    ria, rib, rh = orc.hclust(d, method)
+    assert np.array_equal(ia, ria) and np.array_equal(ib, rib)
+    assert np.array_equal(h, rh)  # same operations in the same order: bit-identical heights
+
+
+def test_hclust_ties(ctx):
+    """similarity-like matrix full of exact ties (0 / 0.5 / 1): the merge order must be hclust.f's."""
+    rng = np.random.default_rng(9)
+    n = 90
+    d = rng.choice([0.0, 0.5, 1.0], size=(n, n), p=[0.1, 0.2, 0.7])
+    d = np.triu(d, 1)
+    d = d + d.T
+    for method in (1, 3, 4):
+        ia, ib, h = ctx.hclust(d, method)
+        ria, rib, rh = orc.hclust(d, method)
+        assert np.array_equal(ia, ria) and np.array_equal(ib, rib) and np.array_equal(h, rh)
+
+
+def test_hclust_large(ctx):
+    rng = np.random.default_rng(11)
+    X = rng.normal(size=(1203, 40))
+    X[:400] += 1.5
+    _, d = orc.zscore_corrdist(X)
+    ia, ib, h = ctx.hclust(d, 1)
+    ria, rib, rh = orc.hclust(d, 1)
+    assert np.array_equal(ia, ria) and np.array_equal(ib, rib) and np.array_equal(h, rh)
+
+
+# --------------------------------------------------------------------------------------------- K4-K6
+def _blobs(n, p, g, seed, sep=2.0):
+    rng = np.random.default_rng(seed)
+    lab = rng.integers(0, g, n)
+    cen = rng.normal(size=(g, p)) * sep
+    return cen[lab] + rng.normal(size=(n, p)), lab
+
+
+@pytest.mark.parametrize("exact", [False, True])
+@pytest.mark.parametrize("n,p,g,sep", [(400, 50, 5, 2.0), (333, 31, 3, 0.3), (45, 20, 2, 1.0)])
+def test_opt_hclust_feature(ctx, exact, n, p, g, sep):
+    X, _ = _blobs(n, p, g, seed=n, sep=sep)
+    prm = hc_params()
+    got = ctx.opt_hclust(X, False, prm, exact=exact)
+    ref = orc.opt_hclust(X, 0, orc_prm(prm))
+    assert got["v"].shape == ref["v"].shape
+    assert np.array_equal(got["v"], ref["v"])
+    assert np.allclose(got["height"], ref["height"], rtol=1e-10, atol=1e-13)
+    assert np.allclose(got["msil"], ref["msil"], rtol=0, atol=1e-12)
+    assert np.allclose(got["CHind"], ref["CHind"], rtol=1e-8)
+    assert got["oind"] == ref["oind"] and got["optN.cluster"] == ref["optN.cluster"]
+    assert np.array_equal(got["f"], ref["f"])
+    assert abs(got["maxsil"] - ref["maxsil"]) <= 1e-12
+
+
+def test_opt_hclust_ch_and_height_paths(ctx):
+    """weak structure -> max(msil) <= sil.thre -> CH index, possibly the height-gap rule"""
+    for seed, sil in [(1, 0.9), (2, 0.9), (3, 2.0)]:
+        X, _ = _blobs(260, 40, 4, seed=seed, sep=0.6)
+        prm = hc_params(sil_thre=sil, height_ntimes=1.05)
+        try:
+            ref = orc.opt_hclust(X, 0, orc_prm(prm))
+        except orc.OracleError as e:
+            with pytest.raises(RStop):
+                ctx.opt_hclust(X, False, prm)
+            continue
+        got = ctx.opt_hclust(X, False, prm)
+        assert got["oind"] == ref["oind"]
+        assert np.array_equal(got["f"], ref["f"])
+
+
+def test_opt_hclust_fixed_k(ctx):
+    X, _ = _blobs(300, 30, 4, seed=8)
+    prm = hc_params(n_cluster=6)
+    got = ctx.opt_hclust(X, False, prm)
+    ref = orc.opt_hclust(X, 0, orc_prm(prm))
+    assert np.array_equal(got["f"], ref["f"]) and got["optN.cluster"] == 6
+    assert abs(got["msil"][0] - ref["msil"][0]) <= 1e-12
+
+
+def test_opt_hclust_symmetric_bit_exact(ctx):
+    """similarity branch: the sweep follows the reference's summation order -> msil identical to the last bit"""
+    rng = np.random.default_rng(4)
+    lab = np.stack([rng.integers(1, 6, 300) for _ in range(4)], 1)
+    # a similarity matrix with plenty of exact structure: correlation of one-hot cluster indicators
+    H = np.concatenate([(lab[:, [c]] == np.arange(1, 6)[None, :]).astype(float) for c in range(4)], 1)
+    S = np.corrcoef(H.T)
+    S = (S + S.T) / 2
+    np.fill_diagonal(S, 1.0)
+    prm = hc_params(max_n=15)
+    got = ctx.opt_hclust(S, True, prm)
+    ref = orc.opt_hclust(S, 1, orc_prm(prm))
+    assert np.array_equal(got["v"], ref["v"])
+    assert np.array_equal(got["height"], ref["height"])
+    assert np.array_equal(got["msil"], ref["msil"])
+    assert np.allclose(got["CHind"], ref["CHind"], rtol=1e-9)
+    assert np.array_equal(got["f"], ref["f"])
+
+
+def test_opt_hclust_too_few_points(ctx):
+    X = np.random.default_rng(0).normal(size=(2, 10))
+    with pytest.raises(RStop):
+        ctx.opt_hclust(X, False, hc_params())
+
+
+def test_getrowcolor(ctx):
+    X, _ = _blobs(500, 40, 6, seed=21)
+    prm = hc_params()
+    col, ms = ctx.getrowcolor(X, prm)
+    rcol, rms = orc.getrowcolor(X, orc_prm(prm))
+    assert np.array_equal(col, rcol) and abs(ms - rms) <= 1e-12
+
+
+# --------------------------------------------------------------------------------------------- K7-K9
+def _ensemble_labels(N, C, g, noise, seed):
+    rng = np.random.default_rng(seed)
+    truth = rng.integers(0, g, N)
+    cols = []
+    for c in range(C):
+        perm = rng.permutation(g + 2)
+        l = perm[truth]
+        flip = rng.random(N) < noise
+        l = np.where(flip, rng.integers(0, g + 2, N), l)
+        # relabel by first appearance, 1-based (what getrowColor produces)
+        _, first = np.unique(l, return_index=True)
+        order = np.argsort(first)
+        m = {int(np.unique(l)[o]): i + 1 for i, o in enumerate(order)}
+        cols.append(np.array([m[int(v)] for v in l]))
+    return np.stack(cols, 1)
+
+
+@pytest.mark.parametrize("N,C,g,noise", [(600, 5, 4, 0.1), (350, 15, 6, 0.3), (200, 3, 2, 0.0), (501, 5, 9, 0.5)])
+def test_wmetac(ctx, N, C, g, noise):
+    lab = _ensemble_labels(N, C, g, noise, seed=N + C)
+    prm = hc_params()
+    try:
+        ref = orc.wmetac(lab, orc_prm(prm))
+    except orc.OracleError:
+        with pytest.raises(_lib.SharpError):
+            ctx.wmetac(lab, prm)
+        return
+    got = ctx.wmetac(lab, prm)
+    assert np.array_equal(got["w1"], ref["w1"])          # same sums in the same order
+    assert np.array_equal(got["finalC"], ref["finalC"])
+    assert got["N.cluster"] == ref["N.cluster"]
+    assert np.array_equal(got["x0"], ref["x0"])
+
+
+def test_wmetac_fixed_k_and_arbitrary_codes(ctx):
+    lab = _ensemble_labels(400, 5, 5, 0.2, seed=2) * 7 + 100  # any integer coding is valid
+    prm = hc_params(n_cluster=3)
+    got = ctx.wmetac(lab, prm)
+    ref = orc.wmetac(lab, orc_prm(prm))
+    assert np.array_equal(got["finalC"], ref["finalC"])
+
+
+# --------------------------------------------------------------------------------------------- K10
+@pytest.mark.parametrize("ncells,p,nclu", [(3000, 50, 23), (12000, 64, 60)])
+def test_smetac(ctx, ncells, p, nclu):
+    rng = np.random.default_rng(ncells)
+    groups = rng.integers(0, 6, nclu)
+    cen = rng.normal(size=(6, p)) * 3
+    lab = rng.integers(0, nclu, ncells)
+    E = cen[groups[lab]] + rng.normal(size=(ncells, p))
+    codes = lab * 13 + 5
+    prm = hc_params()
+    got = ctx.smetac(codes, E, prm)
+    ref = orc.smetac(codes, E, orc_prm(prm))
+    assert np.array_equal(got["tf"], ref["tf"])
+    assert np.array_equal(got["finalColor"], ref["finalColor"])
