@@ -76,6 +76,15 @@ int sharp_timer_stop_ms(sharp_ctx *ctx, double *ms);
 /* number of kernels this library launched on the context since creation (bench.py's gpu_launches). */
 int64_t sharp_ctx_launch_count(sharp_ctx *ctx);
 
+/* per-kernel device-time profile (off by default): while enabled, every launch of this library on the context's
+ * stream is bracketed by CUDA events and accumulated per kernel class.  bench.py's roofline object is computed from
+ * these (live, over the timed region). */
+int sharp_prof_enable(sharp_ctx *ctx, int on);
+int sharp_prof_reset(sharp_ctx *ctx);
+int sharp_prof_kernels(void);              /* number of kernel classes */
+const char *sharp_prof_name(int kid);      /* name of class kid */
+int sharp_prof_get(sharp_ctx *ctx, int kid, double *ms, int64_t *launches);
+
 /* ---- ranM matrices ----------------------------------------------------------------------------
  * Replaces nothing: ranM()/ranM2() stay in R (R/ranM.R:11-33, R/ranM2.R:11-35) and their dgCMatrix slots
  * are handed in.  K matrices, each m x p: colptr K x (p+1) (slot `p`), rowidx (slot `i`, ascending inside a
@@ -183,6 +192,14 @@ int sharp_run_dev(sharp_ctx *ctx, const sharp_expr_dev *e, const double *colsum,
 /* centroids of the LAST sharp_run/sharp_run_dev on this context: for cluster ids 1..nclust (values of `labels`,
  * e.g. pred_clusters after the host relabel), cen row-major nclust x p = colMeans(viE[labels == c, ]). */
 int sharp_centroids(sharp_ctx *ctx, int64_t n, const int32_t *labels, int nclust, double *cen, int64_t *counts);
+
+/* Per-member results of the LAST sharp_run/sharp_run_dev on this context (SHARP_small's `allrpinfo`,
+ * R/SHARP.R:366-385): rowcolor[n] = the member's colour index per cell (getrowColor), inde[n*p] row-major = the
+ * member's projection (`tmp$mat`).  Either may be NULL.  Rows are in the order the run clustered them, i.e. the
+ * input order for SHARP_small (SHARP_large shuffles; it has no allrpinfo). */
+int sharp_last_member(sharp_ctx *ctx, int k, int64_t n, int32_t *rowcolor, double *inde);
+/* viE = enE/K of the LAST run (row-major n x p, un-shuffled), for callers that did not ask sharp_run for it. */
+int sharp_last_vie(sharp_ctx *ctx, int64_t n, int p, double *vie);
 
 /* sMetaC given precomputed centroids (what SHARP_unlimited's global step needs when parts live on several
  * GPUs): cen row-major nC x p in unique(fColor) order; ncells_total drives the k-range tweak (R/sMetaC.R:101-119).

@@ -7,7 +7,13 @@ Importing the package does not need a GPU; every compute call does (there is no 
 """
 from . import _lib
 from ._lib import Context, HcParams, RStop, RunParams, SharpError, device_count, device_info, hc_params
-from .rrng import ranM, ranM2, r_sample_perm
+from .rrng import r_sample_perm
+from .api import (ARI, SHARP, Expression, RPmat, SHARP_fpart, SHARP_large, SHARP_small, SHARP_unlimited,
+                  SHARP_unlimited2, SHARP_unlimited3, colorL, get_context, get_opt_hclust, getA, getrowColor, getss,
+                  ranM, ranM2, run_Mtimes_SHARP, sMetaC, set_devices, set_verbose, testlog, wMetaC)
 
 __all__ = ["_lib", "Context", "HcParams", "RunParams", "SharpError", "RStop", "device_count", "device_info",
-           "hc_params", "ranM", "ranM2", "r_sample_perm"]
+           "hc_params", "ranM", "ranM2", "r_sample_perm", "SHARP", "SHARP_small", "SHARP_large", "SHARP_unlimited",
+           "SHARP_unlimited2", "SHARP_fpart", "SHARP_unlimited3", "RPmat", "get_opt_hclust", "getrowColor", "wMetaC",
+           "sMetaC", "getA", "getss", "testlog", "ARI", "run_Mtimes_SHARP", "Expression", "get_context", "set_devices",
+           "set_verbose", "colorL"]

@@ -52,6 +52,8 @@ EXPORTS = [
     "sharp_ctx_launch_count", "sharp_rm_upload", "sharp_rm_free", "sharp_rp_project", "sharp_corrdist",
     "sharp_hclust", "sharp_opt_hclust", "sharp_getrowcolor", "sharp_wmetac", "sharp_smetac", "sharp_run",
     "sharp_expr_upload", "sharp_expr_free", "sharp_run_dev", "sharp_centroids", "sharp_smetac_centroids",
+    "sharp_last_member", "sharp_last_vie", "sharp_prof_enable", "sharp_prof_reset", "sharp_prof_kernels", "sharp_prof_name",
+    "sharp_prof_get",
 ]
 
 _lib = None
@@ -69,6 +71,7 @@ def load():
     lib = C.CDLL(SO_PATH)
     lib.sharp_last_error.restype = C.c_char_p
     lib.sharp_ctx_stream.restype = C.c_void_p
+    lib.sharp_prof_name.restype = C.c_char_p
     lib.sharp_ctx_launch_count.restype = C.c_int64
     lib.sharp_ctx_destroy.restype = None
     lib.sharp_rm_free.restype = None
@@ -223,6 +226,23 @@ class Context:
     def launch_count(self) -> int:
         return int(load().sharp_ctx_launch_count(self._h))
 
+    def prof_enable(self, on=True):
+        _check(load().sharp_prof_enable(self._h, int(bool(on))))
+
+    def prof_reset(self):
+        _check(load().sharp_prof_reset(self._h))
+
+    def prof_get(self) -> dict:
+        """{kernel class: (total device ms, launches)} accumulated while profiling was enabled"""
+        lib = load()
+        out = {}
+        for kid in range(lib.sharp_prof_kernels()):
+            ms, n = C.c_double(), C.c_int64()
+            _check(lib.sharp_prof_get(self._h, kid, C.byref(ms), C.byref(n)))
+            if n.value:
+                out[lib.sharp_prof_name(kid).decode()] = (ms.value, n.value)
+        return out
+
     def upload_rm(self, rms: list) -> RmDev:
         return RmDev(self, rms)
 
@@ -358,3 +378,16 @@ class Context:
         _check(load().sharp_centroids(self._h, C.c_int64(len(lab)), _ptr(lab, C.c_int32), int(nclust),
                                       _ptr(cen, C.c_double), _ptr(cnt, C.c_int64)))
         return cen, cnt
+
+    def last_member(self, k, n, p):
+        """member k of the last run -> (colour index per cell, projection n x p)   (SHARP_small's allrpinfo)"""
+        col = np.empty(n, dtype=np.int32)
+        inde = np.empty((n, p))
+        _check(load().sharp_last_member(self._h, int(k), C.c_int64(n), _ptr(col, C.c_int32), _ptr(inde, C.c_double)))
+        return col, inde
+
+    def last_vie(self, n, p):
+        """viE = enE/K of the last run (n x p, un-shuffled)"""
+        vie = np.empty((n, p))
+        _check(load().sharp_last_vie(self._h, C.c_int64(n), int(p), _ptr(vie, C.c_double)))
+        return vie

@@ -42,8 +42,9 @@ int launch_unit_rows(sharp_ctx *c, const double *X, int64_t rows, int p, int ldu
     if (rows <= 0) return 0;
     const int wpb = 8;
     int64_t blocks = (rows + wpb - 1) / wpb;
+    prof_begin(c, KID_UNIT_ROWS);
     unit_rows_kernel<<<(unsigned)blocks, wpb * 32, 0, c->stream>>>(X, rows, p, ldu, U);
-    c->launches++;
+    prof_end(c);
     SHARP_CUDA(cudaGetLastError());
     return 0;
 }
@@ -178,8 +179,9 @@ int launch_corrdist_batched(sharp_ctx *c, const GemmProb *probs_dev, const int *
     if (nprob <= 0 || total_tiles <= 0) return 0;
     size_t smem = (size_t)4 * GT * GLD * sizeof(double);
     SHARP_CUDA(cudaFuncSetAttribute(corrdist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    prof_begin(c, KID_CORRDIST);
     corrdist_kernel<<<total_tiles, G_THREADS, smem, c->stream>>>(probs_dev, tile_prefix_dev, nprob, ldu);
-    c->launches++;
+    prof_end(c);
     SHARP_CUDA(cudaGetLastError());
     return 0;
 }

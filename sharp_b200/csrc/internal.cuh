@@ -84,6 +84,14 @@ const char *status_message(int st);
 
 }  // namespace sharp
 
+namespace sharp {
+// kernel classes of the per-kernel device-time profile (sharp_prof_*; bench.py's roofline object)
+enum KernelId { KID_RP_PROJECT = 0, KID_COLSUM, KID_UNIT_ROWS, KID_CORRDIST, KID_HCLUST, KID_HCLUST_SMALL,
+                KID_SWEEP_NESTED, KID_SWEEP_EXACT, KID_WM_WEIGHTS, KID_WM_SIMILARITY, KID_WMETAC, KID_SM_CENTROIDS,
+                KID_SMETAC, KID_ENE, KID_MISC, KID_COUNT };
+struct ProfPending { int kid; cudaEvent_t a, b; };
+}  // namespace sharp
+
 struct sharp_ctx {
     int device = 0;
     int sm_count = 0;
@@ -95,7 +103,15 @@ struct sharp_ctx {
     size_t pinned_cap = 0;
     int64_t last_n = 0;     // state of the last run (for sharp_centroids)
     int last_p = 0;
+    int last_K = 0;
     int reserve_pinned(size_t bytes);
+    // per-kernel profile: CUDA events around every launch on `stream` while prof_on (off by default)
+    bool prof_on = false;
+    std::vector<cudaEvent_t> prof_pool;
+    std::vector<sharp::ProfPending> prof_pending;
+    int prof_open = -1;
+    double prof_ms[sharp::KID_COUNT] = {0};
+    int64_t prof_n[sharp::KID_COUNT] = {0};
 };
 
 struct sharp_rm_dev {
@@ -124,6 +140,11 @@ struct sharp_expr_dev {
 namespace sharp {
 
 constexpr int RP_TILE_GENES_HOST = 512;
+
+// every launch site brackets its <<<>>> with these (prof_end also counts the launch)
+void prof_begin(sharp_ctx *c, int kid);
+void prof_end(sharp_ctx *c);
+void prof_collect(sharp_ctx *c);
 
 // ---- kernel launchers (each returns after enqueueing on ctx->stream) ---------------------------------
 // rp_project.cu

@@ -361,22 +361,26 @@ wm_x0_kernel(WmArgs A, const SweepOut *outs, const int *coloff, const int *colma
 
 int launch_wmetac_front(sharp_ctx *c, const WmArgs &A, int T, int max_block_n) {
     if (A.K > WM_MAXK) return set_error(SHARP_E_LIMIT, "wMetaC: at most %d clustering solutions per cell (got %d)", WM_MAXK, A.K);
+    prof_begin(c, KID_WMETAC);
     wm_enumerate_kernel<<<T, MT, 0, c->stream>>>(A);
-    c->launches++;
+    prof_end(c);
     dim3 g1((max_block_n + MT - 1) / MT, T);
+    prof_begin(c, KID_WM_WEIGHTS);
     wm_weights_kernel<<<g1, MT, 0, c->stream>>>(A);
-    c->launches++;
+    prof_end(c);
     dim3 g2(((size_t)A.capC * A.capC + MT - 1) / MT, T);
+    prof_begin(c, KID_WM_SIMILARITY);
     wm_similarity_kernel<<<g2, MT, 0, c->stream>>>(A);
-    c->launches++;
+    prof_end(c);
     SHARP_CUDA(cudaGetLastError());
     return 0;
 }
 
 int launch_wmetac_vote(sharp_ctx *c, const WmArgs &A, const SweepOut *outs, int T) {
     size_t smem = (size_t)(A.capC + 2) * 4;
+    prof_begin(c, KID_WMETAC);
     wm_vote_kernel<<<T, MT, smem, c->stream>>>(A, outs);
-    c->launches++;
+    prof_end(c);
     SHARP_CUDA(cudaGetLastError());
     return 0;
 }
@@ -384,8 +388,9 @@ int launch_wmetac_vote(sharp_ctx *c, const WmArgs &A, const SweepOut *outs, int 
 int launch_wmetac_x0(sharp_ctx *c, const WmArgs &A, const SweepOut *outs, int T, int max_block_n, const int *coloff,
                      const int *colmap, const int64_t *out_row, double *x0, int ncol) {
     dim3 g((max_block_n + MT - 1) / MT, T);
+    prof_begin(c, KID_WMETAC);
     wm_x0_kernel<<<g, MT, 0, c->stream>>>(A, outs, coloff, colmap, out_row, x0, ncol);
-    c->launches++;
+    prof_end(c);
     SHARP_CUDA(cudaGetLastError());
     return 0;
 }
@@ -622,10 +627,12 @@ sm_relabel_kernel(int64_t ncells, const int *__restrict__ code, const int *__res
 int launch_sm_codes(sharp_ctx *c, const WmArgs &A, int T, int *coloff, int *nc_out, int *status_out, int *code,
                     int *corder, int *coff) {
     if (A.capU > WM_MAXU) return set_error(SHARP_E_LIMIT, "more than %d clusters per block", WM_MAXU);
+    prof_begin(c, KID_SMETAC);
     sm_prefix_kernel<<<1, 32, 0, c->stream>>>(A.ucount, A.status, T, coloff, nc_out, status_out);
-    c->launches++;
+    prof_end(c);
+    prof_begin(c, KID_SMETAC);
     sm_codes_kernel<<<T, MT, 0, c->stream>>>(A, coloff, code, corder, coff);
-    c->launches++;
+    prof_end(c);
     SHARP_CUDA(cudaGetLastError());
     return 0;
 }
@@ -633,20 +640,24 @@ int launch_sm_codes(sharp_ctx *c, const WmArgs &A, int T, int *coloff, int *nc_o
 int launch_sm_centroids(sharp_ctx *c, const double *E1, int p, const int *corder, const int *coff, const int *nc_ptr,
                         int nc_cap, double *cen, int64_t *counts) {
     if (nc_cap <= 0) return 0;
+    prof_begin(c, KID_SM_CENTROIDS);
     sm_centroids_kernel<<<nc_cap, MT, 0, c->stream>>>(E1, p, corder, coff, nc_ptr, cen, counts);
-    c->launches++;
+    prof_end(c);
     SHARP_CUDA(cudaGetLastError());
     return 0;
 }
 
 int launch_sm_similarity(sharp_ctx *c, const SmArgs &A, const double *cen, int p, int nc_cap, double *mean, double *sdev) {
+    prof_begin(c, KID_SMETAC);
     sm_stats_kernel<<<(nc_cap + MT - 1) / MT, MT, 0, c->stream>>>(cen, p, A.nc_ptr, mean, sdev);
-    c->launches++;
+    prof_end(c);
     size_t pairs = (size_t)nc_cap * nc_cap;
+    prof_begin(c, KID_SMETAC);
     sm_cor_kernel<<<(unsigned)((pairs + MT - 1) / MT), MT, 0, c->stream>>>(cen, p, A.nc_ptr, mean, sdev, A.ld, A.S, A.D, A.Dw);
-    c->launches++;
+    prof_end(c);
+    prof_begin(c, KID_SMETAC);
     sm_setup_kernel<<<1, 32, 0, c->stream>>>(A);
-    c->launches++;
+    prof_end(c);
     SHARP_CUDA(cudaGetLastError());
     return 0;
 }
@@ -654,16 +665,18 @@ int launch_sm_similarity(sharp_ctx *c, const SmArgs &A, const double *cen, int p
 int launch_sm_finish(sharp_ctx *c, const SmArgs &A, const SweepOut *out) {
     size_t smem = (size_t)4 * A.ld * 4;
     SHARP_CUDA(cudaFuncSetAttribute(sm_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    prof_begin(c, KID_SMETAC);
     sm_finish_kernel<<<1, MT, smem, c->stream>>>(A, out);
-    c->launches++;
+    prof_end(c);
     SHARP_CUDA(cudaGetLastError());
     return 0;
 }
 
 int launch_sm_relabel(sharp_ctx *c, int64_t ncells, const int *code, const int *tf, int add, const int64_t *out_row, int *out) {
     if (ncells <= 0) return 0;
+    prof_begin(c, KID_SMETAC);
     sm_relabel_kernel<<<(unsigned)((ncells + MT - 1) / MT), MT, 0, c->stream>>>(ncells, code, tf, add, out_row, out);
-    c->launches++;
+    prof_end(c);
     SHARP_CUDA(cudaGetLastError());
     return 0;
 }

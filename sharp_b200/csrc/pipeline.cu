@@ -86,6 +86,48 @@ int sharp_ctx::reserve_pinned(size_t bytes) {
 
 namespace sharp {
 
+// ---- per-kernel device-time profile -------------------------------------------------------------------
+static cudaEvent_t prof_event(sharp_ctx *c) {
+    if (!c->prof_pool.empty()) {
+        cudaEvent_t e = c->prof_pool.back();
+        c->prof_pool.pop_back();
+        return e;
+    }
+    cudaEvent_t e = nullptr;
+    cudaEventCreate(&e);
+    return e;
+}
+void prof_begin(sharp_ctx *c, int kid) {
+    if (!c->prof_on) return;
+    ProfPending p;
+    p.kid = kid;
+    p.a = prof_event(c);
+    p.b = prof_event(c);
+    cudaEventRecord(p.a, c->stream);
+    c->prof_pending.push_back(p);
+    c->prof_open = (int)c->prof_pending.size() - 1;
+}
+void prof_end(sharp_ctx *c) {
+    c->launches++;
+    if (!c->prof_on || c->prof_open < 0) return;
+    cudaEventRecord(c->prof_pending[c->prof_open].b, c->stream);
+    c->prof_open = -1;
+    if (c->prof_pending.size() >= 4096) prof_collect(c);
+}
+void prof_collect(sharp_ctx *c) {
+    for (auto &p : c->prof_pending) {
+        float ms = 0.f;
+        if (cudaEventSynchronize(p.b) == cudaSuccess && cudaEventElapsedTime(&ms, p.a, p.b) == cudaSuccess) {
+            c->prof_ms[p.kid] += ms;
+            c->prof_n[p.kid]++;
+        }
+        c->prof_pool.push_back(p.a);
+        c->prof_pool.push_back(p.b);
+    }
+    c->prof_pending.clear();
+    cudaGetLastError();
+}
+
 // workspace slots
 enum Slot {
     WS_SRC = 0, WS_COLSUM, WS_PROJ, WS_U, WS_D, WS_DW, WS_HC_INT, WS_HC_DBL, WS_DESC, WS_SWEEP_SCRATCH, WS_ENRP, WS_E1,
@@ -250,8 +292,9 @@ static int opt_hclust_dev(sharp_ctx *c, int nrow, int ncol, const double *mat_de
     const double *Y;
     int yp, ldy;
     if (symmetric) {
+        prof_begin(c, KID_MISC);
         sym_to_dist_kernel<<<grid1d((size_t)n * n, 256), 256, 0, c->stream>>>(n, mat_dev, ncol, D, Dw, ld);
-        c->launches++;
+        prof_end(c);
         Y = mat_dev;
         yp = n;
         ldy = ncol;
@@ -685,13 +728,15 @@ static int run_core(sharp_ctx *c, const sharp_expr_dev &e, const double *colsum_
             SHARP_TRY(launch_sweep_exact(c, hpd + w.q0, sod + w.q0, w.nq, max_bn, p, ppd + w.q0, maxlev, std::max(kcap_ind, 2),
                                          c->ws[WS_SWEEP_SCRATCH].as<double>(), sweep_scr));
     }
+    prof_begin(c, KID_MISC);
     colour_wrap_kernel<<<grid1d((size_t)K * n, 256), 256, 0, c->stream>>>(enrp, (int64_t)K * n);
-    c->launches++;
+    prof_end(c);
     // ---- enE / K ----
     SHARP_TRY(c->ws[WS_E1].reserve(np * 8));
     double *E1 = c->ws[WS_E1].as<double>();
+    prof_begin(c, KID_ENE);
     ene_kernel<<<grid1d(np, 256), 256, 0, c->stream>>>(proj, (int64_t)np, K, E1);
-    c->launches++;
+    prof_end(c);
     // status of the block problems (also makes the pinned staging reusable)
     {
         std::vector<int> meta((size_t)nprob * 8);
@@ -785,10 +830,12 @@ static int run_core(sharp_ctx *c, const sharp_expr_dev &e, const double *colsum_
     // viE = enE/K, un-shuffled; kept on the device for sharp_centroids
     SHARP_TRY(c->ws[WS_VIEU].reserve(np * 8));
     double *vieu = c->ws[WS_VIEU].as<double>();
+    prof_begin(c, KID_ENE);
     scatter_rows_kernel<<<(unsigned)n, 128, 0, c->stream>>>(E1, n, p, src_dev, vieu);
-    c->launches++;
+    prof_end(c);
     c->last_n = n;
     c->last_p = p;
+    c->last_K = K;
     if (vie_out) SHARP_TRY(d2h(c, vie_out, vieu, np * 8));
     SHARP_TRY(sync(c));
     (void)colmap_dev;
@@ -857,6 +904,8 @@ void sharp_ctx_destroy(sharp_ctx *c) {
     if (!c) return;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
+    prof_collect(c);
+    for (cudaEvent_t e : c->prof_pool) cudaEventDestroy(e);
     for (auto &b : c->ws) b.release();
     if (c->pinned) cudaFreeHost(c->pinned);
     cudaEventDestroy(c->ev0);
@@ -885,6 +934,33 @@ int sharp_timer_stop_ms(sharp_ctx *c, double *ms) {
     return 0;
 }
 int64_t sharp_ctx_launch_count(sharp_ctx *c) { return c ? c->launches : 0; }
+
+static const char *const g_kernel_names[KID_COUNT] = {
+    "rp_project", "colsum", "unit_rows", "corrdist", "hclust", "hclust_small", "sweep_nested", "sweep_exact",
+    "wm_weights", "wm_similarity", "wmetac_misc", "sm_centroids", "smetac_misc", "ene_scatter", "misc"};
+
+int sharp_prof_enable(sharp_ctx *c, int on) {
+    SHARP_TRY(use(c));
+    prof_collect(c);
+    c->prof_on = on != 0;
+    return 0;
+}
+int sharp_prof_reset(sharp_ctx *c) {
+    SHARP_TRY(use(c));
+    prof_collect(c);
+    for (int i = 0; i < KID_COUNT; i++) { c->prof_ms[i] = 0; c->prof_n[i] = 0; }
+    return 0;
+}
+int sharp_prof_kernels(void) { return KID_COUNT; }
+const char *sharp_prof_name(int kid) { return (kid >= 0 && kid < KID_COUNT) ? g_kernel_names[kid] : ""; }
+int sharp_prof_get(sharp_ctx *c, int kid, double *ms, int64_t *launches) {
+    SHARP_TRY(use(c));
+    if (kid < 0 || kid >= KID_COUNT) return set_error(SHARP_E_ARG, "prof_get: bad kernel id %d", kid);
+    prof_collect(c);
+    if (ms) *ms = c->prof_ms[kid];
+    if (launches) *launches = c->prof_n[kid];
+    return 0;
+}
 
 // ---- ranM upload: dgCMatrix slots of K matrices -> gene-major ternary entries -------------------------
 int sharp_rm_upload(sharp_ctx *c, int m, int p, int K, const int32_t *colptr, const int32_t *rowidx, const double *x,
@@ -1048,8 +1124,9 @@ int sharp_corrdist(sharp_ctx *c, int n, int p, const double *mat, double *dist) 
     int *tpd = db.take<int>(2);
     SHARP_TRY(h2d(c, c->ws[WS_DESC].ptr, c->pinned, hb.off));
     SHARP_TRY(launch_corrdist_batched(c, gpd, tpd, 1, tp[1], ldu));
+    prof_begin(c, KID_MISC);
     pad_copy_kernel<<<grid1d((size_t)n * n, 256), 256, 0, c->stream>>>(n, n, c->ws[WS_D].as<double>(), ld, c->ws[WS_TMP1].as<double>(), n);
-    c->launches++;
+    prof_end(c);
     SHARP_TRY(d2h(c, dist, c->ws[WS_TMP1].ptr, (size_t)n * n * 8));
     return sync(c);
 }
@@ -1062,8 +1139,9 @@ int sharp_hclust(sharp_ctx *c, int n, const double *dist, int method, int32_t *i
     SHARP_TRY(c->ws[WS_TMP1].reserve((size_t)n * n * 8));
     SHARP_TRY(c->ws[WS_DW].reserve((size_t)n * ld * 8));
     SHARP_TRY(h2d(c, c->ws[WS_TMP1].ptr, dist, (size_t)n * n * 8));
+    prof_begin(c, KID_MISC);
     pad_copy_kernel<<<grid1d((size_t)n * n, 256), 256, 0, c->stream>>>(n, n, c->ws[WS_TMP1].as<double>(), n, c->ws[WS_DW].as<double>(), ld);
-    c->launches++;
+    prof_end(c);
     size_t ibytes = bump_size({(size_t)n * 4, (size_t)n * 4}), dbytes = bump_size({(size_t)n * 8});
     SHARP_TRY(c->ws[WS_HC_INT].reserve(ibytes));
     SHARP_TRY(c->ws[WS_HC_DBL].reserve(dbytes));
@@ -1126,8 +1204,9 @@ int sharp_getrowcolor(sharp_ctx *c, int n, int p, const double *emat, const shar
     SHARP_TRY(h2d(c, c->ws[WS_TMP0].ptr, emat, (size_t)n * p * 8));
     OptResult R;
     SHARP_TRY(opt_hclust_dev(c, n, p, c->ws[WS_TMP0].as<double>(), 0, 0, *prm, false, &R));
+    prof_begin(c, KID_MISC);
     colour_wrap_kernel<<<grid1d(n, 256), 256, 0, c->stream>>>(R.f, n);
-    c->launches++;
+    prof_end(c);
     return fetch_opt(c, n, R, color, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, maxsil, nullptr, "getrowColor");
 }
 
@@ -1278,6 +1357,25 @@ int sharp_run(sharp_ctx *c, int m, int64_t n, const double *dense, const int64_t
     cudaStreamSynchronize(c->stream);
     free_expr(&e);
     return rc;
+}
+
+int sharp_last_member(sharp_ctx *c, int k, int64_t n, int32_t *rowcolor, double *inde) {
+    SHARP_TRY(use(c));
+    if (n != c->last_n || !c->ws[WS_ENRP].ptr || !c->ws[WS_PROJ].ptr)
+        return set_error(SHARP_E_ARG, "last_member: no matching run on this context");
+    if (k < 0 || k >= c->last_K) return set_error(SHARP_E_ARG, "last_member: member %d out of range (0..%d)", k, c->last_K - 1);
+    if (rowcolor) SHARP_TRY(d2h(c, rowcolor, c->ws[WS_ENRP].as<int32_t>() + (size_t)k * n, (size_t)n * 4));
+    if (inde) SHARP_TRY(d2h(c, inde, c->ws[WS_PROJ].as<double>() + (size_t)k * n * c->last_p, (size_t)n * c->last_p * 8));
+    return sync(c);
+}
+
+int sharp_last_vie(sharp_ctx *c, int64_t n, int p, double *vie) {
+    SHARP_TRY(use(c));
+    if (!vie) return set_error(SHARP_E_ARG, "last_vie: null output");
+    if (n != c->last_n || p != c->last_p || !c->ws[WS_VIEU].ptr)
+        return set_error(SHARP_E_ARG, "last_vie: no matching run on this context");
+    SHARP_TRY(d2h(c, vie, c->ws[WS_VIEU].ptr, (size_t)n * p * 8));
+    return sync(c);
 }
 
 int sharp_centroids(sharp_ctx *c, int64_t n, const int32_t *labels, int nclust, double *cen, int64_t *counts) {

@@ -66,8 +66,9 @@ colsum_kernel(int m, int64_t n, const double *__restrict__ dense, const int64_t 
 int launch_colsum(sharp_ctx *c, const sharp_expr_dev &e, double *colsum) {
     if (e.n <= 0) return 0;
     int64_t blocks = (e.n + 7) / 8;
+    prof_begin(c, KID_COLSUM);
     colsum_kernel<<<(unsigned)blocks, 256, 0, c->stream>>>(e.m, e.n, e.dense, e.colptr, e.val, colsum);
-    c->launches++;
+    prof_end(c);
     SHARP_CUDA(cudaGetLastError());
     return 0;
 }
@@ -242,6 +243,7 @@ int launch_rp_project(sharp_ctx *c, const sharp_expr_dev &e, const int64_t *cell
     smem = (smem + 15) & ~(size_t)15;
     int64_t nbatch = (ncell + W - 1) / W;
     int grid = (int)std::min<int64_t>(nbatch, (int64_t)c->sm_count * (smem <= 100 * 1024 ? 2 : 1));
+    prof_begin(c, KID_RP_PROJECT);
     if (e16) {
         SHARP_CUDA(cudaFuncSetAttribute(rp_project_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         rp_project_kernel<true><<<grid, W * 32, smem, c->stream>>>(A, W);
@@ -249,7 +251,7 @@ int launch_rp_project(sharp_ctx *c, const sharp_expr_dev &e, const int64_t *cell
         SHARP_CUDA(cudaFuncSetAttribute(rp_project_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         rp_project_kernel<false><<<grid, W * 32, smem, c->stream>>>(A, W);
     }
-    c->launches++;
+    prof_end(c);
     SHARP_CUDA(cudaGetLastError());
     return 0;
 }

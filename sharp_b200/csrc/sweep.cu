@@ -380,9 +380,10 @@ int launch_sweep_nested(sharp_ctx *c, HcProb *probs_dev, SweepOut *outs_dev, int
     if (L.total > 220 * 1024)
         return set_error(SHARP_E_LIMIT, "nested sweep: %d objects need %zu bytes of shared memory", max_n, L.total);
     SHARP_CUDA(cudaFuncSetAttribute(sweep_nested_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
+    prof_begin(c, KID_SWEEP_NESTED);
     sweep_nested_kernel<<<nprob, SW_THREADS, L.total, c->stream>>>(probs_dev, outs_dev, prm, max_n, kcap, nlevcap,
                                                                    scratch, scratch_per_prob);
-    c->launches++;
+    prof_end(c);
     SHARP_CUDA(cudaGetLastError());
     return 0;
 }
@@ -590,18 +591,21 @@ int launch_sweep_exact(sharp_ctx *c, HcProb *probs_dev, SweepOut *outs_dev, int 
         return set_error(SHARP_E_LIMIT, "exact sweep: %d objects need %zu bytes of shared memory", max_n, smem);
     {
         dim3 g((max_n + SW_THREADS - 1) / SW_THREADS, nprob);
+        prof_begin(c, KID_SWEEP_EXACT);
         exact_prep_kernel<<<g, SW_THREADS, 0, c->stream>>>(probs_dev, scratch, scratch_per_prob / 8);
-        c->launches++;
+        prof_end(c);
     }
     SHARP_CUDA(cudaFuncSetAttribute(sweep_exact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid(max_levels, nprob);
+    prof_begin(c, KID_SWEEP_EXACT);
     sweep_exact_kernel<<<grid, SW_THREADS, smem, c->stream>>>(probs_dev, outs_dev, prm_dev, max_n, kcap, scratch,
                                                               scratch_per_prob / 8);
-    c->launches++;
+    prof_end(c);
     size_t smem2 = (size_t)4 * max_n * 4;
     SHARP_CUDA(cudaFuncSetAttribute(sweep_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+    prof_begin(c, KID_SWEEP_EXACT);
     sweep_select_kernel<<<nprob, SW_THREADS, smem2, c->stream>>>(probs_dev, outs_dev, prm_dev, max_n);
-    c->launches++;
+    prof_end(c);
     SHARP_CUDA(cudaGetLastError());
     return 0;
 }

@@ -186,6 +186,7 @@ int launch_hclust(sharp_ctx *c, HcProb *probs_dev, int nprob, int max_n, int met
     size_t smem = hclust_smem_bytes(max_n);
     if (smem > 200 * 1024)
         return set_error(SHARP_E_LIMIT, "hclust: %d objects exceed the shared-memory NN list (max ~9700)", max_n);
+    prof_begin(c, max_n > 384 ? KID_HCLUST : KID_HCLUST_SMALL);
     if (max_n > 384) {
         SHARP_CUDA(cudaFuncSetAttribute(hclust_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         hclust_kernel<512><<<nprob, 512, smem, c->stream>>>(probs_dev, method);
@@ -193,7 +194,7 @@ int launch_hclust(sharp_ctx *c, HcProb *probs_dev, int nprob, int max_n, int met
         SHARP_CUDA(cudaFuncSetAttribute(hclust_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         hclust_kernel<128><<<nprob, 128, smem, c->stream>>>(probs_dev, method);
     }
-    c->launches++;
+    prof_end(c);
     SHARP_CUDA(cudaGetLastError());
     return 0;
 }
