@@ -94,6 +94,13 @@ int sharp_rm_upload(sharp_ctx *ctx, int m, int p, int K, const int32_t *colptr, 
                     const double *x, const int64_t *nnz_off, sharp_rm_dev **out);
 void sharp_rm_free(sharp_rm_dev *rm);
 
+/* R-compatible generators for hosts without R (sharp_b200/csrc/rrng.cpp; the reference's own calls are cited there).
+ * sharp_r_ranm = ranM2(m, p, seed) for an integer seed (R/ranM2.R:11-35 == R/ranM.R:11-33 with m = nrow(scdata)) as
+ * dgCMatrix slots; cap = room in rowidx / x, *nnz always set, SHARP_E_NOMEM if cap is too small.
+ * sharp_r_sample_perm = set.seed(seed); sample(n) (R/SHARP.R:495-498), 1-based.  Both are pure host code. */
+int sharp_r_ranm(int m, int p, int64_t seed, int32_t *colptr, int32_t *rowidx, double *x, int64_t cap, int64_t *nnz);
+int sharp_r_sample_perm(int64_t seed, int64_t n, int64_t *out);
+
 /* ---- a2/a3/a4: random projection with the normalisation fused into the load ---------------------
  * Replaces: RPmat()'s `1/sqrt(p) * t(x) %*% scdata` (R/RPmat.R:32), the inline projection of SHARP_large /
  * SHARP_fpart / testlog (R/SHARP.R:567-585, 899-905; R/SHARP_unlimited2.R:388-410), log2(x+1)

@@ -53,7 +53,7 @@ EXPORTS = [
     "sharp_hclust", "sharp_opt_hclust", "sharp_getrowcolor", "sharp_wmetac", "sharp_smetac", "sharp_run",
     "sharp_expr_upload", "sharp_expr_free", "sharp_run_dev", "sharp_centroids", "sharp_smetac_centroids",
     "sharp_last_member", "sharp_last_vie", "sharp_prof_enable", "sharp_prof_reset", "sharp_prof_kernels", "sharp_prof_name",
-    "sharp_prof_get",
+    "sharp_prof_get", "sharp_r_ranm", "sharp_r_sample_perm",
 ]
 
 _lib = None
@@ -137,6 +137,34 @@ def _expr_args(m, n, dense, csc):
     if cp.shape[0] != n + 1:
         raise ValueError("CSC colptr must have ncells + 1 entries")
     return (cp, ri, v), None, _ptr(cp, C.c_int64), _ptr(ri, C.c_int32), _ptr(v, C.c_double)
+
+
+def r_ranm(m: int, p: int, seed: int) -> dict:
+    """ranM2(m, p, seed) through the native generator (sharp_r_ranm) -> dgCMatrix slots"""
+    lib = load()
+    cap = int(p * (m ** 0.5) * 1.15) + 4096
+    colptr = np.empty(p + 1, dtype=np.int32)
+    while True:
+        ri = np.empty(cap, dtype=np.int32)
+        x = np.empty(cap, dtype=np.float64)
+        nnz = C.c_int64()
+        rc = lib.sharp_r_ranm(int(m), int(p), C.c_int64(int(seed)), _ptr(colptr, C.c_int32), _ptr(ri, C.c_int32),
+                              _ptr(x, C.c_double), C.c_int64(cap), C.byref(nnz))
+        if rc == E_NOMEM:
+            cap = nnz.value
+            continue
+        if rc != 0:
+            raise SharpError(rc, "sharp_r_ranm failed")
+        return {"Dim": (int(m), int(p)), "p": colptr, "i": ri[:nnz.value], "x": x[:nnz.value]}
+
+
+def r_sample_perm_native(n: int, seed: int) -> np.ndarray:
+    """set.seed(seed); sample(n) through the native generator (sharp_r_sample_perm)"""
+    out = np.empty(int(n), dtype=np.int64)
+    rc = load().sharp_r_sample_perm(C.c_int64(int(seed)), C.c_int64(int(n)), _ptr(out, C.c_int64))
+    if rc != 0:
+        raise SharpError(rc, "sharp_r_sample_perm failed")
+    return out
 
 
 class RmDev:

@@ -38,7 +38,7 @@ from .rrng import RRandom, r_sample_perm, ranM, ranM2  # noqa: F401  (ranM / ran
 __all__ = ["SHARP", "SHARP_small", "SHARP_large", "SHARP_unlimited", "SHARP_unlimited2", "SHARP_fpart",
            "SHARP_unlimited3", "RPmat", "ranM", "ranM2", "get_opt_hclust", "getrowColor", "wMetaC", "sMetaC",
            "getA", "getss", "testlog", "ARI", "run_Mtimes_SHARP", "Expression", "get_context", "set_devices",
-           "set_verbose", "colorL"]
+           "set_verbose", "colorL", "stream_contexts"]
 
 # R/getrowColor.R:52-58
 colorL = ["red", "purple", "blue", "yellow", "green", "orange", "brown", "gray", "black", "coral", "beige", "cyan",
@@ -76,6 +76,24 @@ def get_context(device: int | None = None) -> Context:
         c = Context(d)
         _contexts[d] = c
     return c
+
+
+_stream_ctxs: dict[int, list] = {}
+_default_streams = 8
+
+
+def stream_contexts(n: int, device: int | None = None) -> list:
+    """``n`` contexts (CUDA stream + workspace each) on one device; the first is the module-level context.
+    Parts of a SHARP_unlimited call are clustered concurrently on them: the Ward agglomeration is latency-bound
+    (one CTA per 2000-cell problem, 125 problems per 50 000-cell part), so several parts in flight are what fills
+    the 148 SMs, and one part's H2D copy overlaps the others' kernels."""
+    d = _current_device if device is None else int(device)
+    lst = _stream_ctxs.setdefault(d, [])
+    if not lst or not lst[0]._h:
+        lst[:] = [get_context(d)]
+    while len(lst) < n:
+        lst.append(Context(d))
+    return lst[:n]
 
 
 def _kw(kwargs: dict) -> dict:
@@ -253,25 +271,26 @@ def _ncl(x) -> int:
     return int(x)
 
 
-_reind_cache: dict[tuple, np.ndarray] = {}
+def _entropy_seed() -> int:
+    return int(np.random.SeedSequence().entropy % (2 ** 31))
 
 
 def _reind(n: int, rN_seed) -> np.ndarray:
     """R/SHARP.R:493-498: unseeded sample(ncells), or set.seed(50); sample(ncells)"""
     if rN_seed == 0.5:
-        return r_sample_perm(n, None)
-    key = (int(n), 50)
-    r = _reind_cache.get(key)
-    if r is None:
-        r = r_sample_perm(n, 50)
-        if len(_reind_cache) > 8:
-            _reind_cache.clear()
-        _reind_cache[key] = r
-    return r
+        return _lib.r_sample_perm_native(n, _entropy_seed())
+    return _lib.r_sample_perm_native(n, 50)
 
 
 def _rm_list(m, p, K, rN_seed):
-    return [ranM2(m, p, _member_seed(rN_seed, k)) for k in range(1, K + 1)]
+    """K x ranM(E, p, 50 + rN.seed + k) (R/SHARP.R:539-549) with R's RNG stream, one host thread per member (the
+    native generator releases the GIL); an unseeded run (rN.seed = 0.5) draws its seeds from the OS entropy."""
+    from concurrent.futures import ThreadPoolExecutor
+    seeds = [_entropy_seed() if rN_seed == 0.5 else _member_seed(rN_seed, k) for k in range(1, K + 1)]
+    if K == 1:
+        return [_lib.r_ranm(m, p, seeds[0])]
+    with ThreadPoolExecutor(max_workers=min(K, 16)) as ex:
+        return list(ex.map(lambda sd: _lib.r_ranm(m, p, sd), seeds))
 
 
 def _as_rmdev(ctx: Context, rM, m, p, K, rN_seed) -> tuple[RmDev, bool]:
@@ -664,8 +683,8 @@ def _unlimited_result(final, ncells, ngenes, y0, start):
 
 
 def SHARP_unlimited(scExp, viewflag=True, n_cores=None, ensize_K=None, N_cluster=None, minN_cluster=None,
-                    maxN_cluster=None, rN_seed=None, ctx: Context | None = None, comm=None, _part_logflag=False,
-                    **kwargs) -> dict:
+                    maxN_cluster=None, rN_seed=None, ctx: Context | None = None, comm=None, n_streams=None,
+                    _part_logflag=False, **kwargs) -> dict:
     """R/SHARP_unlimited.R:29-242.  ``scExp``: a LIST of genes x cells matrices (parts).  Every part runs SHARP()
     with the shared ranM matrices; the part-level clusters are merged by one global sMetaC over their centroids
     (computed on the device from the part's viE, which never leaves it unless ``viewflag``).
@@ -699,14 +718,46 @@ def SHARP_unlimited(scExp, viewflag=True, n_cores=None, ensize_K=None, N_cluster
     rank, world = (comm.rank, comm.world) if comm is not None else (0, 1)
     mine = [i for i in range(nnp) if i % world == rank]
     y, cens, viEs = {}, {}, {}
+    if isinstance(n_streams, (list, tuple)):  # explicit contexts, one per stream
+        ctxs = list(n_streams)[:max(1, len(mine))]
+    else:
+        S = max(1, min(int(n_streams or _default_streams), len(mine)))
+        if ctx is get_context(ctx.device) if _contexts.get(ctx.device) is ctx else False:
+            ctxs = stream_contexts(S, ctx.device)
+        else:  # a caller-owned context: its siblings (same type, same device) are created once and kept on it
+            sib = ctx.__dict__.setdefault("_siblings", [])
+            while len(sib) < S - 1:
+                sib.append(type(ctx)(ctx.device))
+            ctxs = [ctx] + sib[:S - 1]
+
+    def one_part(i, c):
+        _cat("Processing Partition", i + 1, "of the scRNA-seq data...")
+        yi = SHARP(parts[i], reduced_ndim=p, prep=False, logflag=_part_logflag, n_cores=n_cores, rM=rM, ensize_K=ensize_K,
+                   rN_seed=rN_seed, forview=False, ctx=c, **k)
+        cen, _ = c.centroids(yi["pred_clusters"], yi["N.pred_cluster"], p)
+        return yi, cen, (c.last_vie(nnc[i], p) if viewflag else None)
+
     try:
-        for i in mine:
-            _cat("Processing Partition", i + 1, "of the scRNA-seq data...")
-            y[i] = SHARP(parts[i], reduced_ndim=p, prep=False, logflag=_part_logflag, n_cores=n_cores, rM=rM, ensize_K=ensize_K,
-                         rN_seed=rN_seed, forview=False, ctx=ctx, **k)
-            cens[i], _ = ctx.centroids(y[i]["pred_clusters"], y[i]["N.pred_cluster"], p)
-            if viewflag:
-                viEs[i] = ctx.last_vie(nnc[i], p)
+        if len(ctxs) == 1:
+            for i in mine:
+                y[i], cens[i], viEs[i] = one_part(i, ctx)
+        else:  # one host thread per stream; the C ABI calls release the GIL
+            import queue
+            from concurrent.futures import ThreadPoolExecutor
+            free = queue.SimpleQueue()
+            for c in ctxs:
+                free.put(c)
+
+            def job(i):
+                c = free.get()
+                try:
+                    return one_part(i, c)
+                finally:
+                    free.put(c)
+
+            with ThreadPoolExecutor(max_workers=len(ctxs)) as ex:
+                for i, r in zip(mine, ex.map(job, mine)):
+                    y[i], cens[i], viEs[i] = r
     finally:
         rM.close()
     if comm is not None:

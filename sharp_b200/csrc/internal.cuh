@@ -26,6 +26,11 @@ int set_error(int code, const char *fmt, ...);
         if (_rc != 0) return _rc; \
     } while (0)
 
+// Dynamic shared memory opt-in of every kernel: always the sm_100 maximum (227 KB), never the per-launch size -- host
+// threads driving different contexts set it concurrently, and a smaller value set by one thread between another
+// thread's attribute call and its launch would make that launch fail.
+constexpr int SHARP_SMEM_OPTIN = 223 * 1024;  /* 227 KB minus room for the kernels' small static arrays */
+
 // ---- device buffer that grows and never shrinks (workspace slot) -------------------------------------
 struct DevBuf {
     void *ptr = nullptr;

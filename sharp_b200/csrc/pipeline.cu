@@ -2,6 +2,7 @@
 // fused SHARP_small / SHARP_large device pipeline.  No CPU fallback anywhere: every entry point enqueues CUDA
 // kernels of this library on the context's stream and fails with SHARP_E_CUDA when there is no device.
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdarg>
 #include <cstring>
@@ -14,6 +15,7 @@ namespace sharp {
 
 // ---- errors ------------------------------------------------------------------------------------
 static thread_local char g_err[1024] = "";
+static std::atomic<int> g_live_ctx{0};
 
 int set_error(int code, const char *fmt, ...) {
     va_list ap;
@@ -54,7 +56,9 @@ int DevBuf::reserve(size_t bytes) {
         cap = 0;
         if (e != cudaSuccess) return set_error(SHARP_E_CUDA, "cudaFree: %s", cudaGetErrorString(e));
     }
-    size_t want = (bytes + (1 << 20) - 1) & ~(size_t)((1 << 20) - 1);
+    /* 1/8 headroom: the parts of one job differ a little in size, and a regrow is a cudaFree, i.e. a device-wide
+       synchronisation that stalls the contexts working on other streams */
+    size_t want = (bytes + bytes / 8 + (1 << 20) - 1) & ~(size_t)((1 << 20) - 1);
     cudaError_t e = cudaMalloc(&ptr, want);
     if (e != cudaSuccess) {
         ptr = nullptr;
@@ -132,7 +136,7 @@ void prof_collect(sharp_ctx *c) {
 enum Slot {
     WS_SRC = 0, WS_COLSUM, WS_PROJ, WS_U, WS_D, WS_DW, WS_HC_INT, WS_HC_DBL, WS_DESC, WS_SWEEP_SCRATCH, WS_ENRP, WS_E1,
     WS_WM_INT, WS_WM_DBL, WS_WM_S, WS_WM_DESC, WS_WM_SCRATCH, WS_SM_INT, WS_SM_DBL, WS_SM_S, WS_SM_SCRATCH, WS_VIEU,
-    WS_LABELS, WS_X0, WS_TMP0, WS_TMP1, WS_TMP2, WS_TMP3, WS_START, WS_CEN, WS_COUNT
+    WS_LABELS, WS_X0, WS_TMP0, WS_TMP1, WS_TMP2, WS_TMP3, WS_START, WS_CEN, WS_EX_A, WS_EX_B, WS_EX_C, WS_COUNT
 };
 
 // bump allocator over a byte region
@@ -204,23 +208,35 @@ __global__ void scatter_rows_kernel(const double *__restrict__ src, int64_t n, i
 static int grid1d(size_t n, int threads) { return (int)((n + threads - 1) / threads); }
 
 // ---- upload helpers -------------------------------------------------------------------------------
+// staged = true: the device copy lives in the context's grow-only workspace (no cudaMalloc / cudaFree per call --
+// cudaFree synchronises the whole device, which would serialise contexts working on other streams) and is valid
+// until the next staged upload on this context; staged = false: the caller owns it (sharp_expr_upload).
 static int upload_expr(sharp_ctx *c, int m, int64_t n, const double *dense, const int64_t *colptr, const int32_t *rowidx,
-                       const double *val, sharp_expr_dev *e) {
+                       const double *val, sharp_expr_dev *e, bool staged = false) {
     e->device = c->device;
     e->m = m;
     e->n = n;
+    e->owned = !staged;
     if (m <= 0 || n < 0) return set_error(SHARP_E_ARG, "expression matrix: bad dimensions %d x %lld", m, (long long)n);
+    auto get = [&](int slot, void **ptr, size_t bytes) -> int {
+        bytes = std::max<size_t>(bytes, 8);
+        if (staged) {
+            SHARP_TRY(c->ws[slot].reserve(bytes));
+            *ptr = c->ws[slot].ptr;
+        } else SHARP_CUDA(cudaMalloc(ptr, bytes));
+        return 0;
+    };
     if (dense) {
         size_t bytes = (size_t)m * n * sizeof(double);
-        SHARP_CUDA(cudaMalloc((void **)&e->dense, std::max<size_t>(bytes, 8)));
+        SHARP_TRY(get(WS_EX_A, (void **)&e->dense, bytes));
         SHARP_CUDA(cudaMemcpyAsync(e->dense, dense, bytes, cudaMemcpyHostToDevice, c->stream));
     } else {
         if (!colptr || (!rowidx && colptr[n] > 0) || (!val && colptr[n] > 0))
             return set_error(SHARP_E_ARG, "expression matrix: neither dense nor complete CSC slots given");
         e->nnz = colptr[n];
-        SHARP_CUDA(cudaMalloc((void **)&e->colptr, (size_t)(n + 1) * 8));
-        SHARP_CUDA(cudaMalloc((void **)&e->rowidx, std::max<size_t>((size_t)e->nnz * 4, 8)));
-        SHARP_CUDA(cudaMalloc((void **)&e->val, std::max<size_t>((size_t)e->nnz * 8, 8)));
+        SHARP_TRY(get(WS_EX_A, (void **)&e->colptr, (size_t)(n + 1) * 8));
+        SHARP_TRY(get(WS_EX_B, (void **)&e->rowidx, (size_t)e->nnz * 4));
+        SHARP_TRY(get(WS_EX_C, (void **)&e->val, (size_t)e->nnz * 8));
         SHARP_CUDA(cudaMemcpyAsync(e->colptr, colptr, (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, c->stream));
         SHARP_CUDA(cudaMemcpyAsync(e->rowidx, rowidx, (size_t)e->nnz * 4, cudaMemcpyHostToDevice, c->stream));
         SHARP_CUDA(cudaMemcpyAsync(e->val, val, (size_t)e->nnz * 8, cudaMemcpyHostToDevice, c->stream));
@@ -230,6 +246,13 @@ static int upload_expr(sharp_ctx *c, int m, int64_t n, const double *dense, cons
 
 static void free_expr(sharp_expr_dev *e) {
     if (!e) return;
+    if (!e->owned) {
+        e->dense = nullptr;
+        e->colptr = nullptr;
+        e->rowidx = nullptr;
+        e->val = nullptr;
+        return;
+    }
     if (e->dense) cudaFree(e->dense);
     if (e->colptr) cudaFree(e->colptr);
     if (e->rowidx) cudaFree(e->rowidx);
@@ -653,7 +676,9 @@ static int run_core(sharp_ctx *c, const sharp_expr_dev &e, const double *colsum_
     size_t free_b = 0, total_b = 0;
     SHARP_CUDA(cudaMemGetInfo(&free_b, &total_b));
     size_t have = c->ws[WS_D].cap + c->ws[WS_DW].cap;
-    size_t budget = std::min<size_t>((size_t)48 << 30, (size_t)((free_b + have) * 0.6));
+    /* contexts on other streams of the same device run concurrently: share the free memory between them */
+    const int live = std::max(1, g_live_ctx.load());
+    size_t budget = std::min<size_t>((size_t)48 << 30, (size_t)(free_b * 0.6 / live) + have);
     const size_t per_prob = (size_t)max_bn * ld_of(max_bn) * 8;
     int wave_blocks = (int)std::max<size_t>(1, (budget / 2 / per_prob) / K);
     wave_blocks = std::min(wave_blocks, T);
@@ -897,11 +922,13 @@ int sharp_ctx_create(int device, sharp_ctx **out) {
     SHARP_CUDA(cudaEventCreate(&c->ev0));
     SHARP_CUDA(cudaEventCreate(&c->ev1));
     *out = c;
+    g_live_ctx++;
     return 0;
 }
 
 void sharp_ctx_destroy(sharp_ctx *c) {
     if (!c) return;
+    g_live_ctx--;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     prof_collect(c);
@@ -1071,7 +1098,7 @@ int sharp_rp_project(sharp_ctx *c, int m, int64_t n, const double *dense, const 
     SHARP_TRY(use(c));
     if (!rm || !out) return set_error(SHARP_E_ARG, "rp_project: null argument");
     sharp_expr_dev e;
-    int rc = upload_expr(c, m, n, dense, colptr, rowidx, val, &e);
+    int rc = upload_expr(c, m, n, dense, colptr, rowidx, val, &e, true);
     auto body = [&]() -> int {
         if (rc) return rc;
         int64_t *cells_dev = nullptr;
@@ -1352,7 +1379,7 @@ int sharp_run(sharp_ctx *c, int m, int64_t n, const double *dense, const int64_t
     SHARP_TRY(use(c));
     if (!rm || !prm || !labels) return set_error(SHARP_E_ARG, "run: null argument");
     sharp_expr_dev e;
-    int rc = upload_expr(c, m, n, dense, colptr, rowidx, val, &e);
+    int rc = upload_expr(c, m, n, dense, colptr, rowidx, val, &e, true);
     if (!rc) rc = sharp_run_dev(c, &e, colsum, rm, reind, prm, labels, vie, x0, x0_cols, max_x0_cols);
     cudaStreamSynchronize(c->stream);
     free_expr(&e);

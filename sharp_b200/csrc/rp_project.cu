@@ -9,19 +9,21 @@
 // That is 10-15x fewer operations than gathering along the projection columns, and the expression matrix is
 // read exactly once for all K members (HBM traffic = the input as stored + the K*p outputs).
 //   * the ternary matrices are re-laid out gene-major (CSR over genes of the concatenated m x K*p matrix,
-//     16-bit column + sign per entry) and streamed through shared memory in tiles of TILE_GENES genes, shared
-//     by all cells a CTA is working on;
-//   * one warp owns one cell: its K*p fp64 accumulators live in shared memory, its non-zeros are loaded 32 at a
-//     time (coalesced), log-transformed in parallel, then applied one gene at a time with the lanes spread over
-//     that gene's entries (distinct columns, so no atomics and a deterministic result);
+//     16-bit column + sign per entry, ~1 MB in all): they stay L2/L1-resident and are read directly, 30 B per
+//     non-zero of the cell;
+//   * one warp owns one cell: its K*p fp64 accumulators live in shared memory (20 KB at K = 5, p = 508), its
+//     non-zeros are loaded 32 at a time (coalesced), log-transformed in parallel, staged in shared memory, then
+//     applied one gene at a time with the lanes spread over that gene's entries (distinct columns, so no atomics
+//     and every accumulator receives its terms in ascending gene order: bit-identical to a sequential sparse
+//     product).  The entry loads of 4 genes are in flight before the first add.
+//   * bound: the kernel is limited by shared-memory read-modify-write wavefronts of the scattered adds (random
+//     columns -> bank conflicts), not by HBM: ~30 k adds per cell against 44 KB of HBM traffic per cell.
 //   * a dense tcgen05 contraction is not used: with density 1/sqrt(m) it would execute ~150x more MACs than
 //     this kernel does adds (DESIGN.md has the arithmetic).
 #include "devutil.cuh"
 #include "internal.cuh"
 
 namespace sharp {
-
-constexpr int RP_TILE_GENES = 512;
 
 __device__ __forceinline__ double rp_transform(double x, double cs, int normalize, double norm_mul, int logkind) {
     double v = x;
@@ -93,125 +95,107 @@ struct RpArgs {
     const uint32_t *rowptr; // [m+1]
     const uint16_t *ent16;
     const uint32_t *ent32;
-    int tile_genes, ntiles, max_tile_entries;
     double *out;
 };
 
+// one staged non-zero of the current cell: where its ranM entries are and the transformed value
+struct __align__(16) RpGene {
+    uint32_t r0, cnt;
+    double v;
+};
+
 template <bool ENT16>
-__device__ __forceinline__ void rp_apply(double *acc, const void *s_ent, int r0, int r1, int lane, double vv) {
-    for (int e = r0 + lane; e < r1; e += 32) {
-        unsigned col, neg;
-        if (ENT16) {
-            unsigned v = reinterpret_cast<const uint16_t *>(s_ent)[e];
-            col = v & 0x7fffu;
-            neg = v & 0x8000u;
-        } else {
-            unsigned v = reinterpret_cast<const uint32_t *>(s_ent)[e];
-            col = v & 0x7fffffffu;
-            neg = v & 0x80000000u;
-        }
-        acc[col] += neg ? -vv : vv;
-    }
-    __syncwarp();
+__device__ __forceinline__ unsigned rp_load_ent(const RpArgs &A, uint32_t at) {
+    return ENT16 ? (unsigned)__ldg(A.ent16 + at) : __ldg(A.ent32 + at);
 }
 
 template <bool ENT16>
-__global__ void __launch_bounds__(256) rp_project_kernel(RpArgs A, int warps_per_cta) {
+__device__ __forceinline__ void rp_add(double *acc, unsigned e, double v) {
+    const unsigned col = ENT16 ? (e & 0x7fffu) : (e & 0x7fffffffu);
+    const unsigned neg = ENT16 ? (e & 0x8000u) : (e & 0x80000000u);
+    acc[col] += neg ? -v : v;
+}
+
+// Apply up to 32 staged genes (in order) to the warp's accumulators.  Lanes spread over the entries of ONE gene
+// (distinct columns: no conflicts, and every accumulator receives its terms in ascending gene order, like the
+// reference's sparse product).  The accumulators take almost all of the SM's shared memory, so L1 is tiny and every
+// entry load is an L2 round trip: the first 32 entries of ALL staged genes are loaded before the first add (one
+// round trip per 32 genes instead of one per gene).
+template <bool ENT16>
+__device__ __forceinline__ void rp_apply_staged(const RpArgs &A, double *acc, const RpGene *st, int nst, int lane) {
+    unsigned e[32];
+#pragma unroll
+    for (int t = 0; t < 32; t++) {
+        e[t] = 0u;
+        if (t < nst) {
+            const uint32_t r0 = st[t].r0, cnt = st[t].cnt;
+            if ((uint32_t)lane < cnt) e[t] = rp_load_ent<ENT16>(A, r0 + lane);
+        }
+    }
+#pragma unroll
+    for (int t = 0; t < 32; t++) {
+        if (t < nst) { /* nst is warp-uniform */
+            const RpGene g = st[t];
+            if ((uint32_t)lane < g.cnt) rp_add<ENT16>(acc, e[t], g.v);
+            for (uint32_t x = 32 + lane; x < g.cnt; x += 32) rp_add<ENT16>(acc, rp_load_ent<ENT16>(A, g.r0 + x), g.v);
+            __syncwarp();
+        }
+    }
+}
+
+// one warp per cell; dynamic shared memory: [W][KP] fp64 accumulators, then [W][32] staged genes
+template <bool ENT16>
+__global__ void __launch_bounds__(320) rp_project_kernel(RpArgs A, int warps_per_cta) {
     extern __shared__ __align__(16) unsigned char rsm[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int nthreads = warps_per_cta * 32;
-    double *acc_all = reinterpret_cast<double *>(rsm);                         // [W][KP]
-    uint32_t *s_rowptr = reinterpret_cast<uint32_t *>(acc_all + (size_t)warps_per_cta * A.KP);  // [tile_genes+1]
-    unsigned char *s_ent = reinterpret_cast<unsigned char *>(s_rowptr + A.tile_genes + 4);
-    double *acc = acc_all + (size_t)warp * A.KP;
-    const int esz = ENT16 ? 2 : 4;
+    double *acc = reinterpret_cast<double *>(rsm) + (size_t)warp * A.KP;
+    RpGene *stage = reinterpret_cast<RpGene *>(reinterpret_cast<double *>(rsm) + (size_t)warps_per_cta * A.KP) + warp * 32;
 
-    const int64_t nbatch = (A.ncell + warps_per_cta - 1) / warps_per_cta;
-    for (int64_t batch = blockIdx.x; batch < nbatch; batch += gridDim.x) {
-        const int64_t pos = batch * warps_per_cta + warp;   // output cell of this warp
-        const bool active = pos < A.ncell;
-        const int64_t src = active ? (A.cells ? A.cells[pos] : pos) : 0;
-        const double cs = (A.normalize && active) ? A.colsum[src] : 1.0;
+    const int64_t nwarps = (int64_t)gridDim.x * warps_per_cta;
+    for (int64_t pos = (int64_t)blockIdx.x * warps_per_cta + warp; pos < A.ncell; pos += nwarps) {
+        const int64_t src = A.cells ? A.cells[pos] : pos;
+        const double cs = A.normalize ? A.colsum[src] : 1.0;
         for (int i = lane; i < A.KP; i += 32) acc[i] = 0.0;
-        // CSC cursor
-        int64_t q = 0, qend = 0;
-        if (!A.dense && active) { q = A.colptr[src]; qend = A.colptr[src + 1]; }
-        int chunk_len = 0, consumed = 0;
-        int g = INT_MAX;
-        double v = 0.0;
-        const double *dcol = A.dense ? A.dense + src * A.m : nullptr;
-
-        for (int tile = 0; tile < A.ntiles; tile++) {
-            const int g0 = tile * A.tile_genes;
-            const int g1 = min(A.m, g0 + A.tile_genes);
-            const uint32_t ebase = A.rowptr[g0];
-            const uint32_t eend = A.rowptr[g1];
-            __syncthreads(); /* previous tile fully consumed */
-            for (int i = threadIdx.x; i <= g1 - g0; i += nthreads) s_rowptr[i] = A.rowptr[g0 + i] - ebase;
-            {
-                /* entries: copy as 4-byte words (ebase*esz may be only 2-byte aligned -> start from the aligned word) */
-                const size_t b0 = (size_t)ebase * esz, b1 = (size_t)eend * esz;
-                const size_t w0 = b0 & ~(size_t)3;
-                const uint32_t *srcw = reinterpret_cast<const uint32_t *>(
-                    (ENT16 ? reinterpret_cast<const unsigned char *>(A.ent16) : reinterpret_cast<const unsigned char *>(A.ent32)) + w0);
-                uint32_t *dstw = reinterpret_cast<uint32_t *>(s_ent);
-                const size_t nw = (b1 - w0 + 3) >> 2;
-                for (size_t i = threadIdx.x; i < nw; i += nthreads) dstw[i] = srcw[i];
+        __syncwarp();
+        if (A.dense) {
+            const double *dcol = A.dense + src * A.m;
+            for (int c0 = 0; c0 < A.m; c0 += 32) {
+                const int gi = c0 + lane;
+                const double x = (gi < A.m) ? dcol[gi] : 0.0;
+                const unsigned mask = __ballot_sync(0xffffffffu, x != 0.0);
+                if (!mask) continue;
+                if (x != 0.0) {
+                    RpGene g;
+                    g.r0 = __ldg(A.rowptr + gi);
+                    g.cnt = __ldg(A.rowptr + gi + 1) - g.r0;
+                    g.v = rp_transform(x, cs, A.normalize, A.norm_mul, A.logkind);
+                    stage[__popc(mask & ((1u << lane) - 1u))] = g;
+                }
+                __syncwarp();
+                rp_apply_staged<ENT16>(A, acc, stage, __popc(mask), lane);
             }
-            __syncthreads();
-            const unsigned char *ent = s_ent + (((size_t)ebase * esz) & 3); /* skip the alignment slack */
-            if (!active) continue;
-            if (dcol) {
-                for (int c0 = g0; c0 < g1; c0 += 32) {
-                    const int gi = c0 + lane;
-                    double x = (gi < g1) ? dcol[gi] : 0.0;
-                    unsigned mask = __ballot_sync(0xffffffffu, x != 0.0);
-                    if (!mask) continue;
-                    double tv = (x != 0.0) ? rp_transform(x, cs, A.normalize, A.norm_mul, A.logkind) : 0.0;
-                    while (mask) {
-                        const int t = __ffs(mask) - 1;
-                        mask &= mask - 1;
-                        const double vv = __shfl_sync(0xffffffffu, tv, t);
-                        const int gl = c0 + t - g0;
-                        rp_apply<ENT16>(acc, ent, (int)s_rowptr[gl], (int)s_rowptr[gl + 1], lane, vv);
-                    }
+        } else {
+            const int64_t q0 = A.colptr[src], q1 = A.colptr[src + 1];
+            for (int64_t q = q0; q < q1; q += 32) {
+                const int nst = (int)min((int64_t)32, q1 - q);
+                if (lane < nst) {
+                    const int gi = A.rowidx[q + lane];
+                    const double x = A.val[q + lane];
+                    RpGene g;
+                    g.r0 = __ldg(A.rowptr + gi);
+                    g.cnt = (x != 0.0) ? __ldg(A.rowptr + gi + 1) - g.r0 : 0u; /* explicit zeros contribute nothing */
+                    g.v = rp_transform(x, cs, A.normalize, A.norm_mul, A.logkind);
+                    stage[lane] = g;
                 }
-            } else {
-                while (true) {
-                    if (consumed == chunk_len) {
-                        q += chunk_len;
-                        chunk_len = (int)min((int64_t)32, qend - q);
-                        consumed = 0;
-                        if (chunk_len <= 0) { chunk_len = 0; break; }
-                        if (lane < chunk_len) {
-                            g = A.rowidx[q + lane];
-                            v = rp_transform(A.val[q + lane], cs, A.normalize, A.norm_mul, A.logkind);
-                        } else {
-                            g = INT_MAX;
-                            v = 0.0;
-                        }
-                    }
-                    unsigned mask = __ballot_sync(0xffffffffu, lane >= consumed && lane < chunk_len && g < g1);
-                    const int cnt = __popc(mask);
-                    if (cnt == 0) break;
-                    for (int t = consumed; t < consumed + cnt; t++) {
-                        const int gl = __shfl_sync(0xffffffffu, g, t) - g0;
-                        const double vv = __shfl_sync(0xffffffffu, v, t);
-                        if (vv != 0.0) rp_apply<ENT16>(acc, ent, (int)s_rowptr[gl], (int)s_rowptr[gl + 1], lane, vv);
-                    }
-                    consumed += cnt;
-                    if (consumed < chunk_len) break;
-                }
+                __syncwarp();
+                rp_apply_staged<ENT16>(A, acc, stage, nst, lane);
             }
         }
-        __syncwarp();
-        if (active) {
-            for (int i = lane; i < A.KP; i += 32) {
-                const int k = i / A.p, j = i - k * A.p;
-                double r = __dmul_rn(acc[i], A.scale);
-                if (A.round_digits >= 0) r = rp_round(r, A.round_digits);
-                A.out[((size_t)k * A.ncell + pos) * A.p + j] = r;
-            }
+        for (int i = lane; i < A.KP; i += 32) {
+            const int k = i / A.p, j = i - k * A.p;
+            double r = __dmul_rn(acc[i], A.scale);
+            if (A.round_digits >= 0) r = rp_round(r, A.round_digits);
+            A.out[((size_t)k * A.ncell + pos) * A.p + j] = r;
         }
         __syncwarp();
     }
@@ -229,26 +213,23 @@ int launch_rp_project(sharp_ctx *c, const sharp_expr_dev &e, const int64_t *cell
     A.p = rm.p; A.K = rm.K; A.KP = rm.K * rm.p;
     A.scale = (1.0 / sqrt((double)rm.p)) * rm.mag;   /* entry of 1/sqrt(p) * t(rM) */
     A.rowptr = rm.rowptr; A.ent16 = rm.ent16; A.ent32 = rm.ent32;
-    A.tile_genes = rm.tile_genes; A.ntiles = rm.ntiles; A.max_tile_entries = rm.max_tile_entries;
     A.out = out;
     const bool e16 = rm.ent16 != nullptr;
-    const size_t tile_bytes = (size_t)(rm.tile_genes + 4) * 4 + (size_t)rm.max_tile_entries * (e16 ? 2 : 4) + 16;
-    const size_t budget = 200 * 1024;
-    const size_t per_warp = (size_t)A.KP * 8;
-    if (tile_bytes + per_warp > budget)
+    const size_t budget = 220 * 1024;
+    const size_t per_warp = (size_t)A.KP * 8 + 32 * sizeof(RpGene);
+    if (per_warp > budget)
         return set_error(SHARP_E_LIMIT, "rp_project: K*p = %d accumulators do not fit in shared memory", A.KP);
-    int W = (int)((budget - tile_bytes) / per_warp);
-    if (W > 8) W = 8;
-    size_t smem = tile_bytes + per_warp * W;
-    smem = (smem + 15) & ~(size_t)15;
-    int64_t nbatch = (ncell + W - 1) / W;
-    int grid = (int)std::min<int64_t>(nbatch, (int64_t)c->sm_count * (smem <= 100 * 1024 ? 2 : 1));
+    int W = (int)(budget / per_warp);
+    if (W > 10) W = 10;
+    const size_t smem = per_warp * W;
+    const int64_t nbatch = (ncell + W - 1) / W;
+    const int grid = (int)std::min<int64_t>(nbatch, (int64_t)c->sm_count);
     prof_begin(c, KID_RP_PROJECT);
     if (e16) {
-        SHARP_CUDA(cudaFuncSetAttribute(rp_project_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SHARP_CUDA(cudaFuncSetAttribute(rp_project_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SHARP_SMEM_OPTIN));
         rp_project_kernel<true><<<grid, W * 32, smem, c->stream>>>(A, W);
     } else {
-        SHARP_CUDA(cudaFuncSetAttribute(rp_project_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SHARP_CUDA(cudaFuncSetAttribute(rp_project_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SHARP_SMEM_OPTIN));
         rp_project_kernel<false><<<grid, W * 32, smem, c->stream>>>(A, W);
     }
     prof_end(c);

@@ -1,0 +1,205 @@
+// rrng.cpp -- R-compatible random numbers for the host glue (no R interpreter next to this library).
+//
+// The reference draws its projection matrices and its cell shuffle with base R:
+//   set.seed(seedn); sample(c(sqrt(s), 0, -sqrt(s)), m*p, replace = TRUE, prob = c(1/(2s), 1-1/s, 1/(2s)))
+//   Matrix(x0, nrow = m, byrow = TRUE, sparse = TRUE)                       (R/ranM.R:17-30, R/ranM2.R:17-32)
+//   set.seed(50); sample(ncells)                                             (R/SHARP.R:495-498)
+// Where R exists those calls stay in R and the dgCMatrix slots / the permutation are handed to the C ABI.
+// These two entry points reproduce the same streams (Mersenne-Twister + Inversion + Rejection, R >= 3.6;
+// SURVEY.md Appendix A.1) so that a seeded run is identical without R.  sharp_b200/rrng.py is the readable
+// restatement the tests compare this file with.
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <vector>
+
+#include "../../include/sharp_b200.h"
+
+namespace {
+
+struct RMersenne {
+    static constexpr int N = 624, M = 397;
+    uint32_t mt[N];
+    int mti;
+
+    explicit RMersenne(uint32_t seed) {
+        // set.seed(): Randomize(kind) -> RNG_Init: 50 scrambling steps, then 625 words of i_seed;
+        // FixupSeeds sets i_seed[0] (= mti) to N, so the first draw regenerates the table
+        for (int j = 0; j < 50; j++) seed = 69069u * seed + 1u;
+        seed = 69069u * seed + 1u; /* i_seed[0], overwritten by mti */
+        for (int j = 0; j < N; j++) {
+            seed = 69069u * seed + 1u;
+            mt[j] = seed;
+        }
+        mti = N;
+    }
+    void regen() {
+        static const uint32_t mag01[2] = {0x0u, 0x9908b0dfu};
+        int kk;
+        uint32_t y;
+        for (kk = 0; kk < N - M; kk++) {
+            y = (mt[kk] & 0x80000000u) | (mt[kk + 1] & 0x7fffffffu);
+            mt[kk] = mt[kk + M] ^ (y >> 1) ^ mag01[y & 1u];
+        }
+        for (; kk < N - 1; kk++) {
+            y = (mt[kk] & 0x80000000u) | (mt[kk + 1] & 0x7fffffffu);
+            mt[kk] = mt[kk + (M - N)] ^ (y >> 1) ^ mag01[y & 1u];
+        }
+        y = (mt[N - 1] & 0x80000000u) | (mt[0] & 0x7fffffffu);
+        mt[N - 1] = mt[M - 1] ^ (y >> 1) ^ mag01[y & 1u];
+        mti = 0;
+    }
+    inline uint32_t next32() {
+        if (mti >= N) regen();
+        uint32_t y = mt[mti++];
+        y ^= (y >> 11);
+        y ^= (y << 7) & 0x9d2c5680u;
+        y ^= (y << 15) & 0xefc60000u;
+        y ^= (y >> 18);
+        return y;
+    }
+    static inline double to_unif(uint32_t y) {
+        double u = (double)y * 2.3283064365386963e-10; /* MT_genrand: [0,1) */
+        const double i2_32m1 = 2.328306437080797e-10;  /* fixup(): strictly inside (0,1) */
+        if (u <= 0.0) return 0.5 * i2_32m1;
+        if (1.0 - u <= 0.0) return 1.0 - 0.5 * i2_32m1;
+        return u;
+    }
+    inline double unif() { return to_unif(next32()); }
+};
+
+// R's revsort(a, ib, n): sort a[] into descending order by heapsort, carrying ib[] (NOT stable).
+// a and ib are 1-BASED here (element 0 unused), like the shifted pointers of the C original.
+void revsort(double *a, int *ib, int n) {
+    if (n <= 1) return;
+    int l = (n >> 1) + 1, ir = n, i, j, ii;
+    double ra;
+    for (;;) {
+        if (l > 1) {
+            l = l - 1;
+            ra = a[l];
+            ii = ib[l];
+        } else {
+            ra = a[ir];
+            ii = ib[ir];
+            a[ir] = a[1];
+            ib[ir] = ib[1];
+            if (--ir == 1) {
+                a[1] = ra;
+                ib[1] = ii;
+                return;
+            }
+        }
+        i = l;
+        j = l << 1;
+        while (j <= ir) {
+            if (j < ir && a[j] > a[j + 1]) ++j;
+            if (ra > a[j]) {
+                a[i] = a[j];
+                ib[i] = ib[j];
+                j += (i = j);
+            } else
+                j = ir + 1;
+        }
+        a[i] = ra;
+        ib[i] = ii;
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+// ranM2(m, p, seedn) for an integer seed: dgCMatrix slots of the m x p matrix (colptr[p+1], rowidx ascending
+// inside a column, x = +-sqrt(sqrt(m))).  cap = room in rowidx/x; *nnz is always set; returns SHARP_E_NOMEM when
+// cap is too small (call again with *nnz).
+int sharp_r_ranm(int m, int p, int64_t seed, int32_t *colptr, int32_t *rowidx, double *x, int64_t cap, int64_t *nnz) {
+    if (m <= 0 || p <= 0 || !colptr || !nnz) return SHARP_E_ARG;
+    const double s = std::sqrt((double)m);
+    const double vals[3] = {std::sqrt(s), 0.0, -std::sqrt(s)};
+    double pr1[4] = {0.0, 1.0 / (2.0 * s), 1.0 - 1.0 / s, 1.0 / (2.0 * s)};
+    double sum = 0.0;
+    for (int i = 1; i <= 3; i++) sum += pr1[i];
+    for (int i = 1; i <= 3; i++) pr1[i] /= sum; /* FixupProb */
+    int perm1[4] = {0, 1, 2, 3};
+    revsort(pr1, perm1, 3);
+    const double *pr0 = pr1 + 1;
+    const int *perm = perm1 + 1;
+    double pr[3] = {pr0[0], pr0[1], pr0[2]};
+    for (int i = 1; i < 3; i++) pr[i] += pr[i - 1];
+    const double v0 = vals[perm[0] - 1], v1 = vals[perm[1] - 1], v2 = vals[perm[2] - 1];
+    // ProbSampleReplace: first j in 0..n-2 with rU <= p[j], else n-1.  to_unif is monotone in the 32-bit word, so
+    // the common case (the most probable value, 0) is decided by one integer comparison against the largest word
+    // whose uniform is <= p[0]
+    uint32_t thr = (uint32_t)std::floor(pr[0] / 2.3283064365386963e-10);
+    while (thr < 0xffffffffu && RMersenne::to_unif(thr + 1u) <= pr[0]) thr++;
+    while (thr > 0u && !(RMersenne::to_unif(thr) <= pr[0])) thr--;
+    const bool fast = (v0 == 0.0);
+    RMersenne rng((uint32_t)seed);
+    std::vector<uint32_t> pos;   /* (row * p + col) of the non-zeros, row-major order */
+    std::vector<double> val;
+    pos.reserve((size_t)((double)p * s * 1.1) + 1024);
+    val.reserve(pos.capacity());
+    const int64_t total = (int64_t)m * p;
+    if (total > 0xffffffffLL) return SHARP_E_LIMIT;
+    for (int64_t q = 0; q < total; q++) {
+        const uint32_t w = rng.next32();
+        if (fast && w <= thr) continue;
+        const double u = RMersenne::to_unif(w);
+        const double v = (u <= pr[0]) ? v0 : (u <= pr[1]) ? v1 : v2;
+        if (v != 0.0) {
+            pos.push_back((uint32_t)q);
+            val.push_back(v);
+        }
+    }
+    const int64_t nz = (int64_t)pos.size();
+    *nnz = nz;
+    std::memset(colptr, 0, sizeof(int32_t) * (size_t)(p + 1));
+    for (int64_t q = 0; q < nz; q++) colptr[pos[q] % (uint32_t)p + 1]++;
+    for (int j = 0; j < p; j++) colptr[j + 1] += colptr[j];
+    if (nz > cap || (nz > 0 && (!rowidx || !x))) return SHARP_E_NOMEM;
+    std::vector<int32_t> fill(colptr, colptr + p);
+    for (int64_t q = 0; q < nz; q++) { /* row-major scan => rows ascend inside every column */
+        const uint32_t j = pos[q] % (uint32_t)p, i = pos[q] / (uint32_t)p;
+        const int32_t at = fill[j]++;
+        rowidx[at] = (int32_t)i;
+        x[at] = val[q];
+    }
+    return SHARP_OK;
+}
+
+// set.seed(seed); sample(n): 1-based permutation (R >= 3.6, sample.kind = "Rejection")
+int sharp_r_sample_perm(int64_t seed, int64_t n, int64_t *out) {
+    if (n < 0 || (n > 0 && !out)) return SHARP_E_ARG;
+    if (n > 2147483647LL) return SHARP_E_LIMIT;
+    RMersenne rng((uint32_t)seed);
+    std::vector<int32_t> x((size_t)n);
+    for (int64_t i = 0; i < n; i++) x[i] = (int32_t)i;
+    int64_t remaining = n;
+    for (int64_t i = 0; i < n; i++) {
+        const double dn = (double)remaining;
+        // R_unif_index(dn): bits = ceil(log2(dn)); repeat dv = rbits(bits) until dv < dn
+        int64_t j;
+        if (dn <= 0) j = 0;
+        else {
+            const int bits = (int)std::ceil(std::log2(dn));
+            double dv;
+            do {
+                int64_t v = 0;
+                for (int nb = 0; nb <= bits; nb += 16) {
+                    int v1 = (int)std::floor(rng.unif() * 65536);
+                    v = 65536 * v + v1;
+                }
+                const int64_t one64 = 1L;
+                if (bits < 64) v &= ((one64 << bits) - 1);
+                dv = (double)v;
+            } while (dn <= dv);
+            j = (int64_t)dv;
+        }
+        out[i] = (int64_t)x[j] + 1;
+        x[j] = x[--remaining];
+    }
+    return SHARP_OK;
+}
+
+}  // extern "C"

@@ -11,7 +11,7 @@
 // HBM; 32 MB for a 2000-cell block), so every read is a contiguous row segment; the only strided accesses are
 // the mirror writes of the updated row.  NN list, flags and cluster sizes live in shared memory.
 // The kernel is latency-bound by design (n-1 dependent steps); throughput comes from the number of problems
-// resident at once (up to 4 CTAs of 512 threads per SM).
+// resident at once (3 CTAs of 256 threads per SM) -- callers keep several waves in flight on different streams.
 #include "devutil.cuh"
 #include "internal.cuh"
 
@@ -42,8 +42,38 @@ __device__ __forceinline__ double lance_williams(int method, double d1, double d
     }
 }
 
+// Lane-strided scan of row[j], j in [j0, j1), for the first minimum under (value, index).  The loads of a whole
+// 256-element chunk are issued before any of them is used (8 independent loads in flight per lane): the scan is a
+// chain of L2 round trips otherwise.  CHECK: skip retired columns (flag == 0).
+constexpr int SCAN_U = 4;
+template <bool CHECK>
+__device__ __forceinline__ DI scan_row(const double *row, const unsigned char *flag, int j0, int j1, int lane) {
+    DI best;
+    best.d = SHARP_INF;
+    best.i = INT_MAX;
+    for (int base = j0; base < j1; base += 32 * SCAN_U) {
+        double v[SCAN_U];
+#pragma unroll
+        for (int u = 0; u < SCAN_U; u++) {
+            const int j = base + u * 32 + lane;
+            v[u] = (j < j1) ? row[j] : SHARP_INF;
+        }
+#pragma unroll
+        for (int u = 0; u < SCAN_U; u++) {
+            const int j = base + u * 32 + lane;
+            if (j < j1 && (!CHECK || flag[j]) && v[u] < best.d) { best.d = v[u]; best.i = j; }
+        }
+    }
+    return best;
+}
+
+constexpr int LW_U = 8;                   // Lance-Williams columns per thread per pass
+constexpr int RESCAN_TPW = 4;             // (row, chunk) rescan tasks a warp has in flight
+constexpr int RESCAN_ROWS = 16;            // rows rescanned per batch
+constexpr int RESCAN_CHUNK = 32 * SCAN_U;  // columns per (row, chunk) task
+
 template <int THREADS>
-__global__ void __launch_bounds__(THREADS) hclust_kernel(HcProb *probs, int method) {
+__global__ void __launch_bounds__(THREADS, 768 / THREADS) hclust_kernel(HcProb *probs, int method, int maxc) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ DI red[THREADS / 32];
     __shared__ int s_cnt;
@@ -57,7 +87,8 @@ __global__ void __launch_bounds__(THREADS) hclust_kernel(HcProb *probs, int meth
     constexpr int NW = THREADS / 32;
 
     double *disnn = reinterpret_cast<double *>(smem_raw);  // [n]
-    int *nn = reinterpret_cast<int *>(disnn + n);           // [n]
+    DI *part = reinterpret_cast<DI *>(disnn + n);           // [RESCAN_ROWS][maxc] partial minima of the rescans
+    int *nn = reinterpret_cast<int *>(part + RESCAN_ROWS * maxc);  // [n]
     int *membr = nn + n;                                    // [n]
     int *list = membr + n;                                  // [n]
     unsigned char *flag = reinterpret_cast<unsigned char *>(list + n);  // [n]
@@ -75,15 +106,7 @@ __global__ void __launch_bounds__(THREADS) hclust_kernel(HcProb *probs, int meth
 
     // initial nearest neighbours: NN(i) = first minimum over j > i
     for (int i = warp; i < n - 1; i += NW) {
-        DI best;
-        best.d = SHARP_INF;
-        best.i = INT_MAX;
-        const double *row = D + (size_t)i * ld;
-        for (int j = i + 1 + lane; j < n; j += 32) {
-            double d = row[j];
-            if (d < best.d) { best.d = d; best.i = j; }
-        }
-        best = warp_argmin(best);
+        DI best = warp_argmin(scan_row<false>(D + (size_t)i * ld, flag, i + 1, n, lane));
         if (lane == 0) {
             nn[i] = (best.i == INT_MAX) ? -1 : best.i;
             disnn[i] = best.d;
@@ -109,76 +132,128 @@ __global__ void __launch_bounds__(THREADS) hclust_kernel(HcProb *probs, int meth
         }
         const int im = c.i, jm = nn[im];
         const int i2 = min(im, jm), j2 = max(im, jm);
-        const double d12 = D[(size_t)i2 * ld + j2];
+        const double *rowi = D + (size_t)i2 * ld;
+        const double *rowj = D + (size_t)j2 * ld;
+        const double d12 = rowi[j2];
         const double mi = (double)membr[i2], mj = (double)membr[j2];
         if (tid == 0) {
             P.ia[step] = i2 + 1;
             P.ib[step] = j2 + 1;
             P.crit[step] = (method == SHARP_WARD_D2) ? sqrt(c.d) : c.d;
+            s_cnt = 0;
         }
-        __syncthreads(); /* everybody has read nn[im], membr[] before they change */
-        if (tid == 0) flag[j2] = 0;
-        __syncthreads();
 
-        // ---- update dissimilarities from the new cluster (kept under index i2) ----
+        // ---- update dissimilarities from the new cluster (kept under index i2); j2 retires ----
         DI nb;
         nb.d = SHARP_INF;
         nb.i = INT_MAX;
-        const double *rowi = D + (size_t)i2 * ld;
-        const double *rowj = D + (size_t)j2 * ld;
-        for (int k = tid; k < n; k += THREADS) {
-            if (!flag[k] || k == i2) continue;
-            double r = lance_williams(method, rowi[k], rowj[k], d12, mi, mj, (double)membr[k]);
-            D[(size_t)i2 * ld + k] = r;
-            D[(size_t)k * ld + i2] = r;
-            if (k > i2) {
-                if (r < nb.d) { nb.d = r; nb.i = k; }
-            } else if (r < disnn[k]) { /* hclust.f "FIX by JB": i2 may become the NN of a smaller index */
-                disnn[k] = r;
-                nn[k] = i2;
+        for (int kb = 0; kb < n; kb += THREADS * LW_U) { /* both rows' loads of LW_U columns in flight per thread */
+            double a[LW_U], b[LW_U];
+            bool act[LW_U];
+#pragma unroll
+            for (int u = 0; u < LW_U; u++) {
+                const int k = kb + u * THREADS + tid;
+                act[u] = k < n && flag[k] && k != i2 && k != j2;
+                a[u] = act[u] ? rowi[k] : 0.0;
+                b[u] = act[u] ? rowj[k] : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < LW_U; u++) {
+                if (!act[u]) continue;
+                const int k = kb + u * THREADS + tid;
+                const double r = lance_williams(method, a[u], b[u], d12, mi, mj, (double)membr[k]);
+                D[(size_t)i2 * ld + k] = r;
+                D[(size_t)k * ld + i2] = r;
+                if (k > i2) {
+                    if (r < nb.d) { nb.d = r; nb.i = k; }
+                } else if (r < disnn[k]) { /* hclust.f "FIX by JB": i2 may become the NN of a smaller index */
+                    disnn[k] = r;
+                    nn[k] = i2;
+                }
             }
         }
-        nb = block_argmin<THREADS>(nb, red);
+        nb = block_argmin<THREADS>(nb, red); /* its barriers also order the reads of nn / membr above */
         if (tid == 0) {
+            flag[j2] = 0;
             membr[i2] = membr[i2] + membr[j2];
             disnn[i2] = nb.d;
             nn[i2] = (nb.i == INT_MAX) ? -1 : nb.i;
-            s_cnt = 0;
         }
         __syncthreads();
 
         // ---- redetermine the NN of every i whose NN was i2 or j2 ----
         for (int i = tid; i < n - 1; i += THREADS) {
-            if (flag[i]) {
+            if (flag[i] && i != i2) {
                 int q = nn[i];
                 if (q == i2 || q == j2) list[atomicAdd(&s_cnt, 1)] = i;
             }
         }
         __syncthreads();
         const int cnt = s_cnt;
-        for (int r = warp; r < cnt; r += NW) {
-            const int i = list[r];
-            DI best;
-            best.d = SHARP_INF;
-            best.i = INT_MAX;
-            const double *row = D + (size_t)i * ld;
-            for (int j = i + 1 + lane; j < n; j += 32) {
-                if (flag[j]) {
-                    double d = row[j];
-                    if (d < best.d) { best.d = d; best.i = j; }
+        for (int r0 = 0; r0 < cnt; r0 += RESCAN_ROWS) {
+            const int nr = min(RESCAN_ROWS, cnt - r0);
+            // (row, chunk) tasks over all warps, RESCAN_TPW tasks per warp at a time: their loads (RESCAN_TPW x
+            // SCAN_U per lane) are all issued before the first comparison -- the matrices of the problems resident
+            // on the GPU exceed L2 by far, so every round of loads is an HBM round trip
+            const int ntask = nr * maxc;
+            for (int base = warp * RESCAN_TPW; base < ntask; base += NW * RESCAN_TPW) {
+                double v[RESCAN_TPW][SCAN_U];
+                int jb[RESCAN_TPW], je[RESCAN_TPW];
+#pragma unroll
+                for (int q = 0; q < RESCAN_TPW; q++) {
+                    const int t = base + q;
+                    jb[q] = je[q] = 0;
+                    if (t < ntask) {
+                        const int r = t / maxc, ch = t - r * maxc;
+                        const int i = list[r0 + r];
+                        const double *row = D + (size_t)i * ld;
+                        jb[q] = i + 1 + ch * RESCAN_CHUNK;
+                        je[q] = min(n, jb[q] + RESCAN_CHUNK);
+#pragma unroll
+                        for (int u = 0; u < SCAN_U; u++) {
+                            const int j = jb[q] + u * 32 + lane;
+                            v[q][u] = (j < je[q]) ? row[j] : SHARP_INF;
+                        }
+                    }
+                }
+#pragma unroll
+                for (int q = 0; q < RESCAN_TPW; q++) {
+                    const int t = base + q;
+                    if (t >= ntask) break;
+                    DI best;
+                    best.d = SHARP_INF;
+                    best.i = INT_MAX;
+#pragma unroll
+                    for (int u = 0; u < SCAN_U; u++) {
+                        const int j = jb[q] + u * 32 + lane;
+                        if (j < je[q] && flag[j] && v[q][u] < best.d) { best.d = v[q][u]; best.i = j; }
+                    }
+                    best = warp_argmin(best);
+                    if (lane == 0) part[t] = best;
                 }
             }
-            best = warp_argmin(best);
-            if (lane == 0) {
-                nn[i] = (best.i == INT_MAX) ? -1 : best.i;
-                disnn[i] = best.d;
+            __syncthreads();
+            for (int r = warp; r < nr; r += NW) {
+                DI best;
+                best.d = SHARP_INF;
+                best.i = INT_MAX;
+                for (int ch = lane; ch < maxc; ch += 32) best = di_better(best, part[r * maxc + ch]);
+                best = warp_argmin(best);
+                if (lane == 0) {
+                    const int i = list[r0 + r];
+                    nn[i] = (best.i == INT_MAX) ? -1 : best.i;
+                    disnn[i] = best.d;
+                }
             }
+            __syncthreads();
         }
-        __syncthreads();
     }
 }
 
-static size_t hclust_smem_bytes(int n) { return ((size_t)n * (8 + 4 + 4 + 4 + 1) + 15) & ~(size_t)15; }
+static int hclust_maxc(int n) { return (n + RESCAN_CHUNK - 1) / RESCAN_CHUNK; }
+static size_t hclust_smem_bytes(int n) {
+    return ((size_t)n * (8 + 4 + 4 + 4 + 1) + (size_t)RESCAN_ROWS * hclust_maxc(n) * sizeof(DI) + 15) & ~(size_t)15;
+}
 
 int launch_hclust(sharp_ctx *c, HcProb *probs_dev, int nprob, int max_n, int method) {
     if (nprob <= 0) return 0;
@@ -188,11 +263,11 @@ int launch_hclust(sharp_ctx *c, HcProb *probs_dev, int nprob, int max_n, int met
         return set_error(SHARP_E_LIMIT, "hclust: %d objects exceed the shared-memory NN list (max ~9700)", max_n);
     prof_begin(c, max_n > 384 ? KID_HCLUST : KID_HCLUST_SMALL);
     if (max_n > 384) {
-        SHARP_CUDA(cudaFuncSetAttribute(hclust_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        hclust_kernel<512><<<nprob, 512, smem, c->stream>>>(probs_dev, method);
+        SHARP_CUDA(cudaFuncSetAttribute(hclust_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, SHARP_SMEM_OPTIN));
+        hclust_kernel<256><<<nprob, 256, smem, c->stream>>>(probs_dev, method, hclust_maxc(max_n));
     } else {
-        SHARP_CUDA(cudaFuncSetAttribute(hclust_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        hclust_kernel<128><<<nprob, 128, smem, c->stream>>>(probs_dev, method);
+        SHARP_CUDA(cudaFuncSetAttribute(hclust_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, SHARP_SMEM_OPTIN));
+        hclust_kernel<128><<<nprob, 128, smem, c->stream>>>(probs_dev, method, hclust_maxc(max_n));
     }
     prof_end(c);
     SHARP_CUDA(cudaGetLastError());

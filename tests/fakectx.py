@@ -1,0 +1,95 @@
+"""A stand-in for sharp_b200.Context whose compute calls are answered by the CPU ORACLE -- test infrastructure for
+the `-m "not gpu"` tests of the HOST glue (argument defaults, seeds, block layout, gather / relabel / merge rules,
+sharding over ranks).  It lets the Python mirror of SHARP() / SHARP_unlimited() run end to end on a machine without
+a GPU; it is never importable from the product package."""
+import numpy as np
+
+import orc
+
+
+class FakeRm:
+    def __init__(self, rms):
+        self.rms = list(rms)
+        self.K = len(rms)
+        self.m, self.p = int(rms[0]["Dim"][0]), int(rms[0]["Dim"][1])
+        self._h = True
+
+    def close(self):
+        pass
+
+
+def _orc_hc(prm):
+    return orc.hc_params(prm.hmethod, prm.n_cluster, prm.min_n, prm.max_n, prm.sil_thre, prm.height_ntimes)
+
+
+class FakeContext:
+    """answers the subset of Context used by sharp_b200.api with oracle calls"""
+
+    def __init__(self, device=0):
+        self.device = device
+        self._h = True
+        self.calls = []
+        self._last = None
+
+    def upload_rm(self, rms):
+        return FakeRm(rms)
+
+    def rp_project(self, m, n, rm, dense=None, csc=None, cells=None, normalize=0, colsum=None, norm_mul=1e6, logkind=2,
+                   round_digits=-1):
+        if normalize == 2:
+            colsum = dense.sum(0) if dense is not None else np.add.reduceat(csc[2], csc[0][:-1])
+        kw = dict(dense=dense) if dense is not None else dict(csc=csc)
+        return np.stack([orc.rp_project(m, n, r, cells=cells, colsum=colsum if normalize else None, norm_mul=norm_mul,
+                                        logkind=logkind, round_digits=round_digits, **kw) for r in rm.rms])
+
+    def getrowcolor(self, emat, prm):
+        return orc.getrowcolor(emat, _orc_hc(prm))
+
+    def opt_hclust(self, mat, symmetric, prm, exact=False, want_v=True):
+        return orc.opt_hclust(mat, int(bool(symmetric)), _orc_hc(prm))
+
+    def wmetac(self, labels, prm, want_x0=True):
+        return orc.wmetac(labels, _orc_hc(prm))
+
+    def smetac(self, labels, se1, prm):
+        return orc.smetac(labels, se1, _orc_hc(prm))
+
+    def smetac_centroids(self, cen, ncells_total, prm):
+        # every centroid as a one-cell cluster: colMeans of one row is the row.  (The k-range tweak of
+        # R/sMetaC.R:101-119 depends on ncells; the fake is only used below 1e4 cells where it is inactive.)
+        assert ncells_total < 10000
+        return orc.smetac(np.arange(1, cen.shape[0] + 1), cen, _orc_hc(prm))["tf"]
+
+    def run(self, rm, prm, m=None, n=None, dense=None, csc=None, expr=None, colsum=None, reind=None, want_vie=True,
+            want_x0=True, max_x0_cols=None):
+        self.calls.append(("run", n, prm.large, prm.logflag, prm.partition_ncells, prm.normalize, rm.K))
+        if prm.normalize == 2:
+            colsum = dense.sum(0) if dense is not None else np.add.reduceat(csc[2], csc[0][:-1])
+        oprm = orc.SharpParams(prm.large, prm.logflag, rm.K, rm.p, prm.partition_ncells, prm.n_cluster, prm.enp_n_cluster,
+                               prm.ind_n_cluster, _orc_hc(prm.hc), prm.logkind or 2, prm.round_digits)
+        kw = dict(dense=dense) if dense is not None else dict(csc=csc)
+        r = orc.sharp(m, n, rm.rms, oprm, colsum=colsum if prm.normalize else None, reind=reind, **kw)
+        # the oracle returns pred_clusters AFTER the host glue (merge + relabel); relabelling is idempotent, and the
+        # merge only applies above 1e4 cells, so feeding it back as the "raw" device labels exercises the same glue
+        self._last = r
+        return {"labels": r["pred_clusters"].copy(), "viE": r["viE"] if want_vie else None,
+                "x0": r.get("x0") if want_x0 else None, "x0_cols": 0}
+
+    def centroids(self, labels, nclust, p):
+        vie = self._last["viE"]
+        cen = np.zeros((nclust, p))
+        cnt = np.zeros(nclust, dtype=np.int64)
+        for c in range(1, nclust + 1):
+            rows = np.flatnonzero(labels == c)
+            s = np.zeros(p)
+            for i in rows:  # ascending row order, like colMeans
+                s = s + vie[i]
+            cen[c - 1] = s / len(rows)
+            cnt[c - 1] = len(rows)
+        return cen, cnt
+
+    def last_vie(self, n, p):
+        return self._last["viE"]
+
+    def last_member(self, k, n, p):
+        raise NotImplementedError

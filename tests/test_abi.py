@@ -1,0 +1,82 @@
+"""The C-ABI library loads on a machine without a GPU, exports every symbol include/sharp_b200.h declares, and fails
+loudly (no CPU fallback) when a compute call is attempted without a CUDA device."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import sharp_b200
+from sharp_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    src = open(os.path.join(ROOT, "include", "sharp_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(sharp_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_and_binding_agree():
+    decl = declared_symbols()
+    assert len(decl) >= 30
+    assert sorted(_lib.EXPORTS) == decl
+
+
+def test_library_exports_every_declared_symbol():
+    lib = _lib.load()
+    missing = [s for s in declared_symbols() if not hasattr(lib, s)]
+    assert not missing, missing
+    assert lib.sharp_abi_version() == 1
+
+
+def test_no_torch_types_in_the_abi():
+    src = open(os.path.join(ROOT, "include", "sharp_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)   # declarations only
+    assert "torch" not in src.lower() and "at::" not in src and "std::" not in src
+    assert 'extern "C"' in src
+
+
+def test_kernel_classes_are_named():
+    lib = _lib.load()
+    names = [lib.sharp_prof_name(i).decode() for i in range(lib.sharp_prof_kernels())]
+    assert "rp_project" in names and "corrdist" in names and "hclust" in names and all(names)
+
+
+def test_product_does_not_import_the_oracle():
+    # a product path that routes through oracle/ would void every parity claim
+    pkg = os.path.join(ROOT, "sharp_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
+                txt = open(os.path.join(dirpath, f), errors="replace").read()
+                assert "sharp_oracle" not in txt and "import orc" not in txt and "oracle/" not in txt, f
+
+
+@pytest.mark.skipif(_lib.load().sharp_device_count() > 0, reason="a CUDA device is present")
+def test_compute_fails_loudly_without_a_device():
+    assert sharp_b200.device_count() == 0
+    with pytest.raises(sharp_b200.SharpError) as ei:
+        sharp_b200.Context(0)
+    assert ei.value.code == _lib.E_CUDA and "no CPU fallback" in str(ei.value)
+    with pytest.raises(sharp_b200.SharpError):
+        sharp_b200.SHARP(np.ones((10, 20)), rN_seed=1)
+
+
+def test_missing_library_is_an_import_error(monkeypatch):
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "SO_PATH", os.path.join(ROOT, "sharp_b200", "does_not_exist.so"))
+    with pytest.raises(ImportError) as ei:
+        _lib.load()
+    assert "no CPU fallback" in str(ei.value)
+
+
+def test_host_only_entry_points_run_without_a_device():
+    # the R-compatible generators are pure host code
+    out = np.empty(10, dtype=np.int64)
+    assert _lib.load().sharp_r_sample_perm(C.c_int64(42), C.c_int64(10), out.ctypes.data_as(C.POINTER(C.c_int64))) == 0
+    assert list(out) == [1, 5, 10, 8, 2, 4, 6, 9, 7, 3]
+    r = _lib.r_ranm(300, 12, 7)
+    assert r["p"][-1] == len(r["i"]) == len(r["x"])

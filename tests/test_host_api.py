@@ -1,0 +1,200 @@
+"""`-m "not gpu"` tests of the HOST side: the Python mirror of the reference's R closures (sharp_b200/api.py) with its
+compute calls answered by the CPU oracle (tests/fakectx.py).  What is checked is the glue the reference keeps in R:
+defaults, seeds, dispatch small/large, block layout, merge / relabel rules, SHARP_unlimited's combine."""
+import math
+
+import numpy as np
+import pytest
+
+import orc
+import synth
+from fakectx import FakeContext
+from sharp_b200 import api
+from sharp_b200.rrng import r_sample_perm, ranM2
+
+
+def test_first_appearance_merge_and_relabel_rules():
+    codes, uniq = api._first_appearance_codes(np.array([7, 7, 3, 9, 3, 7]))
+    assert list(codes) == [1, 1, 2, 3, 2, 1] and list(uniq) == [7, 3, 9]
+    # clusters with < 10 cells are merged into the SMALLEST such id (R/SHARP.R:816-825)
+    lab = np.array([1] * 30 + [2] * 3 + [5] * 20 + [4] * 9 + [6] * 10)
+    out = api._merge_small(lab)
+    assert set(out[30:33]) == {2} and set(out[53:62]) == {2} and set(out[62:]) == {6}
+    # relabel by decreasing size; ties keep the STRING order of the ids (table() names), R/SHARP_unlimited.R:180-183
+    lab = np.array([10] * 5 + [2] * 5 + [3] * 8 + [1] * 2)
+    out = api._relabel_by_size(lab)
+    assert list(out[:5]) == [2] * 5          # "10" < "2" as strings -> id 10 gets rank 2, id 2 rank 3
+    assert list(out[5:10]) == [3] * 5 and list(out[10:18]) == [1] * 8 and list(out[18:]) == [4] * 2
+
+
+def test_seed_validation_matches_the_reference():
+    with pytest.raises(ValueError, match="should be a numeric"):
+        api._check_seed("a")
+    with pytest.raises(ValueError, match="should be an integer"):
+        api._check_seed(1.5)
+    assert api._check_seed(None) == 0.5 and api._check_seed(0.5) == 0.5 and api._check_seed(2103) == 2103
+    with pytest.raises(ValueError):
+        api._check_seed(0.5, allow_half=False)      # SHARP_unlimited does not accept the sentinel
+    assert api._member_seed(2103, 1) == 2154 and api._member_seed(0.5, 3) == 0.5
+
+
+def test_rm_list_uses_the_reference_seeds():
+    rms = api._rm_list(400, 9, 3, 2103)
+    for k, r in enumerate(rms, 1):
+        ref = ranM2(400, 9, 50 + 2103 + k)
+        assert np.array_equal(r["i"], ref["i"]) and np.array_equal(r["x"], ref["x"]) and np.array_equal(r["p"], ref["p"])
+    assert np.array_equal(api._reind(777, 2103), r_sample_perm(777, 50))
+
+
+def test_expression_wrapping_and_prep():
+    x, _ = synth.make_expression(60, 25, seed=0)
+    x[5, :] = 0
+    x[7, 3] = -2.0
+    e = api.Expression.wrap(x)
+    assert (e.m, e.n) == (60, 25) and e.any_negative()
+    e2 = e.clamp_negative()
+    keep = e2.row_sums() != 0
+    e3 = e2.keep_rows(keep)
+    assert e3.m == int(keep.sum()) and not e3.any_negative()
+    # the same through dgCMatrix slots
+    cp, ri, v = synth.to_csc(x)
+    s = api.Expression.wrap((cp, ri, v, x.shape))
+    s3 = s.clamp_negative()
+    s3 = s3.keep_rows(s3.row_sums() != 0)
+    assert s3.m == e3.m
+    dense = np.zeros((s3.m, s3.n))
+    for c in range(s3.n):
+        dense[s3.csc[1][s3.csc[0][c]:s3.csc[0][c + 1]], c] = s3.csc[2][s3.csc[0][c]:s3.csc[0][c + 1]]
+    assert np.array_equal(dense, e3.dense)
+    import scipy.sparse as sp
+    w = api.Expression.wrap(sp.csr_matrix(x))
+    assert np.array_equal(w.csc[0], cp) and np.array_equal(w.csc[1], ri)
+
+
+def test_sharp_dispatch_defaults_large():
+    x, truth = synth.make_expression(800, 5200, n_types=3, seed=2, sep=2.5, frac=0.5)
+    ctx = FakeContext()
+    r = api.SHARP(x, rN_seed=2103, reduced_ndim=40, partition_ncells=2600, logflag=False, ctx=ctx)
+    # ncells >= base.ncells -> SHARP_large, K = 5, flag forced TRUE, no normalisation without exp.type
+    assert ctx.calls == [("run", 5200, 1, 1, 2600, 0, 5)]
+    assert r["N.cells"] == 5200 and r["N.genes"] == 800 and r["reduced.dim"] == 40 and r["ensize.K"] == 5
+    assert r["paras"]["maxN.cluster"] == 40 and r["paras"]["base.ncells"] == 5000 and r["paras"]["logmark"] is True
+    assert synth.ari(r["pred_clusters"], truth) > 0.9
+    # identical to the oracle driven directly with the reference's seeds
+    rms = [ranM2(800, 40, 50 + 2103 + k) for k in range(1, 6)]
+    prm = orc.SharpParams(1, 1, 5, 40, 2600, 0, 0, 0, orc.hc_params(), 2, -1)
+    ref = orc.sharp(800, 5200, rms, prm, dense=x, reind=r_sample_perm(5200, 50))
+    assert np.array_equal(r["pred_clusters"], ref["pred_clusters"])
+    assert r["N.pred_cluster"] == ref["N.pred_cluster"]
+    assert list(r["unique_pred_clusters"]) == list(range(1, r["N.pred_cluster"] + 1))
+    assert sum(r["distr_pred_clusters"].values()) == 5200
+
+
+def test_sharp_dispatch_small_with_normalisation_and_ncluster():
+    x, truth = synth.make_expression(500, 400, n_types=3, seed=3, kind="umi", sep=2.5, frac=0.5)
+    ctx = FakeContext()
+    r = api.SHARP(x, exp_type="UMI", rN_seed=7, logflag=False, forview=False, ctx=ctx)
+    p = math.ceil(math.log2(400) / 0.04)
+    assert ctx.calls == [("run", 400, 0, 1, 0, 2, 15)] and r["reduced.dim"] == p
+    assert synth.ari(r["pred_clusters"], truth) > 0.9
+    # N.cluster given and ncells < base.ncells: two blocks of ceil(n/2), indN.cluster = N.cluster, K = 15
+    ctx2 = FakeContext()
+    r2 = api.SHARP(x, exp_type="UMI", N_cluster=3, rN_seed=7, logflag=False, forview=False, ctx=ctx2)
+    assert ctx2.calls == [("run", 400, 1, 1, 200, 2, 15)]
+    assert r2["N.pred_cluster"] == 3
+    # dotted R argument names are accepted
+    ctx3 = FakeContext()
+    api.SHARP(x, ctx=ctx3, forview=False, logflag=False, **{"rN.seed": 7, "ensize.K": 3, "exp.type": "CPM"})
+    assert ctx3.calls == [("run", 400, 0, 1, 0, 0, 3)]
+
+
+def test_sharp_argument_errors():
+    with pytest.raises(ValueError, match="No expression data"):
+        api.SHARP(None)
+    x = np.ones((5, 8))
+    with pytest.raises(ValueError, match="should be an integer"):
+        api.SHARP(x, rN_seed=2.5, ctx=FakeContext())
+
+
+def test_testlog_rule():
+    x, _ = synth.make_expression(400, 150, n_types=3, seed=4, sep=2.0, frac=0.5)
+    ctx = FakeContext()
+    flag = api.testlog(x, 150, 60, ctx=ctx, _seed=1)
+    # recompute with the oracle: ranM(E, p, 5), cells reind[1:100], getrowColor(., "ward.D", NULL, 2, 40, 0, 2)
+    cells = r_sample_perm(150, 1)[:100] - 1
+    rm = ranM2(400, 60, 5)
+    ms = []
+    for lk in (0, 2):
+        pr = orc.rp_project(400, 150, rm, dense=x, cells=cells, logkind=lk)
+        ms.append(orc.getrowcolor(pr, orc.hc_params(sil_thre=0.0))[1])
+    assert flag == bool(ms[0] < 0.75 and ms[0] >= 0.95 * ms[1])
+
+
+def make_parts(nparts, n_each, m=700, seed=5):
+    x, truth = synth.make_expression(m, nparts * n_each, n_types=3, seed=seed, sep=2.5, frac=0.5)
+    return [np.asfortranarray(x[:, i * n_each:(i + 1) * n_each]) for i in range(nparts)], truth
+
+
+def unlimited_reference(parts, K, seed):
+    """the oracle driven like R/SHARP_unlimited.R:97-183"""
+    ncells = sum(x.shape[1] for x in parts)
+    p = math.ceil(math.log2(ncells) / 0.04)
+    m = parts[0].shape[0]
+    rms = [ranM2(m, p, 50 + seed + k) for k in range(1, K + 1)]
+    preds, vies, part_of = [], [], []
+    for i, x in enumerate(parts):
+        n = x.shape[1]
+        large = int(n >= 5000)
+        prm = orc.SharpParams(large, 1, K if large else 15, p, 2000, 0, 0, 0, orc.hc_params(), 2, -1)
+        rm_i = rms if large else [ranM2(m, p, 50 + seed + k) for k in range(1, 16)]
+        r = orc.sharp(m, n, rm_i, prm, dense=x, reind=r_sample_perm(n, 50) if large else None)
+        preds.append(r["pred_clusters"])
+        vies.append(r["viE"])
+        part_of.append(np.full(n, i + 1))
+    hc = orc.hc_params(max_n=max(40, -(-ncells // 5000)))
+    final, nf = orc.unlimited_combine(np.concatenate(part_of), np.concatenate(preds), np.concatenate(vies), hc)
+    return final, nf
+
+
+def test_sharp_unlimited_matches_the_oracle_driver():
+    parts, truth = make_parts(3, 300)
+    ref, nf = unlimited_reference(parts, 5, 11)
+    for streams in (1, 2):
+        r = api.SHARP_unlimited(parts, viewflag=False, rN_seed=11, ctx=FakeContext(), n_streams=streams)
+        assert np.array_equal(r["pred_clusters"], ref) and r["N.pred_clusters"] == nf
+        assert r["N.cells"] == 900 and synth.ari(r["pred_clusters"], truth) > 0.9
+    # viewflag: stacked viE and the 0/1 indicator x0
+    r = api.SHARP_unlimited(parts, viewflag=True, rN_seed=11, ctx=FakeContext(), n_streams=1)
+    assert r["viE"].shape == (900, math.ceil(math.log2(900) / 0.04))
+    assert r["x0"].shape == (900, nf) and np.array_equal(r["x0"].argmax(1) + 1, r["pred_clusters"])
+
+
+def test_sharp_unlimited_argument_errors():
+    with pytest.raises(ValueError, match="LIST"):
+        api.SHARP_unlimited("x", ctx=FakeContext())
+    parts, _ = make_parts(2, 100)
+    with pytest.raises(ValueError, match="integer"):
+        api.SHARP_unlimited(parts, rN_seed=0.5, ctx=FakeContext())
+
+
+def test_ari_five_indices():
+    # hand-checkable contingency table
+    r = api.ARI([1, 1, 1, 2, 2, 2], [1, 1, 2, 2, 3, 3])
+    from sklearn.metrics import adjusted_rand_score, rand_score, fowlkes_mallows_score
+    assert np.isclose(r["HA"], adjusted_rand_score([1, 1, 1, 2, 2, 2], [1, 1, 2, 2, 3, 3]))
+    assert np.isclose(r["Rand"], rand_score([1, 1, 1, 2, 2, 2], [1, 1, 2, 2, 3, 3]))
+    assert np.isclose(r["FM"], fowlkes_mallows_score([1, 1, 1, 2, 2, 2], [1, 1, 2, 2, 3, 3]))
+    assert np.isclose(r["Jaccard"], 2 / (6 + 3 - 2))
+    same = api.ARI([1, 2, 3, 1], [5, 6, 7, 5])
+    assert same["HA"] == 1.0 and same["Rand"] == 1.0 and same["Jaccard"] == 1.0
+
+
+def test_geta_and_getss():
+    A = api.getA(["a", "b", "a", "c"]).toarray()
+    assert np.array_equal(A, [[1, 0, 1, 0], [0, 1, 0, 0], [1, 0, 1, 0], [0, 0, 0, 1]])
+    # two solutions over 4 cells, x = c(paste(col1,"_",1), paste(col2,"_",2))
+    x = np.array(["a_1", "a_1", "b_1", "b_1", "u_2", "v_2", "v_2", "v_2"])
+    R = ["a_1", "b_1", "u_2", "v_2"]
+    w1 = np.array([0.1, 0.2, 0.3, 0.4])
+    assert np.isclose(api.getss((1, 4), R, x, w1), 0.2 / (0.1 + 0.2 + 0.3 + 0.4))   # a & v = {2}; a | v = {1,2,3,4}
+    assert api.getss((1, 2), R, x, w1) == 0.0                                       # disjoint
