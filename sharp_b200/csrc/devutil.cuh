@@ -29,17 +29,38 @@ __device__ __forceinline__ DI warp_argmin(DI v) {
     return v;
 }
 
+// Same result as warp_argmin (all lanes receive it) with three REDUX instructions instead of five shuffle rounds:
+// the value is mapped to a 64-bit key whose unsigned order is the numeric order, the minimum key is found high word
+// first, then the smallest index among the lanes that hold it.  Values must not be NaN (callers only keep values that
+// passed a `<` test); -0.0 is canonicalised to +0.0 so that equal values tie on the index like di_better.
+__device__ __forceinline__ DI warp_argmin_redux(DI v) {
+    const unsigned full = 0xffffffffu;
+    unsigned long long b = (unsigned long long)__double_as_longlong(v.d + 0.0);
+    b ^= (b >> 63) ? ~0ull : 0x8000000000000000ull;
+    const unsigned hi = (unsigned)(b >> 32), lo = (unsigned)b;
+    const unsigned mh = __reduce_min_sync(full, hi);
+    const unsigned ml = __reduce_min_sync(full, hi == mh ? lo : 0xffffffffu);
+    const bool win = (hi == mh) && (lo == ml);
+    const unsigned mi = __reduce_min_sync(full, win ? (unsigned)v.i : 0xffffffffu);
+    unsigned long long k = ((unsigned long long)mh << 32) | ml;
+    k ^= (k >> 63) ? 0x8000000000000000ull : ~0ull;
+    DI r;
+    r.d = __longlong_as_double((long long)k);
+    r.i = (int)mi;
+    return r;
+}
+
 // All threads of the block receive the block-wide argmin.  `scratch` is shared memory with one slot per warp.
 template <int THREADS>
 __device__ __forceinline__ DI block_argmin(DI v, DI *scratch) {
-    v = warp_argmin(v);
+    v = warp_argmin_redux(v);
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     if (lane == 0) scratch[w] = v;
     __syncthreads();
     DI r;
     if (lane < THREADS / 32) r = scratch[lane];
     else { r.d = SHARP_INF; r.i = INT_MAX; }
-    r = warp_argmin(r);
+    r = warp_argmin_redux(r);
     __syncthreads();
     return r;
 }

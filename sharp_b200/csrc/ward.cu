@@ -45,7 +45,7 @@ __device__ __forceinline__ double lance_williams(int method, double d1, double d
 // Lane-strided scan of row[j], j in [j0, j1), for the first minimum under (value, index).  The loads of a whole
 // 256-element chunk are issued before any of them is used (8 independent loads in flight per lane): the scan is a
 // chain of L2 round trips otherwise.  CHECK: skip retired columns (flag == 0).
-constexpr int SCAN_U = 4;
+constexpr int SCAN_U = 8;
 template <bool CHECK>
 __device__ __forceinline__ DI scan_row(const double *row, const unsigned char *flag, int j0, int j1, int lane) {
     DI best;
@@ -68,12 +68,9 @@ __device__ __forceinline__ DI scan_row(const double *row, const unsigned char *f
 }
 
 constexpr int LW_U = 8;                   // Lance-Williams columns per thread per pass
-constexpr int RESCAN_TPW = 4;             // (row, chunk) rescan tasks a warp has in flight
-constexpr int RESCAN_ROWS = 16;            // rows rescanned per batch
-constexpr int RESCAN_CHUNK = 32 * SCAN_U;  // columns per (row, chunk) task
 
 template <int THREADS>
-__global__ void __launch_bounds__(THREADS, 768 / THREADS) hclust_kernel(HcProb *probs, int method, int maxc) {
+__global__ void __launch_bounds__(THREADS, 768 / THREADS) hclust_kernel(HcProb *probs, int method) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ DI red[THREADS / 32];
     __shared__ int s_cnt;
@@ -87,8 +84,8 @@ __global__ void __launch_bounds__(THREADS, 768 / THREADS) hclust_kernel(HcProb *
     constexpr int NW = THREADS / 32;
 
     double *disnn = reinterpret_cast<double *>(smem_raw);  // [n]
-    DI *part = reinterpret_cast<DI *>(disnn + n);           // [RESCAN_ROWS][maxc] partial minima of the rescans
-    int *nn = reinterpret_cast<int *>(part + RESCAN_ROWS * maxc);  // [n]
+    DI *part = reinterpret_cast<DI *>(disnn + n);           // [NW][NW] partial minima of the rescans
+    int *nn = reinterpret_cast<int *>(part + NW * NW);      // [n]
     int *membr = nn + n;                                    // [n]
     int *list = membr + n;                                  // [n]
     unsigned char *flag = reinterpret_cast<unsigned char *>(list + n);  // [n]
@@ -106,7 +103,7 @@ __global__ void __launch_bounds__(THREADS, 768 / THREADS) hclust_kernel(HcProb *
 
     // initial nearest neighbours: NN(i) = first minimum over j > i
     for (int i = warp; i < n - 1; i += NW) {
-        DI best = warp_argmin(scan_row<false>(D + (size_t)i * ld, flag, i + 1, n, lane));
+        DI best = warp_argmin_redux(scan_row<false>(D + (size_t)i * ld, flag, i + 1, n, lane));
         if (lane == 0) {
             nn[i] = (best.i == INT_MAX) ? -1 : best.i;
             disnn[i] = best.d;
@@ -190,69 +187,36 @@ __global__ void __launch_bounds__(THREADS, 768 / THREADS) hclust_kernel(HcProb *
         }
         __syncthreads();
         const int cnt = s_cnt;
-        for (int r0 = 0; r0 < cnt; r0 += RESCAN_ROWS) {
-            const int nr = min(RESCAN_ROWS, cnt - r0);
-            // (row, chunk) tasks over all warps, RESCAN_TPW tasks per warp at a time: their loads (RESCAN_TPW x
-            // SCAN_U per lane) are all issued before the first comparison -- the matrices of the problems resident
-            // on the GPU exceed L2 by far, so every round of loads is an HBM round trip
-            const int ntask = nr * maxc;
-            for (int base = warp * RESCAN_TPW; base < ntask; base += NW * RESCAN_TPW) {
-                double v[RESCAN_TPW][SCAN_U];
-                int jb[RESCAN_TPW], je[RESCAN_TPW];
-#pragma unroll
-                for (int q = 0; q < RESCAN_TPW; q++) {
-                    const int t = base + q;
-                    jb[q] = je[q] = 0;
-                    if (t < ntask) {
-                        const int r = t / maxc, ch = t - r * maxc;
-                        const int i = list[r0 + r];
-                        const double *row = D + (size_t)i * ld;
-                        jb[q] = i + 1 + ch * RESCAN_CHUNK;
-                        je[q] = min(n, jb[q] + RESCAN_CHUNK);
-#pragma unroll
-                        for (int u = 0; u < SCAN_U; u++) {
-                            const int j = jb[q] + u * 32 + lane;
-                            v[q][u] = (j < je[q]) ? row[j] : SHARP_INF;
-                        }
-                    }
-                }
-#pragma unroll
-                for (int q = 0; q < RESCAN_TPW; q++) {
-                    const int t = base + q;
-                    if (t >= ntask) break;
-                    DI best;
-                    best.d = SHARP_INF;
-                    best.i = INT_MAX;
-#pragma unroll
-                    for (int u = 0; u < SCAN_U; u++) {
-                        const int j = jb[q] + u * 32 + lane;
-                        if (j < je[q] && flag[j] && v[q][u] < best.d) { best.d = v[q][u]; best.i = j; }
-                    }
-                    best = warp_argmin(best);
-                    if (lane == 0) part[t] = best;
-                }
+        // NW rows per batch; when fewer rows than warps need a rescan, each row's tail is split between NW / rows warps
+        // (short dependent chains: the matrices of the problems resident on the GPU exceed L2 by far, so every batch
+        // of loads is an HBM round trip).  One REDUX argmin per (row, segment), combined in ascending segment order.
+        for (int r0 = 0; r0 < cnt; r0 += NW) {
+            const int nr = min(NW, cnt - r0);
+            const int wpr = NW / nr;
+            const int r = warp / wpr, seg = warp - r * wpr;
+            if (r < nr) {
+                const int i = list[r0 + r];
+                const int len = n - (i + 1);
+                const int seglen = (((len + wpr - 1) / wpr) + 31) & ~31;
+                const int j0 = i + 1 + seg * seglen;
+                DI best = warp_argmin_redux(scan_row<true>(D + (size_t)i * ld, flag, j0, min(n, j0 + seglen), lane));
+                if (lane == 0) part[r * NW + seg] = best;
             }
             __syncthreads();
-            for (int r = warp; r < nr; r += NW) {
-                DI best;
-                best.d = SHARP_INF;
-                best.i = INT_MAX;
-                for (int ch = lane; ch < maxc; ch += 32) best = di_better(best, part[r * maxc + ch]);
-                best = warp_argmin(best);
-                if (lane == 0) {
-                    const int i = list[r0 + r];
-                    nn[i] = (best.i == INT_MAX) ? -1 : best.i;
-                    disnn[i] = best.d;
-                }
+            if (tid < nr) {
+                DI best = part[tid * NW];
+                for (int sgm = 1; sgm < wpr; sgm++) best = di_better(best, part[tid * NW + sgm]);
+                const int i = list[r0 + tid];
+                nn[i] = (best.i == INT_MAX) ? -1 : best.i;
+                disnn[i] = best.d;
             }
             __syncthreads();
         }
     }
 }
 
-static int hclust_maxc(int n) { return (n + RESCAN_CHUNK - 1) / RESCAN_CHUNK; }
 static size_t hclust_smem_bytes(int n) {
-    return ((size_t)n * (8 + 4 + 4 + 4 + 1) + (size_t)RESCAN_ROWS * hclust_maxc(n) * sizeof(DI) + 15) & ~(size_t)15;
+    return ((size_t)n * (8 + 4 + 4 + 4 + 1) + (size_t)16 * 16 * sizeof(DI) + 15) & ~(size_t)15;
 }
 
 int launch_hclust(sharp_ctx *c, HcProb *probs_dev, int nprob, int max_n, int method) {
@@ -264,10 +228,10 @@ int launch_hclust(sharp_ctx *c, HcProb *probs_dev, int nprob, int max_n, int met
     prof_begin(c, max_n > 384 ? KID_HCLUST : KID_HCLUST_SMALL);
     if (max_n > 384) {
         SHARP_CUDA(cudaFuncSetAttribute(hclust_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, SHARP_SMEM_OPTIN));
-        hclust_kernel<256><<<nprob, 256, smem, c->stream>>>(probs_dev, method, hclust_maxc(max_n));
+        hclust_kernel<256><<<nprob, 256, smem, c->stream>>>(probs_dev, method);
     } else {
         SHARP_CUDA(cudaFuncSetAttribute(hclust_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, SHARP_SMEM_OPTIN));
-        hclust_kernel<128><<<nprob, 128, smem, c->stream>>>(probs_dev, method, hclust_maxc(max_n));
+        hclust_kernel<128><<<nprob, 128, smem, c->stream>>>(probs_dev, method);
     }
     prof_end(c);
     SHARP_CUDA(cudaGetLastError());
