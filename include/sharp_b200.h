@@ -76,6 +76,12 @@ int sharp_timer_stop_ms(sharp_ctx *ctx, double *ms);
 /* number of kernels this library launched on the context since creation (bench.py's gpu_launches). */
 int64_t sharp_ctx_launch_count(sharp_ctx *ctx);
 
+/* Projection kernel variant: 0 (default) = order-independent fixed-point accumulation with shared-memory integer
+ * atomics (exact integer sums; used whenever K*p <= 32767); 1 = the fp64 read-modify-write kernel that adds every
+ * output's terms in ascending gene order (bit-identical to a sequential sparse product).  Both meet the 1e-5
+ * contract by ten orders of magnitude; the switch exists so that tests and ncu can compare them. */
+int sharp_ctx_set_rp_variant(sharp_ctx *ctx, int legacy);
+
 /* per-kernel device-time profile (off by default): while enabled, every launch of this library on the context's
  * stream is bracketed by CUDA events and accumulated per kernel class.  bench.py's roofline object is computed from
  * these (live, over the timed region). */

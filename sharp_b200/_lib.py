@@ -53,7 +53,7 @@ EXPORTS = [
     "sharp_hclust", "sharp_opt_hclust", "sharp_getrowcolor", "sharp_wmetac", "sharp_smetac", "sharp_run",
     "sharp_expr_upload", "sharp_expr_free", "sharp_run_dev", "sharp_centroids", "sharp_smetac_centroids",
     "sharp_last_member", "sharp_last_vie", "sharp_prof_enable", "sharp_prof_reset", "sharp_prof_kernels", "sharp_prof_name",
-    "sharp_prof_get", "sharp_r_ranm", "sharp_r_sample_perm",
+    "sharp_prof_get", "sharp_ctx_set_rp_variant", "sharp_r_ranm", "sharp_r_sample_perm",
 ]
 
 _lib = None
@@ -253,6 +253,10 @@ class Context:
 
     def launch_count(self) -> int:
         return int(load().sharp_ctx_launch_count(self._h))
+
+    def set_rp_variant(self, legacy: bool):
+        """False (default): fixed-point atomic projection kernel; True: fp64 gene-order read-modify-write kernel"""
+        _check(load().sharp_ctx_set_rp_variant(self._h, int(bool(legacy))))
 
     def prof_enable(self, on=True):
         _check(load().sharp_prof_enable(self._h, int(bool(on))))

@@ -26,7 +26,9 @@ cell-by-feature results (``viE``, ``x0``, projections) are numpy ``ncells x ncol
 from __future__ import annotations
 
 import math
+import os
 import re
+import sys
 import time
 
 import numpy as np
@@ -48,6 +50,7 @@ colorL = ["red", "purple", "blue", "yellow", "green", "orange", "brown", "gray",
           "deeppink", "lightcoral", "lightcyan"]
 
 _verbose = False
+_TRACE = bool(os.environ.get("SHARP_B200_TRACE"))
 _contexts: dict[int, Context] = {}
 _current_device = 0
 
@@ -714,7 +717,18 @@ def SHARP_unlimited(scExp, viewflag=True, n_cores=None, ensize_K=None, N_cluster
     maxN_cluster = max(40, math.ceil(ncells / 5000)) if maxN_cluster is None else maxN_cluster
     rN_seed = _check_seed(rN_seed, allow_half=False)
     ensize_K = 5 if ensize_K is None else int(ensize_K)
-    rM = ctx.upload_rm(_rm_list(parts[0].m, p, ensize_K, rN_seed))
+    _t = [time.time()]
+
+    def _mark(what):
+        if _TRACE:
+            now = time.time()
+            print(f"[sharp trace py] {what} {1e3 * (now - _t[0]):.2f} ms", file=sys.stderr)
+            _t[0] = now
+
+    rms_host = _rm_list(parts[0].m, p, ensize_K, rN_seed)
+    _mark("ranM")
+    rM = ctx.upload_rm(rms_host)
+    _mark("upload_rm")
     rank, world = (comm.rank, comm.world) if comm is not None else (0, 1)
     mine = [i for i in range(nnp) if i % world == rank]
     y, cens, viEs = {}, {}, {}
@@ -732,9 +746,14 @@ def SHARP_unlimited(scExp, viewflag=True, n_cores=None, ensize_K=None, N_cluster
 
     def one_part(i, c):
         _cat("Processing Partition", i + 1, "of the scRNA-seq data...")
+        t0 = time.time()
         yi = SHARP(parts[i], reduced_ndim=p, prep=False, logflag=_part_logflag, n_cores=n_cores, rM=rM, ensize_K=ensize_K,
                    rN_seed=rN_seed, forview=False, ctx=c, **k)
+        t1 = time.time()
         cen, _ = c.centroids(yi["pred_clusters"], yi["N.pred_cluster"], p)
+        if _TRACE:
+            print(f"[sharp trace py] part {i}: SHARP {1e3 * (t1 - t0):.2f} ms, centroids {1e3 * (time.time() - t1):.2f} ms",
+                  file=sys.stderr)
         return yi, cen, (c.last_vie(nnc[i], p) if viewflag else None)
 
     try:
@@ -760,6 +779,7 @@ def SHARP_unlimited(scExp, viewflag=True, n_cores=None, ensize_K=None, N_cluster
                     y[i], cens[i], viEs[i] = r
     finally:
         rM.close()
+    _mark("parts")
     if comm is not None:
         preds_all = comm.allgather_parts({i: y[i]["pred_clusters"] for i in mine}, nnp)
         cens_all = comm.allgather_parts(cens, nnp)
@@ -774,6 +794,7 @@ def SHARP_unlimited(scExp, viewflag=True, n_cores=None, ensize_K=None, N_cluster
     _cat("Total number of single cells:", ncells, "\nNumber of unique meta-clusters:", cen.shape[0])
     final = _unlimited_combine(ctx, cen, [c.shape[0] for c in cens_all], preds_all, ncells, y0["paras"]["hmethod"],
                                N_cluster, minN_cluster, maxN_cluster, y0["paras"]["sil.thre"], y0["paras"]["height.Ntimes"])
+    _mark("combine")
     res = _unlimited_result(final, ncells, parts[0].m, y0, start)
     # N.pred_clusters / reduced.dim: quirk B5 -- the reference copies the nonexistent y[[1]]$reduced.ndim (NULL)
     if viewflag:

@@ -109,6 +109,7 @@ struct sharp_ctx {
     int64_t last_n = 0;     // state of the last run (for sharp_centroids)
     int last_p = 0;
     int last_K = 0;
+    bool rp_legacy = false; // force the fp64 read-modify-write projection kernel (tests compare both variants)
     int reserve_pinned(size_t bytes);
     // per-kernel profile: CUDA events around every launch on `stream` while prof_on (off by default)
     bool prof_on = false;
@@ -128,6 +129,12 @@ struct sharp_rm_dev {
     uint32_t *rowptr = nullptr;  // [m+1] offsets into ent (gene-major)
     uint16_t *ent16 = nullptr;   // [nnz] (col | sign<<15) when K*p <= 32768
     uint32_t *ent32 = nullptr;   // [nnz] (col | sign<<31) otherwise
+    // padded copy for the fixed-point kernel (K*p <= 32767 only): every gene's entries start on a 16-byte boundary
+    // and are padded to a multiple of 8 with 0xFFFF; vecptr[g] counts 8-entry vectors
+    uint32_t *vecptr = nullptr;  // [m+1]
+    uint4 *entvec = nullptr;     // [vecptr[m]]
+    int max_col_nnz = 0;         // largest number of entries in one column of one member (bound on adds per output)
+    int vec_per_gene = 0;        // vectors preloaded per gene by the kernel (covers ~99 % of the genes)
 };
 
 struct sharp_expr_dev {

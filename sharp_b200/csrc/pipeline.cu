@@ -3,6 +3,8 @@
 // kernels of this library on the context's stream and fails with SHARP_E_CUDA when there is no device.
 #include <algorithm>
 #include <atomic>
+#include <chrono>
+#include <cstdlib>
 #include <cmath>
 #include <cstdarg>
 #include <cstring>
@@ -572,6 +574,32 @@ static int smetac_dev(sharp_ctx *c, int capS, int p, const int *nc_ptr, const in
     return 0;
 }
 
+// SHARP_B200_TRACE=1: host wall-clock per phase of run_core on stderr (development aid)
+struct Trace {
+    bool on;
+    std::chrono::steady_clock::time_point t0, last;
+    std::string line;
+    sharp_ctx *c;
+    explicit Trace(sharp_ctx *ctx) : c(ctx) {
+        static const bool env = getenv("SHARP_B200_TRACE") != nullptr;
+        on = env;
+        if (on) t0 = last = std::chrono::steady_clock::now();
+    }
+    void mark(const char *what, bool dev_sync = false) {
+        if (!on) return;
+        if (dev_sync) cudaStreamSynchronize(c->stream);
+        auto now = std::chrono::steady_clock::now();
+        char buf[96];
+        snprintf(buf, sizeof buf, " %s=%.2f", what, std::chrono::duration<double, std::milli>(now - last).count());
+        line += buf;
+        last = now;
+    }
+    ~Trace() {
+        if (on) fprintf(stderr, "[sharp trace dev%d ctx%p]%s total=%.2f ms\n", c->device, (void *)c, line.c_str(),
+                        std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
+    }
+};
+
 // R/SHARP.R:513-536: block boundaries in the (shuffled) cell order
 static void make_blocks(int64_t n, int large, int ng, std::vector<int64_t> &start) {
     start.clear();
@@ -595,6 +623,7 @@ static int run_core(sharp_ctx *c, const sharp_expr_dev &e, const double *colsum_
                     int *x0_cols, int max_x0_cols) {
     const int64_t n = e.n;
     const int p = rm.p, K = rm.K;
+    Trace tr(c);
     if (n < 2) return set_error(SHARP_E_ARG, "need at least 2 cells");
     if (n > 2000000000LL / std::max(1, K)) return set_error(SHARP_E_LIMIT, "too many cells for one call (%lld); split into parts", (long long)n);
     std::vector<int64_t> start;
@@ -639,7 +668,9 @@ static int run_core(sharp_ctx *c, const sharp_expr_dev &e, const double *colsum_
     const size_t np = (size_t)n * p;
     SHARP_TRY(c->ws[WS_PROJ].reserve((size_t)K * np * 8));
     double *proj = c->ws[WS_PROJ].as<double>();
+    tr.mark("setup", true);
     SHARP_TRY(launch_rp_project(c, e, src_dev, n, colsum_dev, Q.normalize, Q.norm_mul, logkind, Q.round_digits, rm, proj));
+    tr.mark("rp", true);
 
     // ---- K2 input: unit rows ----
     const int ldu = ldu_of(p);
@@ -744,6 +775,7 @@ static int run_core(sharp_ctx *c, const sharp_expr_dev &e, const double *colsum_
         }
     }
     SHARP_TRY(h2d(c, c->ws[WS_DESC].ptr, c->pinned, hb.off));
+    tr.mark("desc", true);
     for (const Wave &w : waves) {
         SHARP_TRY(launch_corrdist_batched(c, gpd + w.q0, tpd + w.tp_off, w.nq, w.tiles, ldu));
         SHARP_TRY(launch_hclust(c, hpd + w.q0, w.nq, max_bn, ind.hmethod));
@@ -754,6 +786,7 @@ static int run_core(sharp_ctx *c, const sharp_expr_dev &e, const double *colsum_
                                          c->ws[WS_SWEEP_SCRATCH].as<double>(), sweep_scr));
     }
     prof_begin(c, KID_MISC);
+    tr.mark("blocks", true);
     colour_wrap_kernel<<<grid1d((size_t)K * n, 256), 256, 0, c->stream>>>(enrp, (int64_t)K * n);
     prof_end(c);
     // ---- enE / K ----
@@ -771,6 +804,7 @@ static int run_core(sharp_ctx *c, const sharp_expr_dev &e, const double *colsum_
             if (meta[(size_t)q * 8 + 3] != 0) return rstop(meta[(size_t)q * 8 + 3], "getrowColor (block clustering)");
     }
 
+    tr.mark("ene+status", true);
     // ---- wMetaC per block ----
     sharp_hc_params wp = Q.hc;
     wp.n_cluster = Q.large ? Q.enp_n_cluster : Q.n_cluster;
@@ -784,6 +818,7 @@ static int run_core(sharp_ctx *c, const sharp_expr_dev &e, const double *colsum_
             if (st[t] != 0) return rstop(st[t], "wMetaC");
     }
 
+    tr.mark("wmetac", true);
     // ---- labels / sMetaC ----
     SHARP_TRY(c->ws[WS_LABELS].reserve((size_t)n * 4));
     int *labels_dev = c->ws[WS_LABELS].as<int>();
@@ -831,6 +866,7 @@ static int run_core(sharp_ctx *c, const sharp_expr_dev &e, const double *colsum_
     }
     if (x0_cols) *x0_cols = ncol_x0;
 
+    tr.mark("smetac", true);
     // ---- outputs ----
     SHARP_TRY(d2h(c, labels_out, labels_dev, (size_t)n * 4));
     if (x0_out) {
@@ -863,6 +899,7 @@ static int run_core(sharp_ctx *c, const sharp_expr_dev &e, const double *colsum_
     c->last_K = K;
     if (vie_out) SHARP_TRY(d2h(c, vie_out, vieu, np * 8));
     SHARP_TRY(sync(c));
+    tr.mark("outputs");
     (void)colmap_dev;
     return 0;
 }
@@ -966,6 +1003,12 @@ static const char *const g_kernel_names[KID_COUNT] = {
     "rp_project", "colsum", "unit_rows", "corrdist", "hclust", "hclust_small", "sweep_nested", "sweep_exact",
     "wm_weights", "wm_similarity", "wmetac_misc", "sm_centroids", "smetac_misc", "ene_scatter", "misc"};
 
+int sharp_ctx_set_rp_variant(sharp_ctx *c, int legacy) {
+    if (!c) return set_error(SHARP_E_ARG, "null context");
+    c->rp_legacy = legacy != 0;
+    return 0;
+}
+
 int sharp_prof_enable(sharp_ctx *c, int on) {
     SHARP_TRY(use(c));
     prof_collect(c);
@@ -1053,6 +1096,31 @@ int sharp_rm_upload(sharp_ctx *c, int m, int p, int K, const int32_t *colptr, co
         if (e1 == cudaSuccess && e2 == cudaSuccess) e2 = cudaMemcpy(r->ent32, ent.data(), ent.size() * 4, cudaMemcpyHostToDevice);
     }
     if (e1 == cudaSuccess) e1 = cudaMemcpy(r->rowptr, rowptr.data(), (size_t)(m + 1) * 4, cudaMemcpyHostToDevice);
+    for (int k = 0; k < K; k++) {
+        const int32_t *cp = colptr + (size_t)k * (p + 1);
+        for (int j = 0; j < p; j++) r->max_col_nnz = std::max(r->max_col_nnz, cp[j + 1] - cp[j]);
+    }
+    if ((int64_t)K * p <= 32767 && e1 == cudaSuccess && e2 == cudaSuccess) {
+        std::vector<uint32_t> vecptr((size_t)m + 1, 0);
+        for (int i = 0; i < m; i++) vecptr[i + 1] = vecptr[i] + (rowptr[i + 1] - rowptr[i] + 7) / 8;
+        std::vector<uint16_t> padded((size_t)vecptr[m] * 8 + 8, 0xFFFFu);
+        double mean = 0, sq = 0;
+        for (int i = 0; i < m; i++) {
+            const uint32_t c = rowptr[i + 1] - rowptr[i];
+            for (uint32_t q = 0; q < c; q++) padded[(size_t)vecptr[i] * 8 + q] = (uint16_t)ent[rowptr[i] + q];
+            mean += c;
+            sq += (double)c * c;
+        }
+        mean /= m;
+        const double sd = std::sqrt(std::max(0.0, sq / m - mean * mean));
+        r->vec_per_gene = std::min(8, std::max(1, (int)std::ceil((mean + 2.5 * sd) / 8.0)));
+        cudaError_t e3 = cudaMalloc((void **)&r->vecptr, (size_t)(m + 1) * 4);
+        cudaError_t e4 = cudaMalloc((void **)&r->entvec, padded.size() * 2);
+        if (e3 == cudaSuccess) e3 = cudaMemcpy(r->vecptr, vecptr.data(), (size_t)(m + 1) * 4, cudaMemcpyHostToDevice);
+        if (e4 == cudaSuccess) e4 = cudaMemcpy(r->entvec, padded.data(), padded.size() * 2, cudaMemcpyHostToDevice);
+        if (e3 != cudaSuccess) e1 = e3;
+        if (e4 != cudaSuccess) e2 = e4;
+    }
     if (e1 != cudaSuccess || e2 != cudaSuccess) {
         sharp_rm_free(r);
         return set_error(SHARP_E_CUDA, "rm_upload: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
@@ -1067,6 +1135,8 @@ void sharp_rm_free(sharp_rm_dev *r) {
     if (r->rowptr) cudaFree(r->rowptr);
     if (r->ent16) cudaFree(r->ent16);
     if (r->ent32) cudaFree(r->ent32);
+    if (r->vecptr) cudaFree(r->vecptr);
+    if (r->entvec) cudaFree(r->entvec);
     delete r;
 }
 

@@ -201,6 +201,210 @@ __global__ void __launch_bounds__(320) rp_project_kernel(RpArgs A, int warps_per
     }
 }
 
+// =====================================================================================================
+// K1, fixed-point variant (the one the pipeline uses whenever K*p <= 32767)
+// =====================================================================================================
+// The scatter above is bound by its dependent shared-memory read-modify-write chain: one warp per cell, at most ten
+// cells per SM (their fp64 accumulators fill shared memory), every gene's add waiting for the previous one.  This
+// variant makes the accumulation ORDER-INDEPENDENT, which removes the chain and the one-warp-per-cell limit:
+//   * every transformed value v is converted to a 64-bit fixed-point integer q = rint(v * 2^f); f is chosen per cell
+//     from max |v| so that |q| < 2^(62 - cb) where 2^cb exceeds the largest number of terms any output can receive
+//     (the longest ranM column) -- sums cannot overflow, and the quantum 2^-f is below the fp64 rounding unit of the
+//     cell's largest value (the integer sum is EXACT; the only roundings are v -> q and the final int64 -> double,
+//     so the result is at least as accurate as the reference's fp64 running sum and bit-reproducible);
+//   * the accumulators are two 32-bit limbs per output in shared memory, updated with native shared-memory integer
+//     atomics: atomicAdd on the low limb returns the old value, from which the carry into the high limb follows;
+//   * lanes map to GENES (32 non-zeros of the cell at a time): a lane fetches its gene's padded entry list with
+//     16-byte loads and issues its adds without waiting for anybody; four warps share one cell, eight cells per SM.
+struct RpFxArgs {
+    RpArgs a;
+    const uint32_t *vecptr;
+    const uint4 *entvec;
+    int cb;     // bits of headroom for the number of terms per output
+    int kpad;   // K*p rounded up to 32 (offset of the high limbs)
+};
+
+constexpr int RPF_THREADS = 128;
+constexpr int RPF_WARPS = RPF_THREADS / 32;
+constexpr int RPF_STAGE = 64;  // per-warp compaction buffer of the dense path
+
+__device__ __forceinline__ void rpf_add(uint32_t *lo, uint32_t *hi, uint32_t ent, uint32_t qlo, uint32_t qhi,
+                                        uint32_t nlo, uint32_t nhi) {
+    if (ent == 0xffffu) return; /* padding */
+    const uint32_t col = ent & 0x7fffu;
+    const bool neg = (ent & 0x8000u) != 0;
+    const uint32_t alo = neg ? nlo : qlo, ahi = neg ? nhi : qhi;
+    const uint32_t old = atomicAdd(lo + col, alo);
+    const uint32_t carry = ((uint32_t)(old + alo) < alo) ? 1u : 0u;
+    atomicAdd(hi + col, ahi + carry);
+}
+
+// one vector = 8 entries: all low-limb atomics are issued before the first carry is consumed
+__device__ __forceinline__ void rpf_add8(uint32_t *lo, uint32_t *hi, uint4 w, uint32_t qlo, uint32_t qhi, uint32_t nlo,
+                                         uint32_t nhi) {
+    const uint32_t ws[4] = {w.x, w.y, w.z, w.w};
+    uint32_t old[8], alo[8], col[8];
+    bool ok[8], neg[8];
+#pragma unroll
+    for (int e = 0; e < 8; e++) {
+        const uint32_t ent = (e & 1) ? (ws[e >> 1] >> 16) : (ws[e >> 1] & 0xffffu);
+        ok[e] = ent != 0xffffu;
+        col[e] = ent & 0x7fffu;
+        neg[e] = (ent & 0x8000u) != 0;
+        alo[e] = neg[e] ? nlo : qlo;
+        old[e] = 0;
+        if (ok[e]) old[e] = atomicAdd(lo + col[e], alo[e]);
+    }
+#pragma unroll
+    for (int e = 0; e < 8; e++) {
+        if (ok[e]) {
+            const uint32_t carry = ((uint32_t)(old[e] + alo[e]) < alo[e]) ? 1u : 0u;
+            atomicAdd(hi + col[e], (neg[e] ? nhi : qhi) + carry);
+        }
+    }
+}
+
+template <int VEC>
+__device__ __forceinline__ void rpf_chunk(const RpFxArgs &A, uint32_t *lo, uint32_t *hi, int gi, double x, bool valid,
+                                          double cs, double qscale, int *bad) {
+    double v = 0.0;
+    if (valid) {
+        v = rp_transform(x, cs, A.a.normalize, A.a.norm_mul, A.a.logkind);
+        if (!isfinite(v)) { *bad = 1; v = 0.0; } /* the whole row becomes NaN, like the reference's NaN propagation */
+    }
+    const long long q = __double2ll_rn(v * qscale);
+    uint32_t v0 = 0, nv = 0;
+    if (q != 0) {
+        v0 = __ldg(A.vecptr + gi);
+        nv = __ldg(A.vecptr + gi + 1) - v0;
+    }
+    const uint32_t qlo = (uint32_t)q, qhi = (uint32_t)((unsigned long long)q >> 32);
+    const unsigned long long nq = 0ull - (unsigned long long)q;
+    const uint32_t nlo = (uint32_t)nq, nhi = (uint32_t)(nq >> 32);
+    uint4 w[VEC];
+#pragma unroll
+    for (int u = 0; u < VEC; u++) {
+        w[u] = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
+        if ((uint32_t)u < nv) w[u] = __ldg(A.entvec + v0 + u);
+    }
+#pragma unroll
+    for (int u = 0; u < VEC; u++)
+        if (__any_sync(0xffffffffu, (uint32_t)u < nv)) rpf_add8(lo, hi, w[u], qlo, qhi, nlo, nhi);
+    for (uint32_t u = VEC; u < nv; u++) rpf_add8(lo, hi, __ldg(A.entvec + v0 + u), qlo, qhi, nlo, nhi); /* rare */
+}
+
+__device__ __forceinline__ double rpf_block_max(double v, double *red) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double r = red[0];
+#pragma unroll
+    for (int w = 1; w < RPF_WARPS; w++) r = fmax(r, red[w]);
+    __syncthreads();
+    return r;
+}
+
+template <int VEC>
+__global__ void __launch_bounds__(RPF_THREADS, 8) rp_project_fx_kernel(RpFxArgs A) {
+    extern __shared__ __align__(16) uint32_t fsm[];
+    __shared__ double red[RPF_WARPS];
+    __shared__ int s_bad;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int KP = A.a.KP;
+    uint32_t *lo = fsm, *hi = fsm + A.kpad;
+    int *sgi = reinterpret_cast<int *>(fsm + 2 * A.kpad) + warp * RPF_STAGE;
+    double *sx = reinterpret_cast<double *>(fsm + 2 * A.kpad + RPF_WARPS * RPF_STAGE) + warp * RPF_STAGE;
+    for (int i = tid; i < 2 * A.kpad; i += RPF_THREADS) fsm[i] = 0u;
+    if (tid == 0) s_bad = 0;
+    __syncthreads();
+
+    for (int64_t pos = blockIdx.x; pos < A.a.ncell; pos += gridDim.x) {
+        const int64_t src = A.a.cells ? A.a.cells[pos] : pos;
+        const double cs = A.a.normalize ? A.a.colsum[src] : 1.0;
+        const double *dcol = A.a.dense ? A.a.dense + src * A.a.m : nullptr;
+        int64_t q0 = 0, q1 = 0;
+        if (!dcol) { q0 = A.a.colptr[src]; q1 = A.a.colptr[src + 1]; }
+        // ---- pass 1: range of the raw values -> bound on |v| (the transform is monotone) -> fixed-point scale ----
+        double xmax = -SHARP_INF, xmin = SHARP_INF;
+        if (dcol) {
+            for (int g = tid; g < A.a.m; g += RPF_THREADS) { const double x = dcol[g]; xmax = fmax(xmax, x); xmin = fmin(xmin, x); }
+        } else {
+            for (int64_t q = q0 + tid; q < q1; q += RPF_THREADS) { const double x = A.a.val[q]; xmax = fmax(xmax, x); xmin = fmin(xmin, x); }
+        }
+        xmax = rpf_block_max(xmax, red);
+        xmin = -rpf_block_max(-xmin, red);
+        double bound = 0.0;
+        if (xmax >= xmin) { /* at least one value */
+            const double b1 = fabs(rp_transform(xmax, cs, A.a.normalize, A.a.norm_mul, A.a.logkind));
+            const double b2 = fabs(rp_transform(xmin, cs, A.a.normalize, A.a.norm_mul, A.a.logkind));
+            bound = fmax(isfinite(b1) ? b1 : 0.0, isfinite(b2) ? b2 : 0.0);
+        }
+        const int e = (bound > 0.0) ? ilogb(bound) + 1 : 0;
+        const int fb = 62 - A.cb - e;
+        const double qscale = ldexp(1.0, fb);
+        // ---- pass 2: scatter ----
+        if (dcol) {
+            int cnt = 0;
+            for (int c0 = warp * 32; c0 < A.a.m; c0 += RPF_THREADS) {
+                const int gi = c0 + lane;
+                const double x = (gi < A.a.m) ? dcol[gi] : 0.0;
+                const unsigned mask = __ballot_sync(0xffffffffu, x != 0.0);
+                if (x != 0.0) {
+                    const int at = cnt + __popc(mask & ((1u << lane) - 1u));
+                    sgi[at] = gi;
+                    sx[at] = x;
+                }
+                cnt += __popc(mask);
+                __syncwarp();
+                if (cnt >= 32) {
+                    rpf_chunk<VEC>(A, lo, hi, sgi[lane], sx[lane], true, cs, qscale, &s_bad);
+                    __syncwarp();
+                    int tg = 0;
+                    double tx = 0.0;
+                    if (lane < cnt - 32) { tg = sgi[32 + lane]; tx = sx[32 + lane]; }
+                    __syncwarp();
+                    if (lane < cnt - 32) { sgi[lane] = tg; sx[lane] = tx; }
+                    cnt -= 32;
+                    __syncwarp();
+                }
+            }
+            if (cnt > 0) rpf_chunk<VEC>(A, lo, hi, lane < cnt ? sgi[lane] : 0, lane < cnt ? sx[lane] : 0.0, lane < cnt, cs, qscale, &s_bad);
+        } else {
+            for (int64_t q = q0 + warp * 32; q < q1; q += RPF_THREADS) {
+                const bool valid = q + lane < q1;
+                const int gi = valid ? A.a.rowidx[q + lane] : 0;
+                const double x = valid ? A.a.val[q + lane] : 0.0;
+                rpf_chunk<VEC>(A, lo, hi, gi, x, valid, cs, qscale, &s_bad);
+            }
+        }
+        __syncthreads();
+        // ---- output: the exact integer sum -> double (one rounding), times the common factor; reset the limbs ----
+        const bool bad = s_bad != 0;
+        const double unscale = ldexp(1.0, -fb);
+        for (int i = tid; i < KP; i += RPF_THREADS) {
+            const long long tot = (long long)(((unsigned long long)hi[i] << 32) | (unsigned long long)lo[i]);
+            lo[i] = 0u;
+            hi[i] = 0u;
+            double r = __dmul_rn(__dmul_rn((double)tot, unscale), A.a.scale);
+            if (A.a.round_digits >= 0) r = rp_round(r, A.a.round_digits);
+            if (bad) r = __longlong_as_double(0x7ff8000000000000LL);
+            const int k = i / A.a.p, j = i - k * A.a.p;
+            A.a.out[((size_t)k * A.a.ncell + pos) * A.a.p + j] = r;
+        }
+        __syncthreads();
+        if (tid == 0) s_bad = 0;
+        __syncthreads();
+    }
+}
+
+template <int VEC>
+static int launch_fx(sharp_ctx *c, const RpFxArgs &A, int grid, size_t smem) {
+    SHARP_CUDA(cudaFuncSetAttribute(rp_project_fx_kernel<VEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, SHARP_SMEM_OPTIN));
+    rp_project_fx_kernel<VEC><<<grid, RPF_THREADS, smem, c->stream>>>(A);
+    return 0;
+}
+
 int launch_rp_project(sharp_ctx *c, const sharp_expr_dev &e, const int64_t *cells_dev, int64_t ncell,
                       const double *colsum_dev, int normalize, double norm_mul, int logkind, int round_digits,
                       const sharp_rm_dev &rm, double *out) {
@@ -214,6 +418,31 @@ int launch_rp_project(sharp_ctx *c, const sharp_expr_dev &e, const int64_t *cell
     A.scale = (1.0 / sqrt((double)rm.p)) * rm.mag;   /* entry of 1/sqrt(p) * t(rM) */
     A.rowptr = rm.rowptr; A.ent16 = rm.ent16; A.ent32 = rm.ent32;
     A.out = out;
+    if (rm.entvec && !c->rp_legacy) { /* fixed-point variant */
+        RpFxArgs F;
+        F.a = A;
+        F.vecptr = rm.vecptr;
+        F.entvec = rm.entvec;
+        F.cb = 1;
+        while ((1 << F.cb) <= rm.max_col_nnz) F.cb++;
+        F.kpad = (A.KP + 31) & ~31;
+        const size_t fsmem = (size_t)2 * F.kpad * 4 + (size_t)RPF_WARPS * RPF_STAGE * 12;
+        if (fsmem <= 200 * 1024) {
+            const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (size_t)(220 * 1024) / (fsmem + 1024)));
+            const int grid = (int)std::min<int64_t>(ncell, (int64_t)c->sm_count * per_sm);
+            prof_begin(c, KID_RP_PROJECT);
+            int rc;
+            if (rm.vec_per_gene <= 2) rc = launch_fx<2>(c, F, grid, fsmem);
+            else if (rm.vec_per_gene <= 3) rc = launch_fx<3>(c, F, grid, fsmem);
+            else if (rm.vec_per_gene <= 4) rc = launch_fx<4>(c, F, grid, fsmem);
+            else if (rm.vec_per_gene <= 6) rc = launch_fx<6>(c, F, grid, fsmem);
+            else rc = launch_fx<8>(c, F, grid, fsmem);
+            prof_end(c);
+            SHARP_TRY(rc);
+            SHARP_CUDA(cudaGetLastError());
+            return 0;
+        }
+    }
     const bool e16 = rm.ent16 != nullptr;
     const size_t budget = 220 * 1024;
     const size_t per_warp = (size_t)A.KP * 8 + 32 * sizeof(RpGene);

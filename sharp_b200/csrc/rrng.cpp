@@ -182,7 +182,9 @@ int sharp_r_sample_perm(int64_t seed, int64_t n, int64_t *out) {
         int64_t j;
         if (dn <= 0) j = 0;
         else {
-            const int bits = (int)std::ceil(std::log2(dn));
+            // bits = (int) ceil(log2(dn)); dn is an integer < 2^31, so this is the bit length of dn - 1 (exact, no libm)
+            const uint32_t dm1 = (uint32_t)remaining - 1u;
+            const int bits = dm1 ? 32 - __builtin_clz(dm1) : 0;
             double dv;
             do {
                 int64_t v = 0;

@@ -45,6 +45,45 @@ def test_rp_project(ctx, fmt, normalize, logkind):
         assert relerr(got[k], ref) <= 1e-11  # what fp64 accumulation should actually deliver
 
 
+@pytest.mark.parametrize("fmt", ["dense", "csc"])
+@pytest.mark.parametrize("logkind", [2, 0])
+def test_rp_project_both_variants_agree(ctx, fmt, logkind):
+    """the fixed-point atomic kernel (default) and the fp64 gene-order kernel against the oracle and each other"""
+    m, n, K, p = 5000, 333, 5, 97
+    x, _ = synth.make_expression(m, n, seed=8, zero_frac=0.9, kind="umi")
+    x[:, 7] = 0.0
+    x[11, 7] = 3.0                      # a cell with a single non-zero gene
+    x[5, 9] = 1e5                       # a wide dynamic range inside one cell
+    rms = [ranM2(m, p, 300 + k) for k in range(K)]
+    rm = ctx.upload_rm(rms)
+    kw = dict(dense=x) if fmt == "dense" else dict(csc=synth.to_csc(x))
+    out = {}
+    for legacy in (False, True):
+        ctx.set_rp_variant(legacy)
+        out[legacy] = ctx.rp_project(m, n, rm, normalize=2, logkind=logkind, **kw)
+    ctx.set_rp_variant(False)
+    again = ctx.rp_project(m, n, rm, normalize=2, logkind=logkind, **kw)
+    assert np.array_equal(again, out[False])      # integer atomics: bit-reproducible whatever the order
+    refs = np.stack([orc.rp_project(m, n, rms[k], colsum=x.sum(0), logkind=logkind, **kw) for k in range(K)])
+    # The fp64 kernel is accurate relative to every member's own projection.  The fixed-point kernel's quantum is set
+    # per CELL from its largest transformed value (2^-55 of it here), so its error is measured against the cell's
+    # largest output over all members (cell 9, whose 1e5 count dwarfs its other genes, is the case in point).
+    per_member = np.maximum(np.max(np.abs(refs), axis=2, keepdims=True), 1e-300)
+    per_cell = np.max(per_member, axis=0, keepdims=True)
+    assert np.max(np.abs(out[True] - refs) / per_member) <= 1e-13
+    assert np.max(np.abs(out[False] - refs) / per_cell) <= 1e-14
+    assert np.max(np.abs(out[False] - refs) / per_member) <= 1e-11
+
+
+def test_rp_project_nonfinite_value_poisons_the_cell(ctx):
+    m, n, p = 800, 20, 16
+    x, _ = synth.make_expression(m, n, seed=9)
+    x[3, 4] = -5.0                      # log2(-5 + 1) = NaN in the reference too
+    rm = ctx.upload_rm([ranM2(m, p, 5)])
+    got = ctx.rp_project(m, n, rm, dense=x, logkind=2)[0]
+    assert np.all(np.isnan(got[4])) and np.all(np.isfinite(np.delete(got, 4, axis=0)))
+
+
 def test_rp_project_cells_and_round(ctx):
     m, n, K, p = 1500, 100, 2, 40
     x, _ = synth.make_expression(m, n, seed=5)
