@@ -199,6 +199,16 @@ class Expression:
 def _first_appearance_codes(y) -> tuple[np.ndarray, np.ndarray]:
     """match(y, unique(y)) -> (codes 1.., unique values in first-appearance order)"""
     y = np.asarray(y)
+    n = len(y)
+    if n and y.dtype.kind in "iu" and 0 <= int(y.min()) and int(y.max()) <= 4 * n + 1024:
+        # small non-negative integers (cluster ids): O(n) with a lookup table instead of a sort
+        first = np.full(int(y.max()) + 1, n, dtype=np.int64)
+        first[y[::-1]] = np.arange(n - 1, -1, -1)          # the last write is the first occurrence
+        present = np.flatnonzero(first < n)
+        order = present[np.argsort(first[present], kind="stable")]
+        rank = np.zeros(len(first), dtype=np.int32)
+        rank[order] = np.arange(1, len(order) + 1, dtype=np.int32)
+        return rank[y], order.astype(y.dtype)
     vals, first, inv = np.unique(y, return_index=True, return_inverse=True)
     order = np.argsort(first, kind="stable")
     rank = np.empty(len(vals), dtype=np.int64)
@@ -206,10 +216,20 @@ def _first_appearance_codes(y) -> tuple[np.ndarray, np.ndarray]:
     return rank[inv].astype(np.int32), vals[order]
 
 
+def _counts(ids: np.ndarray) -> tuple[np.ndarray, np.ndarray]:
+    """(sorted distinct values, counts) -- table(); bincount for small non-negative integers"""
+    ids = np.asarray(ids)
+    if len(ids) and ids.dtype.kind in "iu" and 0 <= int(ids.min()) and int(ids.max()) <= 4 * len(ids) + 1024:
+        c = np.bincount(ids)
+        v = np.flatnonzero(c)
+        return v.astype(ids.dtype), c[v]
+    return np.unique(ids, return_counts=True)
+
+
 def _merge_small(labels: np.ndarray, thre: int = 10) -> np.ndarray:
     """xt = table(x); s = names(which(xt < 10)); x[x in s] = min(as.numeric(s))   (R/SHARP.R:418-427, 816-825)"""
     labels = np.asarray(labels).copy()
-    vals, cnt = np.unique(labels, return_counts=True)
+    vals, cnt = _counts(labels)
     small = vals[cnt < thre]
     if len(small):
         labels[np.isin(labels, small)] = small.min()
@@ -217,16 +237,16 @@ def _merge_small(labels: np.ndarray, thre: int = 10) -> np.ndarray:
 
 
 def _table_sorted(ids: np.ndarray) -> dict:
-    vals, cnt = np.unique(ids, return_counts=True)
+    vals, cnt = _counts(ids)
     return {int(v): int(c) for v, c in zip(vals, cnt)}
 
 
 def _finish(labels: np.ndarray) -> dict:
     """R/SHARP.R:429-443 / 828-843: clusterID = match(y, unique(y)) and the summary fields"""
     cid, _ = _first_appearance_codes(labels)
-    newuy = np.unique(cid)
-    return {"pred_clusters": cid, "unique_pred_clusters": newuy.astype(np.int64), "distr_pred_clusters": _table_sorted(cid),
-            "N.pred_cluster": int(len(newuy))}
+    vals, cnt = _counts(cid)
+    return {"pred_clusters": cid, "unique_pred_clusters": vals.astype(np.int64),
+            "distr_pred_clusters": {int(v): int(c) for v, c in zip(vals, cnt)}, "N.pred_cluster": int(len(vals))}
 
 
 def _check_seed(rN_seed, allow_half=True):
@@ -652,7 +672,7 @@ def _relabel_by_size(labels: np.ndarray) -> np.ndarray:
     """x = sort(table(f), decreasing = TRUE); map names(x) -> 1..length(x)   (R/SHARP_unlimited.R:180-183).
     table() orders its names as STRINGS and sort(decreasing = TRUE) is order(., decreasing = TRUE) (stable), so
     equal counts keep the string order of the ids."""
-    vals, cnt = np.unique(labels, return_counts=True)
+    vals, cnt = _counts(labels)
     names = sorted(range(len(vals)), key=lambda q: str(int(vals[q])))
     order = sorted(names, key=lambda q: -cnt[q])  # Python's sort is stable
     lut = np.zeros(int(vals.max()) + 1, dtype=np.int32)
@@ -678,8 +698,9 @@ def _unlimited_combine(ctx, cen, counts_per_part, preds, ncells, hmethod, N_clus
 
 
 def _unlimited_result(final, ncells, ngenes, y0, start):
-    uf = np.unique(final)
-    return {"pred_clusters": final, "unique_pred_clusters": uf.astype(np.int64), "distr_pred_clusters": _table_sorted(final),
+    uf, ufc = _counts(final)
+    return {"pred_clusters": final, "unique_pred_clusters": uf.astype(np.int64),
+            "distr_pred_clusters": {int(v): int(c) for v, c in zip(uf, ufc)},
             "N.pred_clusters": int(len(uf)), "N.cells": int(ncells), "N.genes": int(ngenes),
             "reduced.dim": y0["reduced.dim"], "ensize.K": y0["ensize.K"], "time": (time.time() - start) / 60.0,
             "paras": y0["paras"]}

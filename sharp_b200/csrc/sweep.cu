@@ -20,6 +20,7 @@ namespace sharp {
 
 constexpr int SW_THREADS = 256;
 constexpr int NESTED_MAXK = 64;
+constexpr int SIL_U = 16;
 
 // ---- dendrogram helpers --------------------------------------------------------------------------
 // hclust.f keeps the merged cluster under the smaller representative I2 and retires J2, so the representative
@@ -223,13 +224,14 @@ sweep_nested_kernel(HcProb *probs, SweepOut *outs, HcParamsDev prm, int n_cap, i
         for (int c = 0; c < kmax; c++) acc[c * SW_THREADS + tid] = 0.0;
         const double *col = D + (valid ? x : 0);
         int y = 0;
-        for (; y + 4 <= n; y += 4) {
-            double d0 = col[(size_t)(y + 0) * ld], d1 = col[(size_t)(y + 1) * ld];
-            double d2 = col[(size_t)(y + 2) * ld], d3 = col[(size_t)(y + 3) * ld];
-            acc[cidf[y + 0] * SW_THREADS + tid] += d0;
-            acc[cidf[y + 1] * SW_THREADS + tid] += d1;
-            acc[cidf[y + 2] * SW_THREADS + tid] += d2;
-            acc[cidf[y + 3] * SW_THREADS + tid] += d3;
+        /* SIL_U rows in flight per thread: with one CTA per SM (the accumulators take 80 KB) the pass over D is bound
+           by the bytes in flight, not by bandwidth; the adds stay in ascending y like cluster::sildist */
+        for (; y + SIL_U <= n; y += SIL_U) {
+            double d[SIL_U];
+#pragma unroll
+            for (int u = 0; u < SIL_U; u++) d[u] = col[(size_t)(y + u) * ld];
+#pragma unroll
+            for (int u = 0; u < SIL_U; u++) acc[cidf[y + u] * SW_THREADS + tid] += d[u];
         }
         for (; y < n; y++) acc[cidf[y] * SW_THREADS + tid] += col[(size_t)y * ld];
         const int myfine = valid ? cidf[x] : 0;
@@ -276,8 +278,17 @@ sweep_nested_kernel(HcProb *probs, SweepOut *outs, HcParamsDev prm, int n_cap, i
         for (int d0 = 0; d0 < p; d0 += SW_THREADS) {
             const int d = d0 + tid;
             for (int c = 0; c < kmax; c++) acc[c * SW_THREADS + tid] = 0.0;
-            if (d < p)
-                for (int x = 0; x < n; x++) acc[cidf[x] * SW_THREADS + tid] += Y[(size_t)x * ldy + d];
+            if (d < p) { /* SIL_U rows in flight per thread (same reason as the pass over D) */
+                int x = 0;
+                for (; x + SIL_U <= n; x += SIL_U) {
+                    double yv[SIL_U];
+#pragma unroll
+                    for (int u = 0; u < SIL_U; u++) yv[u] = Y[(size_t)(x + u) * ldy + d];
+#pragma unroll
+                    for (int u = 0; u < SIL_U; u++) acc[cidf[x + u] * SW_THREADS + tid] += yv[u];
+                }
+                for (; x < n; x++) acc[cidf[x] * SW_THREADS + tid] += Y[(size_t)x * ldy + d];
+            }
             if (d < p)
                 for (int c = 0; c < kmax; c++) csum[(size_t)c * p + d] = acc[c * SW_THREADS + tid];
         }

@@ -69,8 +69,19 @@ __device__ __forceinline__ DI scan_row(const double *row, const unsigned char *f
 
 constexpr int LW_U = 8;                   // Lance-Williams columns per thread per pass
 
-template <int THREADS>
-__global__ void __launch_bounds__(THREADS, 768 / THREADS) hclust_kernel(HcProb *probs, int method) {
+constexpr int RESCAN_PF = 16;  // row elements per lane prefetched for a rescan before the Lance-Williams pass
+
+// Step structure (n - 1 dependent steps, one CTA per problem; the matrices of all resident problems exceed L2, so
+// every batch of loads is an HBM round trip and the step is organised to overlap them):
+//   A  argmin over the NN list                      -> (i2, j2)
+//   B  list of rows whose NN was i2 or j2 (from the PRE-update NN list)
+//   C  prefetch: the first 512 columns of each (row, segment) rescan are loaded into registers
+//   D  Lance-Williams update of row / column i2 (its loads overlap C's); the new column is also kept in shared
+//      memory (rcol) because the prefetched rescans saw the OLD column i2
+//   E  rescans: minimum over active j > i, j != i2, j2 of the prefetched data (+ the rest of long rows), combined
+//      with the candidate (rcol[i], i2) -- exactly the minimum hclust.f finds after its update
+template <int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB) hclust_kernel(HcProb *probs, int method) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ DI red[THREADS / 32];
     __shared__ int s_cnt;
@@ -84,7 +95,8 @@ __global__ void __launch_bounds__(THREADS, 768 / THREADS) hclust_kernel(HcProb *
     constexpr int NW = THREADS / 32;
 
     double *disnn = reinterpret_cast<double *>(smem_raw);  // [n]
-    DI *part = reinterpret_cast<DI *>(disnn + n);           // [NW][NW] partial minima of the rescans
+    double *rcol = disnn + n;                               // [n] new column i2 of the current step
+    DI *part = reinterpret_cast<DI *>(rcol + n);            // [NW][NW] partial minima of the rescans
     int *nn = reinterpret_cast<int *>(part + NW * NW);      // [n]
     int *membr = nn + n;                                    // [n]
     int *list = membr + n;                                  // [n]
@@ -99,6 +111,7 @@ __global__ void __launch_bounds__(THREADS, 768 / THREADS) hclust_kernel(HcProb *
         disnn[i] = SHARP_INF;
         nn[i] = -1;
     }
+    if (tid == 0) s_cnt = 0;
     __syncthreads();
 
     // initial nearest neighbours: NN(i) = first minimum over j > i
@@ -112,7 +125,7 @@ __global__ void __launch_bounds__(THREADS, 768 / THREADS) hclust_kernel(HcProb *
     __syncthreads();
 
     for (int step = 0; step < n - 1; ++step) {
-        // ---- least dissimilarity over the NN list (first strict minimum over i) ----
+        // ---- A: least dissimilarity over the NN list (first strict minimum over i) ----
         DI c;
         c.d = SHARP_INF;
         c.i = INT_MAX;
@@ -137,10 +150,37 @@ __global__ void __launch_bounds__(THREADS, 768 / THREADS) hclust_kernel(HcProb *
             P.ia[step] = i2 + 1;
             P.ib[step] = j2 + 1;
             P.crit[step] = (method == SHARP_WARD_D2) ? sqrt(c.d) : c.d;
-            s_cnt = 0;
         }
-
-        // ---- update dissimilarities from the new cluster (kept under index i2); j2 retires ----
+        // ---- B: rows whose NN is about to disappear ----
+        for (int i = tid; i < n - 1; i += THREADS) {
+            if (flag[i] && i != i2 && i != j2) {
+                const int q = nn[i];
+                if (q == i2 || q == j2) list[atomicAdd(&s_cnt, 1)] = i;
+            }
+        }
+        __syncthreads();
+        const int cnt = s_cnt;
+        // ---- C: prefetch the first rescan pass (NW rows at most; fewer rows -> several warps per row) ----
+        const int nr = min(NW, cnt);
+        const int wpr = nr > 0 ? NW / nr : 1;
+        const int rr = warp / wpr, seg = warp - rr * wpr;
+        const bool scanning = rr < nr;
+        int srow = 0, j0 = 0, j1 = 0;
+        double pv[RESCAN_PF];
+        if (scanning) {
+            srow = list[rr];
+            const int len = n - (srow + 1);
+            const int seglen = (((len + wpr - 1) / wpr) + 31) & ~31;
+            j0 = srow + 1 + seg * seglen;
+            j1 = min(n, j0 + seglen);
+            const double *row = D + (size_t)srow * ld;
+#pragma unroll
+            for (int u = 0; u < RESCAN_PF; u++) {
+                const int j = j0 + u * 32 + lane;
+                pv[u] = (j < j1) ? row[j] : SHARP_INF;
+            }
+        }
+        // ---- D: update dissimilarities from the new cluster (kept under index i2); j2 retires ----
         DI nb;
         nb.d = SHARP_INF;
         nb.i = INT_MAX;
@@ -163,60 +203,93 @@ __global__ void __launch_bounds__(THREADS, 768 / THREADS) hclust_kernel(HcProb *
                 D[(size_t)k * ld + i2] = r;
                 if (k > i2) {
                     if (r < nb.d) { nb.d = r; nb.i = k; }
-                } else if (r < disnn[k]) { /* hclust.f "FIX by JB": i2 may become the NN of a smaller index */
-                    disnn[k] = r;
-                    nn[k] = i2;
+                } else {
+                    rcol[k] = r;
+                    if (r < disnn[k]) { /* hclust.f "FIX by JB": i2 may become the NN of a smaller index */
+                        disnn[k] = r;
+                        nn[k] = i2;
+                    }
                 }
             }
         }
-        nb = block_argmin<THREADS>(nb, red); /* its barriers also order the reads of nn / membr above */
+        nb = block_argmin<THREADS>(nb, red); /* its barriers also order the reads of nn / membr / s_cnt above */
         if (tid == 0) {
             flag[j2] = 0;
             membr[i2] = membr[i2] + membr[j2];
             disnn[i2] = nb.d;
             nn[i2] = (nb.i == INT_MAX) ? -1 : nb.i;
+            s_cnt = 0;
         }
-        __syncthreads();
-
-        // ---- redetermine the NN of every i whose NN was i2 or j2 ----
-        for (int i = tid; i < n - 1; i += THREADS) {
-            if (flag[i] && i != i2) {
-                int q = nn[i];
-                if (q == i2 || q == j2) list[atomicAdd(&s_cnt, 1)] = i;
+        // ---- E: rescans ----
+        if (scanning) {
+            DI best;
+            best.d = SHARP_INF;
+            best.i = INT_MAX;
+#pragma unroll
+            for (int u = 0; u < RESCAN_PF; u++) {
+                const int j = j0 + u * 32 + lane;
+                if (j < j1 && j != i2 && j != j2 && flag[j] && pv[u] < best.d) { best.d = pv[u]; best.i = j; }
             }
+            const double *row = D + (size_t)srow * ld;
+            for (int base = j0 + 32 * RESCAN_PF; base < j1; base += 32 * SCAN_U) { /* rest of a long segment */
+                double v[SCAN_U];
+#pragma unroll
+                for (int u = 0; u < SCAN_U; u++) {
+                    const int j = base + u * 32 + lane;
+                    v[u] = (j < j1) ? row[j] : SHARP_INF;
+                }
+#pragma unroll
+                for (int u = 0; u < SCAN_U; u++) {
+                    const int j = base + u * 32 + lane;
+                    if (j < j1 && j != i2 && j != j2 && flag[j] && v[u] < best.d) { best.d = v[u]; best.i = j; }
+                }
+            }
+            best = warp_argmin_redux(best);
+            if (lane == 0) part[rr * NW + seg] = best;
         }
-        __syncthreads();
-        const int cnt = s_cnt;
-        // NW rows per batch; when fewer rows than warps need a rescan, each row's tail is split between NW / rows warps
-        // (short dependent chains: the matrices of the problems resident on the GPU exceed L2 by far, so every batch
-        // of loads is an HBM round trip).  One REDUX argmin per (row, segment), combined in ascending segment order.
-        for (int r0 = 0; r0 < cnt; r0 += NW) {
-            const int nr = min(NW, cnt - r0);
-            const int wpr = NW / nr;
-            const int r = warp / wpr, seg = warp - r * wpr;
-            if (r < nr) {
+        __syncthreads(); /* part[], rcol[], flag[j2] = 0 and the new row / column i2 in D are visible */
+        if (tid < nr) {
+            DI best = part[tid * NW];
+            for (int sgm = 1; sgm < wpr; sgm++) best = di_better(best, part[tid * NW + sgm]);
+            const int i = list[tid];
+            if (i < i2) { /* the updated column i2, which the prefetched scan skipped */
+                DI cand;
+                cand.d = rcol[i];
+                cand.i = i2;
+                best = di_better(best, cand);
+            }
+            nn[i] = (best.i == INT_MAX) ? -1 : best.i;
+            disnn[i] = best.d;
+        }
+        // further passes when more than NW rows need a rescan (D is up to date now)
+        for (int r0 = NW; r0 < cnt; r0 += NW) {
+            __syncthreads(); /* part[] of the previous pass has been consumed */
+            const int nr2 = min(NW, cnt - r0);
+            const int wpr2 = NW / nr2;
+            const int r = warp / wpr2, sg = warp - r * wpr2;
+            if (r < nr2) {
                 const int i = list[r0 + r];
                 const int len = n - (i + 1);
-                const int seglen = (((len + wpr - 1) / wpr) + 31) & ~31;
-                const int j0 = i + 1 + seg * seglen;
-                DI best = warp_argmin_redux(scan_row<true>(D + (size_t)i * ld, flag, j0, min(n, j0 + seglen), lane));
-                if (lane == 0) part[r * NW + seg] = best;
+                const int seglen = (((len + wpr2 - 1) / wpr2) + 31) & ~31;
+                const int b0 = i + 1 + sg * seglen;
+                DI best = warp_argmin_redux(scan_row<true>(D + (size_t)i * ld, flag, b0, min(n, b0 + seglen), lane));
+                if (lane == 0) part[r * NW + sg] = best;
             }
             __syncthreads();
-            if (tid < nr) {
+            if (tid < nr2) {
                 DI best = part[tid * NW];
-                for (int sgm = 1; sgm < wpr; sgm++) best = di_better(best, part[tid * NW + sgm]);
+                for (int sgm = 1; sgm < wpr2; sgm++) best = di_better(best, part[tid * NW + sgm]);
                 const int i = list[r0 + tid];
                 nn[i] = (best.i == INT_MAX) ? -1 : best.i;
                 disnn[i] = best.d;
             }
-            __syncthreads();
         }
+        __syncthreads();
     }
 }
 
 static size_t hclust_smem_bytes(int n) {
-    return ((size_t)n * (8 + 4 + 4 + 4 + 1) + (size_t)16 * 16 * sizeof(DI) + 15) & ~(size_t)15;
+    return ((size_t)n * (8 + 8 + 4 + 4 + 4 + 1) + (size_t)16 * 16 * sizeof(DI) + 15) & ~(size_t)15;
 }
 
 int launch_hclust(sharp_ctx *c, HcProb *probs_dev, int nprob, int max_n, int method) {
@@ -224,14 +297,14 @@ int launch_hclust(sharp_ctx *c, HcProb *probs_dev, int nprob, int max_n, int met
     if (method < 1 || method > 8) return set_error(SHARP_E_ARG, "invalid clustering method %d", method);
     size_t smem = hclust_smem_bytes(max_n);
     if (smem > 200 * 1024)
-        return set_error(SHARP_E_LIMIT, "hclust: %d objects exceed the shared-memory NN list (max ~9700)", max_n);
+        return set_error(SHARP_E_LIMIT, "hclust: %d objects exceed the shared-memory NN list (max ~7000)", max_n);
     prof_begin(c, max_n > 384 ? KID_HCLUST : KID_HCLUST_SMALL);
     if (max_n > 384) {
-        SHARP_CUDA(cudaFuncSetAttribute(hclust_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, SHARP_SMEM_OPTIN));
-        hclust_kernel<256><<<nprob, 256, smem, c->stream>>>(probs_dev, method);
+        SHARP_CUDA(cudaFuncSetAttribute(hclust_kernel<256, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SHARP_SMEM_OPTIN));
+        hclust_kernel<256, 2><<<nprob, 256, smem, c->stream>>>(probs_dev, method);
     } else {
-        SHARP_CUDA(cudaFuncSetAttribute(hclust_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, SHARP_SMEM_OPTIN));
-        hclust_kernel<128><<<nprob, 128, smem, c->stream>>>(probs_dev, method);
+        SHARP_CUDA(cudaFuncSetAttribute(hclust_kernel<128, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, SHARP_SMEM_OPTIN));
+        hclust_kernel<128, 4><<<nprob, 128, smem, c->stream>>>(probs_dev, method);
     }
     prof_end(c);
     SHARP_CUDA(cudaGetLastError());
