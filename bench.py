@@ -310,6 +310,8 @@ def run_ours(args):
         nnz_all = [int(a[0]) for a in comm.allgather_parts({i: np.array([nnz_all[i]], dtype=np.int64) for i in mine}, len(sizes))]
 
     api.set_devices(local)
+    api._fused_parts = not args.no_fused
+    api._fused_group, api._fused_lanes = args.group, args.lanes
     ctx = api.get_context(local)
     ctxs = api.stream_contexts(args.streams, local)
     kw = dict(n_streams=args.streams, viewflag=False, ensize_K=wl["K"], rN_seed=SEED, exp_type=wl["exp_type"], ctx=ctx, comm=comm)
@@ -424,7 +426,9 @@ def run_ours(args):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": wl["name"], "cells": ncells, "genes": m, "parts": len(sizes), "K": wl["K"], "p": p,
-                       "nnz": int(sum(nnz_all)), "partition": f"parts round-robin over {world} rank(s), {args.streams} streams per GPU",
+                       "nnz": int(sum(nnz_all)), "partition": (f"parts round-robin over {world} rank(s); part-by-part, {args.streams} streams per GPU" if args.no_fused else
+                                     f"parts round-robin over {world} rank(s); fused loop over parts (sharp_run_parts), "
+                                     f"group={args.group or 'default'}, lanes={args.lanes or 'default'}"),
                        "l2": "inputs larger than L2 (CSC input %.1f GB per step)" % (sum(nnz_all) * 12 / 1e9),
                        "generation_s": t_gen},
             "clocks": clocks, "gpu_launches": int(launches / args.steps),
@@ -444,6 +448,9 @@ def main():
     ap.add_argument("--workload", default="cfg4")
     ap.add_argument("--streams", type=int, default=8, help="contexts (CUDA streams) per GPU working on different parts")
     ap.add_argument("--parts", type=int, default=0, help="development: only the first PARTS parts")
+    ap.add_argument("--group", type=int, default=0, help="parts per group of the fused loop over parts (0 = library default)")
+    ap.add_argument("--lanes", type=int, default=0, help="groups in flight (0 = library default)")
+    ap.add_argument("--no-fused", action="store_true", help="part-by-part path (one sharp_run per part, --streams host threads)")
     ap.add_argument("--cpu-sample", type=int, default=20000, help="cells of the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

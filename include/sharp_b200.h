@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define SHARP_B200_ABI_VERSION 1
+#define SHARP_B200_ABI_VERSION 2
 
 enum {
     SHARP_OK = 0,
@@ -205,6 +205,35 @@ int sharp_run_dev(sharp_ctx *ctx, const sharp_expr_dev *e, const double *colsum,
 /* centroids of the LAST sharp_run/sharp_run_dev on this context: for cluster ids 1..nclust (values of `labels`,
  * e.g. pred_clusters after the host relabel), cen row-major nclust x p = colMeans(viE[labels == c, ]). */
 int sharp_centroids(sharp_ctx *ctx, int64_t n, const int32_t *labels, int nclust, double *cen, int64_t *counts);
+
+/* ---- a17: the loop over parts of SHARP_unlimited / SHARP_unlimited3, fused ------------------------------
+ * Replaces  for (i in 1:nnp) y[[i]] = SHARP(scExp[[i]], reduced.ndim = p, prep = FALSE, logflag = FALSE, rM = rM, ...)
+ * (R/SHARP_unlimited.R:125-149, R/SHARP_unlimited3.R:103-131) for parts that take the SHARP_large path, plus the
+ * colMeans of every part-level cluster that the global sMetaC needs (R/sMetaC.R:58-63).  The reference runs the parts
+ * one after the other; here `group` parts share every block-clustering launch (their (member, block) problems are
+ * independent) and `lanes` groups are in flight on different streams, so that the latency-bound agglomeration of one
+ * group overlaps the tensor-pipe-bound distance kernel of another.  Per part: pred[n] = pred_clusters of SHARP()
+ * (after the merge of clusters with < small_thre cells when N.cluster is NULL and n > 1e4, R/SHARP.R:816-825, and the
+ * first-appearance relabel, :828-832), nclust = N.pred_cluster, cen = row-major nclust x p centroids of viE (room for
+ * cen_cap rows), counts[cen_cap]. */
+typedef struct {
+    int64_t n;                 /* cells of this part */
+    const sharp_expr_dev *dev; /* device-resident part (sharp_expr_upload), or NULL and host slots below */
+    const double *dense;       /* host: dense column-major m x n, or */
+    const int64_t *colptr;     /*       dgCMatrix slots p / i / x */
+    const int32_t *rowidx;
+    const double *val;
+    const int64_t *reind;      /* 1-based `set.seed(50); sample(n)` of this part or NULL (applied iff n < 1e5) */
+    int32_t *pred;             /* out [n] */
+    int nclust;                /* out */
+    double *cen;               /* out (may be NULL) */
+    int64_t *counts;           /* out (may be NULL) */
+} sharp_part;
+int sharp_run_parts(sharp_ctx *ctx, int m, int nparts, sharp_part *parts, const sharp_rm_dev *rm,
+                    const sharp_run_params *prm, int small_thre, int cen_cap, int group, int lanes);
+/* cap (GB) of the distance-matrix workspace per context; the (member, block) problems of a group run in waves of
+ * as many problems as fit (default 48) */
+int sharp_ctx_set_block_budget(sharp_ctx *ctx, int gigabytes);
 
 /* Per-member results of the LAST sharp_run/sharp_run_dev on this context (SHARP_small's `allrpinfo`,
  * R/SHARP.R:366-385): rowcolor[n] = the member's colour index per cell (getrowColor), inde[n*p] row-major = the

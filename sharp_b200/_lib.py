@@ -45,6 +45,14 @@ class RunParams(C.Structure):
                 ("ind_n_cluster", C.c_int), ("hc", HcParams), ("normalize", C.c_int), ("norm_mul", C.c_double)]
 
 
+class Part(C.Structure):
+    """sharp_part: one part of SHARP_unlimited for sharp_run_parts"""
+    _fields_ = [("n", C.c_int64), ("dev", C.c_void_p), ("dense", C.POINTER(C.c_double)), ("colptr", C.POINTER(C.c_int64)),
+                ("rowidx", C.POINTER(C.c_int32)), ("val", C.POINTER(C.c_double)), ("reind", C.POINTER(C.c_int64)),
+                ("pred", C.POINTER(C.c_int32)), ("nclust", C.c_int), ("cen", C.POINTER(C.c_double)),
+                ("counts", C.POINTER(C.c_int64))]
+
+
 # every symbol include/sharp_b200.h declares (tests check that the library exports all of them)
 EXPORTS = [
     "sharp_abi_version", "sharp_last_error", "sharp_device_count", "sharp_device_info", "sharp_ctx_create",
@@ -53,7 +61,8 @@ EXPORTS = [
     "sharp_hclust", "sharp_opt_hclust", "sharp_getrowcolor", "sharp_wmetac", "sharp_smetac", "sharp_run",
     "sharp_expr_upload", "sharp_expr_free", "sharp_run_dev", "sharp_centroids", "sharp_smetac_centroids",
     "sharp_last_member", "sharp_last_vie", "sharp_prof_enable", "sharp_prof_reset", "sharp_prof_kernels", "sharp_prof_name",
-    "sharp_prof_get", "sharp_ctx_set_rp_variant", "sharp_r_ranm", "sharp_r_sample_perm",
+    "sharp_prof_get", "sharp_ctx_set_rp_variant", "sharp_r_ranm", "sharp_r_sample_perm", "sharp_run_parts",
+    "sharp_ctx_set_block_budget",
 ]
 
 _lib = None
@@ -400,6 +409,45 @@ class Context:
         res = {"labels": labels, "viE": vie, "x0_cols": x0c.value}
         if want_x0:
             res["x0"] = x0[:n * x0c.value].reshape(n, x0c.value)
+        return res
+
+    def set_block_budget(self, gigabytes: int):
+        _check(load().sharp_ctx_set_block_budget(self._h, int(gigabytes)))
+
+    def run_parts(self, rm: RmDev, prm: RunParams, m: int, parts: list, reinds: list, small_thre=10, cen_cap=64,
+                  group=0, lanes=0) -> list:
+        """The per-part loop of SHARP_unlimited in one call (sharp_run_parts).  ``parts``: list of ExprDev (device
+        resident) or dicts {"n", "dense"} / {"n", "csc": (p, i, x)} (host).  -> per part {"pred_clusters",
+        "N.pred_cluster", "cen" (nclust x p), "counts"}."""
+        nparts = len(parts)
+        arr = (Part * nparts)()
+        keep = []
+        outs = []
+        for i, (pt, re) in enumerate(zip(parts, reinds)):
+            a = arr[i]
+            if isinstance(pt, ExprDev):
+                a.n = pt.n
+                a.dev = pt._h
+            else:
+                a.n = int(pt["n"])
+                a.dev = None
+                k, dp, cp, ri, v = _expr_args(m, a.n, pt.get("dense"), pt.get("csc"))
+                keep.append(k)
+                a.dense, a.colptr, a.rowidx, a.val = dp, cp, ri, v
+            re = _i64(re)
+            keep.append(re)
+            a.reind = _ptr(re, C.c_int64)
+            pred = np.empty(a.n, dtype=np.int32)
+            cen = np.empty((cen_cap, rm.p))
+            cnt = np.zeros(cen_cap, dtype=np.int64)
+            a.pred, a.cen, a.counts = _ptr(pred, C.c_int32), _ptr(cen, C.c_double), _ptr(cnt, C.c_int64)
+            outs.append((pred, cen, cnt))
+        _check(load().sharp_run_parts(self._h, int(m), nparts, arr, rm._h, C.byref(prm), int(small_thre), int(cen_cap),
+                                      int(group), int(lanes)))
+        res = []
+        for i, (pred, cen, cnt) in enumerate(outs):
+            nc = int(arr[i].nclust)
+            res.append({"pred_clusters": pred, "N.pred_cluster": nc, "cen": cen[:nc].copy(), "counts": cnt[:nc].copy()})
         return res
 
     def centroids(self, labels, nclust, p):

@@ -706,6 +706,75 @@ def _unlimited_result(final, ncells, ngenes, y0, start):
             "paras": y0["paras"]}
 
 
+_FUSED_KEYS = {"exp_type", "base_ncells", "partition_ncells", "hmethod", "sil_thre", "height_Ntimes", "flashmark",
+               "enpN_cluster", "indN_cluster"}
+_fused_parts = True     # module switch: False forces the part-by-part path (tests compare the two)
+_fused_group = 0        # parts per group / groups in flight of sharp_run_parts (0 = library default)
+_fused_lanes = 0
+
+
+def _parts_fast_path(parts, mine, k, viewflag, part_logflag, n_streams):
+    """The arguments of the per-part SHARP() calls when ALL of them take the SHARP_large path with identical
+    parameters (then sharp_run_parts runs them as one fused device call), else None."""
+    if not _fused_parts or viewflag or part_logflag or isinstance(n_streams, (list, tuple)) or not mine:
+        return None
+    if set(k) - _FUSED_KEYS:
+        return None
+    base = 5000 if k.get("base_ncells") is None else k["base_ncells"]
+    ns = [parts[i].n for i in mine]
+    if min(ns) < base or min(ns) < 1e4:   # SHARP_small, or the default logflag / prep would switch on
+        return None
+    if len({max(40, math.ceil(n / 5000)) for n in ns}) != 1:   # maxN.cluster differs between the parts
+        return None
+    if any(parts[i].dev is None and parts[i].dense is None and parts[i].csc is None for i in mine):
+        return None
+    return {"exp_type": k.get("exp_type"), "base_ncells": base,
+            "partition_ncells": 2000 if k.get("partition_ncells") is None else k["partition_ncells"],
+            "hmethod": "ward.D" if k.get("hmethod") is None else k["hmethod"],
+            "sil_thre": 0.35 if k.get("sil_thre") is None else k["sil_thre"],
+            "height_Ntimes": 2 if k.get("height_Ntimes") is None else k["height_Ntimes"],
+            "flashmark": bool(k.get("flashmark", False)), "enpN_cluster": k.get("enpN_cluster"),
+            "indN_cluster": k.get("indN_cluster"), "maxN_cluster": max(40, math.ceil(ns[0] / 5000))}
+
+
+def _run_parts_fused(ctx, parts, mine, rM, p, K, rN_seed, a, n_cores):
+    """What the loop `y[[i]] = SHARP(scExp[[i]], reduced.ndim = p, prep = FALSE, logflag = FALSE, rM = rM, ...)` returns
+    for the parts in ``mine`` (R/SHARP_unlimited.R:125-149), computed by ONE sharp_run_parts call."""
+    normalize = a["exp_type"] is not None and a["exp_type"] not in ("CPM", "TPM")
+    hc = _hc(a["hmethod"], None, 2, a["maxN_cluster"], a["sil_thre"], a["height_Ntimes"], a["flashmark"])
+    prm = RunParams(1, 1, 2, -1, int(a["partition_ncells"]), 0, _ncl(a["enpN_cluster"]), _ncl(a["indN_cluster"]), hc,
+                    2 if normalize else 0, 1e6)
+    ins, reinds = [], []
+    for i in mine:
+        e = parts[i]
+        _cat("Processing Partition", i + 1, "of the scRNA-seq data...")
+        if e.dev is not None:
+            ins.append(e.dev)
+        elif e.dense is not None:
+            ins.append({"n": e.n, "dense": e.dense})
+        else:
+            ins.append({"n": e.n, "csc": e.csc})
+        reinds.append(_reind(e.n, rN_seed) if e.n < 1e5 else None)
+    start = time.time()
+    outs = ctx.run_parts(rM, prm, parts[mine[0]].m, ins, reinds, small_thre=10, cen_cap=max(64, a["maxN_cluster"] + 1),
+                         group=_fused_group, lanes=_fused_lanes)
+    res = []
+    for i, o in zip(mine, outs):
+        cid = o["pred_clusters"]
+        vals, cnt = _counts(cid)
+        r = {"pred_clusters": cid, "unique_pred_clusters": vals.astype(np.int64),
+             "distr_pred_clusters": {int(v): int(c) for v, c in zip(vals, cnt)}, "N.pred_cluster": int(len(vals)),
+             "N.cells": parts[i].n, "N.genes": parts[i].m, "reduced.dim": int(p), "ensize.K": int(K),
+             "time": (time.time() - start) / 60.0,
+             "paras": {"ensize.K": int(K), "reduced.ndim": int(p), "base.ncells": a["base_ncells"],
+                       "partition.ncells": a["partition_ncells"], "logmark": True, "hmethod": a["hmethod"],
+                       "N.cluster": None, "minN.cluster": 2, "maxN.cluster": a["maxN_cluster"],
+                       "sil.thre": a["sil_thre"], "height.Ntimes": a["height_Ntimes"], "n.cores": n_cores},
+             "cen": o["cen"]}
+        res.append(r)
+    return res
+
+
 def SHARP_unlimited(scExp, viewflag=True, n_cores=None, ensize_K=None, N_cluster=None, minN_cluster=None,
                     maxN_cluster=None, rN_seed=None, ctx: Context | None = None, comm=None, n_streams=None,
                     _part_logflag=False, **kwargs) -> dict:
@@ -777,8 +846,16 @@ def SHARP_unlimited(scExp, viewflag=True, n_cores=None, ensize_K=None, N_cluster
                   file=sys.stderr)
         return yi, cen, (c.last_vie(nnc[i], p) if viewflag else None)
 
+    fast = _parts_fast_path(parts, mine, k, viewflag, _part_logflag, n_streams)
     try:
-        if len(ctxs) == 1:
+        if fast is not None:  # every part takes the SHARP_large path with the same parameters: one fused device call
+            t0 = time.time()
+            outs = _run_parts_fused(ctx, parts, mine, rM, p, ensize_K, rN_seed, fast, n_cores)
+            for i, o in zip(mine, outs):
+                y[i], cens[i], viEs[i] = o, o.pop("cen"), None
+            if _TRACE:
+                print(f"[sharp trace py] fused parts {1e3 * (time.time() - t0):.2f} ms", file=sys.stderr)
+        elif len(ctxs) == 1:
             for i in mine:
                 y[i], cens[i], viEs[i] = one_part(i, ctx)
         else:  # one host thread per stream; the C ABI calls release the GIL

@@ -53,6 +53,7 @@ struct HcProb {
     int p;            // columns of Y
     int ldy;          // leading dimension of Y
     int status;       // 0 ok, else a SWEEP_E_* / WM_E_* code
+    int fallback;     // set by hclust_rnn_kernel: exact ties, redo with the exact kernel
 };
 
 // results of the cluster-number sweep for one problem (device pointers)
@@ -104,8 +105,21 @@ struct sharp_ctx {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     int64_t launches = 0;
     sharp::DevBuf ws[48];  // grow-only workspaces (slots named in pipeline.cu)
-    void *pinned = nullptr; // pinned staging for descriptor uploads / small downloads
-    size_t pinned_cap = 0;
+    // Pinned staging for descriptor uploads / small downloads: a ring arena.  reserve_pinned(bytes) points `pinned`
+    // at a FRESH chunk, so a chunk handed to cudaMemcpyAsync is never rewritten while the copy is in flight and no
+    // stream synchronisation is needed between the stages of a run; when the arena wraps, the stream is synchronised
+    // once (every staged copy of this context is issued on its own stream).
+    void *pinned = nullptr;
+    size_t pinned_cap = 0;      // size of the chunk `pinned` points at
+    unsigned char *arena = nullptr;
+    size_t arena_cap = 0, arena_off = 0;
+    // sub-contexts of a group run (sharp_run_parts): own workspaces and streams, created on first use
+    std::vector<sharp_ctx *> subs;
+    sharp_ctx *parent = nullptr;
+    cudaEvent_t ev_ready = nullptr, ev_blocks = nullptr, ev_done = nullptr, ev_fork = nullptr;
+    int32_t *h_labels = nullptr;  // pinned label mirror of a group run
+    size_t h_labels_cap = 0;
+    int block_budget_gb = 48;     // cap of the distance-matrix workspace (D + Dw) of one context
     int64_t last_n = 0;     // state of the last run (for sharp_centroids)
     int last_p = 0;
     int last_K = 0;
@@ -177,7 +191,7 @@ int corrdist_tiles(int n);
 int launch_corrdist_batched(sharp_ctx *c, const GemmProb *probs_dev, const int *tile_prefix_dev, int nprob,
                             int total_tiles, int ldu);
 // ward.cu
-int launch_hclust(sharp_ctx *c, HcProb *probs_dev, int nprob, int max_n, int method);
+int launch_hclust(sharp_ctx *c, HcProb *probs_dev, int nprob, int max_n, int method, int fast = 0);
 // sweep.cu
 size_t sweep_nested_scratch_bytes(int max_n, int max_p, HcParamsDev prm);
 int launch_sweep_nested(sharp_ctx *c, HcProb *probs_dev, SweepOut *outs_dev, int nprob, int max_n, int max_p,

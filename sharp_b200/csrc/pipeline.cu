@@ -79,14 +79,28 @@ void DevBuf::release() {
 }  // namespace sharp
 
 int sharp_ctx::reserve_pinned(size_t bytes) {
-    if (bytes <= pinned_cap) return 0;
-    if (pinned) cudaFreeHost(pinned);
-    pinned = nullptr;
-    pinned_cap = 0;
-    size_t want = (bytes + (1 << 16) - 1) & ~(size_t)((1 << 16) - 1);
-    cudaError_t e = cudaMallocHost(&pinned, want);
-    if (e != cudaSuccess) return sharp::set_error(SHARP_E_NOMEM, "cudaMallocHost(%zu) failed: %s", want, cudaGetErrorString(e));
-    pinned_cap = want;
+    bytes = (std::max<size_t>(bytes, 8) + 255) & ~(size_t)255;
+    if (!arena || bytes > arena_cap) {
+        if (arena) {
+            cudaStreamSynchronize(stream);
+            cudaFreeHost(arena);
+        }
+        arena = nullptr;
+        arena_cap = arena_off = 0;
+        pinned = nullptr;
+        size_t want = std::max<size_t>((size_t)8 << 20, 2 * bytes);
+        cudaError_t e = cudaMallocHost((void **)&arena, want);
+        if (e != cudaSuccess) return sharp::set_error(SHARP_E_NOMEM, "cudaMallocHost(%zu) failed: %s", want, cudaGetErrorString(e));
+        arena_cap = want;
+    }
+    if (arena_off + bytes > arena_cap) { /* wrap: every copy staged so far must have completed */
+        cudaError_t e = cudaStreamSynchronize(stream);
+        if (e != cudaSuccess) return sharp::set_error(SHARP_E_CUDA, "cudaStreamSynchronize: %s", cudaGetErrorString(e));
+        arena_off = 0;
+    }
+    pinned = arena + arena_off;
+    pinned_cap = bytes;
+    arena_off += bytes;
     return 0;
 }
 
@@ -138,7 +152,7 @@ void prof_collect(sharp_ctx *c) {
 enum Slot {
     WS_SRC = 0, WS_COLSUM, WS_PROJ, WS_U, WS_D, WS_DW, WS_HC_INT, WS_HC_DBL, WS_DESC, WS_SWEEP_SCRATCH, WS_ENRP, WS_E1,
     WS_WM_INT, WS_WM_DBL, WS_WM_S, WS_WM_DESC, WS_WM_SCRATCH, WS_SM_INT, WS_SM_DBL, WS_SM_S, WS_SM_SCRATCH, WS_VIEU,
-    WS_LABELS, WS_X0, WS_TMP0, WS_TMP1, WS_TMP2, WS_TMP3, WS_START, WS_CEN, WS_EX_A, WS_EX_B, WS_EX_C, WS_COUNT
+    WS_LABELS, WS_X0, WS_TMP0, WS_TMP1, WS_TMP2, WS_TMP3, WS_START, WS_CEN, WS_EX_A, WS_EX_B, WS_EX_C, WS_GDESC, WS_COUNT
 };
 
 // bump allocator over a byte region
@@ -339,7 +353,6 @@ static int opt_hclust_dev(sharp_ctx *c, int nrow, int ncol, const double *mat_de
         int *tpd = db.take<int>(2);
         SHARP_TRY(h2d(c, c->ws[WS_DESC].ptr, c->pinned, hb.off));
         SHARP_TRY(launch_corrdist_batched(c, gpd, tpd, 1, tp[1], ldu));
-        SHARP_TRY(sync(c)); /* pinned staging is reused below */
         Y = U;
         yp = ncol;
         ldy = ldu;
@@ -369,14 +382,14 @@ static int opt_hclust_dev(sharp_ctx *c, int nrow, int ncol, const double *mat_de
     SweepOut *so = hb.take<SweepOut>(1);
     HcParamsDev *pp = hb.take<HcParamsDev>(1);
     hp->n = n; hp->ld = ld; hp->D = D; hp->Dw = Dw; hp->ia = ia; hp->ib = ib; hp->crit = R->crit;
-    hp->Y = Y; hp->p = yp; hp->ldy = ldy; hp->status = 0;
+    hp->Y = Y; hp->p = yp; hp->ldy = ldy; hp->status = 0; hp->fallback = 0;
     so->f = R->f; so->v = R->v; so->msil = R->msil; so->chind = R->chind; so->meta = R->meta; so->maxsil = R->maxsil;
     *pp = prm;
     HcProb *hpd = db.take<HcProb>(1);
     SweepOut *sod = db.take<SweepOut>(1);
     HcParamsDev *ppd = db.take<HcParamsDev>(1);
     SHARP_TRY(h2d(c, c->ws[WS_DESC].ptr, c->pinned, hb.off));
-    SHARP_TRY(launch_hclust(c, hpd, 1, n, prm.hmethod));
+    SHARP_TRY(launch_hclust(c, hpd, 1, n, prm.hmethod, symmetric ? 0 : 1));
     if (exact) {
         size_t sb = sweep_exact_scratch_bytes(n, yp);
         SHARP_TRY(c->ws[WS_SWEEP_SCRATCH].reserve(sb));
@@ -484,7 +497,6 @@ static int wmetac_dev(sharp_ctx *c, const int32_t *labels_dev, int64_t ncells, i
     SHARP_TRY(launch_sweep_exact(c, A.probs, W->outs_dev, T, capC, capC, W->prm_dev, maxlev, std::max(kcap, 2),
                                  c->ws[WS_WM_SCRATCH].as<double>(), sb));
     SHARP_TRY(launch_wmetac_vote(c, A, W->outs_dev, T));
-    SHARP_TRY(sync(c)); /* the pinned descriptor staging may be reused by the caller */
     return 0;
 }
 
@@ -570,7 +582,6 @@ static int smetac_dev(sharp_ctx *c, int capS, int p, const int *nc_ptr, const in
     SHARP_TRY(c->ws[WS_SM_SCRATCH].reserve(sb));
     SHARP_TRY(launch_sweep_exact(c, A.prob, B->out_dev, 1, ld, ld, A.prm_out, maxlev, kcap, c->ws[WS_SM_SCRATCH].as<double>(), sb));
     SHARP_TRY(launch_sm_finish(c, A, B->out_dev));
-    SHARP_TRY(sync(c));
     return 0;
 }
 
@@ -616,43 +627,74 @@ static void make_blocks(int64_t n, int large, int ng, std::vector<int64_t> &star
 }
 
 // =====================================================================================================
-// the fused SHARP_small / SHARP_large pipeline
+// the fused SHARP_small / SHARP_large pipeline, in phases
 // =====================================================================================================
-static int run_core(sharp_ctx *c, const sharp_expr_dev &e, const double *colsum_host, const sharp_rm_dev &rm,
-                    const int64_t *reind, const sharp_run_params &Q, int32_t *labels_out, double *vie_out, double *x0_out,
-                    int *x0_cols, int max_x0_cols) {
-    const int64_t n = e.n;
-    const int p = rm.p, K = rm.K;
-    Trace tr(c);
+// One matrix (or one part of SHARP_unlimited) goes through
+//   part_front   colSums, K1 projection, unit rows, per-problem output tables          (stream of the part's context)
+//   run_blocks   K2 distances, K3 agglomeration, K4-K6 sweep of ALL (member, block) problems of one or SEVERAL parts
+//                in shared launches                                                     (stream of the group context)
+//   part_back    colour wrap, enE/K, wMetaC per block, sMetaC over blocks, relabel, un-shuffle; statuses and labels are
+//                copied to pinned mirrors                                               (stream of the part's context)
+//   part_finish  the only host synchronisation: statuses -> R-style errors, x0 / viE outputs
+// Nothing between part_front and part_finish waits for the device, so the host can enqueue several parts (and the
+// next group) while the GPU works: the agglomeration kernel is latency-bound with one CTA per problem, and several
+// parts' problems in ONE launch are what fills the SMs (3-4 resident CTAs each instead of 0.85).
+struct PartRun {
+    sharp_ctx *c = nullptr;
+    sharp_expr_dev e;
+    const sharp_rm_dev *rm = nullptr;
+    sharp_run_params Q;
+    int64_t n = 0;
+    int p = 0, K = 0, T = 0, max_bn = 0, nprob = 0, ldu = 0, maxlev = 0, kcap_ind = 0;
+    bool shuffle = false, nested = true;
+    std::vector<int64_t> start;
+    int64_t *src_dev = nullptr, *start_dev = nullptr;
+    double *proj = nullptr, *U = nullptr, *E1 = nullptr, *vieu = nullptr;
+    int32_t *enrp = nullptr;
+    int *ia_all = nullptr, *ib_all = nullptr, *meta_all = nullptr;
+    double *crit_all = nullptr, *msil_all = nullptr, *chind_all = nullptr, *maxsil_all = nullptr;
+    HcParamsDev ind;
+    // back
+    WmBuffers W;
+    SmBuffers B;
+    int *labels_dev = nullptr, *coloff_dev = nullptr, *nc_dev = nullptr;
+    int *h_meta = nullptr, *h_wst = nullptr, *h_sst = nullptr, *h_nu = nullptr;  // pinned mirrors
+};
+
+static int part_front(PartRun &R, sharp_ctx *c, const sharp_expr_dev &e, const double *colsum_host,
+                      const sharp_rm_dev &rm, const int64_t *reind, const sharp_run_params &Q) {
+    R.c = c;
+    R.e = e;
+    R.rm = &rm;
+    R.Q = Q;
+    const int64_t n = R.n = e.n;
+    const int p = R.p = rm.p, K = R.K = rm.K;
     if (n < 2) return set_error(SHARP_E_ARG, "need at least 2 cells");
     if (n > 2000000000LL / std::max(1, K)) return set_error(SHARP_E_LIMIT, "too many cells for one call (%lld); split into parts", (long long)n);
-    std::vector<int64_t> start;
-    make_blocks(n, Q.large, Q.partition_ncells, start);
-    const int T = (int)start.size() - 1;
-    int max_bn = 0;
-    for (int t = 0; t < T; t++) max_bn = std::max<int>(max_bn, (int)(start[t + 1] - start[t]));
-    const bool shuffle = Q.large && reind && n < 100000;
+    make_blocks(n, Q.large, Q.partition_ncells, R.start);
+    const int T = R.T = (int)R.start.size() - 1;
+    R.max_bn = 0;
+    for (int t = 0; t < T; t++) R.max_bn = std::max<int>(R.max_bn, (int)(R.start[t + 1] - R.start[t]));
+    R.shuffle = Q.large && reind && n < 100000;
 
-    // ---- inputs: source column per position, column sums ----
-    int64_t *src_dev = nullptr;
-    if (shuffle) {
+    // ---- inputs: source column per position, block boundaries, column sums ----
+    R.src_dev = nullptr;
+    if (R.shuffle) {
         SHARP_TRY(c->ws[WS_SRC].reserve((size_t)n * 8));
-        src_dev = c->ws[WS_SRC].as<int64_t>();
+        R.src_dev = c->ws[WS_SRC].as<int64_t>();
         SHARP_TRY(c->reserve_pinned((size_t)n * 8));
         int64_t *hp = reinterpret_cast<int64_t *>(c->pinned);
         for (int64_t i = 0; i < n; i++) {
             if (reind[i] < 1 || reind[i] > n) return set_error(SHARP_E_ARG, "reind is not a permutation of 1..n");
             hp[i] = reind[i] - 1;
         }
-        SHARP_TRY(h2d(c, src_dev, hp, (size_t)n * 8));
-        SHARP_TRY(sync(c));
+        SHARP_TRY(h2d(c, R.src_dev, hp, (size_t)n * 8));
     }
     SHARP_TRY(c->ws[WS_START].reserve((size_t)(T + 1) * 8));
-    int64_t *start_dev = c->ws[WS_START].as<int64_t>();
+    R.start_dev = c->ws[WS_START].as<int64_t>();
     SHARP_TRY(c->reserve_pinned((size_t)(T + 1) * 8));
-    memcpy(c->pinned, start.data(), (size_t)(T + 1) * 8);
-    SHARP_TRY(h2d(c, start_dev, c->pinned, (size_t)(T + 1) * 8));
-    SHARP_TRY(sync(c));
+    memcpy(c->pinned, R.start.data(), (size_t)(T + 1) * 8);
+    SHARP_TRY(h2d(c, R.start_dev, c->pinned, (size_t)(T + 1) * 8));
     double *colsum_dev = nullptr;
     if (Q.normalize) {
         SHARP_TRY(c->ws[WS_COLSUM].reserve((size_t)n * 8));
@@ -667,215 +709,254 @@ static int run_core(sharp_ctx *c, const sharp_expr_dev &e, const double *colsum_
     // ---- K1: projection of every cell for all K members ----
     const size_t np = (size_t)n * p;
     SHARP_TRY(c->ws[WS_PROJ].reserve((size_t)K * np * 8));
-    double *proj = c->ws[WS_PROJ].as<double>();
-    tr.mark("setup", true);
-    SHARP_TRY(launch_rp_project(c, e, src_dev, n, colsum_dev, Q.normalize, Q.norm_mul, logkind, Q.round_digits, rm, proj));
-    tr.mark("rp", true);
+    R.proj = c->ws[WS_PROJ].as<double>();
+    SHARP_TRY(launch_rp_project(c, e, R.src_dev, n, colsum_dev, Q.normalize, Q.norm_mul, logkind, Q.round_digits, rm, R.proj));
 
     // ---- K2 input: unit rows ----
-    const int ldu = ldu_of(p);
+    const int ldu = R.ldu = ldu_of(p);
     SHARP_TRY(c->ws[WS_U].reserve((size_t)K * n * ldu * 8));
-    double *U = c->ws[WS_U].as<double>();
-    SHARP_TRY(launch_unit_rows(c, proj, (int64_t)K * n, p, ldu, U));
+    R.U = c->ws[WS_U].as<double>();
+    SHARP_TRY(launch_unit_rows(c, R.proj, (int64_t)K * n, p, ldu, R.U));
 
-    // ---- per-(member, block) clustering in waves ----
+    // ---- per-(member, block) problems: parameters and small output tables ----
     sharp_hc_params indp = Q.hc;
     indp.n_cluster = Q.ind_n_cluster;
-    HcParamsDev ind = to_dev(indp);
-    if (ind.n_cluster != 0 && ind.n_cluster < 2)
+    R.ind = to_dev(indp);
+    if (R.ind.n_cluster != 0 && R.ind.n_cluster < 2)
         return set_error(SHARP_E_RSTOP, "The given N.cluster is less than 2, which is not suitable for clustering!");
-    const int kcap_ind = ind.n_cluster ? ind.n_cluster : ind.max_n;
-    const bool nested = std::min(kcap_ind, max_bn - 1) <= NESTED_MAXK_HOST;
-    const int maxlev = ind.n_cluster ? 1 : std::max(1, ind.max_n - ind.min_n + 1);
-    const int nprob = K * T;
+    R.kcap_ind = R.ind.n_cluster ? R.ind.n_cluster : R.ind.max_n;
+    R.nested = std::min(R.kcap_ind, R.max_bn - 1) <= NESTED_MAXK_HOST;
+    const int maxlev = R.maxlev = R.ind.n_cluster ? 1 : std::max(1, R.ind.max_n - R.ind.min_n + 1);
+    const int nprob = R.nprob = K * T;
     SHARP_TRY(c->ws[WS_ENRP].reserve((size_t)K * n * 4));
-    int32_t *enrp = c->ws[WS_ENRP].as<int32_t>();
-    // per-problem small outputs
+    R.enrp = c->ws[WS_ENRP].as<int32_t>();
     size_t ibytes = bump_size({(size_t)K * n * 4, (size_t)K * n * 4, (size_t)nprob * 8 * 4});
     size_t dbytes = bump_size({(size_t)K * n * 8, (size_t)nprob * maxlev * 8, (size_t)nprob * maxlev * 8, (size_t)nprob * 8});
     SHARP_TRY(c->ws[WS_HC_INT].reserve(ibytes));
     SHARP_TRY(c->ws[WS_HC_DBL].reserve(dbytes));
     Bump bi(c->ws[WS_HC_INT].ptr, ibytes), bd(c->ws[WS_HC_DBL].ptr, dbytes);
-    int *ia_all = bi.take<int>((size_t)K * n), *ib_all = bi.take<int>((size_t)K * n);
-    int *meta_all = bi.take<int>((size_t)nprob * 8);
-    double *crit_all = bd.take<double>((size_t)K * n);
-    double *msil_all = bd.take<double>((size_t)nprob * maxlev);
-    double *chind_all = bd.take<double>((size_t)nprob * maxlev);
-    double *maxsil_all = bd.take<double>(nprob);
-    SHARP_CUDA(cudaMemsetAsync(meta_all, 0, (size_t)nprob * 8 * 4, c->stream));
+    R.ia_all = bi.take<int>((size_t)K * n);
+    R.ib_all = bi.take<int>((size_t)K * n);
+    R.meta_all = bi.take<int>((size_t)nprob * 8);
+    R.crit_all = bd.take<double>((size_t)K * n);
+    R.msil_all = bd.take<double>((size_t)nprob * maxlev);
+    R.chind_all = bd.take<double>((size_t)nprob * maxlev);
+    R.maxsil_all = bd.take<double>(nprob);
+    SHARP_CUDA(cudaMemsetAsync(R.meta_all, 0, (size_t)nprob * 8 * 4, c->stream));
+    return 0;
+}
+
+// K2-K6 for every (member, block) problem of the given parts, on the stream of `g`.  The distance matrices live in
+// g's workspace; the problems are processed in waves sized from the memory budget (normally one wave).
+static int run_blocks(sharp_ctx *g, PartRun *const *parts, int np_parts) {
+    if (np_parts <= 0) return 0;
+    const PartRun &R0 = *parts[0];
+    int nprob = 0, max_bn = 0;
+    for (int i = 0; i < np_parts; i++) {
+        const PartRun &R = *parts[i];
+        if (R.ldu != R0.ldu || R.p != R0.p || R.nested != R0.nested || R.maxlev != R0.maxlev || R.kcap_ind != R0.kcap_ind ||
+            R.ind.hmethod != R0.ind.hmethod)
+            return set_error(SHARP_E_ARG, "run_blocks: the parts of a group must share the ranM matrices and parameters");
+        nprob += R.nprob;
+        max_bn = std::max(max_bn, R.max_bn);
+    }
+    const int ldu = R0.ldu, p = R0.p;
+    const HcParamsDev ind = R0.ind;
     // wave size from the distance-matrix budget
     size_t free_b = 0, total_b = 0;
     SHARP_CUDA(cudaMemGetInfo(&free_b, &total_b));
-    size_t have = c->ws[WS_D].cap + c->ws[WS_DW].cap;
-    /* contexts on other streams of the same device run concurrently: share the free memory between them */
+    const size_t have = g->ws[WS_D].cap + g->ws[WS_DW].cap;
+    /* top-level contexts on other streams of the same device run concurrently: share the free memory between them */
     const int live = std::max(1, g_live_ctx.load());
-    size_t budget = std::min<size_t>((size_t)48 << 30, (size_t)(free_b * 0.6 / live) + have);
+    const size_t budget = std::min<size_t>((size_t)g->block_budget_gb << 30, (size_t)(free_b * 0.6 / live) + have);
     const size_t per_prob = (size_t)max_bn * ld_of(max_bn) * 8;
-    int wave_blocks = (int)std::max<size_t>(1, (budget / 2 / per_prob) / K);
-    wave_blocks = std::min(wave_blocks, T);
-    const int wave_probs = wave_blocks * K;
-    SHARP_TRY(c->ws[WS_D].reserve(per_prob * wave_probs));
-    SHARP_TRY(c->ws[WS_DW].reserve(per_prob * wave_probs));
-    double *Dall = c->ws[WS_D].as<double>(), *Dwall = c->ws[WS_DW].as<double>();
-    size_t sweep_scr = nested ? sweep_nested_scratch_bytes(max_bn, ldu, ind) : sweep_exact_scratch_bytes(max_bn, ldu);
-    SHARP_TRY(c->ws[WS_SWEEP_SCRATCH].reserve(sweep_scr * wave_probs));
-    // descriptors of ALL problems, built once
-    size_t desc = bump_size({(size_t)nprob * sizeof(GemmProb), (size_t)(nprob + T + 2) * 4, (size_t)nprob * sizeof(HcProb),
+    const int wave_probs = (int)std::min<size_t>((size_t)nprob, std::max<size_t>(1, budget / 2 / per_prob));
+    SHARP_TRY(g->ws[WS_D].reserve(per_prob * wave_probs));
+    SHARP_TRY(g->ws[WS_DW].reserve(per_prob * wave_probs));
+    double *Dall = g->ws[WS_D].as<double>(), *Dwall = g->ws[WS_DW].as<double>();
+    const size_t sweep_scr = R0.nested ? sweep_nested_scratch_bytes(max_bn, ldu, ind) : sweep_exact_scratch_bytes(max_bn, ldu);
+    SHARP_TRY(g->ws[WS_SWEEP_SCRATCH].reserve(sweep_scr * wave_probs));
+    // descriptors of ALL problems (part-major, then block, then member), built once
+    const int nwaves = (nprob + wave_probs - 1) / wave_probs;
+    size_t desc = bump_size({(size_t)nprob * sizeof(GemmProb), (size_t)(nprob + nwaves + 2) * 4, (size_t)nprob * sizeof(HcProb),
                              (size_t)nprob * sizeof(SweepOut), (size_t)nprob * sizeof(HcParamsDev)});
-    SHARP_TRY(c->reserve_pinned(desc));
-    SHARP_TRY(c->ws[WS_DESC].reserve(desc));
-    Bump hb(c->pinned, desc), db(c->ws[WS_DESC].ptr, desc);
+    SHARP_TRY(g->reserve_pinned(desc));
+    SHARP_TRY(g->ws[WS_GDESC].reserve(desc));
+    Bump hb(g->pinned, desc), db(g->ws[WS_GDESC].ptr, desc);
     GemmProb *gp = hb.take<GemmProb>(nprob);
-    int *tp = hb.take<int>(nprob + T + 2);
+    int *tp = hb.take<int>(nprob + nwaves + 2);
     HcProb *hp = hb.take<HcProb>(nprob);
     SweepOut *so = hb.take<SweepOut>(nprob);
     HcParamsDev *pp = hb.take<HcParamsDev>(nprob);
     GemmProb *gpd = db.take<GemmProb>(nprob);
-    int *tpd = db.take<int>(nprob + T + 2);
+    int *tpd = db.take<int>(nprob + nwaves + 2);
     HcProb *hpd = db.take<HcProb>(nprob);
     SweepOut *sod = db.take<SweepOut>(nprob);
     HcParamsDev *ppd = db.take<HcParamsDev>(nprob);
     struct Wave { int q0, nq, tiles, tp_off; };
     std::vector<Wave> waves;
     {
-        int q = 0, tpo = 0;
-        for (int t0 = 0; t0 < T; t0 += wave_blocks) {
-            int t1 = std::min(T, t0 + wave_blocks);
-            Wave w;
-            w.q0 = q;
-            w.tp_off = tpo;
-            int tiles = 0, slot = 0;
-            tp[tpo] = 0;
-            for (int t = t0; t < t1; t++)
-                for (int k = 0; k < K; k++) {
-                    int nq = (int)(start[t + 1] - start[t]);
-                    int ld = ld_of(nq);
-                    size_t row0 = (size_t)k * n + start[t];
-                    gp[q].U = U + row0 * ldu;
+        int q = 0;
+        for (int i = 0; i < np_parts; i++) {
+            const PartRun &R = *parts[i];
+            for (int t = 0; t < R.T; t++)
+                for (int k = 0; k < R.K; k++) {
+                    const int nq = (int)(R.start[t + 1] - R.start[t]);
+                    const int ld = ld_of(nq);
+                    const int slot = q % wave_probs;
+                    const size_t row0 = (size_t)k * R.n + R.start[t];
+                    const int ql = t * R.K + k; /* index of the problem inside its part */
+                    gp[q].U = R.U + row0 * ldu;
                     gp[q].n = nq;
                     gp[q].ld = ld;
                     gp[q].D = Dall + (size_t)slot * (per_prob / 8);
                     gp[q].Dw = Dwall + (size_t)slot * (per_prob / 8);
-                    tiles += corrdist_tiles(nq);
-                    tp[tpo + slot + 1] = tiles;
                     hp[q].n = nq; hp[q].ld = ld; hp[q].D = gp[q].D; hp[q].Dw = gp[q].Dw;
-                    hp[q].ia = ia_all + row0; hp[q].ib = ib_all + row0; hp[q].crit = crit_all + row0;
-                    hp[q].Y = gp[q].U; hp[q].p = p; hp[q].ldy = ldu; hp[q].status = 0;
-                    so[q].f = enrp + row0; so[q].v = nullptr;
-                    so[q].msil = msil_all + (size_t)q * maxlev; so[q].chind = chind_all + (size_t)q * maxlev;
-                    so[q].meta = meta_all + (size_t)q * 8; so[q].maxsil = maxsil_all + q;
+                    hp[q].ia = R.ia_all + row0; hp[q].ib = R.ib_all + row0; hp[q].crit = R.crit_all + row0;
+                    hp[q].Y = gp[q].U; hp[q].p = p; hp[q].ldy = ldu; hp[q].status = 0; hp[q].fallback = 0;
+                    so[q].f = R.enrp + row0; so[q].v = nullptr;
+                    so[q].msil = R.msil_all + (size_t)ql * R.maxlev; so[q].chind = R.chind_all + (size_t)ql * R.maxlev;
+                    so[q].meta = R.meta_all + (size_t)ql * 8; so[q].maxsil = R.maxsil_all + ql;
                     pp[q] = ind;
                     q++;
-                    slot++;
                 }
-            w.nq = q - w.q0;
+        }
+        int tpo = 0;
+        for (int q0 = 0; q0 < nprob; q0 += wave_probs) {
+            Wave w;
+            w.q0 = q0;
+            w.nq = std::min(wave_probs, nprob - q0);
+            w.tp_off = tpo;
+            int tiles = 0;
+            tp[tpo] = 0;
+            for (int j = 0; j < w.nq; j++) {
+                tiles += corrdist_tiles(gp[q0 + j].n);
+                tp[tpo + j + 1] = tiles;
+            }
             w.tiles = tiles;
             tpo += w.nq + 1;
             waves.push_back(w);
         }
     }
-    SHARP_TRY(h2d(c, c->ws[WS_DESC].ptr, c->pinned, hb.off));
-    tr.mark("desc", true);
+    SHARP_TRY(h2d(g, g->ws[WS_GDESC].ptr, g->pinned, hb.off));
     for (const Wave &w : waves) {
-        SHARP_TRY(launch_corrdist_batched(c, gpd + w.q0, tpd + w.tp_off, w.nq, w.tiles, ldu));
-        SHARP_TRY(launch_hclust(c, hpd + w.q0, w.nq, max_bn, ind.hmethod));
-        if (nested)
-            SHARP_TRY(launch_sweep_nested(c, hpd + w.q0, sod + w.q0, w.nq, max_bn, ldu, ind, c->ws[WS_SWEEP_SCRATCH].as<double>(), sweep_scr));
+        SHARP_TRY(launch_corrdist_batched(g, gpd + w.q0, tpd + w.tp_off, w.nq, w.tiles, ldu));
+        SHARP_TRY(launch_hclust(g, hpd + w.q0, w.nq, max_bn, ind.hmethod, 1));
+        if (R0.nested)
+            SHARP_TRY(launch_sweep_nested(g, hpd + w.q0, sod + w.q0, w.nq, max_bn, ldu, ind, g->ws[WS_SWEEP_SCRATCH].as<double>(), sweep_scr));
         else
-            SHARP_TRY(launch_sweep_exact(c, hpd + w.q0, sod + w.q0, w.nq, max_bn, p, ppd + w.q0, maxlev, std::max(kcap_ind, 2),
-                                         c->ws[WS_SWEEP_SCRATCH].as<double>(), sweep_scr));
+            SHARP_TRY(launch_sweep_exact(g, hpd + w.q0, sod + w.q0, w.nq, max_bn, p, ppd + w.q0, R0.maxlev, std::max(R0.kcap_ind, 2),
+                                         g->ws[WS_SWEEP_SCRATCH].as<double>(), sweep_scr));
     }
+    return 0;
+}
+
+// everything after the block clusterings, without waiting for the device
+static int part_back(PartRun &R) {
+    sharp_ctx *c = R.c;
+    const int64_t n = R.n;
+    const int p = R.p, K = R.K, T = R.T, nprob = R.nprob;
+    const size_t np = (size_t)n * p;
+    const sharp_run_params &Q = R.Q;
     prof_begin(c, KID_MISC);
-    tr.mark("blocks", true);
-    colour_wrap_kernel<<<grid1d((size_t)K * n, 256), 256, 0, c->stream>>>(enrp, (int64_t)K * n);
+    colour_wrap_kernel<<<grid1d((size_t)K * n, 256), 256, 0, c->stream>>>(R.enrp, (int64_t)K * n);
     prof_end(c);
     // ---- enE / K ----
     SHARP_TRY(c->ws[WS_E1].reserve(np * 8));
-    double *E1 = c->ws[WS_E1].as<double>();
+    R.E1 = c->ws[WS_E1].as<double>();
     prof_begin(c, KID_ENE);
-    ene_kernel<<<grid1d(np, 256), 256, 0, c->stream>>>(proj, (int64_t)np, K, E1);
+    ene_kernel<<<grid1d(np, 256), 256, 0, c->stream>>>(R.proj, (int64_t)np, K, R.E1);
     prof_end(c);
-    // status of the block problems (also makes the pinned staging reusable)
-    {
-        std::vector<int> meta((size_t)nprob * 8);
-        SHARP_TRY(d2h(c, meta.data(), meta_all, meta.size() * 4));
-        SHARP_TRY(sync(c));
-        for (int q = 0; q < nprob; q++)
-            if (meta[(size_t)q * 8 + 3] != 0) return rstop(meta[(size_t)q * 8 + 3], "getrowColor (block clustering)");
-    }
-
-    tr.mark("ene+status", true);
+    // pinned mirrors of every status word of this run (read by part_finish)
+    SHARP_TRY(c->reserve_pinned(((size_t)nprob * 8 + T + 8) * 4));
+    R.h_meta = reinterpret_cast<int *>(c->pinned);
+    R.h_wst = R.h_meta + (size_t)nprob * 8;
+    R.h_sst = R.h_wst + T;
+    R.h_nu = R.h_sst + 1;
+    R.h_sst[0] = 0;
+    R.h_nu[0] = 0;
+    SHARP_TRY(d2h(c, R.h_meta, R.meta_all, (size_t)nprob * 8 * 4));
     // ---- wMetaC per block ----
     sharp_hc_params wp = Q.hc;
     wp.n_cluster = Q.large ? Q.enp_n_cluster : Q.n_cluster;
-    WmBuffers W;
-    SHARP_TRY(wmetac_dev(c, enrp, n, K, T, start.data(), start_dev, 40, wp, &W));
-    {
-        std::vector<int> st(T);
-        SHARP_TRY(d2h(c, st.data(), W.A.status, (size_t)T * 4));
-        SHARP_TRY(sync(c));
-        for (int t = 0; t < T; t++)
-            if (st[t] != 0) return rstop(st[t], "wMetaC");
-    }
-
-    tr.mark("wmetac", true);
+    SHARP_TRY(wmetac_dev(c, R.enrp, n, K, T, R.start.data(), R.start_dev, 40, wp, &R.W));
+    SHARP_TRY(d2h(c, R.h_wst, R.W.A.status, (size_t)T * 4));
     // ---- labels / sMetaC ----
     SHARP_TRY(c->ws[WS_LABELS].reserve((size_t)n * 4));
-    int *labels_dev = c->ws[WS_LABELS].as<int>();
-    int ncol_x0 = 0;
-    std::vector<int> colmap_host;
-    int *coloff_dev = nullptr, *colmap_dev = nullptr;
+    R.labels_dev = c->ws[WS_LABELS].as<int>();
+    R.coloff_dev = nullptr;
+    R.nc_dev = nullptr;
     if (T == 1) {
-        if (!Q.large) SHARP_TRY(launch_sm_relabel(c, n, W.A.finalc, nullptr, 0, src_dev, labels_dev)); /* finalC ids */
-        else SHARP_TRY(launch_sm_relabel(c, n, W.A.fcode, nullptr, 1, src_dev, labels_dev)); /* position in unique(fColor) */
-        int nu = 0;
-        SHARP_TRY(d2h(c, &nu, W.A.ucount, 4));
-        SHARP_TRY(sync(c));
-        ncol_x0 = nu;
+        if (!Q.large) SHARP_TRY(launch_sm_relabel(c, n, R.W.A.finalc, nullptr, 0, R.src_dev, R.labels_dev)); /* finalC ids */
+        else SHARP_TRY(launch_sm_relabel(c, n, R.W.A.fcode, nullptr, 1, R.src_dev, R.labels_dev)); /* position in unique(fColor) */
+        SHARP_TRY(d2h(c, R.h_nu, R.W.A.ucount, 4));
     } else {
-        const int capS = T * W.A.capU;
+        const int capS = T * R.W.A.capU;
         size_t ib2 = bump_size({(size_t)(T + 1) * 4, 64, 64, (size_t)n * 4, (size_t)n * 4, (size_t)(capS + 1) * 4});
         SHARP_TRY(c->ws[WS_TMP0].reserve(ib2));
         Bump b2(c->ws[WS_TMP0].ptr, ib2);
-        coloff_dev = b2.take<int>(T + 1);
-        int *nc_dev = b2.take<int>(1);
+        R.coloff_dev = b2.take<int>(T + 1);
+        R.nc_dev = b2.take<int>(1);
         int *st_dev = b2.take<int>(1);
         int *code = b2.take<int>(n);
         int *corder = b2.take<int>(n);
         int *coff = b2.take<int>(capS + 1);
-        SHARP_TRY(launch_sm_codes(c, W.A, T, coloff_dev, nc_dev, st_dev, code, corder, coff));
+        SHARP_TRY(launch_sm_codes(c, R.W.A, T, R.coloff_dev, R.nc_dev, st_dev, code, corder, coff));
         sharp_hc_params sp = Q.hc;
         sp.n_cluster = Q.n_cluster;
-        SmBuffers B;
-        SHARP_TRY(smetac_dev(c, capS, p, nc_dev, st_dev, E1, corder, coff, nullptr, n, sp, &B));
-        int st = 0;
-        SHARP_TRY(d2h(c, &st, B.status, 4));
+        SHARP_TRY(smetac_dev(c, capS, p, R.nc_dev, st_dev, R.E1, corder, coff, nullptr, n, sp, &R.B));
+        SHARP_TRY(d2h(c, R.h_sst, R.B.status, 4));
+        SHARP_TRY(launch_sm_relabel(c, n, code, R.B.tf, 0, R.src_dev, R.labels_dev));
+    }
+    // viE = enE/K, un-shuffled; kept on the device for sharp_centroids
+    SHARP_TRY(c->ws[WS_VIEU].reserve(np * 8));
+    R.vieu = c->ws[WS_VIEU].as<double>();
+    prof_begin(c, KID_ENE);
+    scatter_rows_kernel<<<(unsigned)n, 128, 0, c->stream>>>(R.E1, n, p, R.src_dev, R.vieu);
+    prof_end(c);
+    c->last_n = n;
+    c->last_p = p;
+    c->last_K = K;
+    return 0;
+}
+
+// statuses -> errors (after the caller synchronised the part's stream)
+static int part_status(const PartRun &R) {
+    for (int q = 0; q < R.nprob; q++)
+        if (R.h_meta[(size_t)q * 8 + 3] != 0) return rstop(R.h_meta[(size_t)q * 8 + 3], "getrowColor (block clustering)");
+    for (int t = 0; t < R.T; t++)
+        if (R.h_wst[t] != 0) return rstop(R.h_wst[t], "wMetaC");
+    if (R.h_sst[0] != 0) return rstop(R.h_sst[0], "sMetaC");
+    return 0;
+}
+
+static int part_finish(PartRun &R, int32_t *labels_out, double *vie_out, double *x0_out, int *x0_cols, int max_x0_cols) {
+    sharp_ctx *c = R.c;
+    const int64_t n = R.n;
+    const int p = R.p, T = R.T;
+    SHARP_TRY(d2h(c, labels_out, R.labels_dev, (size_t)n * 4));
+    SHARP_TRY(sync(c));
+    SHARP_TRY(part_status(R));
+    int ncol_x0 = 0;
+    std::vector<int> colmap_host;
+    if (T == 1) ncol_x0 = R.h_nu[0];
+    else if (x0_out || x0_cols) {
+        int nC = 0;
+        SHARP_TRY(d2h(c, &nC, R.nc_dev, 4));
         SHARP_TRY(sync(c));
-        if (st != 0) return rstop(st, "sMetaC");
-        SHARP_TRY(launch_sm_relabel(c, n, code, B.tf, 0, src_dev, labels_dev));
-        colmap_dev = B.tf;
-        if (x0_out || x0_cols) {
-            int nC = 0;
-            SHARP_TRY(d2h(c, &nC, nc_dev, 4));
-            SHARP_TRY(sync(c));
-            colmap_host.resize(nC);
-            SHARP_TRY(d2h(c, colmap_host.data(), B.tf, (size_t)nC * 4));
-            SHARP_TRY(sync(c));
-            for (int v : colmap_host) ncol_x0 = std::max(ncol_x0, v);
-        }
+        colmap_host.resize(nC);
+        SHARP_TRY(d2h(c, colmap_host.data(), R.B.tf, (size_t)nC * 4));
+        SHARP_TRY(sync(c));
+        for (int v : colmap_host) ncol_x0 = std::max(ncol_x0, v);
     }
     if (x0_cols) *x0_cols = ncol_x0;
-
-    tr.mark("smetac", true);
-    // ---- outputs ----
-    SHARP_TRY(d2h(c, labels_out, labels_dev, (size_t)n * 4));
     if (x0_out) {
         if (ncol_x0 > max_x0_cols) return set_error(SHARP_E_NOMEM, "x0 needs %d columns but the buffer has %d", ncol_x0, max_x0_cols);
         SHARP_TRY(c->ws[WS_X0].reserve((size_t)n * ncol_x0 * 8));
         double *x0d = c->ws[WS_X0].as<double>();
         SHARP_CUDA(cudaMemsetAsync(x0d, 0, (size_t)n * ncol_x0 * 8, c->stream));
         if (T == 1) {
-            SHARP_TRY(launch_wmetac_x0(c, W.A, W.outs_dev, T, W.max_block_n, nullptr, nullptr, src_dev, x0d, ncol_x0));
+            SHARP_TRY(launch_wmetac_x0(c, R.W.A, R.W.outs_dev, T, R.W.max_block_n, nullptr, nullptr, R.src_dev, x0d, ncol_x0));
         } else {
             /* colmap = tf - 1 (0-based output column of every block-level cluster) */
             SHARP_TRY(c->ws[WS_TMP1].reserve(colmap_host.size() * 4 + 64));
@@ -884,23 +965,210 @@ static int run_core(sharp_ctx *c, const sharp_expr_dev &e, const double *colsum_
             SHARP_TRY(c->reserve_pinned(colmap_host.size() * 4 + 64));
             memcpy(c->pinned, colmap_host.data(), colmap_host.size() * 4);
             SHARP_TRY(h2d(c, cm, c->pinned, colmap_host.size() * 4));
-            SHARP_TRY(launch_wmetac_x0(c, W.A, W.outs_dev, T, W.max_block_n, coloff_dev, cm, src_dev, x0d, ncol_x0));
+            SHARP_TRY(launch_wmetac_x0(c, R.W.A, R.W.outs_dev, T, R.W.max_block_n, R.coloff_dev, cm, R.src_dev, x0d, ncol_x0));
         }
         SHARP_TRY(d2h(c, x0_out, x0d, (size_t)n * ncol_x0 * 8));
     }
-    // viE = enE/K, un-shuffled; kept on the device for sharp_centroids
-    SHARP_TRY(c->ws[WS_VIEU].reserve(np * 8));
-    double *vieu = c->ws[WS_VIEU].as<double>();
-    prof_begin(c, KID_ENE);
-    scatter_rows_kernel<<<(unsigned)n, 128, 0, c->stream>>>(E1, n, p, src_dev, vieu);
-    prof_end(c);
-    c->last_n = n;
-    c->last_p = p;
-    c->last_K = K;
-    if (vie_out) SHARP_TRY(d2h(c, vie_out, vieu, np * 8));
+    if (vie_out) SHARP_TRY(d2h(c, vie_out, R.vieu, (size_t)n * p * 8));
     SHARP_TRY(sync(c));
-    tr.mark("outputs");
-    (void)colmap_dev;
+    return 0;
+}
+
+static int run_core(sharp_ctx *c, const sharp_expr_dev &e, const double *colsum_host, const sharp_rm_dev &rm,
+                    const int64_t *reind, const sharp_run_params &Q, int32_t *labels_out, double *vie_out, double *x0_out,
+                    int *x0_cols, int max_x0_cols) {
+    Trace tr(c);
+    PartRun R;
+    SHARP_TRY(part_front(R, c, e, colsum_host, rm, reind, Q));
+    tr.mark("front", true);
+    PartRun *one = &R;
+    SHARP_TRY(run_blocks(c, &one, 1));
+    tr.mark("blocks", true);
+    SHARP_TRY(part_back(R));
+    tr.mark("back", true);
+    SHARP_TRY(part_finish(R, labels_out, vie_out, x0_out, x0_cols, max_x0_cols));
+    tr.mark("finish");
+    return 0;
+}
+
+// =====================================================================================================
+// SHARP_unlimited's loop over parts as ONE call: groups of parts share the block-clustering launches
+// =====================================================================================================
+static int make_child(sharp_ctx *parent, sharp_ctx **out) {
+    sharp_ctx *c = new sharp_ctx();
+    c->device = parent->device;
+    c->sm_count = parent->sm_count;
+    c->parent = parent;
+    c->rp_legacy = parent->rp_legacy;
+    c->block_budget_gb = parent->block_budget_gb;
+    cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_ready, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_blocks, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_done, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreate(&c->ev0);
+    if (e == cudaSuccess) e = cudaEventCreate(&c->ev1);
+    if (e != cudaSuccess) {
+        delete c;
+        return set_error(SHARP_E_CUDA, "creating a sub-context: %s", cudaGetErrorString(e));
+    }
+    c->prof_on = parent->prof_on;
+    *out = c;
+    return 0;
+}
+
+void destroy_ctx_resources(sharp_ctx *c) {
+    for (sharp_ctx *s : c->subs) {
+        destroy_ctx_resources(s);
+        delete s;
+    }
+    c->subs.clear();
+    cudaStreamSynchronize(c->stream);
+    prof_collect(c);
+    for (cudaEvent_t e : c->prof_pool) cudaEventDestroy(e);
+    c->prof_pool.clear();
+    for (auto &b : c->ws) b.release();
+    if (c->arena) cudaFreeHost(c->arena);
+    if (c->h_labels) cudaFreeHost(c->h_labels);
+    c->arena = nullptr;
+    c->h_labels = nullptr;
+    if (c->ev0) cudaEventDestroy(c->ev0);
+    if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->ev_ready) cudaEventDestroy(c->ev_ready);
+    if (c->ev_blocks) cudaEventDestroy(c->ev_blocks);
+    if (c->ev_done) cudaEventDestroy(c->ev_done);
+    if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+    cudaStreamDestroy(c->stream);
+}
+
+// R/SHARP.R:816-843 on the labels of one part: clusters with fewer than `thre` cells are merged into the smallest such
+// id, then clusterID = match(y, unique(y)).  Returns the number of clusters; lab is rewritten in place (1-based).
+static int host_merge_relabel(int32_t *lab, int64_t n, int thre, std::vector<int> &coff, std::vector<int> &corder) {
+    int mx = 0;
+    for (int64_t i = 0; i < n; i++) mx = std::max(mx, lab[i]);
+    std::vector<int64_t> cnt((size_t)mx + 1, 0);
+    for (int64_t i = 0; i < n; i++) cnt[lab[i]]++;
+    if (thre > 0) {
+        int smallest = 0;
+        for (int v = 1; v <= mx; v++)
+            if (cnt[v] > 0 && cnt[v] < thre) { smallest = v; break; }
+        if (smallest)
+            for (int64_t i = 0; i < n; i++)
+                if (cnt[lab[i]] < thre) lab[i] = smallest;
+    }
+    std::vector<int> code((size_t)mx + 1, 0);
+    int next = 0;
+    for (int64_t i = 0; i < n; i++) {
+        int &cd = code[lab[i]];
+        if (!cd) cd = ++next;
+        lab[i] = cd;
+    }
+    coff.assign((size_t)next + 1, 0);
+    for (int64_t i = 0; i < n; i++) coff[lab[i]]++;
+    for (int q = 0; q < next; q++) coff[q + 1] += coff[q];
+    corder.resize(n);
+    std::vector<int> fill(coff.begin(), coff.end() - 1);
+    for (int64_t i = 0; i < n; i++) corder[fill[lab[i] - 1]++] = (int)i;
+    return next;
+}
+
+struct GroupRun {
+    std::vector<int> idx;          // part indices
+    std::vector<PartRun> runs;
+    sharp_ctx *blocks = nullptr;
+    std::vector<sharp_ctx *> subs;
+    // centroid staging per part
+    std::vector<int> nclust;
+    std::vector<double *> h_cen;
+    std::vector<int64_t *> h_cnt;
+};
+
+static int group_issue(GroupRun &G, sharp_part *parts, int m, const sharp_rm_dev &rm, const sharp_run_params &Q) {
+    const int np = (int)G.idx.size();
+    G.runs.assign(np, PartRun());
+    for (int j = 0; j < np; j++) {
+        sharp_part &P = parts[G.idx[j]];
+        sharp_ctx *s = G.subs[j];
+        sharp_expr_dev e;
+        if (P.dev) {
+            e = *P.dev;
+            e.owned = false;
+        } else SHARP_TRY(upload_expr(s, m, P.n, P.dense, P.colptr, P.rowidx, P.val, &e, true));
+        if (e.m != rm.m) return set_error(SHARP_E_ARG, "run_parts: part %d has %d genes but ranM has %d rows", G.idx[j], e.m, rm.m);
+        SHARP_TRY(part_front(G.runs[j], s, e, nullptr, rm, P.reind, Q));
+        SHARP_CUDA(cudaEventRecord(s->ev_ready, s->stream));
+    }
+    for (int j = 0; j < np; j++) SHARP_CUDA(cudaStreamWaitEvent(G.blocks->stream, G.subs[j]->ev_ready, 0));
+    std::vector<PartRun *> ptrs(np);
+    for (int j = 0; j < np; j++) ptrs[j] = &G.runs[j];
+    SHARP_TRY(run_blocks(G.blocks, ptrs.data(), np));
+    SHARP_CUDA(cudaEventRecord(G.blocks->ev_blocks, G.blocks->stream));
+    for (int j = 0; j < np; j++) {
+        sharp_ctx *s = G.subs[j];
+        PartRun &R = G.runs[j];
+        SHARP_CUDA(cudaStreamWaitEvent(s->stream, G.blocks->ev_blocks, 0));
+        SHARP_TRY(part_back(R));
+        if ((size_t)R.n * 4 > s->h_labels_cap) {
+            if (s->h_labels) cudaFreeHost(s->h_labels);
+            s->h_labels = nullptr;
+            s->h_labels_cap = 0;
+            size_t want = ((size_t)R.n * 4 * 9 / 8 + 4095) & ~(size_t)4095;
+            SHARP_CUDA(cudaMallocHost((void **)&s->h_labels, want));
+            s->h_labels_cap = want;
+        }
+        SHARP_TRY(d2h(s, s->h_labels, R.labels_dev, (size_t)R.n * 4));
+        SHARP_CUDA(cudaEventRecord(s->ev_done, s->stream));
+    }
+    return 0;
+}
+
+static int group_complete(GroupRun &G, sharp_part *parts, int small_thre, int cen_cap) {
+    const int np = (int)G.idx.size();
+    G.nclust.assign(np, 0);
+    G.h_cen.assign(np, nullptr);
+    G.h_cnt.assign(np, nullptr);
+    std::vector<int> coff, corder;
+    for (int j = 0; j < np; j++) {
+        sharp_part &P = parts[G.idx[j]];
+        sharp_ctx *s = G.subs[j];
+        PartRun &R = G.runs[j];
+        SHARP_CUDA(cudaEventSynchronize(s->ev_done));
+        SHARP_TRY(part_status(R));
+        memcpy(P.pred, s->h_labels, (size_t)R.n * 4);
+        const int thre = (R.Q.n_cluster == 0 && R.n > 10000) ? small_thre : 0;
+        const int nclust = host_merge_relabel(P.pred, R.n, thre, coff, corder);
+        G.nclust[j] = nclust;
+        P.nclust = nclust;
+        if (!P.cen) continue;
+        if (nclust > cen_cap) return set_error(SHARP_E_NOMEM, "run_parts: part %d has %d clusters but cen has room for %d", G.idx[j], nclust, cen_cap);
+        // centroids of viE per final cluster (colMeans of R/sMetaC.R:58-63 for the global sMetaC)
+        const size_t ib = bump_size({(size_t)R.n * 4, (size_t)(nclust + 1) * 4, 64, (size_t)nclust * 8});
+        SHARP_TRY(s->ws[WS_TMP0].reserve(ib));
+        Bump b(s->ws[WS_TMP0].ptr, ib);
+        int *corder_d = b.take<int>(R.n), *coff_d = b.take<int>(nclust + 1), *nc_d = b.take<int>(1);
+        int64_t *cnt_d = b.take<int64_t>(nclust);
+        SHARP_TRY(s->ws[WS_CEN].reserve((size_t)nclust * R.p * 8));
+        SHARP_TRY(s->reserve_pinned((size_t)R.n * 4 + (size_t)(nclust + 2) * 4));
+        int *hp = reinterpret_cast<int *>(s->pinned);
+        memcpy(hp, corder.data(), (size_t)R.n * 4);
+        memcpy(hp + R.n, coff.data(), (size_t)(nclust + 1) * 4);
+        hp[R.n + nclust + 1] = nclust;
+        SHARP_TRY(h2d(s, corder_d, hp, (size_t)R.n * 4));
+        SHARP_TRY(h2d(s, coff_d, hp + R.n, (size_t)(nclust + 1) * 4));
+        SHARP_TRY(h2d(s, nc_d, hp + R.n + nclust + 1, 4));
+        SHARP_TRY(launch_sm_centroids(s, R.vieu, R.p, corder_d, coff_d, nc_d, nclust, s->ws[WS_CEN].as<double>(), cnt_d));
+        SHARP_TRY(s->reserve_pinned((size_t)nclust * R.p * 8 + (size_t)nclust * 8));
+        G.h_cen[j] = reinterpret_cast<double *>(s->pinned);
+        G.h_cnt[j] = reinterpret_cast<int64_t *>(G.h_cen[j] + (size_t)nclust * R.p);
+        SHARP_TRY(d2h(s, G.h_cen[j], s->ws[WS_CEN].ptr, (size_t)nclust * R.p * 8));
+        SHARP_TRY(d2h(s, G.h_cnt[j], cnt_d, (size_t)nclust * 8));
+    }
+    for (int j = 0; j < np; j++) {
+        sharp_part &P = parts[G.idx[j]];
+        sharp_ctx *s = G.subs[j];
+        SHARP_TRY(sync(s));
+        if (P.cen) memcpy(P.cen, G.h_cen[j], (size_t)G.nclust[j] * G.runs[j].p * 8);
+        if (P.counts) memcpy(P.counts, G.h_cnt[j], (size_t)G.nclust[j] * 8);
+    }
     return 0;
 }
 
@@ -958,6 +1226,7 @@ int sharp_ctx_create(int device, sharp_ctx **out) {
     SHARP_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     SHARP_CUDA(cudaEventCreate(&c->ev0));
     SHARP_CUDA(cudaEventCreate(&c->ev1));
+    SHARP_CUDA(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
     *out = c;
     g_live_ctx++;
     return 0;
@@ -967,14 +1236,7 @@ void sharp_ctx_destroy(sharp_ctx *c) {
     if (!c) return;
     g_live_ctx--;
     cudaSetDevice(c->device);
-    cudaStreamSynchronize(c->stream);
-    prof_collect(c);
-    for (cudaEvent_t e : c->prof_pool) cudaEventDestroy(e);
-    for (auto &b : c->ws) b.release();
-    if (c->pinned) cudaFreeHost(c->pinned);
-    cudaEventDestroy(c->ev0);
-    cudaEventDestroy(c->ev1);
-    cudaStreamDestroy(c->stream);
+    destroy_ctx_resources(c);
     delete c;
 }
 
@@ -997,7 +1259,17 @@ int sharp_timer_stop_ms(sharp_ctx *c, double *ms) {
     if (ms) *ms = f;
     return 0;
 }
-int64_t sharp_ctx_launch_count(sharp_ctx *c) { return c ? c->launches : 0; }
+int64_t sharp_ctx_launch_count(sharp_ctx *c) {
+    if (!c) return 0;
+    int64_t n = c->launches;
+    for (sharp_ctx *s : c->subs) n += s->launches;
+    return n;
+}
+int sharp_ctx_set_block_budget(sharp_ctx *c, int gigabytes) {
+    if (!c || gigabytes < 1) return set_error(SHARP_E_ARG, "set_block_budget: bad arguments");
+    c->block_budget_gb = gigabytes;
+    return 0;
+}
 
 static const char *const g_kernel_names[KID_COUNT] = {
     "rp_project", "colsum", "unit_rows", "corrdist", "hclust", "hclust_small", "sweep_nested", "sweep_exact",
@@ -1013,12 +1285,17 @@ int sharp_prof_enable(sharp_ctx *c, int on) {
     SHARP_TRY(use(c));
     prof_collect(c);
     c->prof_on = on != 0;
+    for (sharp_ctx *s : c->subs) { prof_collect(s); s->prof_on = on != 0; }
     return 0;
 }
 int sharp_prof_reset(sharp_ctx *c) {
     SHARP_TRY(use(c));
     prof_collect(c);
     for (int i = 0; i < KID_COUNT; i++) { c->prof_ms[i] = 0; c->prof_n[i] = 0; }
+    for (sharp_ctx *s : c->subs) {
+        prof_collect(s);
+        for (int i = 0; i < KID_COUNT; i++) { s->prof_ms[i] = 0; s->prof_n[i] = 0; }
+    }
     return 0;
 }
 int sharp_prof_kernels(void) { return KID_COUNT; }
@@ -1027,8 +1304,15 @@ int sharp_prof_get(sharp_ctx *c, int kid, double *ms, int64_t *launches) {
     SHARP_TRY(use(c));
     if (kid < 0 || kid >= KID_COUNT) return set_error(SHARP_E_ARG, "prof_get: bad kernel id %d", kid);
     prof_collect(c);
-    if (ms) *ms = c->prof_ms[kid];
-    if (launches) *launches = c->prof_n[kid];
+    double t = c->prof_ms[kid];
+    int64_t n = c->prof_n[kid];
+    for (sharp_ctx *s : c->subs) { /* the sub-contexts of group runs */
+        prof_collect(s);
+        t += s->prof_ms[kid];
+        n += s->prof_n[kid];
+    }
+    if (ms) *ms = t;
+    if (launches) *launches = n;
     return 0;
 }
 
@@ -1454,6 +1738,64 @@ int sharp_run(sharp_ctx *c, int m, int64_t n, const double *dense, const int64_t
     cudaStreamSynchronize(c->stream);
     free_expr(&e);
     return rc;
+}
+
+int sharp_run_parts(sharp_ctx *c, int m, int nparts, sharp_part *parts, const sharp_rm_dev *rm,
+                    const sharp_run_params *prm, int small_thre, int cen_cap, int group, int lanes) {
+    SHARP_TRY(use(c));
+    if (!parts || !rm || !prm || nparts < 1) return set_error(SHARP_E_ARG, "run_parts: bad arguments");
+    if (!prm->large) return set_error(SHARP_E_ARG, "run_parts: only the SHARP_large path (every part >= base.ncells cells)");
+    for (int i = 0; i < nparts; i++) {
+        if (!parts[i].pred) return set_error(SHARP_E_ARG, "run_parts: part %d has no output buffer", i);
+        if (!parts[i].dev && !parts[i].dense && !parts[i].colptr) return set_error(SHARP_E_ARG, "run_parts: part %d has no data", i);
+        if (parts[i].dev && parts[i].dev->n != parts[i].n) return set_error(SHARP_E_ARG, "run_parts: part %d: n does not match the device matrix", i);
+    }
+    if (group <= 0) group = 4;
+    if (lanes <= 0) lanes = 2;
+    group = std::min(group, nparts);
+    const int ngroups = (nparts + group - 1) / group;
+    lanes = std::min(lanes, ngroups);
+    const size_t need = (size_t)lanes * (group + 1);
+    while (c->subs.size() < need) {
+        sharp_ctx *s = nullptr;
+        SHARP_TRY(make_child(c, &s));
+        c->subs.push_back(s);
+    }
+    for (sharp_ctx *s : c->subs) {
+        s->prof_on = c->prof_on;
+        s->rp_legacy = c->rp_legacy;
+        s->block_budget_gb = std::max(1, c->block_budget_gb / lanes);
+    }
+    // children start after whatever is queued on the context's own stream (and the timer's start event)
+    SHARP_CUDA(cudaEventRecord(c->ev_fork, c->stream));
+    for (size_t i = 0; i < need; i++) SHARP_CUDA(cudaStreamWaitEvent(c->subs[i]->stream, c->ev_fork, 0));
+    std::vector<GroupRun> G(ngroups);
+    int rc = 0;
+    for (int gi = 0; gi < ngroups && !rc; gi++) {
+        GroupRun &g = G[gi];
+        const int lane = gi % lanes;
+        for (int i = gi * group; i < std::min(nparts, (gi + 1) * group); i++) g.idx.push_back(i);
+        g.blocks = c->subs[(size_t)lane * (group + 1) + group];
+        for (size_t j = 0; j < g.idx.size(); j++) g.subs.push_back(c->subs[(size_t)lane * (group + 1) + j]);
+        rc = group_issue(g, parts, m, *rm, *prm);
+        /* the group that used this lane's contexts `lanes` groups ago has been completed below before its contexts are
+           reused here; complete the oldest outstanding group while the newer ones keep the device busy */
+        if (!rc && gi + 1 >= lanes) rc = group_complete(G[gi + 1 - lanes], parts, small_thre, cen_cap);
+    }
+    for (int gi = std::max(0, ngroups - lanes + 1); gi < ngroups && !rc; gi++) rc = group_complete(G[gi], parts, small_thre, cen_cap);
+    // join: the context's stream (and its timer) sees the end of all the work
+    for (size_t i = 0; i < need; i++) {
+        cudaEventRecord(c->subs[i]->ev_ready, c->subs[i]->stream);
+        cudaStreamWaitEvent(c->stream, c->subs[i]->ev_ready, 0);
+    }
+    if (rc) {
+        std::string msg = g_err; /* keep the first error across the drain */
+        for (size_t i = 0; i < need; i++) cudaStreamSynchronize(c->subs[i]->stream);
+        cudaGetLastError();
+        snprintf(g_err, sizeof g_err, "%s", msg.c_str());
+        return rc;
+    }
+    return sync(c);
 }
 
 int sharp_last_member(sharp_ctx *c, int k, int64_t n, int32_t *rowcolor, double *inde) {

@@ -12,6 +12,9 @@
 // the mirror writes of the updated row.  NN list, flags and cluster sizes live in shared memory.
 // The kernel is latency-bound by design (n-1 dependent steps); throughput comes from the number of problems
 // resident at once (3 CTAs of 256 threads per SM) -- callers keep several waves in flight on different streams.
+#include <algorithm>
+#include <cstdlib>
+
 #include "devutil.cuh"
 #include "internal.cuh"
 
@@ -81,7 +84,7 @@ constexpr int RESCAN_PF = 16;  // row elements per lane prefetched for a rescan 
 //   E  rescans: minimum over active j > i, j != i2, j2 of the prefetched data (+ the rest of long rows), combined
 //      with the candidate (rcol[i], i2) -- exactly the minimum hclust.f finds after its update
 template <int THREADS, int MINB>
-__global__ void __launch_bounds__(THREADS, MINB) hclust_kernel(HcProb *probs, int method) {
+__global__ void __launch_bounds__(THREADS, MINB) hclust_kernel(HcProb *probs, int method, int only_fallback) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ DI red[THREADS / 32];
     __shared__ int s_cnt;
@@ -102,6 +105,12 @@ __global__ void __launch_bounds__(THREADS, MINB) hclust_kernel(HcProb *probs, in
     int *list = membr + n;                                  // [n]
     unsigned char *flag = reinterpret_cast<unsigned char *>(list + n);  // [n]
 
+    if (only_fallback) { /* second pass after hclust_rnn_kernel: only the problems it handed back (exact ties) */
+        if (!P.fallback) return;
+        const double *src = P.D;
+        for (size_t idx = tid; idx < (size_t)n * ld; idx += THREADS) D[idx] = src[idx];
+        __syncthreads();
+    }
     if (method == SHARP_WARD_D2) { /* hclust.f: iOpt 8 works on squared dissimilarities */
         for (size_t idx = tid; idx < (size_t)n * ld; idx += THREADS) D[idx] = __dmul_rn(D[idx], D[idx]);
     }
@@ -288,27 +297,307 @@ __global__ void __launch_bounds__(THREADS, MINB) hclust_kernel(HcProb *probs, in
     }
 }
 
+// =====================================================================================================
+// K3, round-parallel variant for the 2000-cell feature blocks: all reciprocal-nearest-neighbour pairs per round
+// =====================================================================================================
+// hclust.f merges the globally closest pair, n - 1 dependent steps.  For a REDUCIBLE linkage (ward.D, ward.D2, single,
+// complete, average, mcquitty: d(k, i+j) >= min(d(k,i), d(k,j))) every pair of clusters that are each other's nearest
+// neighbour is merged by that sequential algorithm sooner or later, whatever happens elsewhere, and the merge heights
+// are monotone -- so all reciprocal pairs of the current partition can be merged AT ONCE and the reference's merge
+// order is recovered at the end by sorting the merges by height.  On a 2000-cell block this takes ~40 rounds instead
+// of 1999 steps; a round is wide (hundreds of independent Lance-Williams row updates and row scans), so the kernel is
+// bound by memory throughput instead of by a chain of dependent round trips.
+//   * The merges and therefore the labels are those of hclust.f.  The heights agree to rounding only: a distance
+//     between two clusters that were both built after the previous global step is reached through the same
+//     Lance-Williams recurrences associated in a different order (a few ulps).
+//   * Everything above assumes there are no exact ties.  Any tie that could matter -- a row minimum attained twice, an
+//     updated distance that is not strictly above the row's nearest-neighbour distance, two merges of equal height,
+//     no reciprocal pair at all (NaN / Inf) -- sets P.fallback and the problem is redone by the exact kernel
+//     (launch_hclust runs hclust_kernel in only_fallback mode right after), so tie-heavy input costs time, not parity.
+constexpr int RNN_THREADS = 512;
+constexpr int RNN_U = 4;
+
+__device__ __forceinline__ DI rnn_scan_row(const double *row, const unsigned char *flag, int n, int self, int lane, bool *tie) {
+    DI best;
+    best.d = SHARP_INF;
+    best.i = INT_MAX;
+    bool t = false;
+    for (int base = 0; base < n; base += 32 * SCAN_U) {
+        double v[SCAN_U];
+#pragma unroll
+        for (int u = 0; u < SCAN_U; u++) {
+            const int j = base + u * 32 + lane;
+            v[u] = (j < n) ? row[j] : SHARP_INF;
+        }
+#pragma unroll
+        for (int u = 0; u < SCAN_U; u++) {
+            const int j = base + u * 32 + lane;
+            if (j < n && j != self && flag[j]) {
+                if (v[u] < best.d) { best.d = v[u]; best.i = j; t = false; }
+                else if (v[u] == best.d) t = true;
+            }
+        }
+    }
+    const DI w = warp_argmin_redux(best);
+    const bool mine = best.i != INT_MAX && best.d == w.d && (best.i != w.i || t);
+    *tie = __any_sync(0xffffffffu, mine);
+    return w;
+}
+
+// ascending bitonic sort of (key, payload) pairs in shared memory; P2 a power of two
+template <int THREADS>
+__device__ __forceinline__ void block_bitonic_sort_kv(double *key, int *val, int P2) {
+    for (int k = 2; k <= P2; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int t = threadIdx.x; t < P2 / 2; t += THREADS) {
+                const int i = 2 * t - (t & (j - 1));
+                const int l = i + j;
+                const bool up = ((i & k) == 0);
+                const double x = key[i], y = key[l];
+                if ((x > y) == up && x != y) {
+                    const int vi = val[i], vl = val[l];
+                    key[i] = y; key[l] = x;
+                    val[i] = vl; val[l] = vi;
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+__global__ void __launch_bounds__(RNN_THREADS, 2) hclust_rnn_kernel(HcProb *probs, int method) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ int s_np, s_cnt, s_tie, s_nm;
+    constexpr int THREADS = RNN_THREADS, NW = RNN_THREADS / 32;
+
+    HcProb &P = probs[blockIdx.x];
+    const int n = P.n;
+    if (n < 2) return;
+    const int ld = P.ld;
+    double *D = P.Dw; /* read and written by the whole CTA: no __restrict__, no ld.global.nc */
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int hp = n / 2 + 1;
+
+    double *dnn = reinterpret_cast<double *>(smem_raw);  // [n] distance to the nearest neighbour (all j != i)
+    double *ph = dnn + n;                                 // [hp] heights of this round's pairs
+    int *nn = reinterpret_cast<int *>(ph + hp);           // [n]
+    int *size = nn + n;                                   // [n]
+    int *list = size + n;                                 // [n] rows to rescan
+    int *mrg = list + n;                                  // [n] 0, +(q+1): kept representative of pair q, -(q+1): retired
+    int *pa = mrg + n;                                    // [hp]
+    int *pb = pa + hp;                                    // [hp]
+    unsigned char *flag = reinterpret_cast<unsigned char *>(pb + hp);  // [n]
+
+    if (method == SHARP_WARD_D2) { /* hclust.f: iOpt 8 works on squared dissimilarities */
+        for (size_t idx = tid; idx < (size_t)n * ld; idx += THREADS) D[idx] = __dmul_rn(D[idx], D[idx]);
+    }
+    for (int i = tid; i < n; i += THREADS) {
+        flag[i] = 1;
+        size[i] = 1;
+        mrg[i] = 0;
+    }
+    if (tid == 0) { s_tie = 0; s_nm = 0; P.fallback = 0; }
+    __syncthreads();
+    for (int i = warp; i < n; i += NW) {
+        bool tie;
+        const DI b = rnn_scan_row(D + (size_t)i * ld, flag, n, i, lane, &tie);
+        if (lane == 0) {
+            nn[i] = (b.i == INT_MAX) ? -1 : b.i;
+            dnn[i] = b.d;
+            if (tie || b.i == INT_MAX) s_tie = 1;
+        }
+    }
+    __syncthreads();
+
+    int nact = n;
+    bool failed = false;
+    while (nact > 1) {
+        if (s_tie) { failed = true; break; }
+        if (tid == 0) s_np = 0;
+        __syncthreads();
+        // ---- reciprocal nearest neighbours ----
+        for (int i = tid; i < n; i += THREADS) {
+            if (!flag[i]) continue;
+            const int j = nn[i];
+            if (j > i && nn[j] == i) {
+                const int q = atomicAdd(&s_np, 1);
+                pa[q] = i;
+                pb[q] = j;
+                ph[q] = dnn[i];
+            }
+        }
+        __syncthreads();
+        const int np = s_np;
+        if (np == 0) { failed = true; break; }
+        const int base = s_nm;
+        for (int q = tid; q < np; q += THREADS) {
+            const int a = pa[q], b = pb[q];
+            mrg[a] = q + 1;
+            mrg[b] = -(q + 1);
+            P.ia[base + q] = a + 1;
+            P.ib[base + q] = b + 1;
+            P.crit[base + q] = ph[q];
+        }
+        __syncthreads();
+        // ---- Lance-Williams: merged cluster (kept under a) against every cluster that does not merge this round ----
+        for (int q = warp; q < np; q += NW) {
+            const int a = pa[q], b = pb[q];
+            const double h = ph[q], mi = (double)size[a], mj = (double)size[b];
+            double *rowa = D + (size_t)a * ld;
+            const double *rowb = D + (size_t)b * ld;
+            bool bad = false;
+            for (int kb = 0; kb < n; kb += 32 * RNN_U) {
+                double x[RNN_U], y[RNN_U];
+                bool act[RNN_U];
+#pragma unroll
+                for (int u = 0; u < RNN_U; u++) {
+                    const int k = kb + u * 32 + lane;
+                    act[u] = k < n && flag[k] && mrg[k] == 0;
+                    x[u] = act[u] ? rowa[k] : 0.0;
+                    y[u] = act[u] ? rowb[k] : 0.0;
+                }
+#pragma unroll
+                for (int u = 0; u < RNN_U; u++) {
+                    if (!act[u]) continue;
+                    const int k = kb + u * 32 + lane;
+                    const double r = lance_williams(method, x[u], y[u], h, mi, mj, (double)size[k]);
+                    rowa[k] = r;
+                    D[(size_t)k * ld + a] = r;
+                    /* a row whose nearest neighbour survives keeps it only if the new distance is strictly larger */
+                    if (!(r > dnn[k]) && mrg[nn[k]] == 0) bad = true;
+                }
+            }
+            if (bad) s_tie = 1;
+        }
+        // ---- two clusters that both merge this round: the two updates in the order of their heights ----
+        for (int idx = tid; idx < np * np; idx += THREADS) {
+            const int p1 = idx / np, q1 = idx - p1 * np;
+            if (p1 >= q1) continue;
+            int f = p1, g = q1; /* f merges first */
+            if (ph[q1] < ph[p1]) { f = q1; g = p1; }
+            if (ph[p1] == ph[q1]) s_tie = 1;
+            const int a = pa[f], b = pb[f], c = pa[g], d = pb[g];
+            const double ma = (double)size[a], mb = (double)size[b], mc = (double)size[c], md = (double)size[d];
+            const double tc = lance_williams(method, D[(size_t)a * ld + c], D[(size_t)b * ld + c], ph[f], ma, mb, mc);
+            const double td = lance_williams(method, D[(size_t)a * ld + d], D[(size_t)b * ld + d], ph[f], ma, mb, md);
+            const double r = lance_williams(method, tc, td, ph[g], mc, md, ma + mb);
+            D[(size_t)a * ld + c] = r;
+            D[(size_t)c * ld + a] = r;
+        }
+        __syncthreads();
+        for (int q = tid; q < np; q += THREADS) {
+            const int a = pa[q], b = pb[q];
+            size[a] += size[b];
+            flag[b] = 0;
+        }
+        if (tid == 0) { s_nm = base + np; s_cnt = 0; }
+        __syncthreads();
+        nact -= np;
+        if (nact > 1) {
+            // ---- rows whose nearest neighbour merged, and the merged rows themselves ----
+            for (int k = tid; k < n; k += THREADS)
+                if (flag[k] && (mrg[k] > 0 || mrg[nn[k]] != 0)) list[atomicAdd(&s_cnt, 1)] = k;
+            __syncthreads();
+            const int cnt = s_cnt;
+            for (int r = warp; r < cnt; r += NW) {
+                const int i = list[r];
+                bool tie;
+                const DI b = rnn_scan_row(D + (size_t)i * ld, flag, n, i, lane, &tie);
+                if (lane == 0) {
+                    nn[i] = (b.i == INT_MAX) ? -1 : b.i;
+                    dnn[i] = b.d;
+                    if (tie || b.i == INT_MAX) s_tie = 1;
+                }
+            }
+            __syncthreads();
+        }
+        for (int q = tid; q < np; q += THREADS) {
+            mrg[pa[q]] = 0;
+            mrg[pb[q]] = 0;
+        }
+        __syncthreads();
+    }
+    if (!failed && s_tie) failed = true;
+    // ---- the reference's merge order: ascending height ----
+    const int nm = n - 1;
+    int P2 = 1;
+    while (P2 < nm) P2 <<= 1;
+    double *key = reinterpret_cast<double *>(smem_raw);          // [P2]
+    int *perm = reinterpret_cast<int *>(key + P2);               // [P2]
+    int *ias = perm + P2;                                        // [nm]
+    int *ibs = ias + nm;                                         // [nm]
+    if (!failed) {
+        __syncthreads();
+        for (int i = tid; i < P2; i += THREADS) {
+            key[i] = (i < nm) ? P.crit[i] : SHARP_INF;
+            perm[i] = i;
+        }
+        for (int i = tid; i < nm; i += THREADS) { ias[i] = P.ia[i]; ibs[i] = P.ib[i]; }
+        __syncthreads();
+        block_bitonic_sort_kv<THREADS>(key, perm, P2);
+        for (int i = tid; i + 1 < nm; i += THREADS)
+            if (!(key[i] < key[i + 1])) s_tie = 1; /* equal heights (or NaN): the order is the reference's business */
+        __syncthreads();
+        if (s_tie) failed = true;
+    }
+    if (failed) {
+        if (tid == 0) P.fallback = 1;
+        return;
+    }
+    for (int i = tid; i < nm; i += THREADS) {
+        P.ia[i] = ias[perm[i]];
+        P.ib[i] = ibs[perm[i]];
+        P.crit[i] = (method == SHARP_WARD_D2) ? sqrt(key[i]) : key[i];
+    }
+}
+
+static size_t hclust_rnn_smem_bytes(int n) {
+    const size_t hp = (size_t)n / 2 + 1;
+    size_t rounds = (size_t)n * 8 + hp * 8 + (size_t)n * 16 + hp * 8 + (size_t)n;
+    size_t p2 = 1;
+    while ((int)p2 < n - 1) p2 <<= 1;
+    size_t sort = p2 * 12 + (size_t)n * 8;
+    return (std::max(rounds, sort) + 31) & ~(size_t)15;
+}
+
 static size_t hclust_smem_bytes(int n) {
     return ((size_t)n * (8 + 8 + 4 + 4 + 4 + 1) + (size_t)16 * 16 * sizeof(DI) + 15) & ~(size_t)15;
 }
 
-int launch_hclust(sharp_ctx *c, HcProb *probs_dev, int nprob, int max_n, int method) {
-    if (nprob <= 0) return 0;
-    if (method < 1 || method > 8) return set_error(SHARP_E_ARG, "invalid clustering method %d", method);
+static int launch_exact(sharp_ctx *c, HcProb *probs_dev, int nprob, int max_n, int method, int only_fallback) {
     size_t smem = hclust_smem_bytes(max_n);
     if (smem > 200 * 1024)
         return set_error(SHARP_E_LIMIT, "hclust: %d objects exceed the shared-memory NN list (max ~7000)", max_n);
     prof_begin(c, max_n > 384 ? KID_HCLUST : KID_HCLUST_SMALL);
     if (max_n > 384) {
         SHARP_CUDA(cudaFuncSetAttribute(hclust_kernel<256, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SHARP_SMEM_OPTIN));
-        hclust_kernel<256, 2><<<nprob, 256, smem, c->stream>>>(probs_dev, method);
+        hclust_kernel<256, 2><<<nprob, 256, smem, c->stream>>>(probs_dev, method, only_fallback);
     } else {
         SHARP_CUDA(cudaFuncSetAttribute(hclust_kernel<128, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, SHARP_SMEM_OPTIN));
-        hclust_kernel<128, 4><<<nprob, 128, smem, c->stream>>>(probs_dev, method);
+        hclust_kernel<128, 4><<<nprob, 128, smem, c->stream>>>(probs_dev, method, only_fallback);
     }
     prof_end(c);
     SHARP_CUDA(cudaGetLastError());
     return 0;
+}
+
+// fast = 1: feature problems (continuous data, P.D holds a pristine copy of the dissimilarities): the round-parallel
+// kernel, then the exact kernel for the problems that reported ties.  fast = 0: hclust.f's order to the last bit.
+int launch_hclust(sharp_ctx *c, HcProb *probs_dev, int nprob, int max_n, int method, int fast) {
+    if (nprob <= 0) return 0;
+    if (method < 1 || method > 8) return set_error(SHARP_E_ARG, "invalid clustering method %d", method);
+    static const bool no_rnn = getenv("SHARP_HCLUST_EXACT") != nullptr; /* development switch */
+    const bool reducible = method != SHARP_MEDIAN && method != SHARP_CENTROID;
+    const size_t rsmem = hclust_rnn_smem_bytes(max_n);
+    if (fast && reducible && !no_rnn && max_n > 384 && rsmem <= (size_t)SHARP_SMEM_OPTIN) {
+        SHARP_CUDA(cudaFuncSetAttribute(hclust_rnn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SHARP_SMEM_OPTIN));
+        prof_begin(c, KID_HCLUST);
+        hclust_rnn_kernel<<<nprob, RNN_THREADS, rsmem, c->stream>>>(probs_dev, method);
+        prof_end(c);
+        SHARP_CUDA(cudaGetLastError());
+        return launch_exact(c, probs_dev, nprob, max_n, method, 1);
+    }
+    return launch_exact(c, probs_dev, nprob, max_n, method, 0);
 }
 
 }  // namespace sharp

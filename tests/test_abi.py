@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol():
     lib = _lib.load()
     missing = [s for s in declared_symbols() if not hasattr(lib, s)]
     assert not missing, missing
-    assert lib.sharp_abi_version() == 1
+    assert lib.sharp_abi_version() == 2
 
 
 def test_no_torch_types_in_the_abi():

@@ -79,3 +79,61 @@ def test_sharp_large_given_colsum_and_ncluster(ctx):
     x, _ = synth.make_expression(1000, 640, n_types=3, seed=4, kind="umi")
     got, ref = run_both(ctx, x, K=3, p=48, large=1, ng=200, fmt="csc", normalize=1, n_cluster=4)
     check(got, ref, 640)
+
+
+# ---- SHARP_unlimited: the fused loop over parts (sharp_run_parts) -------------------------------------------
+def _unlimited_parts(nparts=3, m=900, seed=21):
+    sizes = [10000, 10650, 11200][:nparts]
+    x, truth = synth.make_expression(m, sum(sizes), n_types=5, seed=seed, kind="umi", zero_frac=0.8, sep=2.0, frac=0.4)
+    parts, o = [], 0
+    for n in sizes:
+        parts.append(np.asfortranarray(x[:, o:o + n]))
+        o += n
+    return parts, truth
+
+
+def test_unlimited_fused_equals_part_by_part_and_oracle():
+    """sharp_run_parts (groups of parts sharing the block-clustering launches, two groups in flight) must give exactly
+    what the reference's serial loop gives: compared with the part-by-part GPU path and with the oracle driver."""
+    import math
+    from sharp_b200 import api
+    from sharp_b200.rrng import ranM2 as ranm2
+    parts, truth = _unlimited_parts()
+    csc_parts = [synth.to_csc(x) + (x.shape,) for x in parts]
+    K, seed = 3, 31
+    c = Context(0)
+    try:
+        api._fused_parts = False
+        a = api.SHARP_unlimited(csc_parts, viewflag=False, rN_seed=seed, ensize_K=K, exp_type="UMI", ctx=c, n_streams=1)
+        api._fused_parts = True
+        for group, lanes in ((1, 1), (2, 2), (3, 1)):
+            api._fused_group, api._fused_lanes = group, lanes
+            b = api.SHARP_unlimited(csc_parts, viewflag=False, rN_seed=seed, ensize_K=K, exp_type="UMI", ctx=c)
+            assert np.array_equal(a["pred_clusters"], b["pred_clusters"]), (group, lanes)
+            assert a["N.pred_clusters"] == b["N.pred_clusters"] and a["paras"] == b["paras"]
+        # device-resident parts give the same result as host buffers
+        devs = [c.upload_expr(x.shape[0], x.shape[1], csc=synth.to_csc(x)) for x in parts]
+        d = api.SHARP_unlimited(devs, viewflag=False, rN_seed=seed, ensize_K=K, exp_type="UMI", ctx=c)
+        assert np.array_equal(a["pred_clusters"], d["pred_clusters"])
+        for e in devs:
+            e.close()
+    finally:
+        api._fused_parts, api._fused_group, api._fused_lanes = True, 0, 0
+        c.close()
+    # the oracle, driven like R/SHARP_unlimited.R:97-183
+    ncells = sum(x.shape[1] for x in parts)
+    p = math.ceil(math.log2(ncells) / 0.04)
+    m = parts[0].shape[0]
+    rms = [ranm2(m, p, 50 + seed + k) for k in range(1, K + 1)]
+    preds, vies, part_of = [], [], []
+    for i, x in enumerate(parts):
+        n = x.shape[1]
+        prm = orc.SharpParams(1, 1, K, p, 2000, 0, 0, 0, orc.hc_params(max_n=max(40, -(-n // 5000))), 2, -1)
+        r = orc.sharp(m, n, rms, prm, csc=synth.to_csc(x), colsum=x.sum(0), reind=r_sample_perm(n, 50))
+        preds.append(r["pred_clusters"])
+        vies.append(r["viE"])
+        part_of.append(np.full(n, i + 1))
+    hc = orc.hc_params(max_n=max(40, -(-ncells // 5000)))
+    final, nf = orc.unlimited_combine(np.concatenate(part_of), np.concatenate(preds), np.concatenate(vies), hc)
+    assert np.array_equal(a["pred_clusters"], final) and a["N.pred_clusters"] == nf
+    assert synth.ari(final, truth) > 0.8

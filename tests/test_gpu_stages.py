@@ -179,6 +179,34 @@ def test_opt_hclust_feature(ctx, exact, n, p, g, sep):
     assert abs(got["maxsil"] - ref["maxsil"]) <= 1e-12
 
 
+@pytest.mark.parametrize("n,p,g,sep,method", [(1203, 64, 6, 1.5, "ward.D"), (2000, 120, 9, 1.0, "ward.D"), (900, 40, 4, 2.0, "ward.D2"),
+                                              (700, 30, 3, 1.0, "average"), (650, 30, 3, 1.0, "complete")])
+def test_opt_hclust_round_parallel(ctx, n, p, g, sep, method):
+    """n > 384 feature problems run the round-parallel (reciprocal nearest neighbour) agglomeration: identical
+    dendrogram / cuts / selection, heights equal to rounding"""
+    X, _ = _blobs(n, p, g, seed=n, sep=sep)
+    prm = hc_params(hmethod=method)
+    got = ctx.opt_hclust(X, False, prm)
+    ref = orc.opt_hclust(X, 0, orc_prm(prm))
+    assert np.array_equal(got["v"], ref["v"])
+    assert np.allclose(got["height"], ref["height"], rtol=1e-10, atol=1e-13)
+    assert np.allclose(got["msil"], ref["msil"], rtol=0, atol=1e-12)
+    assert got["oind"] == ref["oind"] and got["optN.cluster"] == ref["optN.cluster"]
+    assert np.array_equal(got["f"], ref["f"])
+
+
+def test_opt_hclust_round_parallel_ties_fall_back(ctx):
+    """duplicated cells give exact ties (d = 0, equal rows): the round-parallel kernel must hand the problem to the
+    exact kernel, and the result is still hclust.f's"""
+    X, _ = _blobs(300, 25, 4, seed=5, sep=2.0)
+    X = np.concatenate([X, X[:150], X[:40]], 0)  # n = 490 > 384 with duplicate and triplicate rows
+    prm = hc_params()
+    got = ctx.opt_hclust(X, False, prm)
+    ref = orc.opt_hclust(X, 0, orc_prm(prm))
+    assert np.array_equal(got["v"], ref["v"]) and np.array_equal(got["f"], ref["f"])
+    assert np.allclose(got["height"], ref["height"], rtol=1e-10, atol=1e-13)
+
+
 def test_opt_hclust_ch_and_height_paths(ctx):
     """weak structure -> max(msil) <= sil.thre -> CH index, possibly the height-gap rule"""
     for seed, sil in [(1, 0.9), (2, 0.9), (3, 2.0)]:
