@@ -39,6 +39,9 @@ for _p in (ROOT, os.path.join(ROOT, "tests")):
         sys.path.insert(0, _p)
 
 SEED = 2103
+# the fused loop over parts keeps ~10 streams busy; with the default 8 hardware queues, streams alias and false
+# dependencies serialise copies and kernels of different parts (must be set before CUDA initialises)
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 
 
 def workload(name: str) -> dict:
@@ -313,7 +316,7 @@ def run_ours(args):
     api._fused_parts = not args.no_fused
     api._fused_group, api._fused_lanes = args.group, args.lanes
     ctx = api.get_context(local)
-    ctxs = api.stream_contexts(args.streams, local)
+    ctxs = api.stream_contexts(args.streams, local) if args.no_fused else [ctx]
     kw = dict(n_streams=args.streams, viewflag=False, ensize_K=wl["K"], rN_seed=SEED, exp_type=wl["exp_type"], ctx=ctx, comm=comm)
 
     def placeholder(i):  # parts owned by other ranks: only their shape is needed

@@ -5,6 +5,12 @@ get_opt_hclust, getrowColor, wMetaC, sMetaC ...) over the C ABI of ``libsharpb20
 R is not available in this image; INTEGRATION.md shows the `.Call` glue a maintainer of the reference adds.
 Importing the package does not need a GPU; every compute call does (there is no CPU fallback).
 """
+import os as _os
+
+# sharp_run_parts drives ~10 CUDA streams; with the default 8 hardware queues streams alias and copies / kernels of
+# different parts serialise on false dependencies.  Read by the CUDA driver at initialisation: set before first use.
+_os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 from . import _lib
 from ._lib import Context, HcParams, RStop, RunParams, SharpError, device_count, device_info, hc_params
 from .rrng import r_sample_perm

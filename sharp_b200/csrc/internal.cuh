@@ -54,6 +54,8 @@ struct HcProb {
     int ldy;          // leading dimension of Y
     int status;       // 0 ok, else a SWEEP_E_* / WM_E_* code
     int fallback;     // set by hclust_rnn_kernel: exact ties, redo with the exact kernel
+    double *E;        // second working buffer of hclust_rnn_kernel (ecap doubles), else null
+    long long ecap;
 };
 
 // results of the cluster-number sweep for one problem (device pointers)
@@ -94,7 +96,7 @@ namespace sharp {
 // kernel classes of the per-kernel device-time profile (sharp_prof_*; bench.py's roofline object)
 enum KernelId { KID_RP_PROJECT = 0, KID_COLSUM, KID_UNIT_ROWS, KID_CORRDIST, KID_HCLUST, KID_HCLUST_SMALL,
                 KID_SWEEP_NESTED, KID_SWEEP_EXACT, KID_WM_WEIGHTS, KID_WM_SIMILARITY, KID_WMETAC, KID_SM_CENTROIDS,
-                KID_SMETAC, KID_ENE, KID_MISC, KID_COUNT };
+                KID_SMETAC, KID_ENE, KID_MISC, KID_H2D, KID_COUNT };
 struct ProfPending { int kid; cudaEvent_t a, b; };
 }  // namespace sharp
 
@@ -192,6 +194,9 @@ int launch_corrdist_batched(sharp_ctx *c, const GemmProb *probs_dev, const int *
                             int total_tiles, int ldu);
 // ward.cu
 int launch_hclust(sharp_ctx *c, HcProb *probs_dev, int nprob, int max_n, int method, int fast = 0);
+// fast = 1 will take the round-parallel kernel: the problems then need HcProb::E, and the distance kernel need not
+// write the working copy Dw (round 1 reads the pristine D)
+bool hclust_fast_ok(int max_n, int method);
 // sweep.cu
 size_t sweep_nested_scratch_bytes(int max_n, int max_p, HcParamsDev prm);
 int launch_sweep_nested(sharp_ctx *c, HcProb *probs_dev, SweepOut *outs_dev, int nprob, int max_n, int max_p,

@@ -152,7 +152,7 @@ void prof_collect(sharp_ctx *c) {
 enum Slot {
     WS_SRC = 0, WS_COLSUM, WS_PROJ, WS_U, WS_D, WS_DW, WS_HC_INT, WS_HC_DBL, WS_DESC, WS_SWEEP_SCRATCH, WS_ENRP, WS_E1,
     WS_WM_INT, WS_WM_DBL, WS_WM_S, WS_WM_DESC, WS_WM_SCRATCH, WS_SM_INT, WS_SM_DBL, WS_SM_S, WS_SM_SCRATCH, WS_VIEU,
-    WS_LABELS, WS_X0, WS_TMP0, WS_TMP1, WS_TMP2, WS_TMP3, WS_START, WS_CEN, WS_EX_A, WS_EX_B, WS_EX_C, WS_GDESC, WS_COUNT
+    WS_LABELS, WS_X0, WS_TMP0, WS_TMP1, WS_TMP2, WS_TMP3, WS_START, WS_CEN, WS_EX_A, WS_EX_B, WS_EX_C, WS_GDESC, WS_HC_E, WS_COUNT
 };
 
 // bump allocator over a byte region
@@ -383,6 +383,12 @@ static int opt_hclust_dev(sharp_ctx *c, int nrow, int ncol, const double *mat_de
     HcParamsDev *pp = hb.take<HcParamsDev>(1);
     hp->n = n; hp->ld = ld; hp->D = D; hp->Dw = Dw; hp->ia = ia; hp->ib = ib; hp->crit = R->crit;
     hp->Y = Y; hp->p = yp; hp->ldy = ldy; hp->status = 0; hp->fallback = 0;
+    hp->E = nullptr; hp->ecap = 0;
+    if (!symmetric && hclust_fast_ok(n, prm.hmethod)) {
+        SHARP_TRY(c->ws[WS_HC_E].reserve((size_t)n * ld * 8));
+        hp->E = c->ws[WS_HC_E].as<double>();
+        hp->ecap = (long long)n * ld;
+    }
     so->f = R->f; so->v = R->v; so->msil = R->msil; so->chind = R->chind; so->meta = R->meta; so->maxsil = R->maxsil;
     *pp = prm;
     HcProb *hpd = db.take<HcProb>(1);
@@ -765,15 +771,20 @@ static int run_blocks(sharp_ctx *g, PartRun *const *parts, int np_parts) {
     // wave size from the distance-matrix budget
     size_t free_b = 0, total_b = 0;
     SHARP_CUDA(cudaMemGetInfo(&free_b, &total_b));
-    const size_t have = g->ws[WS_D].cap + g->ws[WS_DW].cap;
+    const size_t have = g->ws[WS_D].cap + g->ws[WS_DW].cap + g->ws[WS_HC_E].cap;
     /* top-level contexts on other streams of the same device run concurrently: share the free memory between them */
     const int live = std::max(1, g_live_ctx.load());
     const size_t budget = std::min<size_t>((size_t)g->block_budget_gb << 30, (size_t)(free_b * 0.6 / live) + have);
     const size_t per_prob = (size_t)max_bn * ld_of(max_bn) * 8;
-    const int wave_probs = (int)std::min<size_t>((size_t)nprob, std::max<size_t>(1, budget / 2 / per_prob));
+    /* round-parallel agglomeration: a third (smaller) matrix per problem, and the distance kernel writes D only */
+    const bool fast = hclust_fast_ok(max_bn, ind.hmethod);
+    const size_t ecap = fast ? (((size_t)(0.8 * max_bn * ld_of(max_bn)) + 31) & ~(size_t)31) : 0;
+    const size_t per_all = 2 * per_prob + ecap * 8;
+    const int wave_probs = (int)std::min<size_t>((size_t)nprob, std::max<size_t>(1, budget / per_all));
     SHARP_TRY(g->ws[WS_D].reserve(per_prob * wave_probs));
     SHARP_TRY(g->ws[WS_DW].reserve(per_prob * wave_probs));
-    double *Dall = g->ws[WS_D].as<double>(), *Dwall = g->ws[WS_DW].as<double>();
+    if (ecap) SHARP_TRY(g->ws[WS_HC_E].reserve(ecap * 8 * wave_probs));
+    double *Dall = g->ws[WS_D].as<double>(), *Dwall = g->ws[WS_DW].as<double>(), *Eall = g->ws[WS_HC_E].as<double>();
     const size_t sweep_scr = R0.nested ? sweep_nested_scratch_bytes(max_bn, ldu, ind) : sweep_exact_scratch_bytes(max_bn, ldu);
     SHARP_TRY(g->ws[WS_SWEEP_SCRATCH].reserve(sweep_scr * wave_probs));
     // descriptors of ALL problems (part-major, then block, then member), built once
@@ -810,8 +821,9 @@ static int run_blocks(sharp_ctx *g, PartRun *const *parts, int np_parts) {
                     gp[q].n = nq;
                     gp[q].ld = ld;
                     gp[q].D = Dall + (size_t)slot * (per_prob / 8);
-                    gp[q].Dw = Dwall + (size_t)slot * (per_prob / 8);
-                    hp[q].n = nq; hp[q].ld = ld; hp[q].D = gp[q].D; hp[q].Dw = gp[q].Dw;
+                    gp[q].Dw = fast ? nullptr : Dwall + (size_t)slot * (per_prob / 8);
+                    hp[q].n = nq; hp[q].ld = ld; hp[q].D = gp[q].D; hp[q].Dw = Dwall + (size_t)slot * (per_prob / 8);
+                    hp[q].E = ecap ? Eall + (size_t)slot * ecap : nullptr; hp[q].ecap = (long long)ecap;
                     hp[q].ia = R.ia_all + row0; hp[q].ib = R.ib_all + row0; hp[q].crit = R.crit_all + row0;
                     hp[q].Y = gp[q].U; hp[q].p = p; hp[q].ldy = ldu; hp[q].status = 0; hp[q].fallback = 0;
                     so[q].f = R.enrp + row0; so[q].v = nullptr;
@@ -1092,7 +1104,13 @@ static int group_issue(GroupRun &G, sharp_part *parts, int m, const sharp_rm_dev
         if (P.dev) {
             e = *P.dev;
             e.owned = false;
-        } else SHARP_TRY(upload_expr(s, m, P.n, P.dense, P.colptr, P.rowidx, P.val, &e, true));
+        } else {
+            prof_begin(s, KID_H2D);
+            int urc = upload_expr(s, m, P.n, P.dense, P.colptr, P.rowidx, P.val, &e, true);
+            prof_end(s);
+            s->launches--; /* a copy, not a kernel */
+            SHARP_TRY(urc);
+        }
         if (e.m != rm.m) return set_error(SHARP_E_ARG, "run_parts: part %d has %d genes but ranM has %d rows", G.idx[j], e.m, rm.m);
         SHARP_TRY(part_front(G.runs[j], s, e, nullptr, rm, P.reind, Q));
         SHARP_CUDA(cudaEventRecord(s->ev_ready, s->stream));
@@ -1209,6 +1227,9 @@ int sharp_device_info(int device, char *name, int name_len, int *sm_count, int *
 
 int sharp_ctx_create(int device, sharp_ctx **out) {
     if (!out) return set_error(SHARP_E_ARG, "null output pointer");
+    /* sharp_run_parts keeps ~10 streams busy: more hardware queues than the default 8, or streams alias and copies /
+       kernels of different parts serialise on false dependencies (only effective before CUDA initialises) */
+    setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0);
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
     if (e != cudaSuccess || ndev == 0) {
@@ -1273,7 +1294,7 @@ int sharp_ctx_set_block_budget(sharp_ctx *c, int gigabytes) {
 
 static const char *const g_kernel_names[KID_COUNT] = {
     "rp_project", "colsum", "unit_rows", "corrdist", "hclust", "hclust_small", "sweep_nested", "sweep_exact",
-    "wm_weights", "wm_similarity", "wmetac_misc", "sm_centroids", "smetac_misc", "ene_scatter", "misc"};
+    "wm_weights", "wm_similarity", "wmetac_misc", "sm_centroids", "smetac_misc", "ene_scatter", "misc", "h2d_expr"};
 
 int sharp_ctx_set_rp_variant(sharp_ctx *c, int legacy) {
     if (!c) return set_error(SHARP_E_ARG, "null context");
@@ -1771,16 +1792,27 @@ int sharp_run_parts(sharp_ctx *c, int m, int nparts, sharp_part *parts, const sh
     for (size_t i = 0; i < need; i++) SHARP_CUDA(cudaStreamWaitEvent(c->subs[i]->stream, c->ev_fork, 0));
     std::vector<GroupRun> G(ngroups);
     int rc = 0;
+    static const bool trace = getenv("SHARP_B200_TRACE") != nullptr;
+    const auto t_start = std::chrono::steady_clock::now();
     for (int gi = 0; gi < ngroups && !rc; gi++) {
         GroupRun &g = G[gi];
         const int lane = gi % lanes;
         for (int i = gi * group; i < std::min(nparts, (gi + 1) * group); i++) g.idx.push_back(i);
         g.blocks = c->subs[(size_t)lane * (group + 1) + group];
         for (size_t j = 0; j < g.idx.size(); j++) g.subs.push_back(c->subs[(size_t)lane * (group + 1) + j]);
+        const auto t_a = std::chrono::steady_clock::now();
         rc = group_issue(g, parts, m, *rm, *prm);
+        const auto t_b = std::chrono::steady_clock::now();
         /* the group that used this lane's contexts `lanes` groups ago has been completed below before its contexts are
            reused here; complete the oldest outstanding group while the newer ones keep the device busy */
         if (!rc && gi + 1 >= lanes) rc = group_complete(G[gi + 1 - lanes], parts, small_thre, cen_cap);
+        if (trace) {
+            const auto t_c = std::chrono::steady_clock::now();
+            fprintf(stderr, "[sharp trace run_parts] group %d lane %d: issue %.2f ms, complete(prev) %.2f ms, t=%.2f ms\n", gi, lane,
+                    std::chrono::duration<double, std::milli>(t_b - t_a).count(),
+                    std::chrono::duration<double, std::milli>(t_c - t_b).count(),
+                    std::chrono::duration<double, std::milli>(t_c - t_start).count());
+        }
     }
     for (int gi = std::max(0, ngroups - lanes + 1); gi < ngroups && !rc; gi++) rc = group_complete(G[gi], parts, small_thre, cen_cap);
     // join: the context's stream (and its timer) sees the end of all the work

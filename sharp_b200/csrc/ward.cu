@@ -304,45 +304,25 @@ __global__ void __launch_bounds__(THREADS, MINB) hclust_kernel(HcProb *probs, in
 // complete, average, mcquitty: d(k, i+j) >= min(d(k,i), d(k,j))) every pair of clusters that are each other's nearest
 // neighbour is merged by that sequential algorithm sooner or later, whatever happens elsewhere, and the merge heights
 // are monotone -- so all reciprocal pairs of the current partition can be merged AT ONCE and the reference's merge
-// order is recovered at the end by sorting the merges by height.  On a 2000-cell block this takes ~40 rounds instead
-// of 1999 steps; a round is wide (hundreds of independent Lance-Williams row updates and row scans), so the kernel is
-// bound by memory throughput instead of by a chain of dependent round trips.
+// order is recovered at the end by sorting the merges by height.  A 2000-cell block takes ~40 rounds instead of 1999
+// steps.  Each round is one streaming pass: the n_r x n_r matrix of the current partition is read once and the
+// (n_r - m) x (n_r - m) matrix of the next partition is written, compacted, one warp per output row (which needs only
+// the one or two input rows of its cluster), with the row minimum -- the next round's nearest neighbour -- found on
+// the way.  No strided mirror stores, no dependent round trips: the kernel is bound by HBM throughput
+// (about 10.6 n^2 x 8 bytes per problem on the benchmark's blocks).
 //   * The merges and therefore the labels are those of hclust.f.  The heights agree to rounding only: a distance
 //     between two clusters that were both built after the previous global step is reached through the same
 //     Lance-Williams recurrences associated in a different order (a few ulps).
-//   * Everything above assumes there are no exact ties.  Any tie that could matter -- a row minimum attained twice, an
-//     updated distance that is not strictly above the row's nearest-neighbour distance, two merges of equal height,
-//     no reciprocal pair at all (NaN / Inf) -- sets P.fallback and the problem is redone by the exact kernel
-//     (launch_hclust runs hclust_kernel in only_fallback mode right after), so tie-heavy input costs time, not parity.
+//   * Everything above assumes there are no exact ties.  Any tie that could matter -- a row minimum attained twice,
+//     two merges of equal height, no reciprocal pair at all (NaN / Inf) -- and any input on which the rounds are not
+//     productive (work guard) sets P.fallback, and the problem is redone from the pristine matrix by the exact kernel
+//     (launch_hclust runs hclust_kernel in only_fallback mode right after): tie-heavy input costs time, not parity.
+// Buffers: round 1 reads the pristine P.D and writes P.Dw, round 2 writes P.E, round 3 P.Dw, ...
 constexpr int RNN_THREADS = 512;
-constexpr int RNN_U = 4;
-
-__device__ __forceinline__ DI rnn_scan_row(const double *row, const unsigned char *flag, int n, int self, int lane, bool *tie) {
-    DI best;
-    best.d = SHARP_INF;
-    best.i = INT_MAX;
-    bool t = false;
-    for (int base = 0; base < n; base += 32 * SCAN_U) {
-        double v[SCAN_U];
-#pragma unroll
-        for (int u = 0; u < SCAN_U; u++) {
-            const int j = base + u * 32 + lane;
-            v[u] = (j < n) ? row[j] : SHARP_INF;
-        }
-#pragma unroll
-        for (int u = 0; u < SCAN_U; u++) {
-            const int j = base + u * 32 + lane;
-            if (j < n && j != self && flag[j]) {
-                if (v[u] < best.d) { best.d = v[u]; best.i = j; t = false; }
-                else if (v[u] == best.d) t = true;
-            }
-        }
-    }
-    const DI w = warp_argmin_redux(best);
-    const bool mine = best.i != INT_MAX && best.d == w.d && (best.i != w.i || t);
-    *tie = __any_sync(0xffffffffu, mine);
-    return w;
-}
+constexpr int RNN_UC = 8;   // columns per lane in flight: rows that do not merge (copy + a few updates)
+constexpr int RNN_UM = 4;   // merged rows (two source rows)
+typedef unsigned short u16;
+constexpr u16 RNN_NONE = 0xffffu;
 
 // ascending bitonic sort of (key, payload) pairs in shared memory; P2 a power of two
 template <int THREADS>
@@ -365,157 +345,252 @@ __device__ __forceinline__ void block_bitonic_sort_kv(double *key, int *val, int
     }
 }
 
+struct RnnBest {
+    double d;
+    int i;
+    bool tie;
+};
+__device__ __forceinline__ void rnn_consider(RnnBest &b, double v, int j) {
+    if (v < b.d) { b.d = v; b.i = j; b.tie = false; }
+    else if (v == b.d) b.tie = true;
+}
+// warp-wide result in all lanes; *tie: the minimum is attained more than once (or there is no finite entry)
+__device__ __forceinline__ DI rnn_finish(const RnnBest &b, bool *tie) {
+    DI mine;
+    mine.d = b.d;
+    mine.i = b.i;
+    const DI w = warp_argmin_redux(mine);
+    const bool dup = b.i != INT_MAX && b.d == w.d && (b.i != w.i || b.tie);
+    *tie = __any_sync(0xffffffffu, dup) || w.i == INT_MAX;
+    return w;
+}
+
 __global__ void __launch_bounds__(RNN_THREADS, 2) hclust_rnn_kernel(HcProb *probs, int method) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    __shared__ int s_np, s_cnt, s_tie, s_nm;
+    __shared__ int s_tie, s_nm;
+    __shared__ int tmp_scan[RNN_THREADS];
     constexpr int THREADS = RNN_THREADS, NW = RNN_THREADS / 32;
 
     HcProb &P = probs[blockIdx.x];
     const int n = P.n;
     if (n < 2) return;
-    const int ld = P.ld;
-    double *D = P.Dw; /* read and written by the whole CTA: no __restrict__, no ld.global.nc */
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int hp = n / 2 + 1;
 
-    double *dnn = reinterpret_cast<double *>(smem_raw);  // [n] distance to the nearest neighbour (all j != i)
-    double *ph = dnn + n;                                 // [hp] heights of this round's pairs
-    int *nn = reinterpret_cast<int *>(ph + hp);           // [n]
-    int *size = nn + n;                                   // [n]
-    int *list = size + n;                                 // [n] rows to rescan
-    int *mrg = list + n;                                  // [n] 0, +(q+1): kept representative of pair q, -(q+1): retired
-    int *pa = mrg + n;                                    // [hp]
-    int *pb = pa + hp;                                    // [hp]
-    unsigned char *flag = reinterpret_cast<unsigned char *>(pb + hp);  // [n]
+    // shared state of the current partition (index cur) and the next one (cur ^ 1)
+    double *dnn0 = reinterpret_cast<double *>(smem_raw);   // [2][n] distance to the nearest neighbour
+    double *hrow = dnn0 + 2 * (size_t)n;                    // [n] height of the merge that built new cluster i'
+    int *rank = reinterpret_cast<int *>(hrow + n);          // [n] scan scratch
+    u16 *nn0 = reinterpret_cast<u16 *>(rank + n);           // [2][n] nearest neighbour
+    u16 *size0 = nn0 + 2 * (size_t)n;                       // [2][n] cluster sizes
+    u16 *orig0 = size0 + 2 * (size_t)n;                     // [2][n] representative (smallest original index)
+    u16 *sA = orig0 + 2 * (size_t)n;                        // [n] first source cluster of new cluster i'
+    u16 *sB = sA + n;                                       // [n] second source (RNN_NONE: not merged this round)
+    u16 *cmap = sB + n;                                     // [n] old cluster -> index of its cluster in the next partition
+    u16 *pl = cmap + n;                                     // [n/2 + 1] kept members of this round's pairs
+    unsigned char *kind = reinterpret_cast<unsigned char *>(pl + (n / 2 + 1));  // [n] 0 not merging, 1 kept member, 2 retired member
 
-    if (method == SHARP_WARD_D2) { /* hclust.f: iOpt 8 works on squared dissimilarities */
-        for (size_t idx = tid; idx < (size_t)n * ld; idx += THREADS) D[idx] = __dmul_rn(D[idx], D[idx]);
-    }
+    int cur = 0;
     for (int i = tid; i < n; i += THREADS) {
-        flag[i] = 1;
-        size[i] = 1;
-        mrg[i] = 0;
+        size0[i] = 1;
+        orig0[i] = (u16)i;
     }
     if (tid == 0) { s_tie = 0; s_nm = 0; P.fallback = 0; }
     __syncthreads();
+
+    // ---- nearest neighbours of the singletons: one pass over the pristine matrix ----
+    const double *A = P.D;
+    int ldA = P.ld;
+    bool sq = (method == SHARP_WARD_D2); /* hclust.f: iOpt 8 works on squared dissimilarities */
     for (int i = warp; i < n; i += NW) {
+        const double *row = A + (size_t)i * ldA;
+        RnnBest b;
+        b.d = SHARP_INF; b.i = INT_MAX; b.tie = false;
+        for (int base = 0; base < n; base += 32 * SCAN_U) {
+            double v[SCAN_U];
+#pragma unroll
+            for (int u = 0; u < SCAN_U; u++) {
+                const int j = base + u * 32 + lane;
+                v[u] = (j < n) ? row[j] : SHARP_INF;
+            }
+#pragma unroll
+            for (int u = 0; u < SCAN_U; u++) {
+                const int j = base + u * 32 + lane;
+                if (j < n && j != i) rnn_consider(b, sq ? __dmul_rn(v[u], v[u]) : v[u], j);
+            }
+        }
         bool tie;
-        const DI b = rnn_scan_row(D + (size_t)i * ld, flag, n, i, lane, &tie);
+        const DI w = rnn_finish(b, &tie);
         if (lane == 0) {
-            nn[i] = (b.i == INT_MAX) ? -1 : b.i;
-            dnn[i] = b.d;
-            if (tie || b.i == INT_MAX) s_tie = 1;
+            nn0[i] = (u16)(w.i == INT_MAX ? 0 : w.i);
+            dnn0[i] = w.d;
+            if (tie) s_tie = 1;
         }
     }
     __syncthreads();
 
-    int nact = n;
+    int nr = n;
     bool failed = false;
-    while (nact > 1) {
+    double work = 0.0;
+    int round = 0;
+    while (nr > 1) {
         if (s_tie) { failed = true; break; }
-        if (tid == 0) s_np = 0;
-        __syncthreads();
-        // ---- reciprocal nearest neighbours ----
-        for (int i = tid; i < n; i += THREADS) {
-            if (!flag[i]) continue;
+        const u16 *nn = nn0 + (size_t)cur * n, *size = size0 + (size_t)cur * n, *orig = orig0 + (size_t)cur * n;
+        const double *dnn = dnn0 + (size_t)cur * n;
+        u16 *nn2 = nn0 + (size_t)(cur ^ 1) * n, *size2 = size0 + (size_t)(cur ^ 1) * n, *orig2 = orig0 + (size_t)(cur ^ 1) * n;
+        double *dnn2 = dnn0 + (size_t)(cur ^ 1) * n;
+        // ---- survivors: every cluster except the larger-indexed member of a reciprocal pair ----
+        for (int i = tid; i < nr; i += THREADS) {
             const int j = nn[i];
-            if (j > i && nn[j] == i) {
-                const int q = atomicAdd(&s_np, 1);
-                pa[q] = i;
-                pb[q] = j;
-                ph[q] = dnn[i];
-            }
+            rank[i] = (nn[j] == i && j < i) ? 0 : 1;
         }
         __syncthreads();
-        const int np = s_np;
-        if (np == 0) { failed = true; break; }
+        const int nnew = block_exclusive_scan<THREADS>(rank, nr, tmp_scan);
+        const int m = nr - nnew;
+        if (m == 0) { failed = true; break; }
         const int base = s_nm;
-        for (int q = tid; q < np; q += THREADS) {
-            const int a = pa[q], b = pb[q];
-            mrg[a] = q + 1;
-            mrg[b] = -(q + 1);
-            P.ia[base + q] = a + 1;
-            P.ib[base + q] = b + 1;
-            P.crit[base + q] = ph[q];
+        for (int i = tid; i < nr; i += THREADS) {
+            const int j = nn[i];
+            const bool paired = nn[j] == i;
+            if (paired && j < i) { /* retired: i - rank[i] = number of retired clusters before i, a dense numbering */
+                const int q = base + (i - rank[i]);
+                P.ia[q] = (int)orig[j] + 1;
+                P.ib[q] = (int)orig[i] + 1;
+                P.crit[q] = dnn[i];
+                cmap[i] = (u16)rank[j];
+                kind[i] = 2;
+                pl[i - rank[i]] = (u16)j;
+                continue;
+            }
+            const int ip = rank[i];
+            cmap[i] = (u16)ip;
+            kind[i] = paired ? 1 : 0;
+            sA[ip] = (u16)i;
+            orig2[ip] = orig[i];
+            if (paired) {
+                sB[ip] = (u16)j;
+                hrow[ip] = dnn[i];
+                size2[ip] = (u16)(size[i] + size[j]);
+            } else {
+                sB[ip] = RNN_NONE;
+                hrow[ip] = 0.0;
+                size2[ip] = size[i];
+            }
         }
         __syncthreads();
-        // ---- Lance-Williams: merged cluster (kept under a) against every cluster that does not merge this round ----
-        for (int q = warp; q < np; q += NW) {
-            const int a = pa[q], b = pb[q];
-            const double h = ph[q], mi = (double)size[a], mj = (double)size[b];
-            double *rowa = D + (size_t)a * ld;
-            const double *rowb = D + (size_t)b * ld;
-            bool bad = false;
-            for (int kb = 0; kb < n; kb += 32 * RNN_U) {
-                double x[RNN_U], y[RNN_U];
-                bool act[RNN_U];
+        round++;
+        double *B = (round & 1) ? P.Dw : P.E;
+        const int ldB = (nnew + 3) & ~3;
+        const size_t capB = (round & 1) ? (size_t)n * P.ld : (size_t)P.ecap;
+        work += (double)nr * nr;
+        if ((size_t)nnew * ldB > capB || !B || (work > 16.0 * n * n && nr > 256)) { failed = true; break; }
+        if (nnew == 1) { /* the last merge: nothing left to build */
+            if (tid == 0) s_nm = base + m;
+            nr = 1;
+            __syncthreads();
+            break;
+        }
+        // ---- one warp per row of the next partition's matrix.  Pass 1 walks the columns in the OLD order (contiguous,
+        //      address-independent loads; every value lands at the compacted position of its cluster) and handles the
+        //      clusters that do not merge; pass 2 walks this round's pairs densely (no divergence on the 3-update path) ----
+        for (int ip = warp; ip < nnew; ip += NW) {
+            const int a = sA[ip];
+            const u16 b16 = sB[ip];
+            const bool im = b16 != RNN_NONE;
+            const double *rowa = A + (size_t)a * ldA;
+            double *out = B + (size_t)ip * ldB;
+            const double ma = (double)size[a];
+            RnnBest best;
+            best.d = SHARP_INF; best.i = INT_MAX; best.tie = false;
+            if (!im) {
+                for (int jb = 0; jb < nr; jb += 32 * RNN_UC) {
+                    double x[RNN_UC];
 #pragma unroll
-                for (int u = 0; u < RNN_U; u++) {
-                    const int k = kb + u * 32 + lane;
-                    act[u] = k < n && flag[k] && mrg[k] == 0;
-                    x[u] = act[u] ? rowa[k] : 0.0;
-                    y[u] = act[u] ? rowb[k] : 0.0;
+                    for (int u = 0; u < RNN_UC; u++) {
+                        const int j = jb + u * 32 + lane;
+                        x[u] = (j < nr) ? rowa[j] : 0.0;
+                    }
+#pragma unroll
+                    for (int u = 0; u < RNN_UC; u++) {
+                        const int j = jb + u * 32 + lane;
+                        if (j >= nr || kind[j] != 0) continue;
+                        const int jp = cmap[j];
+                        double v = sq ? __dmul_rn(x[u], x[u]) : x[u];
+                        if (jp == ip) v = 0.0;
+                        out[jp] = v;
+                        if (jp != ip) rnn_consider(best, v, jp);
+                    }
                 }
+                for (int q = lane; q < m; q += 32) { /* this row's cluster a against the new cluster (c, d): I2 = c, J2 = d, K = a */
+                    const int c = pl[q], d = nn[c], jp = cmap[c];
+                    double xc = rowa[c], xd = rowa[d];
+                    if (sq) { xc = __dmul_rn(xc, xc); xd = __dmul_rn(xd, xd); }
+                    const double v = lance_williams(method, xc, xd, hrow[jp], (double)size[c], (double)size[d], ma);
+                    out[jp] = v;
+                    rnn_consider(best, v, jp);
+                }
+            } else {
+                const int b = (int)b16;
+                const double *rowb = A + (size_t)b * ldA;
+                const double mb = (double)size[b], hi = hrow[ip];
+                for (int jb = 0; jb < nr; jb += 32 * RNN_UM) {
+                    double x[RNN_UM], y[RNN_UM];
 #pragma unroll
-                for (int u = 0; u < RNN_U; u++) {
-                    if (!act[u]) continue;
-                    const int k = kb + u * 32 + lane;
-                    const double r = lance_williams(method, x[u], y[u], h, mi, mj, (double)size[k]);
-                    rowa[k] = r;
-                    D[(size_t)k * ld + a] = r;
-                    /* a row whose nearest neighbour survives keeps it only if the new distance is strictly larger */
-                    if (!(r > dnn[k]) && mrg[nn[k]] == 0) bad = true;
+                    for (int u = 0; u < RNN_UM; u++) {
+                        const int j = jb + u * 32 + lane;
+                        x[u] = (j < nr) ? rowa[j] : 0.0;
+                        y[u] = (j < nr) ? rowb[j] : 0.0;
+                    }
+#pragma unroll
+                    for (int u = 0; u < RNN_UM; u++) {
+                        const int j = jb + u * 32 + lane;
+                        if (j >= nr || kind[j] != 0) continue;
+                        const int jp = cmap[j];
+                        double x1 = x[u], y1 = y[u];
+                        if (sq) { x1 = __dmul_rn(x1, x1); y1 = __dmul_rn(y1, y1); }
+                        /* new cluster (a, b) against c = j: I2 = a, J2 = b, K = c */
+                        const double v = lance_williams(method, x1, y1, hi, ma, mb, (double)size[j]);
+                        out[jp] = v;
+                        rnn_consider(best, v, jp);
+                    }
+                }
+                for (int q = lane; q < m; q += 32) { /* both are new: the two updates in the order of their heights, like the reference */
+                    const int c = pl[q], d = nn[c], jp = cmap[c];
+                    if (jp == ip) { out[jp] = 0.0; continue; }
+                    double x1 = rowa[c], y1 = rowb[c], x2 = rowa[d], y2 = rowb[d];
+                    if (sq) {
+                        x1 = __dmul_rn(x1, x1); y1 = __dmul_rn(y1, y1);
+                        x2 = __dmul_rn(x2, x2); y2 = __dmul_rn(y2, y2);
+                    }
+                    const double hj = hrow[jp], mc = (double)size[c], md = (double)size[d];
+                    if (hi == hj) s_tie = 1;
+                    const bool first = hi < hj; /* this row's pair merges first */
+                    const double h1 = first ? hi : hj, h2 = first ? hj : hi;
+                    const double p1 = first ? ma : mc, p2 = first ? mb : md; /* sizes of the pair merging first */
+                    const double r1 = first ? mc : ma, r2 = first ? md : mb; /* sizes of the other pair's members */
+                    /* first merge: (I2, J2) of the earlier pair against each member of the later pair */
+                    const double t1 = lance_williams(method, x1, first ? y1 : x2, h1, p1, p2, r1);
+                    const double t2 = lance_williams(method, first ? x2 : y1, y2, h1, p1, p2, r2);
+                    /* second merge: the later pair (I2 = its kept member, J2 = retired) against the merged earlier pair */
+                    const double v = lance_williams(method, t1, t2, h2, r1, r2, p1 + p2);
+                    out[jp] = v;
+                    rnn_consider(best, v, jp);
                 }
             }
-            if (bad) s_tie = 1;
-        }
-        // ---- two clusters that both merge this round: the two updates in the order of their heights ----
-        for (int idx = tid; idx < np * np; idx += THREADS) {
-            const int p1 = idx / np, q1 = idx - p1 * np;
-            if (p1 >= q1) continue;
-            int f = p1, g = q1; /* f merges first */
-            if (ph[q1] < ph[p1]) { f = q1; g = p1; }
-            if (ph[p1] == ph[q1]) s_tie = 1;
-            const int a = pa[f], b = pb[f], c = pa[g], d = pb[g];
-            const double ma = (double)size[a], mb = (double)size[b], mc = (double)size[c], md = (double)size[d];
-            const double tc = lance_williams(method, D[(size_t)a * ld + c], D[(size_t)b * ld + c], ph[f], ma, mb, mc);
-            const double td = lance_williams(method, D[(size_t)a * ld + d], D[(size_t)b * ld + d], ph[f], ma, mb, md);
-            const double r = lance_williams(method, tc, td, ph[g], mc, md, ma + mb);
-            D[(size_t)a * ld + c] = r;
-            D[(size_t)c * ld + a] = r;
-        }
-        __syncthreads();
-        for (int q = tid; q < np; q += THREADS) {
-            const int a = pa[q], b = pb[q];
-            size[a] += size[b];
-            flag[b] = 0;
-        }
-        if (tid == 0) { s_nm = base + np; s_cnt = 0; }
-        __syncthreads();
-        nact -= np;
-        if (nact > 1) {
-            // ---- rows whose nearest neighbour merged, and the merged rows themselves ----
-            for (int k = tid; k < n; k += THREADS)
-                if (flag[k] && (mrg[k] > 0 || mrg[nn[k]] != 0)) list[atomicAdd(&s_cnt, 1)] = k;
-            __syncthreads();
-            const int cnt = s_cnt;
-            for (int r = warp; r < cnt; r += NW) {
-                const int i = list[r];
-                bool tie;
-                const DI b = rnn_scan_row(D + (size_t)i * ld, flag, n, i, lane, &tie);
-                if (lane == 0) {
-                    nn[i] = (b.i == INT_MAX) ? -1 : b.i;
-                    dnn[i] = b.d;
-                    if (tie || b.i == INT_MAX) s_tie = 1;
-                }
+            bool tie;
+            const DI w = rnn_finish(best, &tie);
+            if (lane == 0) {
+                nn2[ip] = (u16)(w.i == INT_MAX ? 0 : w.i);
+                dnn2[ip] = w.d;
+                if (tie) s_tie = 1;
             }
-            __syncthreads();
         }
-        for (int q = tid; q < np; q += THREADS) {
-            mrg[pa[q]] = 0;
-            mrg[pb[q]] = 0;
-        }
+        if (tid == 0) s_nm = base + m;
         __syncthreads();
+        A = B;
+        ldA = ldB;
+        sq = false;
+        nr = nnew;
+        cur ^= 1;
     }
     if (!failed && s_tie) failed = true;
     // ---- the reference's merge order: ascending height ----
@@ -528,6 +603,9 @@ __global__ void __launch_bounds__(RNN_THREADS, 2) hclust_rnn_kernel(HcProb *prob
     int *ibs = ias + nm;                                         // [nm]
     if (!failed) {
         __syncthreads();
+        if (s_nm != nm) failed = true;
+    }
+    if (!failed) {
         for (int i = tid; i < P2; i += THREADS) {
             key[i] = (i < nm) ? P.crit[i] : SHARP_INF;
             perm[i] = i;
@@ -552,12 +630,17 @@ __global__ void __launch_bounds__(RNN_THREADS, 2) hclust_rnn_kernel(HcProb *prob
 }
 
 static size_t hclust_rnn_smem_bytes(int n) {
-    const size_t hp = (size_t)n / 2 + 1;
-    size_t rounds = (size_t)n * 8 + hp * 8 + (size_t)n * 16 + hp * 8 + (size_t)n;
+    size_t rounds = (size_t)n * (16 + 8 + 4) + (size_t)n * 2 * 9 + ((size_t)n / 2 + 1) * 2 + (size_t)n + 16;
     size_t p2 = 1;
     while ((int)p2 < n - 1) p2 <<= 1;
     size_t sort = p2 * 12 + (size_t)n * 8;
     return (std::max(rounds, sort) + 31) & ~(size_t)15;
+}
+
+bool hclust_fast_ok(int max_n, int method) {
+    static const bool no_rnn = getenv("SHARP_HCLUST_EXACT") != nullptr; /* development switch */
+    const bool reducible = method != SHARP_MEDIAN && method != SHARP_CENTROID;
+    return reducible && !no_rnn && max_n > 384 && max_n < 65535 && hclust_rnn_smem_bytes(max_n) <= (size_t)SHARP_SMEM_OPTIN - 4096;
 }
 
 static size_t hclust_smem_bytes(int n) {
@@ -586,13 +669,10 @@ static int launch_exact(sharp_ctx *c, HcProb *probs_dev, int nprob, int max_n, i
 int launch_hclust(sharp_ctx *c, HcProb *probs_dev, int nprob, int max_n, int method, int fast) {
     if (nprob <= 0) return 0;
     if (method < 1 || method > 8) return set_error(SHARP_E_ARG, "invalid clustering method %d", method);
-    static const bool no_rnn = getenv("SHARP_HCLUST_EXACT") != nullptr; /* development switch */
-    const bool reducible = method != SHARP_MEDIAN && method != SHARP_CENTROID;
-    const size_t rsmem = hclust_rnn_smem_bytes(max_n);
-    if (fast && reducible && !no_rnn && max_n > 384 && rsmem <= (size_t)SHARP_SMEM_OPTIN) {
+    if (fast && hclust_fast_ok(max_n, method)) {
         SHARP_CUDA(cudaFuncSetAttribute(hclust_rnn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SHARP_SMEM_OPTIN));
         prof_begin(c, KID_HCLUST);
-        hclust_rnn_kernel<<<nprob, RNN_THREADS, rsmem, c->stream>>>(probs_dev, method);
+        hclust_rnn_kernel<<<nprob, RNN_THREADS, hclust_rnn_smem_bytes(max_n), c->stream>>>(probs_dev, method);
         prof_end(c);
         SHARP_CUDA(cudaGetLastError());
         return launch_exact(c, probs_dev, nprob, max_n, method, 1);
