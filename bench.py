@@ -39,6 +39,8 @@ for _p in (ROOT, os.path.join(ROOT, "tests")):
         sys.path.insert(0, _p)
 
 SEED = 2103
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture (profiles/README.md)
+TRAFFIC = {}
 # the fused loop over parts keeps ~10 streams busy; with the default 8 hardware queues, streams alias and false
 # dependencies serialise copies and kernels of different parts (must be set before CUDA initialises)
 os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
@@ -181,6 +183,24 @@ def peaks() -> dict:
         return {"hbm_gbs": 6650.0, "source": "fallback (B200_PROFILING.md)"}
 
 
+def h2d_bandwidth(torch, dev) -> float:
+    """pinned host -> device copy bandwidth of this box (GB/s): the floor of the e2e leg is h2d_bytes / this"""
+    n = 1 << 30
+    h = torch.empty(n, dtype=torch.uint8, pin_memory=True)
+    d = torch.empty(n, dtype=torch.uint8, device=dev)
+    d.copy_(h, non_blocking=True)
+    torch.cuda.synchronize()
+    best = 1e30
+    for _ in range(3):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        d.copy_(h, non_blocking=True)
+        e1.record()
+        e1.synchronize()
+        best = min(best, e0.elapsed_time(e1))
+    return n / (best * 1e-3) / 1e9
+
+
 def dgemm_peak_tflops(torch, dev) -> float:
     """fp64 tensor-pipe denominator for the DMMA distance kernel: cuBLAS DGEMM measured in this run (there is no
     fp64 figure in MEASURED_PEAKS.json)."""
@@ -316,6 +336,8 @@ def run_ours(args):
     api._fused_parts = not args.no_fused
     api._fused_group, api._fused_lanes = args.group, args.lanes
     ctx = api.get_context(local)
+    if args.budget_gb:
+        ctx.set_block_budget(args.budget_gb)
     ctxs = api.stream_contexts(args.streams, local) if args.no_fused else [ctx]
     kw = dict(n_streams=args.streams, viewflag=False, ensize_K=wl["K"], rN_seed=SEED, exp_type=wl["exp_type"], ctx=ctx, comm=comm)
 
@@ -360,16 +382,32 @@ def run_ours(args):
         sampler.start()
     ms, res, launches = timed(dev_list, args.steps, True)
     clocks = sampler.stop() if rank == 0 else None
-    prof = {}
-    for c in ctxs:
-        for name, (kms, kn) in c.prof_get().items():
-            a = prof.get(name, (0.0, 0))
-            prof[name] = (a[0] + kms, a[1] + kn)
+
+    def collect():
+        out = {}
+        for c in ctxs:
+            for name, (kms, kn) in c.prof_get().items():
+                a = out.get(name, (0.0, 0))
+                out[name] = (a[0] + kms, a[1] + kn)
+        return out
+
+    prof_conc = collect()  # event brackets DURING the timed steps: kernels of different lanes overlap (sum > step)
+    # one more step with every launch on ONE stream: the same launches and grids, none overlapping, so each event
+    # bracket is the kernel's own duration (the roofline object uses these; shares comparable with the ncu list)
+    prof, ms_serial = prof_conc, None
+    if not args.no_fused and not args.no_serial_profile:
+        ctx.set_serial(True)
+        ms_serial, res_serial, _ = timed(dev_list, 1, True)
+        ctx.set_serial(False)
+        prof = collect()
+        if not np.array_equal(res["pred_clusters"], res_serial["pred_clusters"]):
+            raise SystemExit("serialised profile step produced different labels")
     value = ncells * args.steps / (ms * 1e-3)
 
     # ---- end to end on host buffers (e2e) ----
     for ex in dev_exprs.values():
         ex.close()
+    h2d_gbs = h2d_bandwidth(torch, dev)
     api.SHARP_unlimited(host_list, **kw)  # warm-up of the host path
     e2e_steps = max(1, args.steps)
     ms_e2e, res_e2e, _ = timed(host_list, e2e_steps, False)
@@ -391,11 +429,14 @@ def run_ours(args):
     kernels = {}
     total_kernel_ms = sum(v[0] for v in prof.values())
     dgemm = None
+    psteps = 1 if ms_serial is not None else args.steps
     for name, (kms, kn) in sorted(prof.items(), key=lambda kv: -kv[1][0]):
-        ent = {"ms_per_step": kms / args.steps, "launches_per_step": kn / args.steps, "share_of_kernel_time": kms / total_kernel_ms}
+        ent = {"ms_per_step": kms / psteps, "launches_per_step": kn / psteps, "share_of_kernel_time": kms / total_kernel_ms}
+        if ms_serial is not None and name in prof_conc:
+            ent["ms_per_step_in_timed_region"] = prof_conc[name][0] / args.steps  # overlapped with other lanes' kernels
         if name in work:
             bound, amount = work[name]
-            per_s = amount * args.steps / (kms * 1e-3)
+            per_s = amount * psteps / (kms * 1e-3)
             if bound == "hbm":
                 ent.update(bound="hbm", achieved=per_s / 1e9, peak=pk["hbm_gbs"], unit="GB/s", frac=per_s / 1e9 / pk["hbm_gbs"])
             else:
@@ -409,8 +450,18 @@ def run_ours(args):
     if dom:
         e = kernels[dom]
         roofline = {"kernel": dom, "bound": e["bound"], "achieved": e["achieved"], "peak": e["peak"], "unit": e["unit"],
-                    "frac": e["frac"], "traffic": None, "peak_source": e.get("peak_source", pk["source"]),
-                    "ms_per_launch": e["ms_per_step"] / max(e["launches_per_step"], 1e-9)}
+                    "frac": e["frac"], "traffic": TRAFFIC.get(dom), "peak_source": e.get("peak_source", pk["source"]),
+                    "ms_per_launch": e["ms_per_step"] / max(e["launches_per_step"], 1e-9),
+                    "timing": ("CUDA events around every launch of one extra step of the same workload enqueued on ONE stream "
+                               "(kernels of different parts overlap during the timed steps; their overlapped brackets are "
+                               "ms_per_step_in_timed_region)" if ms_serial is not None else
+                               "CUDA events around every launch during the timed steps"),
+                    "serial_step_ms": ms_serial}
+        rp = kernels.get("rp_project")
+        if rp and "frac" in rp:
+            roofline["rp_project"] = {"bound": "hbm", "achieved": rp["achieved"], "peak": rp["peak"], "unit": "GB/s",
+                                      "frac": rp["frac"], "traffic": TRAFFIC.get("rp_project"),
+                                      "ms_per_launch": rp["ms_per_step"] / max(rp["launches_per_step"], 1e-9)}
 
     # ---- CPU baseline: the oracle port on a bounded sample of the same workload, this box's host cores ----
     cpu = None
@@ -436,7 +487,8 @@ def run_ours(args):
                        "generation_s": t_gen},
             "clocks": clocks, "gpu_launches": int(launches / args.steps),
             "e2e": {"value": e2e_value, "unit": "cells/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "ms_per_step": ms_e2e / e2e_steps, "labels_equal_device_resident_run": same},
+                    "ms_per_step": ms_e2e / e2e_steps, "labels_equal_device_resident_run": same,
+                    "h2d_gbs_measured": h2d_gbs, "h2d_floor_ms_per_step": (h2d / max(world, 1)) / (h2d_gbs * 1e9) * 1e3},
             "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu,
             "result": {"N.pred_clusters": int(res.get("N.pred_clusters", res.get("N.pred_cluster", 0)))}}
     print(json.dumps(line))
@@ -453,9 +505,11 @@ def main():
     ap.add_argument("--parts", type=int, default=0, help="development: only the first PARTS parts")
     ap.add_argument("--group", type=int, default=0, help="parts per group of the fused loop over parts (0 = library default)")
     ap.add_argument("--lanes", type=int, default=0, help="groups in flight (0 = library default)")
+    ap.add_argument("--budget-gb", type=int, default=0, help="distance-matrix workspace cap per context in GB (0 = library default)")
     ap.add_argument("--no-fused", action="store_true", help="part-by-part path (one sharp_run per part, --streams host threads)")
     ap.add_argument("--cpu-sample", type=int, default=20000, help="cells of the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-serial-profile", action="store_true", help="skip the extra one-stream step behind the roofline object")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -234,6 +234,10 @@ int sharp_run_parts(sharp_ctx *ctx, int m, int nparts, sharp_part *parts, const 
 /* cap (GB) of the distance-matrix workspace per context; the (member, block) problems of a group run in waves of
  * as many problems as fit (default 48) */
 int sharp_ctx_set_block_budget(sharp_ctx *ctx, int gigabytes);
+/* on = 1: sharp_run_parts enqueues every stage of every part on the context's own stream (no overlap between
+ * kernels), so that the per-kernel profile (sharp_prof_*) times each launch alone -- same launches and grids as the
+ * concurrent run.  Measurement aid; default 0. */
+int sharp_ctx_set_serial(sharp_ctx *ctx, int on);
 
 /* Per-member results of the LAST sharp_run/sharp_run_dev on this context (SHARP_small's `allrpinfo`,
  * R/SHARP.R:366-385): rowcolor[n] = the member's colour index per cell (getrowColor), inde[n*p] row-major = the

@@ -62,7 +62,7 @@ EXPORTS = [
     "sharp_expr_upload", "sharp_expr_free", "sharp_run_dev", "sharp_centroids", "sharp_smetac_centroids",
     "sharp_last_member", "sharp_last_vie", "sharp_prof_enable", "sharp_prof_reset", "sharp_prof_kernels", "sharp_prof_name",
     "sharp_prof_get", "sharp_ctx_set_rp_variant", "sharp_r_ranm", "sharp_r_sample_perm", "sharp_run_parts",
-    "sharp_ctx_set_block_budget",
+    "sharp_ctx_set_block_budget", "sharp_ctx_set_serial",
 ]
 
 _lib = None
@@ -413,6 +413,10 @@ class Context:
 
     def set_block_budget(self, gigabytes: int):
         _check(load().sharp_ctx_set_block_budget(self._h, int(gigabytes)))
+
+    def set_serial(self, on: bool):
+        """sharp_run_parts on ONE stream (isolated per-kernel timings for the roofline object); default off"""
+        _check(load().sharp_ctx_set_serial(self._h, int(bool(on))))
 
     def run_parts(self, rm: RmDev, prm: RunParams, m: int, parts: list, reinds: list, small_thre=10, cen_cap=64,
                   group=0, lanes=0) -> list:

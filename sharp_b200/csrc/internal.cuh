@@ -107,24 +107,34 @@ struct sharp_ctx {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     int64_t launches = 0;
     sharp::DevBuf ws[48];  // grow-only workspaces (slots named in pipeline.cu)
-    // Pinned staging for descriptor uploads / small downloads: a ring arena.  reserve_pinned(bytes) points `pinned`
-    // at a FRESH chunk, so a chunk handed to cudaMemcpyAsync is never rewritten while the copy is in flight and no
-    // stream synchronisation is needed between the stages of a run; when the arena wraps, the stream is synchronised
-    // once (every staged copy of this context is issued on its own stream).
+    // Pinned staging for descriptor uploads / small downloads: a ring arena of two halves.  reserve_pinned(bytes) points
+    // `pinned` at a FRESH chunk, so a chunk handed to cudaMemcpyAsync is never rewritten while the copy is in flight and
+    // no stream synchronisation is needed between the stages of a run; re-entering a half waits for the event recorded
+    // when it was left (every staged copy of this context is issued on its own stream).
     void *pinned = nullptr;
     size_t pinned_cap = 0;      // size of the chunk `pinned` points at
     unsigned char *arena = nullptr;
     size_t arena_cap = 0, arena_off = 0;
+    cudaEvent_t ev_half[2] = {nullptr, nullptr};
+    bool half_used[2] = {false, false};
+    int half_cur = 0;
     // sub-contexts of a group run (sharp_run_parts): own workspaces and streams, created on first use
     std::vector<sharp_ctx *> subs;
     sharp_ctx *parent = nullptr;
     cudaEvent_t ev_ready = nullptr, ev_blocks = nullptr, ev_done = nullptr, ev_fork = nullptr;
+    // upload look-ahead of a group run: the expression buffers of a sub-context are free again as soon as its part's
+    // front stage (projection) is done, so the NEXT part this sub-context will get is copied in behind that event, on a
+    // stream of its own, while the current part is still being clustered
+    cudaStream_t up_stream = nullptr;
+    cudaEvent_t ev_up = nullptr;
+    int pf_part = -1;             // index of the prefetched part (-1: none)
     int32_t *h_labels = nullptr;  // pinned label mirror of a group run
     size_t h_labels_cap = 0;
     int block_budget_gb = 48;     // cap of the distance-matrix workspace (D + Dw) of one context
     int64_t last_n = 0;     // state of the last run (for sharp_centroids)
     int last_p = 0;
     int last_K = 0;
+    bool serial = false;    // sharp_run_parts: every sub-context enqueues on THIS context's stream (isolated kernel timings)
     bool rp_legacy = false; // force the fp64 read-modify-write projection kernel (tests compare both variants)
     int reserve_pinned(size_t bytes);
     // per-kernel profile: CUDA events around every launch on `stream` while prof_on (off by default)
@@ -146,9 +156,10 @@ struct sharp_rm_dev {
     uint16_t *ent16 = nullptr;   // [nnz] (col | sign<<15) when K*p <= 32768
     uint32_t *ent32 = nullptr;   // [nnz] (col | sign<<31) otherwise
     // padded copy for the fixed-point kernel (K*p <= 32767 only): every gene's entries start on a 16-byte boundary
-    // and are padded to a multiple of 8 with 0xFFFF; vecptr[g] counts 8-entry vectors
+    // and are padded to a multiple of 8 with dummy columns kpd-32+(gene&31); vecptr[g] counts 8-entry vectors
     uint32_t *vecptr = nullptr;  // [m+1]
     uint4 *entvec = nullptr;     // [vecptr[m]]
+    int kpd = 0;                 // K*p rounded up to 32, plus the 32 dummy columns the padding entries point at
     int max_col_nnz = 0;         // largest number of entries in one column of one member (bound on adds per output)
     int vec_per_gene = 0;        // vectors preloaded per gene by the kernel (covers ~99 % of the genes)
 };

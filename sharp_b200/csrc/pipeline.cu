@@ -80,7 +80,7 @@ void DevBuf::release() {
 
 int sharp_ctx::reserve_pinned(size_t bytes) {
     bytes = (std::max<size_t>(bytes, 8) + 255) & ~(size_t)255;
-    if (!arena || bytes > arena_cap) {
+    if (!arena || 2 * bytes > arena_cap) {
         if (arena) {
             cudaStreamSynchronize(stream);
             cudaFreeHost(arena);
@@ -88,15 +88,30 @@ int sharp_ctx::reserve_pinned(size_t bytes) {
         arena = nullptr;
         arena_cap = arena_off = 0;
         pinned = nullptr;
-        size_t want = std::max<size_t>((size_t)8 << 20, 2 * bytes);
+        half_used[0] = half_used[1] = false;
+        half_cur = 0;
+        size_t want = std::max<size_t>((size_t)32 << 20, 4 * bytes);
         cudaError_t e = cudaMallocHost((void **)&arena, want);
         if (e != cudaSuccess) return sharp::set_error(SHARP_E_NOMEM, "cudaMallocHost(%zu) failed: %s", want, cudaGetErrorString(e));
         arena_cap = want;
+        for (int h = 0; h < 2; h++)
+            if (!ev_half[h]) cudaEventCreateWithFlags(&ev_half[h], cudaEventDisableTiming);
     }
-    if (arena_off + bytes > arena_cap) { /* wrap: every copy staged so far must have completed */
-        cudaError_t e = cudaStreamSynchronize(stream);
-        if (e != cudaSuccess) return sharp::set_error(SHARP_E_CUDA, "cudaStreamSynchronize: %s", cudaGetErrorString(e));
-        arena_off = 0;
+    /* The arena is used as two halves.  Leaving a half records an event behind every copy staged in it; coming back to
+       it waits for THAT event only -- recorded half an arena ago, normally long complete -- instead of draining the
+       stream (a drain in the middle of a group run stalls the host, and with it every other stream's queue). */
+    const size_t halfcap = arena_cap / 2;
+    const int cur = half_cur;
+    if (arena_off + bytes > (size_t)(cur + 1) * halfcap) {
+        const int nxt = cur ^ 1;
+        cudaEventRecord(ev_half[cur], stream);
+        half_used[cur] = true;
+        if (half_used[nxt]) {
+            cudaError_t e = cudaEventSynchronize(ev_half[nxt]);
+            if (e != cudaSuccess) return sharp::set_error(SHARP_E_CUDA, "cudaEventSynchronize: %s", cudaGetErrorString(e));
+        }
+        arena_off = (size_t)nxt * halfcap;
+        half_cur = nxt;
     }
     pinned = arena + arena_off;
     pinned_cap = bytes;
@@ -228,7 +243,8 @@ static int grid1d(size_t n, int threads) { return (int)((n + threads - 1) / thre
 // cudaFree synchronises the whole device, which would serialise contexts working on other streams) and is valid
 // until the next staged upload on this context; staged = false: the caller owns it (sharp_expr_upload).
 static int upload_expr(sharp_ctx *c, int m, int64_t n, const double *dense, const int64_t *colptr, const int32_t *rowidx,
-                       const double *val, sharp_expr_dev *e, bool staged = false) {
+                       const double *val, sharp_expr_dev *e, bool staged = false, cudaStream_t on = nullptr) {
+    const cudaStream_t st = on ? on : c->stream;
     e->device = c->device;
     e->m = m;
     e->n = n;
@@ -245,7 +261,7 @@ static int upload_expr(sharp_ctx *c, int m, int64_t n, const double *dense, cons
     if (dense) {
         size_t bytes = (size_t)m * n * sizeof(double);
         SHARP_TRY(get(WS_EX_A, (void **)&e->dense, bytes));
-        SHARP_CUDA(cudaMemcpyAsync(e->dense, dense, bytes, cudaMemcpyHostToDevice, c->stream));
+        SHARP_CUDA(cudaMemcpyAsync(e->dense, dense, bytes, cudaMemcpyHostToDevice, st));
     } else {
         if (!colptr || (!rowidx && colptr[n] > 0) || (!val && colptr[n] > 0))
             return set_error(SHARP_E_ARG, "expression matrix: neither dense nor complete CSC slots given");
@@ -253,9 +269,9 @@ static int upload_expr(sharp_ctx *c, int m, int64_t n, const double *dense, cons
         SHARP_TRY(get(WS_EX_A, (void **)&e->colptr, (size_t)(n + 1) * 8));
         SHARP_TRY(get(WS_EX_B, (void **)&e->rowidx, (size_t)e->nnz * 4));
         SHARP_TRY(get(WS_EX_C, (void **)&e->val, (size_t)e->nnz * 8));
-        SHARP_CUDA(cudaMemcpyAsync(e->colptr, colptr, (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, c->stream));
-        SHARP_CUDA(cudaMemcpyAsync(e->rowidx, rowidx, (size_t)e->nnz * 4, cudaMemcpyHostToDevice, c->stream));
-        SHARP_CUDA(cudaMemcpyAsync(e->val, val, (size_t)e->nnz * 8, cudaMemcpyHostToDevice, c->stream));
+        SHARP_CUDA(cudaMemcpyAsync(e->colptr, colptr, (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, st));
+        SHARP_CUDA(cudaMemcpyAsync(e->rowidx, rowidx, (size_t)e->nnz * 4, cudaMemcpyHostToDevice, st));
+        SHARP_CUDA(cudaMemcpyAsync(e->val, val, (size_t)e->nnz * 8, cudaMemcpyHostToDevice, st));
     }
     return 0;
 }
@@ -282,6 +298,22 @@ static void free_expr(sharp_expr_dev *e) {
 static int h2d(sharp_ctx *c, void *dst, const void *src, size_t bytes) {
     if (bytes == 0) return 0;
     SHARP_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, c->stream));
+    return 0;
+}
+// Host -> device copy of a chunk of the context's PINNED arena (descriptor tables, index vectors: bytes to a few hundred
+// KB) done by a kernel that reads the mapped host memory, not by the copy engine: the copy engine serves the streams'
+// copies in order, so behind the multi-GB expression uploads of a group run a 4 KB descriptor copy would wait for
+// every part queued before it -- and the kernels behind that copy with it.
+__global__ void stage_copy_kernel(uint32_t *__restrict__ dst, const uint32_t *__restrict__ src, size_t nwords) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nwords; i += (size_t)gridDim.x * blockDim.x) dst[i] = src[i];
+}
+static int h2d_staged(sharp_ctx *c, void *dst, const void *src, size_t bytes) {
+    if (bytes == 0) return 0;
+    if ((bytes & 3) || ((uintptr_t)dst & 3) || ((uintptr_t)src & 3) || bytes > ((size_t)16 << 20)) return h2d(c, dst, src, bytes);
+    const size_t nw = bytes / 4;
+    const int grid = (int)std::min<size_t>(64, (nw + 255) / 256);
+    stage_copy_kernel<<<grid, 256, 0, c->stream>>>(reinterpret_cast<uint32_t *>(dst), reinterpret_cast<const uint32_t *>(src), nw);
+    SHARP_CUDA(cudaGetLastError());
     return 0;
 }
 static int d2h(sharp_ctx *c, void *dst, const void *src, size_t bytes) {
@@ -351,7 +383,7 @@ static int opt_hclust_dev(sharp_ctx *c, int nrow, int ncol, const double *mat_de
         tp[0] = 0; tp[1] = corrdist_tiles(n);
         GemmProb *gpd = db.take<GemmProb>(1);
         int *tpd = db.take<int>(2);
-        SHARP_TRY(h2d(c, c->ws[WS_DESC].ptr, c->pinned, hb.off));
+        SHARP_TRY(h2d_staged(c, c->ws[WS_DESC].ptr, c->pinned, hb.off));
         SHARP_TRY(launch_corrdist_batched(c, gpd, tpd, 1, tp[1], ldu));
         Y = U;
         yp = ncol;
@@ -394,7 +426,7 @@ static int opt_hclust_dev(sharp_ctx *c, int nrow, int ncol, const double *mat_de
     HcProb *hpd = db.take<HcProb>(1);
     SweepOut *sod = db.take<SweepOut>(1);
     HcParamsDev *ppd = db.take<HcParamsDev>(1);
-    SHARP_TRY(h2d(c, c->ws[WS_DESC].ptr, c->pinned, hb.off));
+    SHARP_TRY(h2d_staged(c, c->ws[WS_DESC].ptr, c->pinned, hb.off));
     SHARP_TRY(launch_hclust(c, hpd, 1, n, prm.hmethod, symmetric ? 0 : 1));
     if (exact) {
         size_t sb = sweep_exact_scratch_bytes(n, yp);
@@ -493,7 +525,7 @@ static int wmetac_dev(sharp_ctx *c, const int32_t *labels_dev, int64_t ncells, i
     A.probs = db.take<HcProb>(T);
     W->outs_dev = db.take<SweepOut>(T);
     W->prm_dev = db.take<HcParamsDev>(T);
-    SHARP_TRY(h2d(c, c->ws[WS_WM_DESC].ptr, c->pinned, hb.off));
+    SHARP_TRY(h2d_staged(c, c->ws[WS_WM_DESC].ptr, c->pinned, hb.off));
     W->T = T;
     W->max_block_n = max_block_n;
     SHARP_TRY(launch_wmetac_front(c, A, T, max_block_n));
@@ -576,7 +608,7 @@ static int smetac_dev(sharp_ctx *c, int capS, int p, const int *nc_ptr, const in
     A.prob = db.take<HcProb>(1);
     B->out_dev = db.take<SweepOut>(1);
     A.prm_out = db.take<HcParamsDev>(1);
-    SHARP_TRY(h2d(c, c->ws[WS_DESC].ptr, c->pinned, hb.off));
+    SHARP_TRY(h2d_staged(c, c->ws[WS_DESC].ptr, c->pinned, hb.off));
     const double *cen = cen_in;
     if (!cen) {
         SHARP_TRY(launch_sm_centroids(c, E1, p, corder, coff, nc_ptr, capS, B->cen, nullptr));
@@ -694,13 +726,13 @@ static int part_front(PartRun &R, sharp_ctx *c, const sharp_expr_dev &e, const d
             if (reind[i] < 1 || reind[i] > n) return set_error(SHARP_E_ARG, "reind is not a permutation of 1..n");
             hp[i] = reind[i] - 1;
         }
-        SHARP_TRY(h2d(c, R.src_dev, hp, (size_t)n * 8));
+        SHARP_TRY(h2d_staged(c, R.src_dev, hp, (size_t)n * 8));
     }
     SHARP_TRY(c->ws[WS_START].reserve((size_t)(T + 1) * 8));
     R.start_dev = c->ws[WS_START].as<int64_t>();
     SHARP_TRY(c->reserve_pinned((size_t)(T + 1) * 8));
     memcpy(c->pinned, R.start.data(), (size_t)(T + 1) * 8);
-    SHARP_TRY(h2d(c, R.start_dev, c->pinned, (size_t)(T + 1) * 8));
+    SHARP_TRY(h2d_staged(c, R.start_dev, c->pinned, (size_t)(T + 1) * 8));
     double *colsum_dev = nullptr;
     if (Q.normalize) {
         SHARP_TRY(c->ws[WS_COLSUM].reserve((size_t)n * 8));
@@ -780,7 +812,14 @@ static int run_blocks(sharp_ctx *g, PartRun *const *parts, int np_parts) {
     const bool fast = hclust_fast_ok(max_bn, ind.hmethod);
     const size_t ecap = fast ? (((size_t)(0.8 * max_bn * ld_of(max_bn)) + 31) & ~(size_t)31) : 0;
     const size_t per_all = 2 * per_prob + ecap * 8;
-    const int wave_probs = (int)std::min<size_t>((size_t)nprob, std::max<size_t>(1, budget / per_all));
+    int wave_probs = (int)std::min<size_t>((size_t)nprob, std::max<size_t>(1, budget / per_all));
+    if (fast) {
+        /* the agglomeration kernel keeps 2 CTAs (= problems) per SM resident: a wave of one problem more than that
+           costs a whole extra pass of a lone CTA, so waves are capped at the resident count and then evened out */
+        wave_probs = std::min(wave_probs, std::max(1, 2 * g->sm_count));
+        const int nw = (nprob + wave_probs - 1) / wave_probs;
+        wave_probs = (nprob + nw - 1) / nw;
+    }
     SHARP_TRY(g->ws[WS_D].reserve(per_prob * wave_probs));
     SHARP_TRY(g->ws[WS_DW].reserve(per_prob * wave_probs));
     if (ecap) SHARP_TRY(g->ws[WS_HC_E].reserve(ecap * 8 * wave_probs));
@@ -850,7 +889,7 @@ static int run_blocks(sharp_ctx *g, PartRun *const *parts, int np_parts) {
             waves.push_back(w);
         }
     }
-    SHARP_TRY(h2d(g, g->ws[WS_GDESC].ptr, g->pinned, hb.off));
+    SHARP_TRY(h2d_staged(g, g->ws[WS_GDESC].ptr, g->pinned, hb.off));
     for (const Wave &w : waves) {
         SHARP_TRY(launch_corrdist_batched(g, gpd + w.q0, tpd + w.tp_off, w.nq, w.tiles, ldu));
         SHARP_TRY(launch_hclust(g, hpd + w.q0, w.nq, max_bn, ind.hmethod, 1));
@@ -976,7 +1015,7 @@ static int part_finish(PartRun &R, int32_t *labels_out, double *vie_out, double 
             for (int &v : colmap_host) v -= 1;
             SHARP_TRY(c->reserve_pinned(colmap_host.size() * 4 + 64));
             memcpy(c->pinned, colmap_host.data(), colmap_host.size() * 4);
-            SHARP_TRY(h2d(c, cm, c->pinned, colmap_host.size() * 4));
+            SHARP_TRY(h2d_staged(c, cm, c->pinned, colmap_host.size() * 4));
             SHARP_TRY(launch_wmetac_x0(c, R.W.A, R.W.outs_dev, T, R.W.max_block_n, R.coloff_dev, cm, R.src_dev, x0d, ncol_x0));
         }
         SHARP_TRY(d2h(c, x0_out, x0d, (size_t)n * ncol_x0 * 8));
@@ -1019,6 +1058,7 @@ static int make_child(sharp_ctx *parent, sharp_ctx **out) {
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_done, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreate(&c->ev0);
     if (e == cudaSuccess) e = cudaEventCreate(&c->ev1);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_up, cudaEventDisableTiming);
     if (e != cudaSuccess) {
         delete c;
         return set_error(SHARP_E_CUDA, "creating a sub-context: %s", cudaGetErrorString(e));
@@ -1040,6 +1080,8 @@ void destroy_ctx_resources(sharp_ctx *c) {
     c->prof_pool.clear();
     for (auto &b : c->ws) b.release();
     if (c->arena) cudaFreeHost(c->arena);
+    for (int h = 0; h < 2; h++)
+        if (c->ev_half[h]) { cudaEventDestroy(c->ev_half[h]); c->ev_half[h] = nullptr; }
     if (c->h_labels) cudaFreeHost(c->h_labels);
     c->arena = nullptr;
     c->h_labels = nullptr;
@@ -1049,6 +1091,8 @@ void destroy_ctx_resources(sharp_ctx *c) {
     if (c->ev_blocks) cudaEventDestroy(c->ev_blocks);
     if (c->ev_done) cudaEventDestroy(c->ev_done);
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+    if (c->ev_up) cudaEventDestroy(c->ev_up);
+    if (c->up_stream) { cudaStreamSynchronize(c->up_stream); cudaStreamDestroy(c->up_stream); }
     cudaStreamDestroy(c->stream);
 }
 
@@ -1087,6 +1131,7 @@ struct GroupRun {
     std::vector<int> idx;          // part indices
     std::vector<PartRun> runs;
     sharp_ctx *blocks = nullptr;
+    cudaStream_t up = nullptr;     // upload stream of the run (null: copies go on each part's own stream)
     std::vector<sharp_ctx *> subs;
     // centroid staging per part
     std::vector<int> nclust;
@@ -1104,6 +1149,22 @@ static int group_issue(GroupRun &G, sharp_part *parts, int m, const sharp_rm_dev
         if (P.dev) {
             e = *P.dev;
             e.owned = false;
+        } else if (s->pf_part == G.idx[j]) { /* copied in by group_prefetch while the previous group was running */
+            s->pf_part = -1;
+            e.device = s->device; e.m = m; e.n = P.n; e.owned = false;
+            if (P.dense) e.dense = s->ws[WS_EX_A].as<double>();
+            else {
+                e.nnz = P.colptr[P.n];
+                e.colptr = s->ws[WS_EX_A].as<int64_t>();
+                e.rowidx = s->ws[WS_EX_B].as<int32_t>();
+                e.val = s->ws[WS_EX_C].as<double>();
+            }
+            SHARP_CUDA(cudaStreamWaitEvent(s->stream, s->ev_up, 0));
+        } else if (G.up) { /* all uploads of a group run go through ONE stream: the copy engine shares the link between
+                              streams, and the first group must not wait for the bytes of the groups behind it */
+            SHARP_TRY(upload_expr(s, m, P.n, P.dense, P.colptr, P.rowidx, P.val, &e, true, G.up));
+            SHARP_CUDA(cudaEventRecord(s->ev_up, G.up));
+            SHARP_CUDA(cudaStreamWaitEvent(s->stream, s->ev_up, 0));
         } else {
             prof_begin(s, KID_H2D);
             int urc = upload_expr(s, m, P.n, P.dense, P.colptr, P.rowidx, P.val, &e, true);
@@ -1139,6 +1200,37 @@ static int group_issue(GroupRun &G, sharp_part *parts, int m, const sharp_rm_dev
     return 0;
 }
 
+// Upload look-ahead: the parts of the group that will run on these sub-contexts NEXT are copied into the sub-contexts'
+// expression buffers as soon as the front stage of the part that occupies them now is done (ev_ready).  Only when
+// the buffers are already large enough (growing one would free memory that is in use); otherwise group_issue uploads
+// the part itself, as it does for the first groups.
+static int group_prefetch(const std::vector<int> &idx, const std::vector<sharp_ctx *> &subs, sharp_part *parts, int m,
+                          cudaStream_t up) {
+    for (size_t j = 0; j < idx.size(); j++) {
+        const sharp_part &P = parts[idx[j]];
+        sharp_ctx *s = subs[j];
+        s->pf_part = -1;
+        if (P.dev || m <= 0 || P.n < 0) continue;
+        if (P.dense) {
+            const size_t bytes = (size_t)m * P.n * sizeof(double);
+            if (s->ws[WS_EX_A].cap < bytes) continue;
+            SHARP_CUDA(cudaStreamWaitEvent(up, s->ev_ready, 0));
+            SHARP_CUDA(cudaMemcpyAsync(s->ws[WS_EX_A].ptr, P.dense, bytes, cudaMemcpyHostToDevice, up));
+        } else {
+            if (!P.colptr || !P.rowidx || !P.val) continue;
+            const int64_t nnz = P.colptr[P.n];
+            if (s->ws[WS_EX_A].cap < (size_t)(P.n + 1) * 8 || s->ws[WS_EX_B].cap < (size_t)nnz * 4 || s->ws[WS_EX_C].cap < (size_t)nnz * 8) continue;
+            SHARP_CUDA(cudaStreamWaitEvent(up, s->ev_ready, 0));
+            SHARP_CUDA(cudaMemcpyAsync(s->ws[WS_EX_A].ptr, P.colptr, (size_t)(P.n + 1) * 8, cudaMemcpyHostToDevice, up));
+            SHARP_CUDA(cudaMemcpyAsync(s->ws[WS_EX_B].ptr, P.rowidx, (size_t)nnz * 4, cudaMemcpyHostToDevice, up));
+            SHARP_CUDA(cudaMemcpyAsync(s->ws[WS_EX_C].ptr, P.val, (size_t)nnz * 8, cudaMemcpyHostToDevice, up));
+        }
+        SHARP_CUDA(cudaEventRecord(s->ev_up, up));
+        s->pf_part = idx[j];
+    }
+    return 0;
+}
+
 static int group_complete(GroupRun &G, sharp_part *parts, int small_thre, int cen_cap) {
     const int np = (int)G.idx.size();
     G.nclust.assign(np, 0);
@@ -1170,9 +1262,9 @@ static int group_complete(GroupRun &G, sharp_part *parts, int small_thre, int ce
         memcpy(hp, corder.data(), (size_t)R.n * 4);
         memcpy(hp + R.n, coff.data(), (size_t)(nclust + 1) * 4);
         hp[R.n + nclust + 1] = nclust;
-        SHARP_TRY(h2d(s, corder_d, hp, (size_t)R.n * 4));
-        SHARP_TRY(h2d(s, coff_d, hp + R.n, (size_t)(nclust + 1) * 4));
-        SHARP_TRY(h2d(s, nc_d, hp + R.n + nclust + 1, 4));
+        SHARP_TRY(h2d_staged(s, corder_d, hp, (size_t)R.n * 4));
+        SHARP_TRY(h2d_staged(s, coff_d, hp + R.n, (size_t)(nclust + 1) * 4));
+        SHARP_TRY(h2d_staged(s, nc_d, hp + R.n + nclust + 1, 4));
         SHARP_TRY(launch_sm_centroids(s, R.vieu, R.p, corder_d, coff_d, nc_d, nclust, s->ws[WS_CEN].as<double>(), cnt_d));
         SHARP_TRY(s->reserve_pinned((size_t)nclust * R.p * 8 + (size_t)nclust * 8));
         G.h_cen[j] = reinterpret_cast<double *>(s->pinned);
@@ -1296,6 +1388,12 @@ static const char *const g_kernel_names[KID_COUNT] = {
     "rp_project", "colsum", "unit_rows", "corrdist", "hclust", "hclust_small", "sweep_nested", "sweep_exact",
     "wm_weights", "wm_similarity", "wmetac_misc", "sm_centroids", "smetac_misc", "ene_scatter", "misc", "h2d_expr"};
 
+int sharp_ctx_set_serial(sharp_ctx *c, int on) {
+    if (!c) return set_error(SHARP_E_ARG, "null context");
+    c->serial = on != 0;
+    return 0;
+}
+
 int sharp_ctx_set_rp_variant(sharp_ctx *c, int legacy) {
     if (!c) return set_error(SHARP_E_ARG, "null context");
     c->rp_legacy = legacy != 0;
@@ -1405,20 +1503,23 @@ int sharp_rm_upload(sharp_ctx *c, int m, int p, int K, const int32_t *colptr, co
         const int32_t *cp = colptr + (size_t)k * (p + 1);
         for (int j = 0; j < p; j++) r->max_col_nnz = std::max(r->max_col_nnz, cp[j + 1] - cp[j]);
     }
-    if ((int64_t)K * p <= 32767 && e1 == cudaSuccess && e2 == cudaSuccess) {
+    if ((int64_t)K * p <= 32700 && e1 == cudaSuccess && e2 == cudaSuccess) {
+        const int kpr = (K * p + 31) & ~31;
+        r->kpd = kpr + 32;
         std::vector<uint32_t> vecptr((size_t)m + 1, 0);
         for (int i = 0; i < m; i++) vecptr[i + 1] = vecptr[i] + (rowptr[i + 1] - rowptr[i] + 7) / 8;
-        std::vector<uint16_t> padded((size_t)vecptr[m] * 8 + 8, 0xFFFFu);
+        std::vector<uint16_t> padded((size_t)vecptr[m] * 8 + 8, (uint16_t)kpr);
         double mean = 0, sq = 0;
         for (int i = 0; i < m; i++) {
             const uint32_t c = rowptr[i + 1] - rowptr[i];
+            for (uint32_t q = c; q < ((c + 7) & ~7u); q++) padded[(size_t)vecptr[i] * 8 + q] = (uint16_t)(kpr + (i & 31));
             for (uint32_t q = 0; q < c; q++) padded[(size_t)vecptr[i] * 8 + q] = (uint16_t)ent[rowptr[i] + q];
             mean += c;
             sq += (double)c * c;
         }
         mean /= m;
         const double sd = std::sqrt(std::max(0.0, sq / m - mean * mean));
-        r->vec_per_gene = std::min(8, std::max(1, (int)std::ceil((mean + 2.5 * sd) / 8.0)));
+        r->vec_per_gene = std::min(6, std::max(1, (int)std::ceil((mean + 2.5 * sd) / 8.0)));
         cudaError_t e3 = cudaMalloc((void **)&r->vecptr, (size_t)(m + 1) * 4);
         cudaError_t e4 = cudaMalloc((void **)&r->entvec, padded.size() * 2);
         if (e3 == cudaSuccess) e3 = cudaMemcpy(r->vecptr, vecptr.data(), (size_t)(m + 1) * 4, cudaMemcpyHostToDevice);
@@ -1524,7 +1625,7 @@ int sharp_corrdist(sharp_ctx *c, int n, int p, const double *mat, double *dist) 
     tp[0] = 0; tp[1] = corrdist_tiles(n);
     GemmProb *gpd = db.take<GemmProb>(1);
     int *tpd = db.take<int>(2);
-    SHARP_TRY(h2d(c, c->ws[WS_DESC].ptr, c->pinned, hb.off));
+    SHARP_TRY(h2d_staged(c, c->ws[WS_DESC].ptr, c->pinned, hb.off));
     SHARP_TRY(launch_corrdist_batched(c, gpd, tpd, 1, tp[1], ldu));
     prof_begin(c, KID_MISC);
     pad_copy_kernel<<<grid1d((size_t)n * n, 256), 256, 0, c->stream>>>(n, n, c->ws[WS_D].as<double>(), ld, c->ws[WS_TMP1].as<double>(), n);
@@ -1774,7 +1875,13 @@ int sharp_run_parts(sharp_ctx *c, int m, int nparts, sharp_part *parts, const sh
     if (group <= 0) group = 4;
     if (lanes <= 0) lanes = 2;
     group = std::min(group, nparts);
-    const int ngroups = (nparts + group - 1) / group;
+    // group boundaries; with host data the first group is half size, so that the clustering of the first group starts
+    // after half as many uploads (every later upload is hidden behind the group before it)
+    std::vector<int> gstart{0};
+    if (!parts[0].dev && group >= 2 && nparts > group) gstart.push_back(group / 2);
+    while (gstart.back() < nparts) gstart.push_back(std::min(nparts, gstart.back() + group));
+    if (gstart.size() == 1) gstart.push_back(nparts);
+    const int ngroups = (int)gstart.size() - 1;
     lanes = std::min(lanes, ngroups);
     const size_t need = (size_t)lanes * (group + 1);
     while (c->subs.size() < need) {
@@ -1783,13 +1890,34 @@ int sharp_run_parts(sharp_ctx *c, int m, int nparts, sharp_part *parts, const sh
         c->subs.push_back(s);
     }
     for (sharp_ctx *s : c->subs) {
+        s->pf_part = -1;
         s->prof_on = c->prof_on;
         s->rp_legacy = c->rp_legacy;
         s->block_budget_gb = std::max(1, c->block_budget_gb / lanes);
     }
+    // serial mode (profiling): all sub-contexts enqueue on the context's own stream, so no two kernels overlap and
+    // the per-kernel event brackets measure each launch alone; same launches and grids as the concurrent run
+    struct StreamSwap {
+        sharp_ctx *c;
+        std::vector<cudaStream_t> saved;
+        ~StreamSwap() {
+            for (size_t i = 0; i < saved.size(); i++) c->subs[i]->stream = saved[i];
+        }
+    } swap{c, {}};
+    if (c->serial)
+        for (size_t i = 0; i < need; i++) {
+            swap.saved.push_back(c->subs[i]->stream);
+            c->subs[i]->stream = c->stream;
+        }
     // children start after whatever is queued on the context's own stream (and the timer's start event)
     SHARP_CUDA(cudaEventRecord(c->ev_fork, c->stream));
     for (size_t i = 0; i < need; i++) SHARP_CUDA(cudaStreamWaitEvent(c->subs[i]->stream, c->ev_fork, 0));
+    cudaStream_t up = nullptr;
+    if (!c->serial) {
+        if (!c->up_stream) SHARP_CUDA(cudaStreamCreateWithFlags(&c->up_stream, cudaStreamNonBlocking));
+        up = c->up_stream;
+        SHARP_CUDA(cudaStreamWaitEvent(up, c->ev_fork, 0));
+    }
     std::vector<GroupRun> G(ngroups);
     int rc = 0;
     static const bool trace = getenv("SHARP_B200_TRACE") != nullptr;
@@ -1797,11 +1925,24 @@ int sharp_run_parts(sharp_ctx *c, int m, int nparts, sharp_part *parts, const sh
     for (int gi = 0; gi < ngroups && !rc; gi++) {
         GroupRun &g = G[gi];
         const int lane = gi % lanes;
-        for (int i = gi * group; i < std::min(nparts, (gi + 1) * group); i++) g.idx.push_back(i);
+        for (int i = gstart[gi]; i < gstart[gi + 1]; i++) g.idx.push_back(i);
         g.blocks = c->subs[(size_t)lane * (group + 1) + group];
+        g.up = up;
         for (size_t j = 0; j < g.idx.size(); j++) g.subs.push_back(c->subs[(size_t)lane * (group + 1) + j]);
         const auto t_a = std::chrono::steady_clock::now();
         rc = group_issue(g, parts, m, *rm, *prm);
+        if (!rc && !c->serial && lanes >= 2 && gi >= 1 && gi - 1 + lanes < ngroups) {
+            /* look-ahead for the group that gets the PREVIOUS group's lane next (its uploads queue up behind this group's,
+               so the copy engine sees the parts in order) */
+            const int ng = gi - 1 + lanes, nlane = (gi - 1) % lanes;
+            std::vector<int> nidx;
+            std::vector<sharp_ctx *> lsubs;
+            for (int i = gstart[ng]; i < gstart[ng + 1]; i++) {
+                nidx.push_back(i);
+                lsubs.push_back(c->subs[(size_t)nlane * (group + 1) + (i - gstart[ng])]);
+            }
+            rc = group_prefetch(nidx, lsubs, parts, m, up);
+        }
         const auto t_b = std::chrono::steady_clock::now();
         /* the group that used this lane's contexts `lanes` groups ago has been completed below before its contexts are
            reused here; complete the oldest outstanding group while the newer ones keep the device busy */
@@ -1822,6 +1963,7 @@ int sharp_run_parts(sharp_ctx *c, int m, int nparts, sharp_part *parts, const sh
     }
     if (rc) {
         std::string msg = g_err; /* keep the first error across the drain */
+        if (up) cudaStreamSynchronize(up);
         for (size_t i = 0; i < need; i++) cudaStreamSynchronize(c->subs[i]->stream);
         cudaGetLastError();
         snprintf(g_err, sizeof g_err, "%s", msg.c_str());

@@ -202,7 +202,7 @@ __global__ void __launch_bounds__(320) rp_project_kernel(RpArgs A, int warps_per
 }
 
 // =====================================================================================================
-// K1, fixed-point variant (the one the pipeline uses whenever K*p <= 32767)
+// K1, fixed-point variant (the one the pipeline uses whenever K*p <= 32700)
 // =====================================================================================================
 // The scatter above is bound by its dependent shared-memory read-modify-write chain: one warp per cell, at most ten
 // cells per SM (their fp64 accumulators fill shared memory), every gene's add waiting for the previous one.  This
@@ -213,84 +213,121 @@ __global__ void __launch_bounds__(320) rp_project_kernel(RpArgs A, int warps_per
 //     cell's largest value (the integer sum is EXACT; the only roundings are v -> q and the final int64 -> double,
 //     so the result is at least as accurate as the reference's fp64 running sum and bit-reproducible);
 //   * the accumulators are two 32-bit limbs per output in shared memory, updated with native shared-memory integer
-//     atomics: atomicAdd on the low limb returns the old value, from which the carry into the high limb follows;
+//     atomics: the atomic add on the low limb returns the old value, from which the carry into the high limb follows;
+//   * COUNT CLASSES.  Single-cell counts are small integers: most non-zeros of a cell are 1, 2, 3 or 4, and all
+//     non-zeros with the same raw value share the same transformed value.  For those the kernel does not add q at
+//     all: it COUNTS, per output, how many +entries and how many -entries each class contributed (8-bit fields, four
+//     per 32-bit word, one non-returning-cost atomic per entry instead of two dependent ones and no log per non-zero),
+//     and the epilogue adds q_class * (n+ - n-) to the limbs -- the same exact integer sum, so the result is
+//     bit-identical to adding every term.  Fields cannot overflow: a field counts entries of ONE ranM column, and the
+//     longest column has < 2^FB entries (FB = 16 with two classes when a column is longer than 255);
 //   * lanes map to GENES (32 non-zeros of the cell at a time): a lane fetches its gene's padded entry list with
-//     16-byte loads and issues its adds without waiting for anybody; four warps share one cell, eight cells per SM.
+//     16-byte loads and issues its adds without waiting for anybody; eight warps share one cell, five cells per SM.
+//     Padding entries point at 32 dummy outputs behind the real ones, so the inner loop has no per-entry branch, and
+//     all shared-memory addresses are 32-bit shared-window addresses computed once (atom.shared / red.shared in PTX).
 struct RpFxArgs {
     RpArgs a;
     const uint32_t *vecptr;
     const uint4 *entvec;
     int cb;     // bits of headroom for the number of terms per output
-    int kpad;   // K*p rounded up to 32 (offset of the high limbs)
+    int kpd;    // words per accumulator array: K*p rounded up to 32, plus 32 dummy outputs for the padding entries
 };
 
-constexpr int RPF_THREADS = 128;
+constexpr int RPF_THREADS = 256;
 constexpr int RPF_WARPS = RPF_THREADS / 32;
 constexpr int RPF_STAGE = 64;  // per-warp compaction buffer of the dense path
+constexpr int RPF_MAXCLS = 4;
 
-__device__ __forceinline__ void rpf_add(uint32_t *lo, uint32_t *hi, uint32_t ent, uint32_t qlo, uint32_t qhi,
-                                        uint32_t nlo, uint32_t nhi) {
-    if (ent == 0xffffu) return; /* padding */
-    const uint32_t col = ent & 0x7fffu;
-    const bool neg = (ent & 0x8000u) != 0;
-    const uint32_t alo = neg ? nlo : qlo, ahi = neg ? nhi : qhi;
-    const uint32_t old = atomicAdd(lo + col, alo);
-    const uint32_t carry = ((uint32_t)(old + alo) < alo) ? 1u : 0u;
-    atomicAdd(hi + col, ahi + carry);
+__device__ __forceinline__ uint32_t atoms_add(uint32_t addr, uint32_t v) {
+    uint32_t old;
+    asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(addr), "r"(v) : "memory");
+    return old;
+}
+__device__ __forceinline__ void reds_add_if(uint32_t addr, uint32_t v, uint32_t pred) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p red.shared.add.u32 [%0], %1;\n\t}" ::"r"(addr), "r"(v), "r"(pred) : "memory");
 }
 
-// one vector = 8 entries: all low-limb atomics are issued before the first carry is consumed
-__device__ __forceinline__ void rpf_add8(uint32_t *lo, uint32_t *hi, uint4 w, uint32_t qlo, uint32_t qhi, uint32_t nlo,
-                                         uint32_t nhi) {
-    const uint32_t ws[4] = {w.x, w.y, w.z, w.w};
-    uint32_t old[8], alo[8], col[8];
-    bool ok[8], neg[8];
+// what one lane adds for its gene: `base` = shared address of the array its first atomic goes to (a class counter array
+// or the low limbs), apos / aneg = the addend for a + / - entry; generic lanes also carry the high words
+struct RpLane {
+    uint32_t base, apos, aneg, hpos, hneg, gen;
+};
+
+// four entries (two packed words): all first atomics are issued before the first carry is consumed
+__device__ __forceinline__ void rpf_add4(const RpLane &L, uint32_t w0, uint32_t w1, uint32_t hoff, bool anygen) {
+    uint32_t ad[4], av[4], old[4];
+    ad[0] = L.base + ((w0 & 0x7fffu) << 2);
+    ad[1] = L.base + ((w0 >> 14) & 0x1fffcu);
+    ad[2] = L.base + ((w1 & 0x7fffu) << 2);
+    ad[3] = L.base + ((w1 >> 14) & 0x1fffcu);
+    av[0] = (w0 & 0x8000u) ? L.aneg : L.apos;
+    av[1] = ((int32_t)w0 < 0) ? L.aneg : L.apos;
+    av[2] = (w1 & 0x8000u) ? L.aneg : L.apos;
+    av[3] = ((int32_t)w1 < 0) ? L.aneg : L.apos;
 #pragma unroll
-    for (int e = 0; e < 8; e++) {
-        const uint32_t ent = (e & 1) ? (ws[e >> 1] >> 16) : (ws[e >> 1] & 0xffffu);
-        ok[e] = ent != 0xffffu;
-        col[e] = ent & 0x7fffu;
-        neg[e] = (ent & 0x8000u) != 0;
-        alo[e] = neg[e] ? nlo : qlo;
-        old[e] = 0;
-        if (ok[e]) old[e] = atomicAdd(lo + col[e], alo[e]);
-    }
+    for (int e = 0; e < 4; e++) old[e] = atoms_add(ad[e], av[e]);
+    if (anygen) { /* warp-uniform */
+        const uint32_t hv[4] = {(w0 & 0x8000u) ? L.hneg : L.hpos, ((int32_t)w0 < 0) ? L.hneg : L.hpos,
+                                (w1 & 0x8000u) ? L.hneg : L.hpos, ((int32_t)w1 < 0) ? L.hneg : L.hpos};
 #pragma unroll
-    for (int e = 0; e < 8; e++) {
-        if (ok[e]) {
-            const uint32_t carry = ((uint32_t)(old[e] + alo[e]) < alo[e]) ? 1u : 0u;
-            atomicAdd(hi + col[e], (neg[e] ? nhi : qhi) + carry);
+        for (int e = 0; e < 4; e++) {
+            const uint32_t carry = ((uint32_t)(old[e] + av[e]) < av[e]) ? 1u : 0u;
+            reds_add_if(ad[e] + hoff, hv[e] + carry, L.gen);
         }
     }
 }
 
-template <int VEC>
-__device__ __forceinline__ void rpf_chunk(const RpFxArgs &A, uint32_t *lo, uint32_t *hi, int gi, double x, bool valid,
-                                          double cs, double qscale, int *bad) {
-    double v = 0.0;
+template <int VEC, int FB>
+__device__ __forceinline__ void rpf_chunk(const RpFxArgs &A, uint32_t s_base, int gi, double x, bool valid, double cs,
+                                          double qscale, int okmask, int *bad) {
+    constexpr int NCLS = (FB == 8) ? 4 : 2;   /* count classes: raw values 1 .. NCLS */
+    constexpr int CPW = 16 / FB;              /* classes per 32-bit word (two fields each) */
+    const uint32_t arr = (uint32_t)A.kpd * 4u;
+    int cls = -1;
     if (valid) {
-        v = rp_transform(x, cs, A.a.normalize, A.a.norm_mul, A.a.logkind);
-        if (!isfinite(v)) { *bad = 1; v = 0.0; } /* the whole row becomes NaN, like the reference's NaN propagation */
+        const int xi = __double2int_rz(x);
+        if (xi >= 1 && xi <= NCLS && (double)xi == x) cls = xi - 1;
     }
-    const long long q = __double2ll_rn(v * qscale);
+    RpLane L;
+    L.gen = (valid && cls < 0) ? 1u : 0u;
+    long long q = 0;
+    if (L.gen) {
+        double v = rp_transform(x, cs, A.a.normalize, A.a.norm_mul, A.a.logkind);
+        if (!isfinite(v)) { *bad = 1; v = 0.0; } /* the whole row becomes NaN, like the reference's NaN propagation */
+        q = __double2ll_rn(v * qscale);
+    } else if (cls >= 0 && !((okmask >> cls) & 1)) *bad = 1;
+    const unsigned long long nq = 0ull - (unsigned long long)q;
+    L.base = s_base + 2u * arr; /* low limbs */
+    L.apos = (uint32_t)q;
+    L.hpos = (uint32_t)((unsigned long long)q >> 32);
+    L.aneg = (uint32_t)nq;
+    L.hneg = (uint32_t)(nq >> 32);
+    if (cls >= 0) {
+        L.base = s_base + (uint32_t)(cls / CPW) * arr;
+        L.apos = 1u << ((cls % CPW) * 2 * FB);
+        L.aneg = L.apos << FB;
+    }
     uint32_t v0 = 0, nv = 0;
-    if (q != 0) {
+    if (cls >= 0 || q != 0) {
         v0 = __ldg(A.vecptr + gi);
         nv = __ldg(A.vecptr + gi + 1) - v0;
     }
-    const uint32_t qlo = (uint32_t)q, qhi = (uint32_t)((unsigned long long)q >> 32);
-    const unsigned long long nq = 0ull - (unsigned long long)q;
-    const uint32_t nlo = (uint32_t)nq, nhi = (uint32_t)(nq >> 32);
     uint4 w[VEC];
 #pragma unroll
-    for (int u = 0; u < VEC; u++) {
-        w[u] = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
+    for (int u = 0; u < VEC; u++)
         if ((uint32_t)u < nv) w[u] = __ldg(A.entvec + v0 + u);
-    }
+    const bool anygen = __any_sync(0xffffffffu, L.gen && nv > 0);
 #pragma unroll
     for (int u = 0; u < VEC; u++)
-        if (__any_sync(0xffffffffu, (uint32_t)u < nv)) rpf_add8(lo, hi, w[u], qlo, qhi, nlo, nhi);
-    for (uint32_t u = VEC; u < nv; u++) rpf_add8(lo, hi, __ldg(A.entvec + v0 + u), qlo, qhi, nlo, nhi); /* rare */
+        if ((uint32_t)u < nv) {
+            rpf_add4(L, w[u].x, w[u].y, arr, anygen);
+            rpf_add4(L, w[u].z, w[u].w, arr, anygen);
+        }
+    for (uint32_t u = VEC; u < nv; u++) { /* rare */
+        const uint4 t = __ldg(A.entvec + v0 + u);
+        rpf_add4(L, t.x, t.y, arr, anygen);
+        rpf_add4(L, t.z, t.w, arr, anygen);
+    }
 }
 
 __device__ __forceinline__ double rpf_block_max(double v, double *red) {
@@ -305,17 +342,24 @@ __device__ __forceinline__ double rpf_block_max(double v, double *red) {
     return r;
 }
 
-template <int VEC>
-__global__ void __launch_bounds__(RPF_THREADS, 8) rp_project_fx_kernel(RpFxArgs A) {
+// dynamic shared memory: [4][kpd] words (class counters 0, class counters 1, low limbs, high limbs), then, for dense
+// input only, the per-warp compaction buffers
+template <int VEC, int FB>
+__global__ void __launch_bounds__(RPF_THREADS, 5) rp_project_fx_kernel(RpFxArgs A) {
     extern __shared__ __align__(16) uint32_t fsm[];
     __shared__ double red[RPF_WARPS];
-    __shared__ int s_bad;
+    __shared__ long long s_qc[RPF_MAXCLS];
+    __shared__ int s_bad, s_ok;
+    constexpr int NCLS = (FB == 8) ? 4 : 2;
+    constexpr int CPW = 16 / FB;
+    constexpr uint32_t FMASK = (1u << FB) - 1u;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int KP = A.a.KP;
-    uint32_t *lo = fsm, *hi = fsm + A.kpad;
-    int *sgi = reinterpret_cast<int *>(fsm + 2 * A.kpad) + warp * RPF_STAGE;
-    double *sx = reinterpret_cast<double *>(fsm + 2 * A.kpad + RPF_WARPS * RPF_STAGE) + warp * RPF_STAGE;
-    for (int i = tid; i < 2 * A.kpad; i += RPF_THREADS) fsm[i] = 0u;
+    const int KP = A.a.KP, kpd = A.kpd;
+    const uint32_t s_base = (uint32_t)__cvta_generic_to_shared(fsm);
+    uint32_t *cw = fsm, *lo = fsm + 2 * kpd, *hi = fsm + 3 * kpd;
+    int *sgi = reinterpret_cast<int *>(fsm + 4 * kpd) + warp * RPF_STAGE;
+    double *sx = reinterpret_cast<double *>(fsm + 4 * kpd + RPF_WARPS * RPF_STAGE) + warp * RPF_STAGE;
+    for (int i = tid; i < 4 * kpd; i += RPF_THREADS) fsm[i] = 0u;
     if (tid == 0) s_bad = 0;
     __syncthreads();
 
@@ -343,6 +387,16 @@ __global__ void __launch_bounds__(RPF_THREADS, 8) rp_project_fx_kernel(RpFxArgs 
         const int e = (bound > 0.0) ? ilogb(bound) + 1 : 0;
         const int fb = 62 - A.cb - e;
         const double qscale = ldexp(1.0, fb);
+        if (tid == 0) s_ok = 0;
+        __syncthreads();
+        if (tid < NCLS) { /* the fixed-point value of every count class (a class that does not occur is multiplied by 0) */
+            const double v = rp_transform((double)(tid + 1), cs, A.a.normalize, A.a.norm_mul, A.a.logkind);
+            const bool ok = isfinite(v) && fabs(v) <= ldexp(bound, 3);
+            s_qc[tid] = ok ? __double2ll_rn(v * qscale) : 0ll;
+            if (ok) atomicOr(&s_ok, 1 << tid);
+        }
+        __syncthreads();
+        const int okmask = s_ok;
         // ---- pass 2: scatter ----
         if (dcol) {
             int cnt = 0;
@@ -358,7 +412,7 @@ __global__ void __launch_bounds__(RPF_THREADS, 8) rp_project_fx_kernel(RpFxArgs 
                 cnt += __popc(mask);
                 __syncwarp();
                 if (cnt >= 32) {
-                    rpf_chunk<VEC>(A, lo, hi, sgi[lane], sx[lane], true, cs, qscale, &s_bad);
+                    rpf_chunk<VEC, FB>(A, s_base, sgi[lane], sx[lane], true, cs, qscale, okmask, &s_bad);
                     __syncwarp();
                     int tg = 0;
                     double tx = 0.0;
@@ -369,23 +423,42 @@ __global__ void __launch_bounds__(RPF_THREADS, 8) rp_project_fx_kernel(RpFxArgs 
                     __syncwarp();
                 }
             }
-            if (cnt > 0) rpf_chunk<VEC>(A, lo, hi, lane < cnt ? sgi[lane] : 0, lane < cnt ? sx[lane] : 0.0, lane < cnt, cs, qscale, &s_bad);
+            if (cnt > 0) rpf_chunk<VEC, FB>(A, s_base, lane < cnt ? sgi[lane] : 0, lane < cnt ? sx[lane] : 0.0, lane < cnt, cs, qscale, okmask, &s_bad);
         } else {
-            for (int64_t q = q0 + warp * 32; q < q1; q += RPF_THREADS) {
-                const bool valid = q + lane < q1;
-                const int gi = valid ? A.a.rowidx[q + lane] : 0;
-                const double x = valid ? A.a.val[q + lane] : 0.0;
-                rpf_chunk<VEC>(A, lo, hi, gi, x, valid, cs, qscale, &s_bad);
+            int64_t q = q0 + warp * 32;
+            bool valid = q + lane < q1;
+            int gi = valid ? A.a.rowidx[q + lane] : 0;
+            double x = valid ? A.a.val[q + lane] : 0.0;
+            while (q < q1) { /* the next 32 non-zeros are requested before this chunk's atomics are issued */
+                const int64_t qn = q + RPF_THREADS;
+                const bool nvalid = qn + lane < q1;
+                const int ngi = nvalid ? A.a.rowidx[qn + lane] : 0;
+                const double nx = nvalid ? A.a.val[qn + lane] : 0.0;
+                rpf_chunk<VEC, FB>(A, s_base, gi, x, valid, cs, qscale, okmask, &s_bad);
+                q = qn; valid = nvalid; gi = ngi; x = nx;
             }
         }
         __syncthreads();
-        // ---- output: the exact integer sum -> double (one rounding), times the common factor; reset the limbs ----
+        // ---- output: the exact integer sum -> double (one rounding), times the common factor; reset the words ----
         const bool bad = s_bad != 0;
         const double unscale = ldexp(1.0, -fb);
+        long long qc[NCLS];
+#pragma unroll
+        for (int c = 0; c < NCLS; c++) qc[c] = s_qc[c];
         for (int i = tid; i < KP; i += RPF_THREADS) {
-            const long long tot = (long long)(((unsigned long long)hi[i] << 32) | (unsigned long long)lo[i]);
+            long long tot = (long long)(((unsigned long long)hi[i] << 32) | (unsigned long long)lo[i]);
             lo[i] = 0u;
             hi[i] = 0u;
+#pragma unroll
+            for (int a = 0; a < NCLS / CPW; a++) {
+                const uint32_t w = cw[a * kpd + i];
+                cw[a * kpd + i] = 0u;
+#pragma unroll
+                for (int f = 0; f < CPW; f++) {
+                    const int np = (int)((w >> (f * 2 * FB)) & FMASK), nn = (int)((w >> (f * 2 * FB + FB)) & FMASK);
+                    tot += qc[a * CPW + f] * (long long)(np - nn);
+                }
+            }
             double r = __dmul_rn(__dmul_rn((double)tot, unscale), A.a.scale);
             if (A.a.round_digits >= 0) r = rp_round(r, A.a.round_digits);
             if (bad) r = __longlong_as_double(0x7ff8000000000000LL);
@@ -394,15 +467,26 @@ __global__ void __launch_bounds__(RPF_THREADS, 8) rp_project_fx_kernel(RpFxArgs 
         }
         __syncthreads();
         if (tid == 0) s_bad = 0;
-        __syncthreads();
+        /* the dummy outputs collect the padding entries; they are never read and only have to be cleared often enough
+           not to matter -- a wrapped dummy word is harmless */
     }
 }
 
-template <int VEC>
-static int launch_fx(sharp_ctx *c, const RpFxArgs &A, int grid, size_t smem) {
-    SHARP_CUDA(cudaFuncSetAttribute(rp_project_fx_kernel<VEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, SHARP_SMEM_OPTIN));
-    rp_project_fx_kernel<VEC><<<grid, RPF_THREADS, smem, c->stream>>>(A);
+template <int VEC, int FB>
+static int launch_fx(sharp_ctx *c, const RpFxArgs &A, int64_t ncell, size_t smem) {
+    SHARP_CUDA(cudaFuncSetAttribute(rp_project_fx_kernel<VEC, FB>, cudaFuncAttributeMaxDynamicSharedMemorySize, SHARP_SMEM_OPTIN));
+    int per_sm = 0; /* a persistent grid: exactly the CTAs that are resident at once (no tail wave) */
+    SHARP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rp_project_fx_kernel<VEC, FB>, RPF_THREADS, smem));
+    const int grid = (int)std::min<int64_t>(ncell, (int64_t)c->sm_count * std::max(1, per_sm));
+    rp_project_fx_kernel<VEC, FB><<<grid, RPF_THREADS, smem, c->stream>>>(A);
     return 0;
+}
+template <int FB>
+static int launch_fx_vec(sharp_ctx *c, const RpFxArgs &A, int vec_per_gene, int64_t grid, size_t smem) {
+    if (vec_per_gene <= 2) return launch_fx<2, FB>(c, A, grid, smem);
+    if (vec_per_gene <= 3) return launch_fx<3, FB>(c, A, grid, smem);
+    if (vec_per_gene <= 4) return launch_fx<4, FB>(c, A, grid, smem);
+    return launch_fx<6, FB>(c, A, grid, smem);
 }
 
 int launch_rp_project(sharp_ctx *c, const sharp_expr_dev &e, const int64_t *cells_dev, int64_t ncell,
@@ -418,25 +502,19 @@ int launch_rp_project(sharp_ctx *c, const sharp_expr_dev &e, const int64_t *cell
     A.scale = (1.0 / sqrt((double)rm.p)) * rm.mag;   /* entry of 1/sqrt(p) * t(rM) */
     A.rowptr = rm.rowptr; A.ent16 = rm.ent16; A.ent32 = rm.ent32;
     A.out = out;
-    if (rm.entvec && !c->rp_legacy) { /* fixed-point variant */
+    if (rm.entvec && !c->rp_legacy && rm.max_col_nnz < 65536) { /* fixed-point variant */
         RpFxArgs F;
         F.a = A;
         F.vecptr = rm.vecptr;
         F.entvec = rm.entvec;
         F.cb = 1;
         while ((1 << F.cb) <= rm.max_col_nnz) F.cb++;
-        F.kpad = (A.KP + 31) & ~31;
-        const size_t fsmem = (size_t)2 * F.kpad * 4 + (size_t)RPF_WARPS * RPF_STAGE * 12;
+        F.kpd = rm.kpd;
+        const size_t fsmem = (size_t)4 * F.kpd * 4 + (e.dense ? (size_t)RPF_WARPS * RPF_STAGE * 12 : 0);
         if (fsmem <= 200 * 1024) {
-            const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (size_t)(220 * 1024) / (fsmem + 1024)));
-            const int grid = (int)std::min<int64_t>(ncell, (int64_t)c->sm_count * per_sm);
             prof_begin(c, KID_RP_PROJECT);
-            int rc;
-            if (rm.vec_per_gene <= 2) rc = launch_fx<2>(c, F, grid, fsmem);
-            else if (rm.vec_per_gene <= 3) rc = launch_fx<3>(c, F, grid, fsmem);
-            else if (rm.vec_per_gene <= 4) rc = launch_fx<4>(c, F, grid, fsmem);
-            else if (rm.vec_per_gene <= 6) rc = launch_fx<6>(c, F, grid, fsmem);
-            else rc = launch_fx<8>(c, F, grid, fsmem);
+            const int rc = rm.max_col_nnz <= 255 ? launch_fx_vec<8>(c, F, rm.vec_per_gene, ncell, fsmem)
+                                                 : launch_fx_vec<16>(c, F, rm.vec_per_gene, ncell, fsmem);
             prof_end(c);
             SHARP_TRY(rc);
             SHARP_CUDA(cudaGetLastError());

@@ -26,32 +26,36 @@ constexpr int SIL_U = 16;
 // hclust.f keeps the merged cluster under the smaller representative I2 and retires J2, so the representative
 // of a cluster is always its minimum index.  step_of[j] = merge step at which j was retired (INT_MAX if never),
 // link[j] = the representative it was merged into.
-__device__ __forceinline__ void build_links(int n, const int *ia, const int *ib, int *step_of, int *link) {
+// IT = int, or unsigned short (n < 65535) where shared memory is tight; "never" is the largest value of IT.
+template <class IT>
+__device__ __forceinline__ void build_links(int n, const int *ia, const int *ib, IT *step_of, IT *link) {
+    const IT never = sizeof(IT) == 2 ? (IT)0xffff : (IT)INT_MAX;
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
-        step_of[i] = INT_MAX;
-        link[i] = i;
+        step_of[i] = never;
+        link[i] = (IT)i;
     }
     __syncthreads();
     for (int s = threadIdx.x; s < n - 1; s += blockDim.x) {
         int j2 = ib[s] - 1;
-        step_of[j2] = s;
-        link[j2] = ia[s] - 1;
+        step_of[j2] = (IT)s;
+        link[j2] = (IT)(ia[s] - 1);
     }
     __syncthreads();
 }
 
-__device__ __forceinline__ int root_at(int x, int nmerge, const int *step_of, const int *link) {
-    while (step_of[x] < nmerge) x = link[x];
+template <class IT>
+__device__ __forceinline__ int root_at(int x, int nmerge, const IT *step_of, const IT *link) {
+    while ((int)step_of[x] < nmerge) x = link[x];
     return x;
 }
 
 // cutree(h, k): labels numbered by first appearance = rank of the cluster's representative (its minimum index)
 // among the live representatives.  rank[] (shared, n ints) is scratch; lab[] receives 0-based ids.
-template <int THREADS>
-__device__ __forceinline__ void labels_at(int n, int k, const int *step_of, const int *link, int *rank, int *tmp,
+template <int THREADS, class IT>
+__device__ __forceinline__ void labels_at(int n, int k, const IT *step_of, const IT *link, int *rank, int *tmp,
                                           int *lab) {
     const int nmerge = n - k;
-    for (int i = threadIdx.x; i < n; i += THREADS) rank[i] = (step_of[i] >= nmerge) ? 1 : 0;
+    for (int i = threadIdx.x; i < n; i += THREADS) rank[i] = ((int)step_of[i] >= nmerge) ? 1 : 0;
     __syncthreads();
     block_exclusive_scan<THREADS>(rank, n, tmp);
     for (int i = threadIdx.x; i < n; i += THREADS) lab[i] = rank[root_at(i, nmerge, step_of, link)];
@@ -111,8 +115,9 @@ __device__ int select_rule(int n, int nlev, const double *msil, const double *ch
 // nested sweep (feature problems)
 // =====================================================================================================
 // dynamic shared memory layout (bytes):
-//   acc      [kcap][SW_THREADS] double   (also: sort buffer P2 doubles; Gram matrix kcap*kcap doubles)
-//   step_of  [n] int, link [n] int, rank [n] int, cidf [n] int
+//   acc      [kcap][SW_THREADS] double   (also: sort buffer P2 doubles; Gram matrix kcap*kcap doubles; the scan
+//            scratch rank [n] int of cutree, which runs before and after the passes that use the accumulators)
+//   cidf [n] int, step_of [n] u16, link [n] u16   -- 105 KB at n = 2000, kmax = 40: TWO problems per SM
 //   small tables: cnt_lv [nlevcap][kcap] int, own map slot_lv [nlevcap][kcap] uint8, mergeA/B [nlevcap] int
 struct NestedLayout {
     size_t acc_off, ints_off, cnt_off, slot_off, merge_off, msil_off, total;
@@ -126,9 +131,10 @@ __host__ __device__ inline NestedLayout nested_layout(int n, int kcap, int nlevc
     size_t gram_bytes = (size_t)kcap * kcap * 8;
     size_t a = acc_bytes > sort_bytes ? acc_bytes : sort_bytes;
     a = a > gram_bytes ? a : gram_bytes;
+    a = a > (size_t)n * 4 ? a : (size_t)n * 4;
     L.acc_off = 0;
     L.ints_off = (a + 15) & ~(size_t)15;
-    L.cnt_off = L.ints_off + (size_t)4 * n * 4;
+    L.cnt_off = (L.ints_off + (size_t)n * 4 + (size_t)2 * n * 2 + 15) & ~(size_t)15;
     L.slot_off = L.cnt_off + (size_t)nlevcap * kcap * 4;
     L.merge_off = (L.slot_off + (size_t)nlevcap * kcap + 15) & ~(size_t)15;
     L.msil_off = (L.merge_off + (size_t)nlevcap * 2 * 4 + 15) & ~(size_t)15;
@@ -144,7 +150,7 @@ size_t sweep_nested_scratch_bytes(int max_n, int max_p, HcParamsDev prm) {
     return ((sil + csum) + 255) & ~(size_t)255;
 }
 
-__global__ void __launch_bounds__(SW_THREADS)
+__global__ void __launch_bounds__(SW_THREADS, 2)
 sweep_nested_kernel(HcProb *probs, SweepOut *outs, HcParamsDev prm, int n_cap, int kcap, int nlevcap, double *scratch,
                     size_t scratch_per_prob) {
     extern __shared__ __align__(16) unsigned char smem[];
@@ -174,10 +180,10 @@ sweep_nested_kernel(HcProb *probs, SweepOut *outs, HcParamsDev prm, int n_cap, i
 
     NestedLayout L = nested_layout(n_cap, kcap, nlevcap);
     double *acc = reinterpret_cast<double *>(smem + L.acc_off);
-    int *step_of = reinterpret_cast<int *>(smem + L.ints_off);
-    int *link = step_of + n_cap;
-    int *rank = link + n_cap;
-    int *cidf = rank + n_cap;
+    int *cidf = reinterpret_cast<int *>(smem + L.ints_off);
+    unsigned short *step_of = reinterpret_cast<unsigned short *>(cidf + n_cap);
+    unsigned short *link = step_of + n_cap;
+    int *rank = reinterpret_cast<int *>(acc);
     int *cnt_lv = reinterpret_cast<int *>(smem + L.cnt_off);          // [nlev][kcap], level 0 = finest (k = kmax)
     unsigned char *slot_lv = smem + L.slot_off;                       // [nlev][kcap]: fine id -> slot at level
     int *mergeA = reinterpret_cast<int *>(smem + L.merge_off);        // [nlev] slot kept when going to level l
@@ -235,21 +241,42 @@ sweep_nested_kernel(HcProb *probs, SweepOut *outs, HcParamsDev prm, int n_cap, i
         }
         for (; y < n; y++) acc[cidf[y] * SW_THREADS + tid] += col[(size_t)y * ld];
         const int myfine = valid ? cidf[x] : 0;
+        /* b_i = min over the OTHER clusters of the mean distance.  Going one level up merges two clusters (B into A) and
+           leaves every other mean untouched, so the minimum is carried along: one division for the new cluster, and a
+           full rescan only when the cluster that held the minimum is one of the two (the quotients that are compared
+           are the same ones a scan computes, so b_i is bit-identical to the scan's) */
+        double a_i = 0.0, b_i = SHARP_INF;
+        int b_arg = -1, own = 0, n_own = 0;
         for (int l = 0; l < nlev; l++) {
-            if (l > 0) acc[mergeA[l] * SW_THREADS + tid] += acc[mergeB[l] * SW_THREADS + tid];
             const int *cnt = cnt_lv + l * kcap;
-            const int own = slot_lv[l * kcap + myfine];
-            const int n_own = cnt[own];
-            double a_i = 0.0, b_i = SHARP_INF;
-            for (int c = 0; c < kmax; c++) {
-                const int nc = cnt[c];
-                if (nc == 0) continue;
-                double v = acc[c * SW_THREADS + tid];
-                if (c == own) {
-                    if (n_own > 1) a_i = __ddiv_rn(v, (double)(n_own - 1));
-                } else {
-                    v = __ddiv_rn(v, (double)nc);
-                    if (v < b_i) b_i = v;
+            bool rescan = (l == 0);
+            if (l > 0) {
+                const int A = mergeA[l], B = mergeB[l];
+                acc[A * SW_THREADS + tid] += acc[B * SW_THREADS + tid];
+                if (own == A || own == B) { /* the own cluster grows; the other of the two stops being a candidate */
+                    const int other = (own == A) ? B : A;
+                    own = A;
+                    n_own = cnt[A];
+                    a_i = (n_own > 1) ? __ddiv_rn(acc[A * SW_THREADS + tid], (double)(n_own - 1)) : 0.0;
+                    if (b_arg == other) rescan = true;
+                } else if (b_arg == A || b_arg == B) rescan = true;
+                else {
+                    const double v = __ddiv_rn(acc[A * SW_THREADS + tid], (double)cnt[A]);
+                    if (v < b_i) { b_i = v; b_arg = A; }
+                }
+            } else {
+                own = slot_lv[myfine];
+                n_own = cnt[own];
+                a_i = (n_own > 1) ? __ddiv_rn(acc[own * SW_THREADS + tid], (double)(n_own - 1)) : 0.0;
+            }
+            if (rescan) {
+                b_i = SHARP_INF;
+                b_arg = -1;
+                for (int c = 0; c < kmax; c++) {
+                    const int nc = cnt[c];
+                    if (nc == 0 || c == own) continue;
+                    const double v = __ddiv_rn(acc[c * SW_THREADS + tid], (double)nc);
+                    if (v < b_i) { b_i = v; b_arg = c; }
                 }
             }
             double s = (n_own > 1 && b_i != a_i) ? __ddiv_rn(__dsub_rn(b_i, a_i), fmax(a_i, b_i)) : 0.0;
