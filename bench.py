@@ -356,6 +356,8 @@ def run_ours(args):
         if comm:
             comm.barrier()
 
+    walls = []  # host wall clock of every call of the last timed() (diagnostic: the steps are timed on the device)
+
     def timed(parts_list, steps, profile):
         barrier()
         if profile:
@@ -365,8 +367,11 @@ def run_ours(args):
         l0 = sum(c.launch_count() for c in ctxs)
         ctx.timer_start()
         res = None
+        walls.clear()
         for _ in range(steps):
+            w0 = time.perf_counter()
             res = api.SHARP_unlimited(parts_list, **kw)
+            walls.append(round(1e3 * (time.perf_counter() - w0), 1))
         ms = ctx.timer_stop_ms()
         barrier()
         if profile:
@@ -382,6 +387,7 @@ def run_ours(args):
         sampler.start()
     ms, res, launches = timed(dev_list, args.steps, True)
     clocks = sampler.stop() if rank == 0 else None
+    walls_dev = list(walls)
 
     def collect():
         out = {}
@@ -411,6 +417,7 @@ def run_ours(args):
     api.SHARP_unlimited(host_list, **kw)  # warm-up of the host path
     e2e_steps = max(1, args.steps)
     ms_e2e, res_e2e, _ = timed(host_list, e2e_steps, False)
+    walls_e2e = list(walls)
     e2e_value = ncells * e2e_steps / (ms_e2e * 1e-3)
     same = bool(np.array_equal(res["pred_clusters"], res_e2e["pred_clusters"]))
     h2d = sum(host_parts[i]["p"].nbytes + host_parts[i]["i"].nbytes + host_parts[i]["x"].nbytes for i in mine)
@@ -485,9 +492,9 @@ def run_ours(args):
                                      f"group={args.group or 'default'}, lanes={args.lanes or 'default'}"),
                        "l2": "inputs larger than L2 (CSC input %.1f GB per step)" % (sum(nnz_all) * 12 / 1e9),
                        "generation_s": t_gen},
-            "clocks": clocks, "gpu_launches": int(launches / args.steps),
+            "step_wall_ms": walls_dev, "clocks": clocks, "gpu_launches": int(launches / args.steps),
             "e2e": {"value": e2e_value, "unit": "cells/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "ms_per_step": ms_e2e / e2e_steps, "labels_equal_device_resident_run": same,
+                    "ms_per_step": ms_e2e / e2e_steps, "labels_equal_device_resident_run": same, "step_wall_ms": walls_e2e,
                     "h2d_gbs_measured": h2d_gbs, "h2d_floor_ms_per_step": (h2d / max(world, 1)) / (h2d_gbs * 1e9) * 1e3},
             "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu,
             "result": {"N.pred_clusters": int(res.get("N.pred_clusters", res.get("N.pred_cluster", 0)))}}

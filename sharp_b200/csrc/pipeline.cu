@@ -3,6 +3,7 @@
 // kernels of this library on the context's stream and fails with SHARP_E_CUDA when there is no device.
 #include <algorithm>
 #include <atomic>
+#include <mutex>
 #include <chrono>
 #include <cstdlib>
 #include <cmath>
@@ -1436,6 +1437,47 @@ int sharp_prof_get(sharp_ctx *c, int kid, double *ms, int64_t *launches) {
 }
 
 // ---- ranM upload: dgCMatrix slots of K matrices -> gene-major ternary entries -------------------------
+// Device buffers of the projection matrices come from a small per-process cache: SHARP_unlimited uploads a fresh set of
+// matrices on every call and frees it at the end, and cudaMalloc / cudaFree are device-wide synchronisations whose cost
+// is unbounded on a busy 180 GB device (hundreds of ms were measured between two steps).  A released buffer is kept
+// (up to 64 of them, a few MB in all) and handed to the next request of at most its size and at least half of it.
+namespace {
+struct RmCacheEnt { int device; size_t cap; void *ptr; };
+std::mutex g_rm_mu;
+std::vector<RmCacheEnt> g_rm_cache;
+std::vector<RmCacheEnt> g_rm_live;
+cudaError_t rm_alloc(int device, void **out, size_t bytes) {
+    bytes = std::max<size_t>(bytes, 256);
+    std::lock_guard<std::mutex> lk(g_rm_mu);
+    for (size_t i = 0; i < g_rm_cache.size(); i++) {
+        RmCacheEnt e = g_rm_cache[i];
+        if (e.device == device && e.cap >= bytes && e.cap <= 2 * bytes) {
+            g_rm_cache.erase(g_rm_cache.begin() + i);
+            g_rm_live.push_back(e);
+            *out = e.ptr;
+            return cudaSuccess;
+        }
+    }
+    const size_t cap = (bytes + bytes / 8 + 4095) & ~(size_t)4095;
+    cudaError_t err = cudaMalloc(out, cap);
+    if (err == cudaSuccess) g_rm_live.push_back({device, cap, *out});
+    return err;
+}
+void rm_release(void *ptr) {
+    if (!ptr) return;
+    std::lock_guard<std::mutex> lk(g_rm_mu);
+    for (size_t i = 0; i < g_rm_live.size(); i++)
+        if (g_rm_live[i].ptr == ptr) {
+            RmCacheEnt e = g_rm_live[i];
+            g_rm_live.erase(g_rm_live.begin() + i);
+            if (g_rm_cache.size() < 64) g_rm_cache.push_back(e);
+            else cudaFree(ptr);
+            return;
+        }
+    cudaFree(ptr);
+}
+}  // namespace
+
 int sharp_rm_upload(sharp_ctx *c, int m, int p, int K, const int32_t *colptr, const int32_t *rowidx, const double *x,
                     const int64_t *nnz_off, sharp_rm_dev **out) {
     SHARP_TRY(use(c));
@@ -1487,15 +1529,15 @@ int sharp_rm_upload(sharp_ctx *c, int m, int p, int K, const int32_t *colptr, co
         int g0 = t * r->tile_genes, g1 = std::min(m, g0 + r->tile_genes);
         r->max_tile_entries = std::max<int>(r->max_tile_entries, (int)(rowptr[g1] - rowptr[g0]));
     }
-    cudaError_t e1 = cudaMalloc((void **)&r->rowptr, (size_t)(m + 1) * 4);
+    cudaError_t e1 = rm_alloc(c->device, (void **)&r->rowptr, (size_t)(m + 1) * 4);
     cudaError_t e2;
     if (e16) {
         std::vector<uint16_t> e16v((size_t)nz + 16, 0);
         for (int64_t q = 0; q < nz; q++) e16v[q] = (uint16_t)ent[q];
-        e2 = cudaMalloc((void **)&r->ent16, e16v.size() * 2);
+        e2 = rm_alloc(c->device, (void **)&r->ent16, e16v.size() * 2);
         if (e1 == cudaSuccess && e2 == cudaSuccess) e2 = cudaMemcpy(r->ent16, e16v.data(), e16v.size() * 2, cudaMemcpyHostToDevice);
     } else {
-        e2 = cudaMalloc((void **)&r->ent32, ent.size() * 4);
+        e2 = rm_alloc(c->device, (void **)&r->ent32, ent.size() * 4);
         if (e1 == cudaSuccess && e2 == cudaSuccess) e2 = cudaMemcpy(r->ent32, ent.data(), ent.size() * 4, cudaMemcpyHostToDevice);
     }
     if (e1 == cudaSuccess) e1 = cudaMemcpy(r->rowptr, rowptr.data(), (size_t)(m + 1) * 4, cudaMemcpyHostToDevice);
@@ -1520,8 +1562,8 @@ int sharp_rm_upload(sharp_ctx *c, int m, int p, int K, const int32_t *colptr, co
         mean /= m;
         const double sd = std::sqrt(std::max(0.0, sq / m - mean * mean));
         r->vec_per_gene = std::min(6, std::max(1, (int)std::ceil((mean + 2.5 * sd) / 8.0)));
-        cudaError_t e3 = cudaMalloc((void **)&r->vecptr, (size_t)(m + 1) * 4);
-        cudaError_t e4 = cudaMalloc((void **)&r->entvec, padded.size() * 2);
+        cudaError_t e3 = rm_alloc(c->device, (void **)&r->vecptr, (size_t)(m + 1) * 4);
+        cudaError_t e4 = rm_alloc(c->device, (void **)&r->entvec, padded.size() * 2);
         if (e3 == cudaSuccess) e3 = cudaMemcpy(r->vecptr, vecptr.data(), (size_t)(m + 1) * 4, cudaMemcpyHostToDevice);
         if (e4 == cudaSuccess) e4 = cudaMemcpy(r->entvec, padded.data(), padded.size() * 2, cudaMemcpyHostToDevice);
         if (e3 != cudaSuccess) e1 = e3;
@@ -1538,11 +1580,11 @@ int sharp_rm_upload(sharp_ctx *c, int m, int p, int K, const int32_t *colptr, co
 void sharp_rm_free(sharp_rm_dev *r) {
     if (!r) return;
     cudaSetDevice(r->device);
-    if (r->rowptr) cudaFree(r->rowptr);
-    if (r->ent16) cudaFree(r->ent16);
-    if (r->ent32) cudaFree(r->ent32);
-    if (r->vecptr) cudaFree(r->vecptr);
-    if (r->entvec) cudaFree(r->entvec);
+    rm_release(r->rowptr);
+    rm_release(r->ent16);
+    rm_release(r->ent32);
+    rm_release(r->vecptr);
+    rm_release(r->entvec);
     delete r;
 }
 
@@ -1872,15 +1914,25 @@ int sharp_run_parts(sharp_ctx *c, int m, int nparts, sharp_part *parts, const sh
         if (!parts[i].dev && !parts[i].dense && !parts[i].colptr) return set_error(SHARP_E_ARG, "run_parts: part %d has no data", i);
         if (parts[i].dev && parts[i].dev->n != parts[i].n) return set_error(SHARP_E_ARG, "run_parts: part %d: n does not match the device matrix", i);
     }
-    if (group <= 0) group = 4;
     if (lanes <= 0) lanes = 2;
+    /* default group size: 4 parts share the block-clustering launches when there are many parts; with few parts (a rank
+       of a multi-GPU job) smaller groups keep both lanes busy -- a group running alone leaves the device half idle
+       during its latency-bound stages */
+    if (group <= 0) group = nparts <= 8 ? 2 : 4; /* measured on B200: 4 parts 160 ms as 2+2 vs 187 ms as 1+1+1+1 */
     group = std::min(group, nparts);
-    // group boundaries; with host data the first group is half size, so that the clustering of the first group starts
-    // after half as many uploads (every later upload is hidden behind the group before it)
+    // group boundaries: the parts are split as evenly as the group size allows, the smaller groups first and last (the
+    // first group's start and the last group's tail are the stretches of the run nothing else overlaps with).  With host
+    // data the first group is half a group: its upload is the only one that is not hidden behind another group.
     std::vector<int> gstart{0};
-    if (!parts[0].dev && group >= 2 && nparts > group) gstart.push_back(group / 2);
-    while (gstart.back() < nparts) gstart.push_back(std::min(nparts, gstart.back() + group));
-    if (gstart.size() == 1) gstart.push_back(nparts);
+    {
+        const bool host_data = !parts[0].dev && group >= 2 && nparts > group;
+        if (host_data) gstart.push_back(group / 2);
+        const int rest = nparts - gstart.back();
+        const int ng = (rest + group - 1) / group;
+        const int base = rest / ng, extra = rest % ng;
+        const int first_big = host_data ? 0 : (ng - extra) / 2; /* groups [first_big, first_big + extra) get base + 1 parts */
+        for (int g = 0; g < ng; g++) gstart.push_back(gstart.back() + base + ((g >= first_big && g < first_big + extra) ? 1 : 0));
+    }
     const int ngroups = (int)gstart.size() - 1;
     lanes = std::min(lanes, ngroups);
     const size_t need = (size_t)lanes * (group + 1);

@@ -254,6 +254,8 @@ struct RpLane {
 };
 
 // four entries (two packed words): all first atomics are issued before the first carry is consumed
+// PH2: 0 = no lane carries high words (class lanes only), 1 = some may (warp-uniform `anygen`), 2 = generic lanes only
+template <int PH2>
 __device__ __forceinline__ void rpf_add4(const RpLane &L, uint32_t w0, uint32_t w1, uint32_t hoff, bool anygen) {
     uint32_t ad[4], av[4], old[4];
     ad[0] = L.base + ((w0 & 0x7fffu) << 2);
@@ -266,7 +268,7 @@ __device__ __forceinline__ void rpf_add4(const RpLane &L, uint32_t w0, uint32_t 
     av[3] = ((int32_t)w1 < 0) ? L.aneg : L.apos;
 #pragma unroll
     for (int e = 0; e < 4; e++) old[e] = atoms_add(ad[e], av[e]);
-    if (anygen) { /* warp-uniform */
+    if (PH2 == 2 || (PH2 == 1 && anygen)) { /* warp-uniform */
         const uint32_t hv[4] = {(w0 & 0x8000u) ? L.hneg : L.hpos, ((int32_t)w0 < 0) ? L.hneg : L.hpos,
                                 (w1 & 0x8000u) ? L.hneg : L.hpos, ((int32_t)w1 < 0) ? L.hneg : L.hpos};
 #pragma unroll
@@ -277,17 +279,24 @@ __device__ __forceinline__ void rpf_add4(const RpLane &L, uint32_t w0, uint32_t 
     }
 }
 
-template <int VEC, int FB>
-__device__ __forceinline__ void rpf_chunk(const RpFxArgs &A, uint32_t s_base, int gi, double x, bool valid, double cs,
+// count class of a raw value: 0 .. NCLS-1 for the integers 1 .. NCLS, else -1 (generic)
+template <int FB>
+__device__ __forceinline__ int rpf_class(double x, bool valid) {
+    constexpr int NCLS = (FB == 8) ? 4 : 2;
+    if (!valid) return -1;
+    const int xi = __double2int_rz(x);
+    return (xi >= 1 && xi <= NCLS && (double)xi == x) ? xi - 1 : -1;
+}
+
+// MODE 0: class and generic lanes mixed (dense input); 1: class lanes only (lanes with cls < 0 idle); 2: generic lanes only
+template <int VEC, int FB, int MODE>
+__device__ __forceinline__ void rpf_chunk(const RpFxArgs &A, uint32_t s_base, int gi, double x, bool valid, int cls, double cs,
                                           double qscale, int okmask, int *bad) {
-    constexpr int NCLS = (FB == 8) ? 4 : 2;   /* count classes: raw values 1 .. NCLS */
     constexpr int CPW = 16 / FB;              /* classes per 32-bit word (two fields each) */
+    constexpr int PH2 = MODE == 1 ? 0 : (MODE == 2 ? 2 : 1);
     const uint32_t arr = (uint32_t)A.kpd * 4u;
-    int cls = -1;
-    if (valid) {
-        const int xi = __double2int_rz(x);
-        if (xi >= 1 && xi <= NCLS && (double)xi == x) cls = xi - 1;
-    }
+    if (MODE == 2) cls = -1;
+    if (MODE == 1) valid = valid && cls >= 0;
     RpLane L;
     L.gen = (valid && cls < 0) ? 1u : 0u;
     long long q = 0;
@@ -316,17 +325,22 @@ __device__ __forceinline__ void rpf_chunk(const RpFxArgs &A, uint32_t s_base, in
 #pragma unroll
     for (int u = 0; u < VEC; u++)
         if ((uint32_t)u < nv) w[u] = __ldg(A.entvec + v0 + u);
-    const bool anygen = __any_sync(0xffffffffu, L.gen && nv > 0);
+    const bool anygen = (MODE == 0) ? __any_sync(0xffffffffu, L.gen && nv > 0) : (MODE == 2);
 #pragma unroll
     for (int u = 0; u < VEC; u++)
         if ((uint32_t)u < nv) {
-            rpf_add4(L, w[u].x, w[u].y, arr, anygen);
-            rpf_add4(L, w[u].z, w[u].w, arr, anygen);
+            rpf_add4<PH2>(L, w[u].x, w[u].y, arr, anygen);
+            rpf_add4<PH2>(L, w[u].z, w[u].w, arr, anygen);
         }
-    for (uint32_t u = VEC; u < nv; u++) { /* rare */
-        const uint4 t = __ldg(A.entvec + v0 + u);
-        rpf_add4(L, t.x, t.y, arr, anygen);
-        rpf_add4(L, t.z, t.w, arr, anygen);
+    if (nv > VEC) { /* longer lists: the next vector is requested before the current one is applied */
+        uint4 t = __ldg(A.entvec + v0 + VEC);
+        for (uint32_t u = VEC; u < nv; u++) {
+            uint4 nx = t;
+            if (u + 1 < nv) nx = __ldg(A.entvec + v0 + u + 1);
+            rpf_add4<PH2>(L, t.x, t.y, arr, anygen);
+            rpf_add4<PH2>(L, t.z, t.w, arr, anygen);
+            t = nx;
+        }
     }
 }
 
@@ -344,7 +358,7 @@ __device__ __forceinline__ double rpf_block_max(double v, double *red) {
 
 // dynamic shared memory: [4][kpd] words (class counters 0, class counters 1, low limbs, high limbs), then, for dense
 // input only, the per-warp compaction buffers
-template <int VEC, int FB>
+template <int VEC, int FB, bool DENSE>
 __global__ void __launch_bounds__(RPF_THREADS, 5) rp_project_fx_kernel(RpFxArgs A) {
     extern __shared__ __align__(16) uint32_t fsm[];
     __shared__ double red[RPF_WARPS];
@@ -366,12 +380,12 @@ __global__ void __launch_bounds__(RPF_THREADS, 5) rp_project_fx_kernel(RpFxArgs 
     for (int64_t pos = blockIdx.x; pos < A.a.ncell; pos += gridDim.x) {
         const int64_t src = A.a.cells ? A.a.cells[pos] : pos;
         const double cs = A.a.normalize ? A.a.colsum[src] : 1.0;
-        const double *dcol = A.a.dense ? A.a.dense + src * A.a.m : nullptr;
+        const double *dcol = DENSE ? A.a.dense + src * A.a.m : nullptr;
         int64_t q0 = 0, q1 = 0;
-        if (!dcol) { q0 = A.a.colptr[src]; q1 = A.a.colptr[src + 1]; }
+        if (!DENSE) { q0 = A.a.colptr[src]; q1 = A.a.colptr[src + 1]; }
         // ---- pass 1: range of the raw values -> bound on |v| (the transform is monotone) -> fixed-point scale ----
         double xmax = -SHARP_INF, xmin = SHARP_INF;
-        if (dcol) {
+        if (DENSE) {
             for (int g = tid; g < A.a.m; g += RPF_THREADS) { const double x = dcol[g]; xmax = fmax(xmax, x); xmin = fmin(xmin, x); }
         } else {
             for (int64_t q = q0 + tid; q < q1; q += RPF_THREADS) { const double x = A.a.val[q]; xmax = fmax(xmax, x); xmin = fmin(xmin, x); }
@@ -398,7 +412,7 @@ __global__ void __launch_bounds__(RPF_THREADS, 5) rp_project_fx_kernel(RpFxArgs 
         __syncthreads();
         const int okmask = s_ok;
         // ---- pass 2: scatter ----
-        if (dcol) {
+        if (DENSE) {
             int cnt = 0;
             for (int c0 = warp * 32; c0 < A.a.m; c0 += RPF_THREADS) {
                 const int gi = c0 + lane;
@@ -412,7 +426,7 @@ __global__ void __launch_bounds__(RPF_THREADS, 5) rp_project_fx_kernel(RpFxArgs 
                 cnt += __popc(mask);
                 __syncwarp();
                 if (cnt >= 32) {
-                    rpf_chunk<VEC, FB>(A, s_base, sgi[lane], sx[lane], true, cs, qscale, okmask, &s_bad);
+                    rpf_chunk<VEC, FB, 0>(A, s_base, sgi[lane], sx[lane], true, rpf_class<FB>(sx[lane], true), cs, qscale, okmask, &s_bad);
                     __syncwarp();
                     int tg = 0;
                     double tx = 0.0;
@@ -423,8 +437,16 @@ __global__ void __launch_bounds__(RPF_THREADS, 5) rp_project_fx_kernel(RpFxArgs 
                     __syncwarp();
                 }
             }
-            if (cnt > 0) rpf_chunk<VEC, FB>(A, s_base, lane < cnt ? sgi[lane] : 0, lane < cnt ? sx[lane] : 0.0, lane < cnt, cs, qscale, okmask, &s_bad);
+            if (cnt > 0) {
+                const double tx = lane < cnt ? sx[lane] : 0.0;
+                rpf_chunk<VEC, FB, 0>(A, s_base, lane < cnt ? sgi[lane] : 0, tx, lane < cnt, rpf_class<FB>(tx, lane < cnt), cs, qscale, okmask, &s_bad);
+            }
         } else {
+            /* Class lanes need one atomic per entry, generic lanes two and a carry: a warp that mixes them pays for both.
+               Generic non-zeros are therefore set aside (their position in the column, 4 bytes each, in a per-warp list)
+               and handled 32 at a time by all-generic passes; the rest of the warp's work is class-only. */
+            uint32_t *stq = reinterpret_cast<uint32_t *>(fsm + 4 * kpd) + warp * RPF_STAGE;
+            int scnt = 0;
             int64_t q = q0 + warp * 32;
             bool valid = q + lane < q1;
             int gi = valid ? A.a.rowidx[q + lane] : 0;
@@ -434,8 +456,29 @@ __global__ void __launch_bounds__(RPF_THREADS, 5) rp_project_fx_kernel(RpFxArgs 
                 const bool nvalid = qn + lane < q1;
                 const int ngi = nvalid ? A.a.rowidx[qn + lane] : 0;
                 const double nx = nvalid ? A.a.val[qn + lane] : 0.0;
-                rpf_chunk<VEC, FB>(A, s_base, gi, x, valid, cs, qscale, okmask, &s_bad);
+                const int cls = rpf_class<FB>(x, valid);
+                const bool gen = valid && cls < 0 && x != 0.0; /* explicit zeros contribute nothing */
+                const unsigned gmask = __ballot_sync(0xffffffffu, gen);
+                if (gen) stq[scnt + __popc(gmask & ((1u << lane) - 1u))] = (uint32_t)(q + lane - q0);
+                scnt += __popc(gmask);
+                rpf_chunk<VEC, FB, 1>(A, s_base, gi, x, valid, cls, cs, qscale, okmask, &s_bad);
+                __syncwarp();
+                if (scnt >= 32) {
+                    const int64_t at = q0 + stq[lane];
+                    rpf_chunk<VEC, FB, 2>(A, s_base, A.a.rowidx[at], A.a.val[at], true, -1, cs, qscale, okmask, &s_bad);
+                    __syncwarp();
+                    const uint32_t t = (lane < scnt - 32) ? stq[32 + lane] : 0u;
+                    __syncwarp();
+                    if (lane < scnt - 32) stq[lane] = t;
+                    scnt -= 32;
+                    __syncwarp();
+                }
                 q = qn; valid = nvalid; gi = ngi; x = nx;
+            }
+            if (scnt > 0) {
+                const bool v = lane < scnt;
+                const int64_t at = q0 + (v ? stq[lane] : 0u);
+                rpf_chunk<VEC, FB, 2>(A, s_base, v ? A.a.rowidx[at] : 0, v ? A.a.val[at] : 0.0, v, -1, cs, qscale, okmask, &s_bad);
             }
         }
         __syncthreads();
@@ -445,7 +488,9 @@ __global__ void __launch_bounds__(RPF_THREADS, 5) rp_project_fx_kernel(RpFxArgs 
         long long qc[NCLS];
 #pragma unroll
         for (int c = 0; c < NCLS; c++) qc[c] = s_qc[c];
-        for (int i = tid; i < KP; i += RPF_THREADS) {
+        for (int k = 0, i0 = 0; k < A.a.K; k++, i0 += A.a.p)
+        for (int j = tid; j < A.a.p; j += RPF_THREADS) { /* (member, column) without an integer division per output */
+            const int i = i0 + j;
             long long tot = (long long)(((unsigned long long)hi[i] << 32) | (unsigned long long)lo[i]);
             lo[i] = 0u;
             hi[i] = 0u;
@@ -462,7 +507,6 @@ __global__ void __launch_bounds__(RPF_THREADS, 5) rp_project_fx_kernel(RpFxArgs 
             double r = __dmul_rn(__dmul_rn((double)tot, unscale), A.a.scale);
             if (A.a.round_digits >= 0) r = rp_round(r, A.a.round_digits);
             if (bad) r = __longlong_as_double(0x7ff8000000000000LL);
-            const int k = i / A.a.p, j = i - k * A.a.p;
             A.a.out[((size_t)k * A.a.ncell + pos) * A.a.p + j] = r;
         }
         __syncthreads();
@@ -472,21 +516,25 @@ __global__ void __launch_bounds__(RPF_THREADS, 5) rp_project_fx_kernel(RpFxArgs 
     }
 }
 
+template <int VEC, int FB, bool DENSE>
+static int launch_fx2(sharp_ctx *c, const RpFxArgs &A, int64_t ncell, size_t smem) {
+    SHARP_CUDA(cudaFuncSetAttribute(rp_project_fx_kernel<VEC, FB, DENSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SHARP_SMEM_OPTIN));
+    int per_sm = 0; /* a persistent grid: exactly the CTAs that are resident at once (no tail wave) */
+    SHARP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rp_project_fx_kernel<VEC, FB, DENSE>, RPF_THREADS, smem));
+    const int grid = (int)std::min<int64_t>(ncell, (int64_t)c->sm_count * std::max(1, per_sm));
+    rp_project_fx_kernel<VEC, FB, DENSE><<<grid, RPF_THREADS, smem, c->stream>>>(A);
+    return 0;
+}
 template <int VEC, int FB>
 static int launch_fx(sharp_ctx *c, const RpFxArgs &A, int64_t ncell, size_t smem) {
-    SHARP_CUDA(cudaFuncSetAttribute(rp_project_fx_kernel<VEC, FB>, cudaFuncAttributeMaxDynamicSharedMemorySize, SHARP_SMEM_OPTIN));
-    int per_sm = 0; /* a persistent grid: exactly the CTAs that are resident at once (no tail wave) */
-    SHARP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rp_project_fx_kernel<VEC, FB>, RPF_THREADS, smem));
-    const int grid = (int)std::min<int64_t>(ncell, (int64_t)c->sm_count * std::max(1, per_sm));
-    rp_project_fx_kernel<VEC, FB><<<grid, RPF_THREADS, smem, c->stream>>>(A);
-    return 0;
+    return A.a.dense ? launch_fx2<VEC, FB, true>(c, A, ncell, smem) : launch_fx2<VEC, FB, false>(c, A, ncell, smem);
 }
 template <int FB>
 static int launch_fx_vec(sharp_ctx *c, const RpFxArgs &A, int vec_per_gene, int64_t grid, size_t smem) {
-    if (vec_per_gene <= 2) return launch_fx<2, FB>(c, A, grid, smem);
-    if (vec_per_gene <= 3) return launch_fx<3, FB>(c, A, grid, smem);
-    if (vec_per_gene <= 4) return launch_fx<4, FB>(c, A, grid, smem);
-    return launch_fx<6, FB>(c, A, grid, smem);
+    /* two vectors (16 entries) are fetched up front, the tail of longer lists one vector ahead: more in registers
+       spills at the 48 registers that keep five cells per SM resident */
+    (void)vec_per_gene;
+    return launch_fx<2, FB>(c, A, grid, smem);
 }
 
 int launch_rp_project(sharp_ctx *c, const sharp_expr_dev &e, const int64_t *cells_dev, int64_t ncell,
@@ -510,7 +558,7 @@ int launch_rp_project(sharp_ctx *c, const sharp_expr_dev &e, const int64_t *cell
         F.cb = 1;
         while ((1 << F.cb) <= rm.max_col_nnz) F.cb++;
         F.kpd = rm.kpd;
-        const size_t fsmem = (size_t)4 * F.kpd * 4 + (e.dense ? (size_t)RPF_WARPS * RPF_STAGE * 12 : 0);
+        const size_t fsmem = (size_t)4 * F.kpd * 4 + (size_t)RPF_WARPS * RPF_STAGE * (e.dense ? 12 : 4);
         if (fsmem <= 200 * 1024) {
             prof_begin(c, KID_RP_PROJECT);
             const int rc = rm.max_col_nnz <= 255 ? launch_fx_vec<8>(c, F, rm.vec_per_gene, ncell, fsmem)
