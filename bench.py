@@ -39,6 +39,7 @@ for _p in (ROOT, os.path.join(ROOT, "tests")):
         sys.path.insert(0, _p)
 
 SEED = 2103
+METRIC = "cells/sec end-to-end SHARP at 1.3M cells"
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture (profiles/README.md)
 TRAFFIC = {}
 # the fused loop over parts keeps ~10 streams busy; with the default 8 hardware queues, streams alias and false
@@ -292,7 +293,7 @@ def run_reference(args):
     n = min(wl["parts"][0], args.cpu_sample)
     val = n * len(times) / sum(times)
     sample = f"first {n} cells of part 1 (SHARP_large, {len(block_sizes(n))} blocks x K={wl['K']}) per step"
-    print(json.dumps({"impl": "reference", "metric": "cells/sec end-to-end SHARP", "value": val, "unit": "cells/s",
+    print(json.dumps({"impl": "reference", "metric": METRIC, "value": val, "unit": "cells/s",
                       "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
                       "ms_per_step": 1e3 * sum(times) / len(times), "higher_is_better": True, "scaling": "strong",
                       "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -483,7 +484,7 @@ def run_ours(args):
         except Exception as ex:  # the oracle is test infrastructure; its absence must not hide the GPU number
             cpu = {"value": None, "unit": "cells/s", "cores": 0, "kind": "port", "sample": f"failed: {ex}"}
 
-    line = {"metric": "cells/sec end-to-end SHARP at 1.3M cells", "value": value, "unit": "cells/s", "n_gpus": world,
+    line = {"metric": METRIC, "value": value, "unit": "cells/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": wl["name"], "cells": ncells, "genes": m, "parts": len(sizes), "K": wl["K"], "p": p,

@@ -62,7 +62,7 @@ EXPORTS = [
     "sharp_expr_upload", "sharp_expr_free", "sharp_run_dev", "sharp_centroids", "sharp_smetac_centroids",
     "sharp_last_member", "sharp_last_vie", "sharp_prof_enable", "sharp_prof_reset", "sharp_prof_kernels", "sharp_prof_name",
     "sharp_prof_get", "sharp_ctx_set_rp_variant", "sharp_r_ranm", "sharp_r_sample_perm", "sharp_run_parts",
-    "sharp_ctx_set_block_budget", "sharp_ctx_set_serial",
+    "sharp_ctx_set_block_budget", "sharp_ctx_set_serial", "sharp_parts_prefetch",
 ]
 
 _lib = None
@@ -417,6 +417,26 @@ class Context:
     def set_serial(self, on: bool):
         """sharp_run_parts on ONE stream (isolated per-kernel timings for the roofline object); default off"""
         _check(load().sharp_ctx_set_serial(self._h, int(bool(on))))
+
+    def parts_prefetch(self, m: int, parts: list, group=0, lanes=0):
+        """sharp_parts_prefetch: start the uploads of the first group of ``parts`` (same list and group / lanes as the
+        run_parts call that follows) and return at once.  -> an object the caller keeps alive until run_parts is done."""
+        nparts = len(parts)
+        arr = (Part * nparts)()
+        keep = [arr]
+        for i, pt in enumerate(parts):
+            a = arr[i]
+            if isinstance(pt, ExprDev):
+                a.n = pt.n
+                a.dev = pt._h
+            else:
+                a.n = int(pt["n"])
+                a.dev = None
+                k, dp, cp, ri, v = _expr_args(m, a.n, pt.get("dense"), pt.get("csc"))
+                keep.append(k)
+                a.dense, a.colptr, a.rowidx, a.val = dp, cp, ri, v
+        _check(load().sharp_parts_prefetch(self._h, int(m), nparts, arr, int(group), int(lanes)))
+        return keep
 
     def run_parts(self, rm: RmDev, prm: RunParams, m: int, parts: list, reinds: list, small_thre=10, cen_cap=64,
                   group=0, lanes=0) -> list:

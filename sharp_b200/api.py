@@ -737,6 +737,20 @@ def _parts_fast_path(parts, mine, k, viewflag, part_logflag, n_streams):
             "indN_cluster": k.get("indN_cluster"), "maxN_cluster": max(40, math.ceil(ns[0] / 5000))}
 
 
+def _fused_inputs(parts, mine):
+    """the parts of this rank as sharp_run_parts / sharp_parts_prefetch take them"""
+    ins = []
+    for i in mine:
+        e = parts[i]
+        if e.dev is not None:
+            ins.append(e.dev)
+        elif e.dense is not None:
+            ins.append({"n": e.n, "dense": e.dense})
+        else:
+            ins.append({"n": e.n, "csc": e.csc})
+    return ins
+
+
 def _run_parts_fused(ctx, parts, mine, rM, p, K, rN_seed, a, n_cores):
     """What the loop `y[[i]] = SHARP(scExp[[i]], reduced.ndim = p, prep = FALSE, logflag = FALSE, rM = rM, ...)` returns
     for the parts in ``mine`` (R/SHARP_unlimited.R:125-149), computed by ONE sharp_run_parts call."""
@@ -744,17 +758,10 @@ def _run_parts_fused(ctx, parts, mine, rM, p, K, rN_seed, a, n_cores):
     hc = _hc(a["hmethod"], None, 2, a["maxN_cluster"], a["sil_thre"], a["height_Ntimes"], a["flashmark"])
     prm = RunParams(1, 1, 2, -1, int(a["partition_ncells"]), 0, _ncl(a["enpN_cluster"]), _ncl(a["indN_cluster"]), hc,
                     2 if normalize else 0, 1e6)
-    ins, reinds = [], []
+    ins, reinds = _fused_inputs(parts, mine), []
     for i in mine:
-        e = parts[i]
         _cat("Processing Partition", i + 1, "of the scRNA-seq data...")
-        if e.dev is not None:
-            ins.append(e.dev)
-        elif e.dense is not None:
-            ins.append({"n": e.n, "dense": e.dense})
-        else:
-            ins.append({"n": e.n, "csc": e.csc})
-        reinds.append(_reind(e.n, rN_seed) if e.n < 1e5 else None)
+        reinds.append(_reind(parts[i].n, rN_seed) if parts[i].n < 1e5 else None)
     start = time.time()
     outs = ctx.run_parts(rM, prm, parts[mine[0]].m, ins, reinds, small_thre=10, cen_cap=max(64, a["maxN_cluster"] + 1),
                          group=_fused_group, lanes=_fused_lanes)
@@ -815,12 +822,17 @@ def SHARP_unlimited(scExp, viewflag=True, n_cores=None, ensize_K=None, N_cluster
             print(f"[sharp trace py] {what} {1e3 * (now - _t[0]):.2f} ms", file=sys.stderr)
             _t[0] = now
 
+    rank, world = (comm.rank, comm.world) if comm is not None else (0, 1)
+    mine = [i for i in range(nnp) if i % world == rank]
+    fast = _parts_fast_path(parts, mine, k, viewflag, _part_logflag, n_streams)
+    # host buffers: the copy of the first parts starts now and runs while the ranM matrices are drawn on the host
+    _pf_keep = None
+    if fast is not None and mine and parts[mine[0]].dev is None:
+        _pf_keep = ctx.parts_prefetch(parts[mine[0]].m, _fused_inputs(parts, mine), _fused_group, _fused_lanes)
     rms_host = _rm_list(parts[0].m, p, ensize_K, rN_seed)
     _mark("ranM")
     rM = ctx.upload_rm(rms_host)
     _mark("upload_rm")
-    rank, world = (comm.rank, comm.world) if comm is not None else (0, 1)
-    mine = [i for i in range(nnp) if i % world == rank]
     y, cens, viEs = {}, {}, {}
     if isinstance(n_streams, (list, tuple)):  # explicit contexts, one per stream
         ctxs = list(n_streams)[:max(1, len(mine))]
@@ -846,7 +858,6 @@ def SHARP_unlimited(scExp, viewflag=True, n_cores=None, ensize_K=None, N_cluster
                   file=sys.stderr)
         return yi, cen, (c.last_vie(nnc[i], p) if viewflag else None)
 
-    fast = _parts_fast_path(parts, mine, k, viewflag, _part_logflag, n_streams)
     try:
         if fast is not None:  # every part takes the SHARP_large path with the same parameters: one fused device call
             t0 = time.time()

@@ -178,7 +178,7 @@ int launch_corrdist_batched(sharp_ctx *c, const GemmProb *probs_dev, const int *
                             int total_tiles, int ldu) {
     if (nprob <= 0 || total_tiles <= 0) return 0;
     size_t smem = (size_t)4 * GT * GLD * sizeof(double);
-    SHARP_CUDA(cudaFuncSetAttribute(corrdist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SHARP_SMEM_OPTIN));
+    SHARP_SMEM_OPTIN_ONCE((corrdist_kernel), c->device);
     prof_begin(c, KID_CORRDIST);
     corrdist_kernel<<<total_tiles, G_THREADS, smem, c->stream>>>(probs_dev, tile_prefix_dev, nprob, ldu);
     prof_end(c);

@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <atomic>
 #include <cstdint>
 #include <cstdio>
 #include <string>
@@ -30,6 +31,19 @@ int set_error(int code, const char *fmt, ...);
 // threads driving different contexts set it concurrently, and a smaller value set by one thread between another
 // thread's attribute call and its launch would make that launch fail.
 constexpr int SHARP_SMEM_OPTIN = 223 * 1024;  /* 227 KB minus room for the kernels' small static arrays */
+
+// The opt-in is set ONCE per kernel and device, not per launch: cudaFuncSetAttribute is not a cheap host-side setter --
+// under SHARP_B200_TRACE it was seen blocking the enqueueing thread for hundreds of ms while other streams were
+// running the same kernel, which stalled the whole group pipeline.  `flags` is a function-local static array.
+#define SHARP_SMEM_OPTIN_ONCE(kernel, device)                                                                     \
+    do {                                                                                                          \
+        static std::atomic<unsigned char> _done[64];                                                              \
+        const int _d = (device) & 63;                                                                             \
+        if (!_done[_d].load(std::memory_order_acquire)) {                                                         \
+            SHARP_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SHARP_SMEM_OPTIN)); \
+            _done[_d].store(1, std::memory_order_release);                                                        \
+        }                                                                                                         \
+    } while (0)
 
 // ---- device buffer that grows and never shrinks (workspace slot) -------------------------------------
 struct DevBuf {
@@ -128,9 +142,11 @@ struct sharp_ctx {
     cudaStream_t up_stream = nullptr;
     cudaEvent_t ev_up = nullptr;
     int pf_part = -1;             // index of the prefetched part (-1: none)
+    const void *pf_src = nullptr; // host buffer it was copied from (a prefetch is only used for the same buffer)
     int32_t *h_labels = nullptr;  // pinned label mirror of a group run
     size_t h_labels_cap = 0;
     int block_budget_gb = 48;     // cap of the distance-matrix workspace (D + Dw) of one context
+    size_t ws_budget = 0, ws_budget_seen = 0;  // last budget derived from cudaMemGetInfo and the workspace state it was derived for
     int64_t last_n = 0;     // state of the last run (for sharp_centroids)
     int last_p = 0;
     int last_K = 0;

@@ -664,7 +664,7 @@ int launch_sm_similarity(sharp_ctx *c, const SmArgs &A, const double *cen, int p
 
 int launch_sm_finish(sharp_ctx *c, const SmArgs &A, const SweepOut *out) {
     size_t smem = (size_t)4 * A.ld * 4;
-    SHARP_CUDA(cudaFuncSetAttribute(sm_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SHARP_SMEM_OPTIN));
+    SHARP_SMEM_OPTIN_ONCE((sm_finish_kernel), c->device);
     prof_begin(c, KID_SMETAC);
     sm_finish_kernel<<<1, MT, smem, c->stream>>>(A, out);
     prof_end(c);

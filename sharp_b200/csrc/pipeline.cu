@@ -148,7 +148,7 @@ void prof_end(sharp_ctx *c) {
     if (!c->prof_on || c->prof_open < 0) return;
     cudaEventRecord(c->prof_pending[c->prof_open].b, c->stream);
     c->prof_open = -1;
-    if (c->prof_pending.size() >= 4096) prof_collect(c);
+    if (c->prof_pending.size() >= 65536) prof_collect(c); /* collecting waits for the events: not inside a run */
 }
 void prof_collect(sharp_ctx *c) {
     for (auto &p : c->prof_pending) {
@@ -188,6 +188,20 @@ static size_t bump_size(std::initializer_list<size_t> bytes) {
     for (size_t b : bytes) t += b + 256;
     return t;
 }
+
+// trace aid (SHARP_B200_TRACE): report any host-side call of the enqueue path that blocks for more than 5 ms
+struct SlowCall {
+    const char *what;
+    std::chrono::steady_clock::time_point t0;
+    explicit SlowCall(const char *w) : what(w), t0(std::chrono::steady_clock::now()) {}
+    ~SlowCall() {
+        static const bool trace = getenv("SHARP_B200_TRACE") != nullptr;
+        if (!trace) return;
+        const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        if (ms > 5.0) fprintf(stderr, "[sharp trace slow] %s blocked the host for %.2f ms\n", what, ms);
+    }
+};
+#define SLOW(name, stmt) do { SlowCall _sc(name); stmt; } while (0)
 
 static int ld_of(int n) { return (n + 3) & ~3; }
 static int ldu_of(int p) { return (p + 15) & ~15; }
@@ -801,13 +815,20 @@ static int run_blocks(sharp_ctx *g, PartRun *const *parts, int np_parts) {
     }
     const int ldu = R0.ldu, p = R0.p;
     const HcParamsDev ind = R0.ind;
-    // wave size from the distance-matrix budget
-    size_t free_b = 0, total_b = 0;
-    SHARP_CUDA(cudaMemGetInfo(&free_b, &total_b));
+    // wave size from the distance-matrix budget.  The free-memory query is a driver call that can block for a long time
+    // while other streams are busy (SHARP_B200_TRACE showed it): it is only made when the workspaces this context already
+    // owns are smaller than its cap, i.e. while they are still growing.
     const size_t have = g->ws[WS_D].cap + g->ws[WS_DW].cap + g->ws[WS_HC_E].cap;
-    /* top-level contexts on other streams of the same device run concurrently: share the free memory between them */
-    const int live = std::max(1, g_live_ctx.load());
-    const size_t budget = std::min<size_t>((size_t)g->block_budget_gb << 30, (size_t)(free_b * 0.6 / live) + have);
+    const size_t cap_b = (size_t)g->block_budget_gb << 30;
+    size_t budget = cap_b;
+    if (have < cap_b && g->ws_budget_seen != have + 1) {
+        size_t free_b = 0, total_b = 0;
+        SLOW("cudaMemGetInfo", SHARP_CUDA(cudaMemGetInfo(&free_b, &total_b)));
+        /* top-level contexts on other streams of the same device run concurrently: share the free memory between them */
+        const int live = std::max(1, g_live_ctx.load());
+        budget = std::min<size_t>(cap_b, (size_t)(free_b * 0.6 / live) + have);
+        g->ws_budget = budget;
+    } else if (have < cap_b) budget = g->ws_budget;
     const size_t per_prob = (size_t)max_bn * ld_of(max_bn) * 8;
     /* round-parallel agglomeration: a third (smaller) matrix per problem, and the distance kernel writes D only */
     const bool fast = hclust_fast_ok(max_bn, ind.hmethod);
@@ -821,18 +842,20 @@ static int run_blocks(sharp_ctx *g, PartRun *const *parts, int np_parts) {
         const int nw = (nprob + wave_probs - 1) / wave_probs;
         wave_probs = (nprob + nw - 1) / nw;
     }
-    SHARP_TRY(g->ws[WS_D].reserve(per_prob * wave_probs));
-    SHARP_TRY(g->ws[WS_DW].reserve(per_prob * wave_probs));
+    SLOW("reserve WS_D", SHARP_TRY(g->ws[WS_D].reserve(per_prob * wave_probs)));
+    SLOW("reserve WS_DW", SHARP_TRY(g->ws[WS_DW].reserve(per_prob * wave_probs)));
     if (ecap) SHARP_TRY(g->ws[WS_HC_E].reserve(ecap * 8 * wave_probs));
+    /* the budget computed above stays valid as long as the workspaces do not change */
+    g->ws_budget_seen = g->ws[WS_D].cap + g->ws[WS_DW].cap + g->ws[WS_HC_E].cap + 1;
     double *Dall = g->ws[WS_D].as<double>(), *Dwall = g->ws[WS_DW].as<double>(), *Eall = g->ws[WS_HC_E].as<double>();
     const size_t sweep_scr = R0.nested ? sweep_nested_scratch_bytes(max_bn, ldu, ind) : sweep_exact_scratch_bytes(max_bn, ldu);
-    SHARP_TRY(g->ws[WS_SWEEP_SCRATCH].reserve(sweep_scr * wave_probs));
+    SLOW("reserve WS_SWEEP_SCRATCH", SHARP_TRY(g->ws[WS_SWEEP_SCRATCH].reserve(sweep_scr * wave_probs)));
     // descriptors of ALL problems (part-major, then block, then member), built once
     const int nwaves = (nprob + wave_probs - 1) / wave_probs;
     size_t desc = bump_size({(size_t)nprob * sizeof(GemmProb), (size_t)(nprob + nwaves + 2) * 4, (size_t)nprob * sizeof(HcProb),
                              (size_t)nprob * sizeof(SweepOut), (size_t)nprob * sizeof(HcParamsDev)});
-    SHARP_TRY(g->reserve_pinned(desc));
-    SHARP_TRY(g->ws[WS_GDESC].reserve(desc));
+    SLOW("blocks reserve_pinned", SHARP_TRY(g->reserve_pinned(desc)));
+    SLOW("reserve WS_GDESC", SHARP_TRY(g->ws[WS_GDESC].reserve(desc)));
     Bump hb(g->pinned, desc), db(g->ws[WS_GDESC].ptr, desc);
     GemmProb *gp = hb.take<GemmProb>(nprob);
     int *tp = hb.take<int>(nprob + nwaves + 2);
@@ -890,12 +913,12 @@ static int run_blocks(sharp_ctx *g, PartRun *const *parts, int np_parts) {
             waves.push_back(w);
         }
     }
-    SHARP_TRY(h2d_staged(g, g->ws[WS_GDESC].ptr, g->pinned, hb.off));
+    SLOW("blocks desc copy", SHARP_TRY(h2d_staged(g, g->ws[WS_GDESC].ptr, g->pinned, hb.off)));
     for (const Wave &w : waves) {
-        SHARP_TRY(launch_corrdist_batched(g, gpd + w.q0, tpd + w.tp_off, w.nq, w.tiles, ldu));
-        SHARP_TRY(launch_hclust(g, hpd + w.q0, w.nq, max_bn, ind.hmethod, 1));
+        SLOW("launch corrdist", SHARP_TRY(launch_corrdist_batched(g, gpd + w.q0, tpd + w.tp_off, w.nq, w.tiles, ldu)));
+        SLOW("launch hclust", SHARP_TRY(launch_hclust(g, hpd + w.q0, w.nq, max_bn, ind.hmethod, 1)));
         if (R0.nested)
-            SHARP_TRY(launch_sweep_nested(g, hpd + w.q0, sod + w.q0, w.nq, max_bn, ldu, ind, g->ws[WS_SWEEP_SCRATCH].as<double>(), sweep_scr));
+            SLOW("launch sweep", SHARP_TRY(launch_sweep_nested(g, hpd + w.q0, sod + w.q0, w.nq, max_bn, ldu, ind, g->ws[WS_SWEEP_SCRATCH].as<double>(), sweep_scr)));
         else
             SHARP_TRY(launch_sweep_exact(g, hpd + w.q0, sod + w.q0, w.nq, max_bn, p, ppd + w.q0, R0.maxlev, std::max(R0.kcap_ind, 2),
                                          g->ws[WS_SWEEP_SCRATCH].as<double>(), sweep_scr));
@@ -931,7 +954,7 @@ static int part_back(PartRun &R) {
     // ---- wMetaC per block ----
     sharp_hc_params wp = Q.hc;
     wp.n_cluster = Q.large ? Q.enp_n_cluster : Q.n_cluster;
-    SHARP_TRY(wmetac_dev(c, R.enrp, n, K, T, R.start.data(), R.start_dev, 40, wp, &R.W));
+    SLOW("back wmetac_dev", SHARP_TRY(wmetac_dev(c, R.enrp, n, K, T, R.start.data(), R.start_dev, 40, wp, &R.W)));
     SHARP_TRY(d2h(c, R.h_wst, R.W.A.status, (size_t)T * 4));
     // ---- labels / sMetaC ----
     SHARP_TRY(c->ws[WS_LABELS].reserve((size_t)n * 4));
@@ -956,7 +979,7 @@ static int part_back(PartRun &R) {
         SHARP_TRY(launch_sm_codes(c, R.W.A, T, R.coloff_dev, R.nc_dev, st_dev, code, corder, coff));
         sharp_hc_params sp = Q.hc;
         sp.n_cluster = Q.n_cluster;
-        SHARP_TRY(smetac_dev(c, capS, p, R.nc_dev, st_dev, R.E1, corder, coff, nullptr, n, sp, &R.B));
+        SLOW("back smetac_dev", SHARP_TRY(smetac_dev(c, capS, p, R.nc_dev, st_dev, R.E1, corder, coff, nullptr, n, sp, &R.B)));
         SHARP_TRY(d2h(c, R.h_sst, R.B.status, 4));
         SHARP_TRY(launch_sm_relabel(c, n, code, R.B.tf, 0, R.src_dev, R.labels_dev));
     }
@@ -1141,6 +1164,15 @@ struct GroupRun {
 };
 
 static int group_issue(GroupRun &G, sharp_part *parts, int m, const sharp_rm_dev &rm, const sharp_run_params &Q) {
+    static const bool trace = getenv("SHARP_B200_TRACE") != nullptr;
+    const auto t0 = std::chrono::steady_clock::now();
+    double t_up = 0, t_front = 0, t_blocks = 0, t_back = 0;
+    auto lap = [&](double &acc, std::chrono::steady_clock::time_point &from) {
+        const auto now = std::chrono::steady_clock::now();
+        acc += std::chrono::duration<double, std::milli>(now - from).count();
+        from = now;
+    };
+    auto tl = t0;
     const int np = (int)G.idx.size();
     G.runs.assign(np, PartRun());
     for (int j = 0; j < np; j++) {
@@ -1150,7 +1182,8 @@ static int group_issue(GroupRun &G, sharp_part *parts, int m, const sharp_rm_dev
         if (P.dev) {
             e = *P.dev;
             e.owned = false;
-        } else if (s->pf_part == G.idx[j]) { /* copied in by group_prefetch while the previous group was running */
+        } else if (s->pf_part == G.idx[j] && s->pf_src == (P.dense ? (const void *)P.dense : (const void *)P.val)) {
+            /* copied in by group_prefetch while the previous group was running (or by sharp_parts_prefetch) */
             s->pf_part = -1;
             e.device = s->device; e.m = m; e.n = P.n; e.owned = false;
             if (P.dense) e.dense = s->ws[WS_EX_A].as<double>();
@@ -1163,7 +1196,7 @@ static int group_issue(GroupRun &G, sharp_part *parts, int m, const sharp_rm_dev
             SHARP_CUDA(cudaStreamWaitEvent(s->stream, s->ev_up, 0));
         } else if (G.up) { /* all uploads of a group run go through ONE stream: the copy engine shares the link between
                               streams, and the first group must not wait for the bytes of the groups behind it */
-            SHARP_TRY(upload_expr(s, m, P.n, P.dense, P.colptr, P.rowidx, P.val, &e, true, G.up));
+            SLOW("inline upload_expr", SHARP_TRY(upload_expr(s, m, P.n, P.dense, P.colptr, P.rowidx, P.val, &e, true, G.up)));
             SHARP_CUDA(cudaEventRecord(s->ev_up, G.up));
             SHARP_CUDA(cudaStreamWaitEvent(s->stream, s->ev_up, 0));
         } else {
@@ -1174,7 +1207,9 @@ static int group_issue(GroupRun &G, sharp_part *parts, int m, const sharp_rm_dev
             SHARP_TRY(urc);
         }
         if (e.m != rm.m) return set_error(SHARP_E_ARG, "run_parts: part %d has %d genes but ranM has %d rows", G.idx[j], e.m, rm.m);
+        lap(t_up, tl);
         SHARP_TRY(part_front(G.runs[j], s, e, nullptr, rm, P.reind, Q));
+        lap(t_front, tl);
         SHARP_CUDA(cudaEventRecord(s->ev_ready, s->stream));
     }
     for (int j = 0; j < np; j++) SHARP_CUDA(cudaStreamWaitEvent(G.blocks->stream, G.subs[j]->ev_ready, 0));
@@ -1182,6 +1217,7 @@ static int group_issue(GroupRun &G, sharp_part *parts, int m, const sharp_rm_dev
     for (int j = 0; j < np; j++) ptrs[j] = &G.runs[j];
     SHARP_TRY(run_blocks(G.blocks, ptrs.data(), np));
     SHARP_CUDA(cudaEventRecord(G.blocks->ev_blocks, G.blocks->stream));
+    lap(t_blocks, tl);
     for (int j = 0; j < np; j++) {
         sharp_ctx *s = G.subs[j];
         PartRun &R = G.runs[j];
@@ -1198,6 +1234,10 @@ static int group_issue(GroupRun &G, sharp_part *parts, int m, const sharp_rm_dev
         SHARP_TRY(d2h(s, s->h_labels, R.labels_dev, (size_t)R.n * 4));
         SHARP_CUDA(cudaEventRecord(s->ev_done, s->stream));
     }
+    lap(t_back, tl);
+    if (trace && t_up + t_front + t_blocks + t_back > 10.0)
+        fprintf(stderr, "[sharp trace group_issue] slow issue: upload %.2f ms, front %.2f ms, blocks %.2f ms, back %.2f ms\n", t_up, t_front,
+                t_blocks, t_back);
     return 0;
 }
 
@@ -1228,6 +1268,7 @@ static int group_prefetch(const std::vector<int> &idx, const std::vector<sharp_c
         }
         SHARP_CUDA(cudaEventRecord(s->ev_up, up));
         s->pf_part = idx[j];
+        s->pf_src = P.dense ? (const void *)P.dense : (const void *)P.val;
     }
     return 0;
 }
@@ -1904,6 +1945,41 @@ int sharp_run(sharp_ctx *c, int m, int64_t n, const double *dense, const int64_t
     return rc;
 }
 
+}  // extern "C"
+
+// group boundaries of a run over `nparts` parts (shared by sharp_run_parts and sharp_parts_prefetch)
+static std::vector<int> plan_groups(int nparts, bool host_first, int &group, int &lanes) {
+    if (lanes <= 0) lanes = 2;
+    /* default group size: 4 parts share the block-clustering launches when there are many parts; with few parts (a rank
+       of a multi-GPU job) smaller groups keep both lanes busy -- a group running alone leaves the device half idle
+       during its latency-bound stages */
+    if (group <= 0) group = nparts <= 8 ? 2 : 4; /* measured on B200: 4 parts 160 ms as 2+2 vs 187 ms as 1+1+1+1 */
+    group = std::min(group, nparts);
+    // the parts are split as evenly as the group size allows, the smaller groups first and last (the first group's start
+    // and the last group's tail are the stretches of the run nothing else overlaps with).  With host data the first
+    // group is half a group: its upload is the only one that is not hidden behind another group.
+    std::vector<int> gstart{0};
+    const bool host_data = host_first && group >= 2 && nparts > group;
+    if (host_data) gstart.push_back(group / 2);
+    const int rest = nparts - gstart.back();
+    const int ng = (rest + group - 1) / group;
+    const int base = rest / ng, extra = rest % ng;
+    const int first_big = host_data ? 0 : (ng - extra) / 2; /* groups [first_big, first_big + extra) get base + 1 parts */
+    for (int g = 0; g < ng; g++) gstart.push_back(gstart.back() + base + ((g >= first_big && g < first_big + extra) ? 1 : 0));
+    return gstart;
+}
+
+static int ensure_subs(sharp_ctx *c, size_t need) {
+    while (c->subs.size() < need) {
+        sharp_ctx *s = nullptr;
+        SHARP_TRY(make_child(c, &s));
+        c->subs.push_back(s);
+    }
+    return 0;
+}
+
+extern "C" {
+
 int sharp_run_parts(sharp_ctx *c, int m, int nparts, sharp_part *parts, const sharp_rm_dev *rm,
                     const sharp_run_params *prm, int small_thre, int cen_cap, int group, int lanes) {
     SHARP_TRY(use(c));
@@ -1914,35 +1990,13 @@ int sharp_run_parts(sharp_ctx *c, int m, int nparts, sharp_part *parts, const sh
         if (!parts[i].dev && !parts[i].dense && !parts[i].colptr) return set_error(SHARP_E_ARG, "run_parts: part %d has no data", i);
         if (parts[i].dev && parts[i].dev->n != parts[i].n) return set_error(SHARP_E_ARG, "run_parts: part %d: n does not match the device matrix", i);
     }
-    if (lanes <= 0) lanes = 2;
-    /* default group size: 4 parts share the block-clustering launches when there are many parts; with few parts (a rank
-       of a multi-GPU job) smaller groups keep both lanes busy -- a group running alone leaves the device half idle
-       during its latency-bound stages */
-    if (group <= 0) group = nparts <= 8 ? 2 : 4; /* measured on B200: 4 parts 160 ms as 2+2 vs 187 ms as 1+1+1+1 */
-    group = std::min(group, nparts);
-    // group boundaries: the parts are split as evenly as the group size allows, the smaller groups first and last (the
-    // first group's start and the last group's tail are the stretches of the run nothing else overlaps with).  With host
-    // data the first group is half a group: its upload is the only one that is not hidden behind another group.
-    std::vector<int> gstart{0};
-    {
-        const bool host_data = !parts[0].dev && group >= 2 && nparts > group;
-        if (host_data) gstart.push_back(group / 2);
-        const int rest = nparts - gstart.back();
-        const int ng = (rest + group - 1) / group;
-        const int base = rest / ng, extra = rest % ng;
-        const int first_big = host_data ? 0 : (ng - extra) / 2; /* groups [first_big, first_big + extra) get base + 1 parts */
-        for (int g = 0; g < ng; g++) gstart.push_back(gstart.back() + base + ((g >= first_big && g < first_big + extra) ? 1 : 0));
-    }
+    std::vector<int> gstart = plan_groups(nparts, !parts[0].dev, group, lanes);
     const int ngroups = (int)gstart.size() - 1;
     lanes = std::min(lanes, ngroups);
     const size_t need = (size_t)lanes * (group + 1);
-    while (c->subs.size() < need) {
-        sharp_ctx *s = nullptr;
-        SHARP_TRY(make_child(c, &s));
-        c->subs.push_back(s);
-    }
+    SHARP_TRY(ensure_subs(c, need));
     for (sharp_ctx *s : c->subs) {
-        s->pf_part = -1;
+        if (c->serial) s->pf_part = -1;
         s->prof_on = c->prof_on;
         s->rp_legacy = c->rp_legacy;
         s->block_budget_gb = std::max(1, c->block_budget_gb / lanes);
@@ -2022,6 +2076,27 @@ int sharp_run_parts(sharp_ctx *c, int m, int nparts, sharp_part *parts, const sh
         return rc;
     }
     return sync(c);
+}
+
+int sharp_parts_prefetch(sharp_ctx *c, int m, int nparts, sharp_part *parts, int group, int lanes) {
+    SHARP_TRY(use(c));
+    if (!parts || nparts < 1) return set_error(SHARP_E_ARG, "parts_prefetch: bad arguments");
+    if (c->serial || parts[0].dev) return 0;
+    std::vector<int> gstart = plan_groups(nparts, true, group, lanes);
+    const int ngroups = (int)gstart.size() - 1;
+    lanes = std::min(lanes, ngroups);
+    SHARP_TRY(ensure_subs(c, (size_t)lanes * (group + 1)));
+    if (!c->up_stream) SHARP_CUDA(cudaStreamCreateWithFlags(&c->up_stream, cudaStreamNonBlocking));
+    /* behind whatever is queued on the context's stream (the caller's timer start, the previous call's end) */
+    SHARP_CUDA(cudaEventRecord(c->ev_fork, c->stream));
+    SHARP_CUDA(cudaStreamWaitEvent(c->up_stream, c->ev_fork, 0));
+    std::vector<int> idx;
+    std::vector<sharp_ctx *> subs;
+    for (int i = gstart[0]; i < gstart[1]; i++) {
+        idx.push_back(i);
+        subs.push_back(c->subs[(size_t)(i - gstart[0])]); /* lane 0 */
+    }
+    return group_prefetch(idx, subs, parts, m, c->up_stream);
 }
 
 int sharp_last_member(sharp_ctx *c, int k, int64_t n, int32_t *rowcolor, double *inde) {

@@ -518,9 +518,16 @@ __global__ void __launch_bounds__(RPF_THREADS, 5) rp_project_fx_kernel(RpFxArgs 
 
 template <int VEC, int FB, bool DENSE>
 static int launch_fx2(sharp_ctx *c, const RpFxArgs &A, int64_t ncell, size_t smem) {
-    SHARP_CUDA(cudaFuncSetAttribute(rp_project_fx_kernel<VEC, FB, DENSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SHARP_SMEM_OPTIN));
-    int per_sm = 0; /* a persistent grid: exactly the CTAs that are resident at once (no tail wave) */
-    SHARP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rp_project_fx_kernel<VEC, FB, DENSE>, RPF_THREADS, smem));
+    SHARP_SMEM_OPTIN_ONCE((rp_project_fx_kernel<VEC, FB, DENSE>), c->device);
+    /* a persistent grid: exactly the CTAs that are resident at once (no tail wave); the occupancy query is a driver call,
+       made once per shared-memory size and host thread */
+    static thread_local size_t q_smem = 0;
+    static thread_local int q_per_sm = 0;
+    if (q_per_sm == 0 || q_smem != smem) {
+        SHARP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&q_per_sm, rp_project_fx_kernel<VEC, FB, DENSE>, RPF_THREADS, smem));
+        q_smem = smem;
+    }
+    const int per_sm = q_per_sm;
     const int grid = (int)std::min<int64_t>(ncell, (int64_t)c->sm_count * std::max(1, per_sm));
     rp_project_fx_kernel<VEC, FB, DENSE><<<grid, RPF_THREADS, smem, c->stream>>>(A);
     return 0;
@@ -581,10 +588,10 @@ int launch_rp_project(sharp_ctx *c, const sharp_expr_dev &e, const int64_t *cell
     const int grid = (int)std::min<int64_t>(nbatch, (int64_t)c->sm_count);
     prof_begin(c, KID_RP_PROJECT);
     if (e16) {
-        SHARP_CUDA(cudaFuncSetAttribute(rp_project_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SHARP_SMEM_OPTIN));
+        SHARP_SMEM_OPTIN_ONCE((rp_project_kernel<true>), c->device);
         rp_project_kernel<true><<<grid, W * 32, smem, c->stream>>>(A, W);
     } else {
-        SHARP_CUDA(cudaFuncSetAttribute(rp_project_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SHARP_SMEM_OPTIN));
+        SHARP_SMEM_OPTIN_ONCE((rp_project_kernel<false>), c->device);
         rp_project_kernel<false><<<grid, W * 32, smem, c->stream>>>(A, W);
     }
     prof_end(c);

@@ -417,7 +417,7 @@ int launch_sweep_nested(sharp_ctx *c, HcProb *probs_dev, SweepOut *outs_dev, int
     NestedLayout L = nested_layout(max_n, kcap, nlevcap);
     if (L.total > 220 * 1024)
         return set_error(SHARP_E_LIMIT, "nested sweep: %d objects need %zu bytes of shared memory", max_n, L.total);
-    SHARP_CUDA(cudaFuncSetAttribute(sweep_nested_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SHARP_SMEM_OPTIN));
+    SHARP_SMEM_OPTIN_ONCE((sweep_nested_kernel), c->device);
     prof_begin(c, KID_SWEEP_NESTED);
     sweep_nested_kernel<<<nprob, SW_THREADS, L.total, c->stream>>>(probs_dev, outs_dev, prm, max_n, kcap, nlevcap,
                                                                    scratch, scratch_per_prob);
@@ -633,14 +633,14 @@ int launch_sweep_exact(sharp_ctx *c, HcProb *probs_dev, SweepOut *outs_dev, int 
         exact_prep_kernel<<<g, SW_THREADS, 0, c->stream>>>(probs_dev, scratch, scratch_per_prob / 8);
         prof_end(c);
     }
-    SHARP_CUDA(cudaFuncSetAttribute(sweep_exact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SHARP_SMEM_OPTIN));
+    SHARP_SMEM_OPTIN_ONCE((sweep_exact_kernel), c->device);
     dim3 grid(max_levels, nprob);
     prof_begin(c, KID_SWEEP_EXACT);
     sweep_exact_kernel<<<grid, SW_THREADS, smem, c->stream>>>(probs_dev, outs_dev, prm_dev, max_n, kcap, scratch,
                                                               scratch_per_prob / 8);
     prof_end(c);
     size_t smem2 = (size_t)4 * max_n * 4;
-    SHARP_CUDA(cudaFuncSetAttribute(sweep_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SHARP_SMEM_OPTIN));
+    SHARP_SMEM_OPTIN_ONCE((sweep_select_kernel), c->device);
     prof_begin(c, KID_SWEEP_EXACT);
     sweep_select_kernel<<<nprob, SW_THREADS, smem2, c->stream>>>(probs_dev, outs_dev, prm_dev, max_n);
     prof_end(c);

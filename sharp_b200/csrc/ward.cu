@@ -653,10 +653,10 @@ static int launch_exact(sharp_ctx *c, HcProb *probs_dev, int nprob, int max_n, i
         return set_error(SHARP_E_LIMIT, "hclust: %d objects exceed the shared-memory NN list (max ~7000)", max_n);
     prof_begin(c, max_n > 384 ? KID_HCLUST : KID_HCLUST_SMALL);
     if (max_n > 384) {
-        SHARP_CUDA(cudaFuncSetAttribute(hclust_kernel<256, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SHARP_SMEM_OPTIN));
+        SHARP_SMEM_OPTIN_ONCE((hclust_kernel<256, 2>), c->device);
         hclust_kernel<256, 2><<<nprob, 256, smem, c->stream>>>(probs_dev, method, only_fallback);
     } else {
-        SHARP_CUDA(cudaFuncSetAttribute(hclust_kernel<128, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, SHARP_SMEM_OPTIN));
+        SHARP_SMEM_OPTIN_ONCE((hclust_kernel<128, 4>), c->device);
         hclust_kernel<128, 4><<<nprob, 128, smem, c->stream>>>(probs_dev, method, only_fallback);
     }
     prof_end(c);
@@ -670,7 +670,7 @@ int launch_hclust(sharp_ctx *c, HcProb *probs_dev, int nprob, int max_n, int met
     if (nprob <= 0) return 0;
     if (method < 1 || method > 8) return set_error(SHARP_E_ARG, "invalid clustering method %d", method);
     if (fast && hclust_fast_ok(max_n, method)) {
-        SHARP_CUDA(cudaFuncSetAttribute(hclust_rnn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SHARP_SMEM_OPTIN));
+        SHARP_SMEM_OPTIN_ONCE((hclust_rnn_kernel), c->device);
         prof_begin(c, KID_HCLUST);
         hclust_rnn_kernel<<<nprob, RNN_THREADS, hclust_rnn_smem_bytes(max_n), c->stream>>>(probs_dev, method);
         prof_end(c);

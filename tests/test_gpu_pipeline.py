@@ -106,11 +106,18 @@ def test_unlimited_fused_equals_part_by_part_and_oracle():
         api._fused_parts = False
         a = api.SHARP_unlimited(csc_parts, viewflag=False, rN_seed=seed, ensize_K=K, exp_type="UMI", ctx=c, n_streams=1)
         api._fused_parts = True
-        for group, lanes in ((1, 1), (2, 2), (3, 1)):
+        # (1, 2) after (1, 1): three groups on two lanes with the expression buffers already sized, i.e. the upload
+        # look-ahead (group_prefetch) is taken; the last entry repeats it with every workspace warm
+        for group, lanes in ((1, 1), (1, 2), (2, 2), (3, 1), (0, 0), (1, 2)):
             api._fused_group, api._fused_lanes = group, lanes
             b = api.SHARP_unlimited(csc_parts, viewflag=False, rN_seed=seed, ensize_K=K, exp_type="UMI", ctx=c)
             assert np.array_equal(a["pred_clusters"], b["pred_clusters"]), (group, lanes)
             assert a["N.pred_clusters"] == b["N.pred_clusters"] and a["paras"] == b["paras"]
+        # the one-stream mode behind bench.py's per-kernel profile runs the same launches
+        c.set_serial(True)
+        e = api.SHARP_unlimited(csc_parts, viewflag=False, rN_seed=seed, ensize_K=K, exp_type="UMI", ctx=c)
+        c.set_serial(False)
+        assert np.array_equal(a["pred_clusters"], e["pred_clusters"])
         # device-resident parts give the same result as host buffers
         devs = [c.upload_expr(x.shape[0], x.shape[1], csc=synth.to_csc(x)) for x in parts]
         d = api.SHARP_unlimited(devs, viewflag=False, rN_seed=seed, ensize_K=K, exp_type="UMI", ctx=c)

@@ -75,6 +75,63 @@ def test_rp_project_both_variants_agree(ctx, fmt, logkind):
     assert np.max(np.abs(out[False] - refs) / per_member) <= 1e-11
 
 
+def test_rp_project_count_classes_exact(ctx):
+    """count data: non-zeros equal to 1..4 are counted per output (+/- fields) instead of added, everything else takes
+    the two-limb generic path.  Both are the same exact integer sum, so the CSC kernel (class passes + compacted generic
+    passes) and the dense kernel (mixed lanes) must agree BITWISE, and both with the oracle and the fp64 kernel to
+    rounding.  Explicit zeros stored in the dgCMatrix and an empty cell contribute nothing."""
+    m, n, K, p = 4000, 120, 5, 101
+    rng = np.random.default_rng(12)
+    x = rng.poisson(0.25, size=(m, n)).astype(np.float64)
+    x[rng.random((m, n)) < 0.01] = 7.0          # some generic integers
+    x[rng.random((m, n)) < 0.005] = 2.5         # and non-integers
+    x[:, 3] = 0.0                               # an empty cell
+    x[:, 5] = 0.0
+    x[17, 5] = 1.0                              # a cell with one class-1 gene
+    cp, ri, xv = synth.to_csc(x)
+    # explicit zeros: append a stored 0.0 to the first cell's column
+    free = int(np.setdiff1d(np.arange(m), ri[cp[0]:cp[1]])[0])
+    ri = np.concatenate([ri[:cp[1]], [free], ri[cp[1]:]]).astype(np.int32)
+    xv = np.concatenate([xv[:cp[1]], [0.0], xv[cp[1]:]])
+    cp = cp.copy()
+    cp[1:] += 1
+    order = np.argsort(ri[cp[0]:cp[1]], kind="stable")
+    ri[cp[0]:cp[1]] = ri[cp[0]:cp[1]][order]
+    xv[cp[0]:cp[1]] = xv[cp[0]:cp[1]][order]
+    rms = [ranM2(m, p, 900 + k) for k in range(K)]
+    rm = ctx.upload_rm(rms)
+    colsum = x.sum(0)
+    colsum[3] = 1.0                             # the reference divides by colSums; keep the empty cell finite
+    for logkind in (2, 0):
+        got_csc = ctx.rp_project(m, n, rm, csc=(cp, ri, xv), normalize=1, colsum=colsum, logkind=logkind)
+        got_dense = ctx.rp_project(m, n, rm, dense=x, normalize=1, colsum=colsum, logkind=logkind)
+        assert np.array_equal(got_csc, got_dense)   # class counting, generic passes and the mixed dense path: same integers
+        ctx.set_rp_variant(True)
+        legacy = ctx.rp_project(m, n, rm, dense=x, normalize=1, colsum=colsum, logkind=logkind)
+        ctx.set_rp_variant(False)
+        for k in range(K):
+            ref = orc.rp_project(m, n, rms[k], dense=x, colsum=colsum, logkind=logkind)
+            assert relerr(got_csc[k], ref) <= 1e-12 and relerr(legacy[k], ref) <= 1e-12
+        assert np.all(got_csc[:, 3, :] == 0.0)
+
+
+def test_rp_project_long_ranm_columns_use_16bit_fields(ctx):
+    """a ranM column with more than 255 entries (m > 65 000 genes) cannot be counted in 8-bit fields: the kernel then
+    counts classes 1 and 2 in 16-bit fields; m = 90 000, all counts 1 or 2 in a few dense cells so that single outputs
+    really receive > 255 terms of one class"""
+    m, n, p = 90000, 6, 12
+    rng = np.random.default_rng(4)
+    x = rng.integers(1, 3, size=(m, n)).astype(np.float64)   # every gene expressed: 1 or 2
+    x[:, 4] = rng.integers(0, 6, size=m)                      # one ordinary cell
+    rms = [ranM2(m, p, 41), ranM2(m, p, 42)]
+    assert max(int(np.max(np.diff(r["p"]))) for r in rms) > 255
+    rm = ctx.upload_rm(rms)
+    got = ctx.rp_project(m, n, rm, csc=synth.to_csc(x), normalize=2, logkind=2)
+    for k in range(2):
+        ref = orc.rp_project(m, n, rms[k], dense=x, colsum=x.sum(0), logkind=2)
+        assert relerr(got[k], ref) <= 1e-12
+
+
 def test_rp_project_nonfinite_value_poisons_the_cell(ctx):
     m, n, p = 800, 20, 16
     x, _ = synth.make_expression(m, n, seed=9)
