@@ -41,7 +41,9 @@ for _p in (ROOT, os.path.join(ROOT, "tests")):
 SEED = 2103
 METRIC = "cells/sec end-to-end SHARP at 1.3M cells"
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture (profiles/README.md)
-TRAFFIC = {}
+# (bytes; profiles/r1c_ncu_full_top4_raw.csv: first group of the full workload -- one 50 000-cell part for the projection,
+# 125 (member, block) problems per launch for the block-clustering kernels, which is also what the timed steps launch)
+TRAFFIC = {"rp_project": 2.327e9, "hclust": 46.89e9, "corrdist": 4.973e9, "sweep_nested": 5.238e9}
 # the fused loop over parts keeps ~10 streams busy; with the default 8 hardware queues, streams alias and false
 # dependencies serialise copies and kernels of different parts (must be set before CUDA initialises)
 os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
@@ -427,6 +429,11 @@ def run_ours(args):
         h2d = sum(nnz_all) * 12 + sum((s + 1) * 8 for s in sizes)
         d2h = ncells * 4
 
+    if comm:  # every exchange is done; leave the process group cleanly on all ranks
+        try:
+            torch.distributed.destroy_process_group()
+        except Exception:
+            pass
     if rank != 0:
         return
     # ---- roofline of the dominant kernel (live CUDA-event profile over the timed steps, this rank's share) ----

@@ -836,9 +836,11 @@ static int run_blocks(sharp_ctx *g, PartRun *const *parts, int np_parts) {
     const size_t per_all = 2 * per_prob + ecap * 8;
     int wave_probs = (int)std::min<size_t>((size_t)nprob, std::max<size_t>(1, budget / per_all));
     if (fast) {
-        /* the agglomeration kernel keeps 2 CTAs (= problems) per SM resident: a wave of one problem more than that
-           costs a whole extra pass of a lone CTA, so waves are capped at the resident count and then evened out */
-        wave_probs = std::min(wave_probs, std::max(1, 2 * g->sm_count));
+        /* One problem per SM and wave (125 of the benchmark's 2000-cell blocks on 148 SMs), evened out over the waves.
+           The agglomeration kernel could keep two problems per SM resident, but a lone problem already streams at the
+           per-SM share of HBM bandwidth (ncu: 0.13 ms per problem at 125 per launch, 0.15 ms at 297), and the shorter
+           launches let the other lane's stages slot in between them: the whole job ran 4 % faster on B200 this way. */
+        wave_probs = std::min(wave_probs, std::max(1, g->sm_count));
         const int nw = (nprob + wave_probs - 1) / wave_probs;
         wave_probs = (nprob + nw - 1) / nw;
     }
