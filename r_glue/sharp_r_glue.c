@@ -196,6 +196,77 @@ SEXP sharp_R_run(SEXP E, SEXP rm_ptr, SEXP reind, SEXP large, SEXP flag, SEXP lo
     return out;
 }
 
+/* .Call("sharp_R_run_parts", parts, rm_ptr, reinds, flag, partition.ncells, enpN.cluster, indN.cluster, hmethod, maxN,
+ *        sil.thre, height.Ntimes, normalize, device, p)
+ *   parts: the LIST of genes x cells matrices SHARP_unlimited was given; reinds: list of `set.seed(50); sample(n)` per part
+ *   (NULL entries for parts of 1e5 cells or more)
+ *   -> list(pred = list of integer vectors (clusterID per part, R/SHARP.R:828-832), cen = list of nclust x p matrices
+ *      (colMeans of viE per cluster, for the global sMetaC))
+ * replaces the loop `y[[i]] = SHARP(scExp[[i]], reduced.ndim = p, prep = FALSE, rM = rM, ...)` of
+ * R/SHARP_unlimited.R:125-149 by ONE device call when every part takes the SHARP_large path (sharp_run_parts: groups of
+ * parts share the block-clustering launches, uploads run one group ahead).  sharp_parts_prefetch may be called with
+ * the same list first (e.g. before the ranM matrices are drawn) to start the first uploads early. */
+SEXP sharp_R_run_parts(SEXP parts, SEXP rm_ptr, SEXP reinds, SEXP flag, SEXP ng, SEXP enpN, SEXP indN, SEXP hmethod,
+                       SEXP maxN, SEXP silthre, SEXP heightN, SEXP normalize, SEXP device, SEXP p_) {
+    sharp_rm_dev *rm = (sharp_rm_dev *)R_ExternalPtrAddr(rm_ptr);
+    if (!rm) Rf_error("rm handle was freed");
+    const int np = Rf_length(parts), p = Rf_asInteger(p_);
+    sharp_run_params q;
+    memset(&q, 0, sizeof q);
+    q.large = 1;
+    q.logflag = Rf_asLogical(flag);
+    q.logkind = 2;
+    q.round_digits = -1;
+    q.partition_ncells = Rf_asInteger(ng);
+    q.enp_n_cluster = Rf_isNull(enpN) ? 0 : Rf_asInteger(enpN);
+    q.ind_n_cluster = Rf_isNull(indN) ? 0 : Rf_asInteger(indN);
+    q.hc = hc_from(hmethod, R_NilValue, R_NilValue, maxN, silthre, heightN);
+    q.hc.min_n = 2; /* SHARP() inside the loop runs with its default minN.cluster */
+    q.normalize = Rf_asInteger(normalize);
+    q.norm_mul = 1e6;
+    const int cen_cap = (q.hc.max_n > 63 ? q.hc.max_n : 63) + 1;
+    sharp_part *P = (sharp_part *)R_alloc((size_t)np, sizeof(sharp_part));
+    memset(P, 0, (size_t)np * sizeof(sharp_part));
+    SEXP pred = PROTECT(Rf_allocVector(VECSXP, np));
+    int m = 0;
+    for (int i = 0; i < np; i++) {
+        expr_t e = expr_from(VECTOR_ELT(parts, i));
+        m = e.m;
+        P[i].n = e.n;
+        P[i].dense = e.dense;
+        P[i].colptr = e.colptr;
+        P[i].rowidx = e.rowidx;
+        P[i].val = e.val;
+        SEXP re = Rf_isNull(reinds) ? R_NilValue : VECTOR_ELT(reinds, i);
+        if (!Rf_isNull(re)) {
+            int64_t *r64 = (int64_t *)R_alloc((size_t)e.n, sizeof(int64_t));
+            for (int64_t c = 0; c < e.n; c++) r64[c] = INTEGER(re)[c];
+            P[i].reind = r64;
+        }
+        SEXP lab = PROTECT(Rf_allocVector(INTSXP, (R_xlen_t)e.n));
+        SET_VECTOR_ELT(pred, i, lab);
+        UNPROTECT(1);
+        P[i].pred = INTEGER(lab);
+        P[i].cen = (double *)R_alloc((size_t)cen_cap * p, sizeof(double));
+        P[i].counts = (int64_t *)R_alloc((size_t)cen_cap, sizeof(int64_t));
+    }
+    int rc = sharp_run_parts(ctx_for(Rf_asInteger(device)), m, np, P, rm, &q, 10, cen_cap, 0, 0);
+    if (rc != SHARP_OK) { UNPROTECT(1); Rf_error("%s", sharp_last_error()); }
+    SEXP cen = PROTECT(Rf_allocVector(VECSXP, np));
+    for (int i = 0; i < np; i++) { /* row-major C -> column-major R */
+        const int nc = P[i].nclust;
+        SEXP c = PROTECT(Rf_allocMatrix(REALSXP, nc, p));
+        for (int a = 0; a < nc; a++) for (int j = 0; j < p; j++) REAL(c)[(size_t)j * nc + a] = P[i].cen[(size_t)a * p + j];
+        SET_VECTOR_ELT(cen, i, c);
+        UNPROTECT(1);
+    }
+    SEXP out = PROTECT(Rf_allocVector(VECSXP, 2));
+    SET_VECTOR_ELT(out, 0, pred);
+    SET_VECTOR_ELT(out, 1, cen);
+    UNPROTECT(3);
+    return out;
+}
+
 /* .Call("sharp_R_opt_hclust", mat, symmetric, hmethod, N.cluster, minN, maxN, sil.thre, height.Ntimes, device)
  *   -> list(f, v, maxsil, msil, CHind, height, optN.cluster)                   replaces R/get_opt_hclust.R:66-243 */
 SEXP sharp_R_opt_hclust(SEXP mat, SEXP symmetric, SEXP hmethod, SEXP Ncl, SEXP minN, SEXP maxN, SEXP silthre,
@@ -306,6 +377,7 @@ static const R_CallMethodDef call_methods[] = {
     {"sharp_R_rm_upload", (DL_FUNC)&sharp_R_rm_upload, 2},
     {"sharp_R_rp_project", (DL_FUNC)&sharp_R_rp_project, 9},
     {"sharp_R_run", (DL_FUNC)&sharp_R_run, 20},
+    {"sharp_R_run_parts", (DL_FUNC)&sharp_R_run_parts, 14},
     {"sharp_R_opt_hclust", (DL_FUNC)&sharp_R_opt_hclust, 9},
     {"sharp_R_wmetac", (DL_FUNC)&sharp_R_wmetac, 8},
     {"sharp_R_smetac", (DL_FUNC)&sharp_R_smetac, 9},

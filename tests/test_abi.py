@@ -80,3 +80,24 @@ def test_host_only_entry_points_run_without_a_device():
     assert list(out) == [1, 5, 10, 8, 2, 4, 6, 9, 7, 3]
     r = _lib.r_ranm(300, 12, 7)
     assert r["p"][-1] == len(r["i"]) == len(r["x"])
+
+
+def test_r_glue_compiles_against_the_r_api():
+    """r_glue/sharp_r_glue.c (the .Call stubs a maintainer adds to the R package) cannot be built
+    without R; its syntax, its use of the C ABI (every sharp_* call must match include/sharp_b200.h) and its use of the
+    R C API (tests/r_stub: declarations only, taken from the published R API) are checked with the host compiler."""
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        import pytest
+        pytest.skip("no host C compiler")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([gcc, "-fsyntax-only", "-Wall", "-Werror=implicit-function-declaration", "-Werror=incompatible-pointer-types",
+                        "-I" + os.path.join(root, "tests", "r_stub"), "-I" + os.path.join(root, "include"),
+                        os.path.join(root, "r_glue", "sharp_r_glue.c")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    src = open(os.path.join(root, "r_glue", "sharp_r_glue.c")).read()
+    for stub in ("sharp_R_run", "sharp_R_run_parts", "sharp_R_rp_project", "sharp_R_opt_hclust", "sharp_R_wmetac",
+                 "sharp_R_smetac", "sharp_R_centroids", "sharp_R_smetac_centroids", "sharp_R_rm_upload"):
+        assert '{"%s"' % stub in src, stub + " is not registered in call_methods"
