@@ -282,3 +282,53 @@ def test_sharp_large_orchestration_transcribed(m, n, K, ng, seed):
     ref = orc.sharp(m, n, rms, prm, dense=x, reind=reind)
     assert np.array_equal(np.asarray(ref["pred_clusters"]).astype(np.int64), pred_t)
     assert np.allclose(ref["viE"], vie_t, rtol=1e-13, atol=1e-13)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# SHARP_unlimited's global step (R/SHARP_unlimited.R:125-183)
+# ---------------------------------------------------------------------------------------------------------
+def unlimited_combine_transcribed(part_of, pred, E1, hc, n_cluster=0):
+    ncells = len(pred)
+    fColor = [f"{c}s{i}" for c, i in zip(pred.tolist(), part_of.tolist())]             # :134 paste(pred, "s", i)
+    codes = {c: k + 1 for k, c in enumerate(dict.fromkeys(fColor))}
+    prm = orc.hc_params(hc.hmethod, n_cluster, hc.min_n, hc.max_n, hc.sil_thre, hc.height_ntimes)
+    s = orc.smetac(np.array([codes[c] for c in fColor]), E1, prm)                       # :151-153
+    # sMetaC assigns numbers INTO a character vector (R/sMetaC.R:182), so finalColor is character from here on:
+    final = [str(int(v)) for v in np.asarray(s["finalColor"]).tolist()]
+    if not n_cluster and ncells > 1e4:                                                  # :158-166
+        names = sorted(set(final))                                                      # table(): names in string order
+        cnt = {k: final.count(k) for k in names}
+        small = [k for k in names if cnt[k] < 10]
+        if small:
+            tgt = str(min(int(k) for k in small))
+            final = [tgt if k in small else k for k in final]
+    names = sorted(set(final))                                                          # :168 sort(table(.), decreasing = TRUE):
+    cnt = np.array([final.count(k) for k in names])                                     # stable, ties keep the STRING order
+    order = np.argsort(-cnt, kind="stable")
+    mp = {names[j]: r + 1 for r, j in enumerate(order)}                                 # :169-171 map[finalrowColor] by NAME
+    return np.array([mp[k] for k in final])
+
+
+@pytest.mark.parametrize("nparts,per_part,g,fixed,seed", [(3, 400, 12, 12, 1), (4, 300, 5, 0, 2), (2, 6000, 3, 0, 3)])
+def test_unlimited_combine_transcribed(nparts, per_part, g, fixed, seed):
+    """g = 12 equally large planted groups with N.cluster = 12: every cluster size ties, so the final numbering is decided
+    by table()'s STRING order of the names ("1", "10", "11", "12", "2", ...)"""
+    rng = np.random.default_rng(seed)
+    p = 30
+    centres = rng.normal(size=(g, p)) * 3.0
+    part_of, pred, rows = [], [], []
+    for i in range(1, nparts + 1):
+        truth = np.arange(per_part) % g
+        rng.shuffle(truth)
+        relabel = rng.permutation(g) + 1                                                 # every part numbers its clusters its own way
+        pred.append(relabel[truth])
+        part_of.append(np.full(per_part, i))
+        rows.append(centres[truth] + 0.3 * rng.normal(size=(per_part, p)))
+    part_of, pred, E1 = np.concatenate(part_of), np.concatenate(pred), np.concatenate(rows)
+    hc = orc.hc_params()
+    got_t = unlimited_combine_transcribed(part_of, pred, E1, hc, fixed)
+    got, nf = orc.unlimited_combine(part_of, pred, E1, hc, fixed)
+    assert np.array_equal(np.asarray(got).astype(np.int64), got_t)
+    assert nf == len(np.unique(got_t))
+    if fixed:
+        assert nf == fixed
