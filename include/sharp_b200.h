@@ -237,6 +237,11 @@ int sharp_run_parts(sharp_ctx *ctx, int m, int nparts, sharp_part *parts, const 
  * effect from the second call on a context (the staging buffers must already have their size); otherwise a no-op.
  * The buffers must stay unchanged until sharp_run_parts returns. */
 int sharp_parts_prefetch(sharp_ctx *ctx, int m, int nparts, sharp_part *parts, int group, int lanes);
+/* How sharp_run_parts / sharp_parts_prefetch split `nparts` parts into groups (pure host logic, no device needed):
+ * gstart[0..*ngroups] receives the group boundaries (gstart[g] .. gstart[g+1]-1 are the parts of group g).
+ * group / lanes <= 0 select the defaults; host_data != 0: the parts are host buffers (half-size first group). */
+int sharp_plan_groups(int nparts, int host_data, int group, int lanes, int *gstart, int cap, int *ngroups, int *group_used,
+                      int *lanes_used);
 /* cap (GB) of the distance-matrix workspace per context; the (member, block) problems of a group run in waves of
  * as many problems as fit (default 48) */
 int sharp_ctx_set_block_budget(sharp_ctx *ctx, int gigabytes);

@@ -62,7 +62,7 @@ EXPORTS = [
     "sharp_expr_upload", "sharp_expr_free", "sharp_run_dev", "sharp_centroids", "sharp_smetac_centroids",
     "sharp_last_member", "sharp_last_vie", "sharp_prof_enable", "sharp_prof_reset", "sharp_prof_kernels", "sharp_prof_name",
     "sharp_prof_get", "sharp_ctx_set_rp_variant", "sharp_r_ranm", "sharp_r_sample_perm", "sharp_run_parts",
-    "sharp_ctx_set_block_budget", "sharp_ctx_set_serial", "sharp_parts_prefetch",
+    "sharp_ctx_set_block_budget", "sharp_ctx_set_serial", "sharp_parts_prefetch", "sharp_plan_groups",
 ]
 
 _lib = None
@@ -174,6 +174,15 @@ def r_sample_perm_native(n: int, seed: int) -> np.ndarray:
     if rc != 0:
         raise SharpError(rc, "sharp_r_sample_perm failed")
     return out
+
+
+def plan_groups(nparts: int, host_data: bool, group=0, lanes=0) -> dict:
+    """sharp_plan_groups: how the loop over parts splits ``nparts`` parts -> {"gstart", "group", "lanes"} (host logic)"""
+    g = np.zeros(nparts + 2, dtype=np.int32)
+    ng, gu, lu = C.c_int(), C.c_int(), C.c_int()
+    _check(load().sharp_plan_groups(int(nparts), int(bool(host_data)), int(group), int(lanes), _ptr(g, C.c_int), len(g),
+                                    C.byref(ng), C.byref(gu), C.byref(lu)))
+    return {"gstart": g[:ng.value + 1].tolist(), "group": gu.value, "lanes": lu.value}
 
 
 class RmDev:

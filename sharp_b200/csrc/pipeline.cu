@@ -2080,6 +2080,18 @@ int sharp_run_parts(sharp_ctx *c, int m, int nparts, sharp_part *parts, const sh
     return sync(c);
 }
 
+int sharp_plan_groups(int nparts, int host_data, int group, int lanes, int *gstart, int cap, int *ngroups, int *group_used,
+                      int *lanes_used) {
+    if (nparts < 1 || !gstart || !ngroups) return set_error(SHARP_E_ARG, "plan_groups: bad arguments");
+    std::vector<int> g = plan_groups(nparts, host_data != 0, group, lanes);
+    if ((int)g.size() > cap) return set_error(SHARP_E_NOMEM, "plan_groups: %d boundaries but room for %d", (int)g.size(), cap);
+    for (size_t i = 0; i < g.size(); i++) gstart[i] = g[i];
+    *ngroups = (int)g.size() - 1;
+    if (group_used) *group_used = group;
+    if (lanes_used) *lanes_used = std::min(lanes, *ngroups);
+    return 0;
+}
+
 int sharp_parts_prefetch(sharp_ctx *c, int m, int nparts, sharp_part *parts, int group, int lanes) {
     SHARP_TRY(use(c));
     if (!parts || nparts < 1) return set_error(SHARP_E_ARG, "parts_prefetch: bad arguments");

@@ -198,3 +198,28 @@ def test_geta_and_getss():
     w1 = np.array([0.1, 0.2, 0.3, 0.4])
     assert np.isclose(api.getss((1, 4), R, x, w1), 0.2 / (0.1 + 0.2 + 0.3 + 0.4))   # a & v = {2}; a | v = {1,2,3,4}
     assert api.getss((1, 2), R, x, w1) == 0.0                                       # disjoint
+
+
+def test_plan_groups_covers_every_part_once():
+    """the split of SHARP_unlimited's parts into groups (sharp_run_parts / sharp_parts_prefetch): contiguous, complete, no
+    group larger than the group size, host data starts with half a group, few parts use small groups"""
+    from sharp_b200 import _lib
+    for nparts in list(range(1, 30)) + [64, 101]:
+        for host in (False, True):
+            for group, lanes in ((0, 0), (1, 1), (2, 2), (4, 2), (3, 3), (8, 2)):
+                pl = _lib.plan_groups(nparts, host, group, lanes)
+                gs, g = pl["gstart"], pl["group"]
+                assert gs[0] == 0 and gs[-1] == nparts and all(b > a for a, b in zip(gs, gs[1:]))
+                sizes = [b - a for a, b in zip(gs, gs[1:])]
+                assert max(sizes) <= g and 1 <= pl["lanes"] <= len(sizes)
+                if group:
+                    assert g == min(group, nparts)
+                else:
+                    assert g == min(nparts, 2 if nparts <= 8 else 4)
+                if host and g >= 2 and nparts > g:
+                    assert sizes[0] == g // 2
+                rest = sizes[1:] if (host and g >= 2 and nparts > g) else sizes
+                assert max(rest) - min(rest) <= 1                       # evenly split
+    assert _lib.plan_groups(26, False)["gstart"] == [0, 3, 7, 11, 15, 19, 23, 26]      # the benchmark, parts in HBM
+    assert _lib.plan_groups(26, True)["gstart"] == [0, 2, 6, 10, 14, 18, 22, 26]       # the benchmark, host buffers
+    assert _lib.plan_groups(13, True)["gstart"] == [0, 2, 6, 10, 13]                   # one of two ranks
