@@ -332,3 +332,40 @@ def test_unlimited_combine_transcribed(nparts, per_part, g, fixed, seed):
     assert nf == len(np.unique(got_t))
     if fixed:
         assert nf == fixed
+
+
+# ---------------------------------------------------------------------------------------------------------
+# SHARP_small (R/SHARP.R:339-454): K x (RPmat -> getrowColor), one wMetaC over all cells, relabel
+# ---------------------------------------------------------------------------------------------------------
+def sharp_small_transcribed(x, rms, p, K, hc):
+    m, ncells = x.shape
+    enrp = np.zeros((ncells, K), dtype=np.int64)
+    enE = np.zeros((ncells, p))
+    for k in range(K):                                                                # :349-372
+        E1 = orc.rp_project(m, ncells, rms[k], dense=np.asfortranarray(x), logkind=2)   # log2(scExp + 1) :343-345, RPmat :356
+        color, _ = orc.getrowcolor(E1, hc)
+        enrp[:, k] = color
+        enE = enE + E1                                                                # :380-385
+    fC = orc.wmetac(enrp, hc)                                                         # :390-391
+    final = np.asarray(fC["finalC"]).astype(np.int64)
+    uy = list(dict.fromkeys(final.tolist()))                                          # :430-432
+    pos = {v: i + 1 for i, v in enumerate(uy)}
+    return np.array([pos[v] for v in final.tolist()]), enE / K, fC["x0"]
+
+
+@pytest.mark.parametrize("m,n,K,seed", [(600, 350, 4, 7), (900, 479, 3, 8)])
+def test_sharp_small_orchestration_transcribed(m, n, K, seed):
+    import math
+
+    import synth
+    from sharp_b200.rrng import ranM2
+    x, _ = synth.make_expression(m, n, n_types=3, seed=seed, kind="tpm", zero_frac=0.7, sep=2.0, frac=0.4)
+    p = math.ceil(math.log2(n) / 0.04)
+    rms = [ranM2(m, p, 50 + 2103 + k) for k in range(1, K + 1)]
+    hc = orc.hc_params()
+    pred_t, vie_t, x0_t = sharp_small_transcribed(np.asarray(x), rms, p, K, hc)
+    prm = orc.SharpParams(0, 1, K, p, 2000, 0, 0, 0, hc, 2, -1)
+    ref = orc.sharp(m, n, rms, prm, dense=x)
+    assert np.array_equal(np.asarray(ref["pred_clusters"]).astype(np.int64), pred_t)
+    assert np.allclose(ref["viE"], vie_t, rtol=1e-13, atol=1e-13)
+    assert ref["x0"].shape == x0_t.shape and np.array_equal(ref["x0"], x0_t)
