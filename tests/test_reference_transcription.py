@@ -369,3 +369,26 @@ def test_sharp_small_orchestration_transcribed(m, n, K, seed):
     assert np.array_equal(np.asarray(ref["pred_clusters"]).astype(np.int64), pred_t)
     assert np.allclose(ref["viE"], vie_t, rtol=1e-13, atol=1e-13)
     assert ref["x0"].shape == x0_t.shape and np.array_equal(ref["x0"], x0_t)
+
+
+def test_getrowcolor_transcribed_including_the_colour_wrap():
+    """R/getrowColor.R:35-68: colour j of the j-th entry of unique(f); beyond 40 colours the index wraps (j %% 40, 0 -> 40),
+    so with indN.cluster = 45 the clusters 41..45 SHARE the colours (and therefore the labels) of clusters 1..5"""
+    rng = np.random.default_rng(5)
+    E = rng.normal(size=(260, 30))
+    for ncl in (0, 7, 45):
+        prm = orc.hc_params(n_cluster=ncl)
+        f = np.asarray(orc.opt_hclust(E, symmetric=0, prm=prm)["f"]).astype(np.int64)
+        unf = list(dict.fromkeys(f.tolist()))
+        colour = np.zeros(len(f), dtype=np.int64)
+        for j, u in enumerate(unf, start=1):
+            jj = j
+            if jj > 40:
+                jj = jj % 40
+                if jj == 0:
+                    jj = 40
+            colour[f == u] = jj
+        got, _ = orc.getrowcolor(E, prm)
+        assert np.array_equal(np.asarray(got).astype(np.int64), colour)
+        if ncl == 45:
+            assert len(np.unique(colour)) == 40
