@@ -1196,17 +1196,22 @@ static int group_issue(GroupRun &G, sharp_part *parts, int m, const sharp_rm_dev
                 e.val = s->ws[WS_EX_C].as<double>();
             }
             SHARP_CUDA(cudaStreamWaitEvent(s->stream, s->ev_up, 0));
-        } else if (G.up) { /* all uploads of a group run go through ONE stream: the copy engine shares the link between
-                              streams, and the first group must not wait for the bytes of the groups behind it */
-            SLOW("inline upload_expr", SHARP_TRY(upload_expr(s, m, P.n, P.dense, P.colptr, P.rowidx, P.val, &e, true, G.up)));
-            SHARP_CUDA(cudaEventRecord(s->ev_up, G.up));
-            SHARP_CUDA(cudaStreamWaitEvent(s->stream, s->ev_up, 0));
         } else {
-            prof_begin(s, KID_H2D);
-            int urc = upload_expr(s, m, P.n, P.dense, P.colptr, P.rowidx, P.val, &e, true);
-            prof_end(s);
-            s->launches--; /* a copy, not a kernel */
-            SHARP_TRY(urc);
+            /* the sub-context's buffers are about to be overwritten: a look-ahead copy that was never used (the caller
+               changed the grouping between sharp_parts_prefetch and this call) must not be matched by a later group */
+            s->pf_part = -1;
+            if (G.up) { /* all uploads of a group run go through ONE stream: the copy engine shares the link between
+                           streams, and the first group must not wait for the bytes of the groups behind it */
+                SLOW("inline upload_expr", SHARP_TRY(upload_expr(s, m, P.n, P.dense, P.colptr, P.rowidx, P.val, &e, true, G.up)));
+                SHARP_CUDA(cudaEventRecord(s->ev_up, G.up));
+                SHARP_CUDA(cudaStreamWaitEvent(s->stream, s->ev_up, 0));
+            } else {
+                prof_begin(s, KID_H2D);
+                int urc = upload_expr(s, m, P.n, P.dense, P.colptr, P.rowidx, P.val, &e, true);
+                prof_end(s);
+                s->launches--; /* a copy, not a kernel */
+                SHARP_TRY(urc);
+            }
         }
         if (e.m != rm.m) return set_error(SHARP_E_ARG, "run_parts: part %d has %d genes but ranM has %d rows", G.idx[j], e.m, rm.m);
         lap(t_up, tl);
