@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define SHARP_B200_ABI_VERSION 2
+#define SHARP_B200_ABI_VERSION 3   /* 3: + sharp_parts_prefetch, sharp_plan_groups, sharp_ctx_set_serial */
 
 enum {
     SHARP_OK = 0,
@@ -77,9 +77,10 @@ int sharp_timer_stop_ms(sharp_ctx *ctx, double *ms);
 int64_t sharp_ctx_launch_count(sharp_ctx *ctx);
 
 /* Projection kernel variant: 0 (default) = order-independent fixed-point accumulation with shared-memory integer
- * atomics (exact integer sums; used whenever K*p <= 32767); 1 = the fp64 read-modify-write kernel that adds every
- * output's terms in ascending gene order (bit-identical to a sequential sparse product).  Both meet the 1e-5
- * contract by ten orders of magnitude; the switch exists so that tests and ncu can compare them. */
+ * atomics (exact 64-bit integer sums; non-zeros equal to 1..4 -- most of a UMI matrix -- are counted per output
+ * instead of added, which gives the same sum; used whenever K*p <= 32700); 1 = the fp64 read-modify-write kernel that
+ * adds every output's terms in ascending gene order (bit-identical to a sequential sparse product).  Both meet the
+ * 1e-5 contract by seven orders of magnitude or more; the switch exists so that tests and ncu can compare them. */
 int sharp_ctx_set_rp_variant(sharp_ctx *ctx, int legacy);
 
 /* per-kernel device-time profile (off by default): while enabled, every launch of this library on the context's

@@ -29,7 +29,8 @@ def test_library_exports_every_declared_symbol():
     lib = _lib.load()
     missing = [s for s in declared_symbols() if not hasattr(lib, s)]
     assert not missing, missing
-    assert lib.sharp_abi_version() == 2
+    hdr = open(os.path.join(ROOT, "include", "sharp_b200.h")).read()
+    assert lib.sharp_abi_version() == int(re.search(r"#define SHARP_B200_ABI_VERSION (\d+)", hdr).group(1)) == 3
 
 
 def test_no_torch_types_in_the_abi():
