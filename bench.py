@@ -480,7 +480,7 @@ def run_ours(args):
 
     # ---- CPU baseline: the oracle port on a bounded sample of the same workload, this box's host cores ----
     cpu = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:  # N = 1 only (torchrun pins OMP_NUM_THREADS=1; the baseline is a host figure)
         try:
             part0 = host_parts[mine[0]]
             cps, threads, dt = cpu_baseline_run(wl, part0, p, args.cpu_sample)
