@@ -281,6 +281,10 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        # torchrun pins OMP_NUM_THREADS=1 for its workers; this arm is the host-side reference and runs alone on rank 0,
+        # with all the host threads (must be set before the OpenMP runtime is loaded, i.e. before torch is imported)
+        os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
     import torch
     wl = workload(args.workload)
     p = math.ceil(math.log2(sum(wl["parts"])) / 0.04)
