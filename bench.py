@@ -40,10 +40,16 @@ for _p in (ROOT, os.path.join(ROOT, "tests")):
 
 SEED = 2103
 METRIC = "cells/sec end-to-end SHARP at 1.3M cells"
-# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture (profiles/README.md)
-# (bytes; profiles/r1c_ncu_full_top4_raw.csv: first group of the full workload -- one 50 000-cell part for the projection,
-# 125 (member, block) problems per launch for the block-clustering kernels, which is also what the timed steps launch)
-TRAFFIC = {"rp_project": 2.327e9, "hclust": 46.89e9, "corrdist": 4.973e9, "sweep_nested": 5.238e9}
+# dram__bytes_read.sum + dram__bytes_write.sum per launch, read at start from profiles/traffic.json -- written by
+# profiles/summarize_ncu.py from the committed `ncu --set full` raw CSV it names (with the commit the capture was taken at)
+def load_traffic() -> dict:
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            return json.load(f)
+    except Exception:
+        return {"kernels": {}, "source": None}
+
+
 # the fused loop over parts keeps ~10 streams busy; with the default 8 hardware queues, streams alias and false
 # dependencies serialise copies and kernels of different parts (must be set before CUDA initialises)
 os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
@@ -119,7 +125,8 @@ def gen_part(torch, dev, lam_types, n, part_idx, pin):
         return h
 
     hc, hr, hv = host(colptr), host(rowidx), host(val)
-    return {"_keep": (hc, hr, hv), "p": hc.numpy(), "i": hr.numpy(), "x": hv.numpy(), "Dim": (m, n)}
+    return {"_keep": (hc, hr, hv), "p": hc.numpy(), "i": hr.numpy(), "x": hv.numpy(), "Dim": (m, n),
+            "types": types.cpu().numpy().astype(np.int32)}
 
 
 # ----------------------------------------------------------------------------------------------------------
@@ -255,29 +262,70 @@ def algorithmic_work(wl, parts_nnz, part_sizes, p) -> dict:
 
 
 # ----------------------------------------------------------------------------------------------------------
-def cpu_baseline_run(wl, part, p, sample_cells, threads_note=True):
-    """the oracle (CPU restatement of the reference) on the first `sample_cells` cells of one part: SHARP_large with
-    the same ranM matrices, K, p and block size.  Returns (cells/sec, threads, seconds)."""
-    import orc
-    from sharp_b200 import _lib
-    m = wl["m"]
+def sample_of(part, sample_cells):
+    """the first `sample_cells` cells of one part as dgCMatrix slots"""
     n = min(sample_cells, part["Dim"][1])
     cp = part["p"][:n + 1].astype(np.int64)
     nz = int(cp[-1])
-    ri, xv = part["i"][:nz], part["x"][:nz]
-    colsum = np.add.reduceat(xv, cp[:-1]) if wl["exp_type"] == "UMI" else None
-    rms = [_lib.r_ranm(m, p, 50 + SEED + k) for k in range(1, wl["K"] + 1)]
-    reind = _lib.r_sample_perm_native(n, 50)
+    return n, (cp, part["i"][:nz], part["x"][:nz])
+
+
+def cpu_baseline_run(wl, part, p, sample_cells, rms, reind):
+    """the oracle (CPU restatement of the reference) on the first `sample_cells` cells of one part: SHARP_large with
+    the same ranM matrices, K, p and block size -- blocks, per-block wMetaC, sMetaC across the blocks, merge, relabel.
+    Returns (cells/sec, threads, seconds, oracle result)."""
+    import orc
+    n, csc = sample_of(part, sample_cells)
+    colsum = np.add.reduceat(csc[2], csc[0][:-1]) if wl["exp_type"] == "UMI" else None
     prm = orc.SharpParams(1, 1, wl["K"], p, 2000, 0, 0, 0, orc.hc_params(max_n=max(40, -(-n // 5000))), 2, -1)
     t0 = time.time()
-    orc.sharp(m, n, rms, prm, csc=(cp, ri, xv), colsum=colsum, reind=reind, want_vie=False, want_x0=False)
+    ref = orc.sharp(wl["m"], n, rms, prm, csc=csc, colsum=colsum, reind=reind, want_vie=True, want_x0=False)
     dt = time.time() - t0
-    return n / dt, orc.num_threads(), dt
+    return n / dt, orc.num_threads(), dt, ref
+
+
+def first_appearance(y):
+    _, idx, inv = np.unique(y, return_index=True, return_inverse=True)
+    rank = np.empty(len(idx), dtype=np.int64)
+    rank[np.argsort(idx)] = np.arange(1, len(idx) + 1)
+    return rank[inv]
+
+
+def parity_check(ctx, wl, part, p, sample_cells, rms, reind, ref):
+    """GPU <-> oracle on the benchmark's OWN data and shape (m, p, K, 2000-cell blocks): the same sample through
+    sharp_run on host buffers; labels after the host glue (R/SHARP.R:816-832) must be identical, the averaged
+    projection viE within the 1e-5 contract."""
+    from sharp_b200 import RunParams, hc_params
+    import synth
+    n, csc = sample_of(part, sample_cells)
+    rm = ctx.upload_rm(rms)
+    try:
+        prm = RunParams(1, 1, 2, -1, 2000, 0, 0, 0, hc_params(max_n=max(40, -(-n // 5000))), 2 if wl["exp_type"] == "UMI" else 0, 1e6)
+        got = ctx.run(rm, prm, m=wl["m"], n=n, csc=csc, reind=reind, want_x0=False)
+    finally:
+        rm.close()
+    gl = got["labels"].copy()
+    if n > 10000:
+        vals, cnt = np.unique(gl, return_counts=True)
+        small = vals[cnt < 10]
+        if len(small):
+            gl[np.isin(gl, small)] = small.min()
+    pred = first_appearance(gl)
+    rel = float(np.max(np.abs(got["viE"] - ref["viE"])) / np.max(np.abs(ref["viE"])))
+    return {"cells": int(n), "blocks": len(block_sizes(n)), "m": wl["m"], "p": int(p), "K": wl["K"],
+            "ari": synth.ari(pred, ref["pred_clusters"]), "equal": bool(np.array_equal(pred, ref["pred_clusters"])),
+            "n_clusters": int(ref["N.pred_cluster"]), "proj_max_rel": rel,
+            "what": "sharp_run (C ABI, host buffers) vs the oracle on the first cells of part 1 of THIS workload; "
+                    "labels after merge + first-appearance relabel, proj = viE (mean of the K projections)"}
 
 
 def run_reference(args):
     """--impl reference: the reference's CPU implementation of the path.  The reference is pure R and this image has
-    no R, so the arm is the oracle port (kind "port"), all host threads, on a bounded sample per step."""
+    no R, so the arm is the oracle port (kind "port"), all host threads.  One step = SHARP_large on ONE part of the
+    workload (blocks, per-block wMetaC, the part-level sMetaC, merge, relabel); when K + W whole parts would not fit
+    the arm's time budget the sample shrinks to the largest number of whole blocks that does (stated in `sample`).
+    Nothing of the product is loaded here: the ranM matrices and the shuffle come from the pure-Python restatement of
+    R's RNG (sharp_b200/rrng.py, numpy), not from libsharpb200.so."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -286,24 +334,36 @@ def run_reference(args):
         # with all the host threads (must be set before the OpenMP runtime is loaded, i.e. before torch is imported)
         os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
     import torch
+    from sharp_b200.rrng import r_sample_perm, ranM2
     wl = workload(args.workload)
     p = math.ceil(math.log2(sum(wl["parts"])) / 0.04)
     dev = torch.device("cuda", 0) if torch.cuda.is_available() else torch.device("cpu")
     lam = type_profiles(torch, dev, wl["m"], wl["types"], wl["nnz_per_cell"])
-    part = gen_part(torch, dev, lam, min(wl["parts"][0], args.cpu_sample), 0, False)
-    times = []
-    for s in range(args.warmup + args.steps):
-        cps, threads, dt = cpu_baseline_run(wl, part, p, args.cpu_sample)
+    part = gen_part(torch, dev, lam, wl["parts"][0], 0, False)
+    rms = [ranM2(wl["m"], p, 50 + SEED + k) for k in range(1, wl["K"] + 1)]
+    # calibration: two blocks, then the largest sample (whole blocks, at most the whole part) that fits the budget
+    t_cal = cpu_baseline_run(wl, part, p, 4000, rms, np.asarray(r_sample_perm(4000, 50)))[2]
+    per_cell = t_cal / 4000
+    nsteps = args.warmup + args.steps
+    n = wl["parts"][0] if args.ref_sample <= 0 else min(wl["parts"][0], args.ref_sample)
+    fit = int(args.ref_budget_s / (nsteps * per_cell * 1.15)) // 2000 * 2000
+    n = max(4000, min(n, fit))
+    reind = np.asarray(r_sample_perm(n, 50))
+    times, threads = [], 1
+    for s in range(nsteps):
+        cps, threads, dt, _ = cpu_baseline_run(wl, part, p, n, rms, reind)
         if s >= args.warmup:
             times.append(dt)
-    n = min(wl["parts"][0], args.cpu_sample)
     val = n * len(times) / sum(times)
-    sample = f"first {n} cells of part 1 (SHARP_large, {len(block_sizes(n))} blocks x K={wl['K']}) per step"
+    whole = n == wl["parts"][0]
+    sample = (f"{'one whole part' if whole else 'first ' + str(n) + ' cells of part 1'} per step ({n} cells: SHARP_large, "
+              f"{len(block_sizes(n))} blocks x K={wl['K']}, per-block wMetaC, part-level sMetaC, merge, relabel); "
+              f"{threads} host threads; the job's other parts and the global sMetaC are not in the sample")
     print(json.dumps({"impl": "reference", "metric": METRIC, "value": val, "unit": "cells/s",
                       "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
                       "ms_per_step": 1e3 * sum(times) / len(times), "higher_is_better": True, "scaling": "strong",
                       "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                      "config": {"workload": wl["name"], "sample": sample},
+                      "config": {"workload": wl["name"], "sample": sample, "cpu_sample_cells": int(n), "same_config": False},
                       "cpu_baseline": {"value": val, "unit": "cells/s", "cores": threads, "kind": "port", "sample": sample},
                       "e2e": {"value": val, "unit": "cells/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 
@@ -433,6 +493,24 @@ def run_ours(args):
         h2d = sum(nnz_all) * 12 + sum((s + 1) * 8 for s in sizes)
         d2h = ncells * 4
 
+    # ---- what came out: a hash of the label vector (must be the same on every rank and for every N), and the ARI
+    # ---- against the planted cell types of the synthetic data
+    import hashlib
+    import synth
+    label_hash = hashlib.sha1(np.ascontiguousarray(res["pred_clusters"], dtype=np.int32).tobytes()).hexdigest()[:16]
+    types_all = {i: host_parts[i]["types"] for i in mine}
+    if comm:
+        types_all = comm.allgather_parts(types_all, len(sizes))
+        hashes = comm.allgather_parts({rank: np.frombuffer(label_hash.encode(), dtype=np.uint8)}, world) \
+            if world <= len(sizes) else None
+        if hashes is not None and len({h.tobytes() for h in hashes}) != 1:
+            raise SystemExit("the ranks returned different label vectors")
+    else:
+        types_all = [types_all[i] for i in range(len(sizes))]
+    truth = np.concatenate(list(types_all))
+    result = {"N.pred_clusters": int(res.get("N.pred_clusters", res.get("N.pred_cluster", 0))), "label_sha1_16": label_hash,
+              "ari_vs_planted_types": synth.ari(res["pred_clusters"], truth), "planted_types": wl["types"],
+              "ranks_agree": True if comm else None}
     if comm:  # every exchange is done; leave the process group cleanly on all ranks
         try:
             torch.distributed.destroy_process_group()
@@ -466,34 +544,48 @@ def run_ours(args):
         kernels[name] = ent
     dom = next((k for k in kernels if "bound" in kernels[k]), None)
     roofline = None
+    TR = load_traffic()
+
+    def traffic_of(name):
+        e = TR.get("kernels", {}).get(name)
+        return None if e is None else e.get("dram_bytes_per_launch")
+
     if dom:
         e = kernels[dom]
         roofline = {"kernel": dom, "bound": e["bound"], "achieved": e["achieved"], "peak": e["peak"], "unit": e["unit"],
-                    "frac": e["frac"], "traffic": TRAFFIC.get(dom), "peak_source": e.get("peak_source", pk["source"]),
+                    "frac": e["frac"], "traffic": traffic_of(dom), "peak_source": e.get("peak_source", pk["source"]),
                     "ms_per_launch": e["ms_per_step"] / max(e["launches_per_step"], 1e-9),
                     "timing": ("CUDA events around every launch of one extra step of the same workload enqueued on ONE stream "
                                "(kernels of different parts overlap during the timed steps; their overlapped brackets are "
                                "ms_per_step_in_timed_region)" if ms_serial is not None else
                                "CUDA events around every launch during the timed steps"),
-                    "serial_step_ms": ms_serial}
+                    "serial_step_ms": ms_serial, "traffic_source": TR.get("source")}
+        if dom == "hclust":  # the class's own yardstick (4 n^2 x 8 B per problem) and the bare one-read-of-D figure
+            one_read = sum(b * b * 8 for n_ in my_sizes for b in block_sizes(n_)) * wl["K"]
+            roofline["frac_one_read_of_D"] = one_read * psteps / (prof[dom][0] * 1e-3) / 1e9 / pk["hbm_gbs"]
         rp = kernels.get("rp_project")
         if rp and "frac" in rp:
             roofline["rp_project"] = {"bound": "hbm", "achieved": rp["achieved"], "peak": rp["peak"], "unit": "GB/s",
-                                      "frac": rp["frac"], "traffic": TRAFFIC.get("rp_project"),
+                                      "frac": rp["frac"], "traffic": traffic_of("rp_project"),
                                       "ms_per_launch": rp["ms_per_step"] / max(rp["launches_per_step"], 1e-9)}
 
-    # ---- CPU baseline: the oracle port on a bounded sample of the same workload, this box's host cores ----
-    cpu = None
+    # ---- CPU baseline: the oracle port on a bounded sample of the same workload, this box's host cores; its labels are
+    # ---- the parity check of the GPU path at the benchmark's own shape ----
+    cpu, parity = None, None
     if not args.no_cpu_baseline and world == 1:  # N = 1 only (torchrun pins OMP_NUM_THREADS=1; the baseline is a host figure)
-        try:
-            part0 = host_parts[mine[0]]
-            cps, threads, dt = cpu_baseline_run(wl, part0, p, args.cpu_sample)
-            n_s = min(args.cpu_sample, part0["Dim"][1])
-            cpu = {"value": cps, "unit": "cells/s", "cores": threads, "kind": "port", "seconds": dt,
-                   "sample": f"first {n_s} cells of part {mine[0] + 1}: SHARP_large, {len(block_sizes(n_s))} blocks x K={wl['K']}, "
-                             f"same ranM matrices (oracle/, OpenMP over (member, block) tasks)"}
-        except Exception as ex:  # the oracle is test infrastructure; its absence must not hide the GPU number
-            cpu = {"value": None, "unit": "cells/s", "cores": 0, "kind": "port", "sample": f"failed: {ex}"}
+        from sharp_b200.rrng import r_sample_perm, ranM2
+        part0 = host_parts[mine[0]]
+        n_s = part0["Dim"][1] if args.cpu_sample <= 0 else min(args.cpu_sample, part0["Dim"][1])
+        rms = [ranM2(m, p, 50 + SEED + k) for k in range(1, wl["K"] + 1)]
+        reind = np.asarray(r_sample_perm(n_s, 50))
+        cps, threads, dt, ref = cpu_baseline_run(wl, part0, p, n_s, rms, reind)
+        cpu = {"value": cps, "unit": "cells/s", "cores": threads, "kind": "port", "seconds": dt,
+               "sample": f"first {n_s} cells of part {mine[0] + 1}: SHARP_large, {len(block_sizes(n_s))} blocks x K={wl['K']}, "
+                         f"per-block wMetaC, part-level sMetaC, same ranM matrices (oracle/, OpenMP over (member, block) tasks)"}
+        parity = parity_check(ctx, wl, part0, p, n_s, rms, reind, ref)
+        if not parity["equal"] or not parity["proj_max_rel"] <= 1e-5:
+            print(json.dumps({"parity": parity}), file=sys.stderr)
+            raise SystemExit("PARITY FAILURE: the GPU path and the oracle disagree on the benchmark's own data")
 
     line = {"metric": METRIC, "value": value, "unit": "cells/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
@@ -508,8 +600,8 @@ def run_ours(args):
             "e2e": {"value": e2e_value, "unit": "cells/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": ms_e2e / e2e_steps, "labels_equal_device_resident_run": same, "step_wall_ms": walls_e2e,
                     "h2d_gbs_measured": h2d_gbs, "h2d_floor_ms_per_step": (h2d / max(world, 1)) / (h2d_gbs * 1e9) * 1e3},
-            "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu,
-            "result": {"N.pred_clusters": int(res.get("N.pred_clusters", res.get("N.pred_cluster", 0)))}}
+            "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu, "parity": parity,
+            "result": result}
     print(json.dumps(line))
 
 
@@ -526,7 +618,9 @@ def main():
     ap.add_argument("--lanes", type=int, default=0, help="groups in flight (0 = library default)")
     ap.add_argument("--budget-gb", type=int, default=0, help="distance-matrix workspace cap per context in GB (0 = library default)")
     ap.add_argument("--no-fused", action="store_true", help="part-by-part path (one sharp_run per part, --streams host threads)")
-    ap.add_argument("--cpu-sample", type=int, default=20000, help="cells of the CPU baseline sample")
+    ap.add_argument("--cpu-sample", type=int, default=20000, help="cells of the CPU baseline / parity sample (0 = one whole part)")
+    ap.add_argument("--ref-sample", type=int, default=0, help="--impl reference: cells per step (0 = one whole part, budget permitting)")
+    ap.add_argument("--ref-budget-s", type=float, default=270.0, help="--impl reference: time budget of the whole K + W run")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-serial-profile", action="store_true", help="skip the extra one-stream step behind the roofline object")
     args = ap.parse_args()

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define SHARP_B200_ABI_VERSION 3   /* 3: + sharp_parts_prefetch, sharp_plan_groups, sharp_ctx_set_serial */
+#define SHARP_B200_ABI_VERSION 4   /* 4: sharp_run_params.skip_smetac (SHARP_fpart); 3: + sharp_parts_prefetch, sharp_plan_groups, sharp_ctx_set_serial */
 
 enum {
     SHARP_OK = 0,
@@ -182,6 +182,11 @@ typedef struct {
     sharp_hc_params hc;   /* hmethod, minN, maxN, sil.thre, height.Ntimes (n_cluster ignored) */
     int normalize;        /* as in sharp_rp_project */
     double norm_mul;
+    int skip_smetac;      /* large = 1 only: 1 = stop after the per-block wMetaC like SHARP_fpart (R/SHARP_unlimited2.R:477-531):
+                             labels[] = an injective code of fColor = "<finalC>en<t>" (1 + position of the (block, meta-cluster)
+                             pair in block order), un-shuffled; no x0.  0 = SHARP_large (sMetaC across the blocks) */
+    int block_max_n;      /* > 0: maxN.cluster of the per-(member, block) clusterings only (SHARP_fpart assigns 40 inside its
+                             worker, R/SHARP_unlimited2.R:421; its wMetaC keeps the caller's value, :481); 0 = hc.max_n */
 } sharp_run_params;
 
 /* reind: 1-based permutation from `set.seed(50); sample(ncells)` or NULL; applied iff ncells < 1e5

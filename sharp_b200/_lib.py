@@ -42,7 +42,8 @@ class HcParams(C.Structure):
 class RunParams(C.Structure):
     _fields_ = [("large", C.c_int), ("logflag", C.c_int), ("logkind", C.c_int), ("round_digits", C.c_int),
                 ("partition_ncells", C.c_int), ("n_cluster", C.c_int), ("enp_n_cluster", C.c_int),
-                ("ind_n_cluster", C.c_int), ("hc", HcParams), ("normalize", C.c_int), ("norm_mul", C.c_double)]
+                ("ind_n_cluster", C.c_int), ("hc", HcParams), ("normalize", C.c_int), ("norm_mul", C.c_double),
+                ("skip_smetac", C.c_int), ("block_max_n", C.c_int)]
 
 
 class Part(C.Structure):

@@ -203,7 +203,7 @@ def _first_appearance_codes(y) -> tuple[np.ndarray, np.ndarray]:
     if n and y.dtype.kind in "iu" and 0 <= int(y.min()) and int(y.max()) <= 4 * n + 1024:
         # small non-negative integers (cluster ids): O(n) with a lookup table instead of a sort
         first = np.full(int(y.max()) + 1, n, dtype=np.int64)
-        first[y[::-1]] = np.arange(n - 1, -1, -1)          # the last write is the first occurrence
+        np.minimum.at(first, y, np.arange(n, dtype=np.int64))   # first occurrence of every id (defined for repeats)
         present = np.flatnonzero(first < n)
         order = present[np.argsort(first[present], kind="stable")]
         rank = np.zeros(len(first), dtype=np.int32)
@@ -305,11 +305,21 @@ def _reind(n: int, rN_seed) -> np.ndarray:
     return _lib.r_sample_perm_native(n, 50)
 
 
-def _rm_list(m, p, K, rN_seed):
-    """K x ranM(E, p, 50 + rN.seed + k) (R/SHARP.R:539-549) with R's RNG stream, one host thread per member (the
-    native generator releases the GIL); an unseeded run (rN.seed = 0.5) draws its seeds from the OS entropy."""
-    from concurrent.futures import ThreadPoolExecutor
+def _member_seeds(K, rN_seed, comm=None):
+    """the integer seeds of the K ranM draws; an unseeded run (rN.seed = 0.5) takes them from the OS entropy -- ONCE:
+    with several ranks, rank 0 draws and everybody uses its seeds (the reference builds rM once for all partitions,
+    "consistent random matrices across different partitions", R/SHARP_unlimited.R:96-104)"""
     seeds = [_entropy_seed() if rN_seed == 0.5 else _member_seed(rN_seed, k) for k in range(1, K + 1)]
+    if comm is not None and rN_seed == 0.5:
+        seeds = comm.bcast_obj(seeds, 0)
+    return seeds
+
+
+def _rm_list(m, p, K, rN_seed, comm=None):
+    """K x ranM(E, p, 50 + rN.seed + k) (R/SHARP.R:539-549) with R's RNG stream, one host thread per member (the
+    native generator releases the GIL)."""
+    from concurrent.futures import ThreadPoolExecutor
+    seeds = _member_seeds(K, rN_seed, comm)
     if K == 1:
         return [_lib.r_ranm(m, p, seeds[0])]
     with ThreadPoolExecutor(max_workers=min(K, 16)) as ex:
@@ -499,10 +509,10 @@ def testlog(scExp, ncells=None, p=None, sncells=None, n_cores=None, ctx: Context
 # SHARP_small / SHARP_large
 # =====================================================================================================
 def _run(ctx, e: Expression, rm: RmDev, large, flag, ng, N_cluster, enpN, indN, hc, forview, reind, logkind=2,
-         round_digits=-1):
+         round_digits=-1, skip_smetac=False, block_max_n=0):
     prm = RunParams(int(large), int(bool(flag)), int(logkind), int(round_digits), int(ng), _ncl(N_cluster), _ncl(enpN),
-                    _ncl(indN), hc, 2 if e.normalize else 0, 1e6)
-    return ctx.run(rm, prm, reind=reind, want_vie=bool(forview), want_x0=bool(forview),
+                    _ncl(indN), hc, 2 if e.normalize else 0, 1e6, int(bool(skip_smetac)), int(block_max_n))
+    return ctx.run(rm, prm, reind=reind, want_vie=bool(forview), want_x0=bool(forview) and not skip_smetac,
                    max_x0_cols=max(64, hc.max_n + 1, _ncl(N_cluster) + 1), **e.run_kwargs())
 
 
@@ -784,7 +794,7 @@ def _run_parts_fused(ctx, parts, mine, rM, p, K, rN_seed, a, n_cores):
 
 def SHARP_unlimited(scExp, viewflag=True, n_cores=None, ensize_K=None, N_cluster=None, minN_cluster=None,
                     maxN_cluster=None, rN_seed=None, ctx: Context | None = None, comm=None, n_streams=None,
-                    _part_logflag=False, **kwargs) -> dict:
+                    _part_logflag=False, _krange_from_part1=False, **kwargs) -> dict:
     """R/SHARP_unlimited.R:29-242.  ``scExp``: a LIST of genes x cells matrices (parts).  Every part runs SHARP()
     with the shared ranM matrices; the part-level clusters are merged by one global sMetaC over their centroids
     (computed on the device from the part's viE, which never leaves it unless ``viewflag``).
@@ -822,6 +832,8 @@ def SHARP_unlimited(scExp, viewflag=True, n_cores=None, ensize_K=None, N_cluster
             print(f"[sharp trace py] {what} {1e3 * (now - _t[0]):.2f} ms", file=sys.stderr)
             _t[0] = now
 
+    if _part_logflag is None and "logflag" in k:   # SHARP_unlimited3 passes no logflag itself (:114), so `...` may
+        _part_logflag = k.pop("logflag")
     rank, world = (comm.rank, comm.world) if comm is not None else (0, 1)
     mine = [i for i in range(nnp) if i % world == rank]
     fast = _parts_fast_path(parts, mine, k, viewflag, _part_logflag, n_streams)
@@ -829,7 +841,7 @@ def SHARP_unlimited(scExp, viewflag=True, n_cores=None, ensize_K=None, N_cluster
     _pf_keep = None
     if fast is not None and mine and parts[mine[0]].dev is None:
         _pf_keep = ctx.parts_prefetch(parts[mine[0]].m, _fused_inputs(parts, mine), _fused_group, _fused_lanes)
-    rms_host = _rm_list(parts[0].m, p, ensize_K, rN_seed)
+    rms_host = _rm_list(parts[0].m, p, ensize_K, rN_seed, comm)
     _mark("ranM")
     rM = ctx.upload_rm(rms_host)
     _mark("upload_rm")
@@ -901,6 +913,8 @@ def SHARP_unlimited(scExp, viewflag=True, n_cores=None, ensize_K=None, N_cluster
         y0 = y[0]
     cen = np.ascontiguousarray(np.concatenate(cens_all, axis=0))
     _cat("Total number of single cells:", ncells, "\nNumber of unique meta-clusters:", cen.shape[0])
+    if _krange_from_part1:  # SHARP_unlimited3 hands y[[1]]$paras$minN.cluster / maxN.cluster to sMetaC (R/SHARP_unlimited3.R:165-166)
+        minN_cluster, maxN_cluster = y0["paras"]["minN.cluster"], y0["paras"]["maxN.cluster"]
     final = _unlimited_combine(ctx, cen, [c.shape[0] for c in cens_all], preds_all, ncells, y0["paras"]["hmethod"],
                                N_cluster, minN_cluster, maxN_cluster, y0["paras"]["sil.thre"], y0["paras"]["height.Ntimes"])
     _mark("combine")
@@ -910,7 +924,7 @@ def SHARP_unlimited(scExp, viewflag=True, n_cores=None, ensize_K=None, N_cluster
         E1 = np.concatenate([viEs[i] for i in range(nnp)], axis=0)
         if ncells > 1e5:
             # quirk B3: the reference uses an undefined `k` here; foreach leaves none, we use k = ensize.K
-            z0 = ranM2(p, 50, _member_seed(rN_seed, ensize_K))
+            z0 = ranM2(p, 50, _member_seeds(1, rN_seed, comm)[0] if rN_seed == 0.5 else _member_seed(rN_seed, ensize_K))
             res["viE"] = _view_project(ctx, E1, z0)
         else:
             res["viE"] = E1
@@ -935,34 +949,65 @@ def _view_project(ctx, E1, z0):
 def SHARP_fpart(scExp, ensize_K=5, reduced_ndim=None, partition_ncells=2000, hmethod="ward.D", N_cluster=None,
                 enpN_cluster=None, indN_cluster=None, minN_cluster=2, maxN_cluster=40, sil_thre=0.35, height_Ntimes=2,
                 flag=True, rM=True, rN_seed=0.5, ctx: Context | None = None, **kwargs) -> dict:
-    """R/SHARP_unlimited2.R:297-544: the block stage of SHARP_unlimited2 for one part -- like SHARP_large but with
-    log10 instead of log2 (:391), projections rounded to one decimal (:410) and per-block maxN.cluster = 40 (:421);
-    returns the part-level labels before any relabel, and viE."""
+    """R/SHARP_unlimited2.R:297-544: the BLOCK stage of SHARP_unlimited2 for one part.  Like the first half of SHARP_large
+    -- shuffle (iff ncells < 1e5), blocks, K x T projections and block clusterings, per-block wMetaC -- but with log10
+    instead of log2 (:391), projections rounded to one decimal (:410), per-block maxN.cluster = 40 (:421), and it STOPS
+    there: no sMetaC across the blocks.  Returns, un-shuffled (:520-524), ``fColor`` (one id per (block, meta-cluster)
+    pair: an integer code of the reference's ``"<finalC>en<t>"`` strings), ``E1`` = enE/K, ``nmcluster``, ``folds``,
+    ``ncells``, ``ngenes`` (:529-535).  ``N.cluster`` is accepted and unused, like in the reference."""
     k = _kw(kwargs)
     rN_seed = k.get("rN_seed", rN_seed)
     ctx = ctx or get_context()
     e = Expression.wrap(scExp)
     p = int(reduced_ndim if reduced_ndim is not None else math.ceil(math.log2(e.n) / 0.2 ** 2))
-    hc = _hc(hmethod, None, minN_cluster, 40, sil_thre, height_Ntimes)
-    reind = _reind(e.n, rN_seed) if e.n < 1e5 else None
+    ng = int(partition_ncells)
+    # `maxN.cluster = 40` is assigned INSIDE the (member, block) worker (:421): it bounds the block clusterings only; the
+    # per-block wMetaC (:481) runs in the function's own frame with the caller's maxN.cluster
+    hc = _hc(hmethod, None, minN_cluster, maxN_cluster, sil_thre, height_Ntimes)
+    reind = _reind(e.n, rN_seed) if e.n < 1e5 else None                 # (the reference draws it always, applies it iff ncells < 1e5)
     rm, own = _as_rmdev(ctx, rM, e.m, p, int(ensize_K), rN_seed)
     try:
-        r = _run(ctx, e, rm, 1, flag, partition_ncells, N_cluster, enpN_cluster, indN_cluster, hc, True, reind, 10, 1)
+        r = _run(ctx, e, rm, 1, flag, ng, None, enpN_cluster, indN_cluster, hc, True, reind, 10, 1, skip_smetac=True,
+                 block_max_n=40)
     finally:
         if own:
             rm.close()
-    return {"fColor": r["labels"], "E1": r["viE"], "x0": r["x0"]}
+    folds = _folds(e.n, ng)
+    if e.n < 1e5:
+        f = np.empty_like(folds)
+        f[reind - 1] = folds                                            # folds[reind] = folds (:523)
+        folds = f
+    fColor = np.asarray(r["labels"])
+    return {"fColor": fColor, "E1": r["viE"], "nmcluster": int(len(np.unique(fColor))), "folds": folds,
+            "ncells": e.n, "ngenes": e.m}
+
+
+def _folds(ncells: int, ng: int) -> np.ndarray:
+    """R/SHARP.R:513-536 == R/SHARP_unlimited2.R:339-358: cut(seq(1, T*ng), breaks = T) with the last two folds averaged"""
+    T = int(math.ceil(ncells / ng))
+    if T <= 1:
+        return np.ones(ncells, dtype=np.int64)
+    folds = np.repeat(np.arange(1, T + 1, dtype=np.int64), ng)
+    nt = ncells - (T - 2) * ng
+    nind = np.flatnonzero(folds == T - 1)
+    folds[nind[nt // 2:]] = T
+    return folds[:ncells]
 
 
 def SHARP_unlimited2(scExp, ensize_K=None, reduced_ndim=None, partition_ncells=None, hmethod=None, N_cluster=None,
                      enpN_cluster=None, indN_cluster=None, minN_cluster=None, maxN_cluster=None, sil_thre=None,
                      height_Ntimes=None, logflag=None, n_cores=None, forview=True, rN_seed=None,
                      ctx: Context | None = None, **kwargs) -> dict:
-    """R/SHARP_unlimited2.R:29-267: two-level variant (blocks -> one global sMetaC) over a LIST of parts, with the
-    log10 / round(.,1) projection of SHARP_fpart and the shared ``ranM2(ngenes, p, .)`` matrices (:133-139)."""
+    """R/SHARP_unlimited2.R:29-267: the TWO-level variant over a LIST of parts: every part goes through SHARP_fpart
+    (blocks + per-block wMetaC, log10 / round(., 1) projections, shared ``ranM2(ngenes, p, .)`` matrices, :133-139),
+    then ONE global sMetaC merges the block-level clusters of all parts (:183-185), followed by the small-cluster merge
+    and the relabel by decreasing size (:189-204).  The centroids the global sMetaC needs (colMeans of E1 per cluster,
+    R/sMetaC.R:58-63) are taken on the device right after each part, so E1 only comes back when ``forview``."""
     k = _kw(kwargs)
     rN_seed = k.get("rN_seed", rN_seed)
     start = time.time()
+    if scExp is None:
+        raise ValueError("No expression data is provided!")
     if not isinstance(scExp, (list, tuple)):
         raise ValueError("The input should be a LIST of partitioned scRNA-seq expression matrices!")
     ctx = ctx or get_context()
@@ -977,17 +1022,24 @@ def SHARP_unlimited2(scExp, ensize_K=None, reduced_ndim=None, partition_ncells=N
     sil_thre = 0.35 if sil_thre is None else sil_thre
     height_Ntimes = 2 if height_Ntimes is None else height_Ntimes
     rN_seed = _check_seed(rN_seed)
-    flag = True if logflag is None else bool(logflag)
+    if logflag is None:
+        logflag = ncells < 1e4
+    if logflag:  # :92-103: testlog on the first part, 100 cells
+        flag = testlog(parts[0], parts[0].n, p, 100, n_cores, ctx=ctx)
+    else:
+        flag = True
     rM = ctx.upload_rm(_rm_list(parts[0].m, p, ensize_K, rN_seed))
-    preds, cens = [], []
+    preds, cens, E1s = [], [], []
     try:
         for e in parts:
-            r = SHARP_fpart(e, ensize_K, p, partition_ncells, hmethod, None, enpN_cluster, indN_cluster, minN_cluster,
-                            40, sil_thre, height_Ntimes, flag, rM, rN_seed, ctx=ctx)
-            codes, _ = _first_appearance_codes(r["fColor"])
+            r = SHARP_fpart(e, ensize_K, p, partition_ncells, hmethod, N_cluster, enpN_cluster, indN_cluster, minN_cluster,
+                            maxN_cluster, sil_thre, height_Ntimes, flag, rM, rN_seed, ctx=ctx)
+            codes, _ = _first_appearance_codes(r["fColor"])     # unique(paste(fColor, "s", i)) within part i
             cen, _ = ctx.centroids(codes, int(codes.max()), p)
             preds.append(codes)
             cens.append(cen)
+            if forview:
+                E1s.append(r["E1"])
     finally:
         rM.close()
     cen = np.ascontiguousarray(np.concatenate(cens, axis=0))
@@ -998,7 +1050,14 @@ def SHARP_unlimited2(scExp, ensize_K=None, reduced_ndim=None, partition_ncells=N
                     "hmethod": hmethod, "N.cluster": N_cluster, "minN.cluster": minN_cluster,
                     "maxN.cluster": maxN_cluster, "sil.thre": sil_thre, "height.Ntimes": height_Ntimes,
                     "n.cores": n_cores}}
-    return _unlimited_result(final, ncells, parts[0].m, y0, start)
+    res = _unlimited_result(final, ncells, parts[0].m, y0, start)
+    res["reduced.ndim"] = p                                   # :233 (this driver does name it reduced.ndim)
+    if forview:                                               # :235-243
+        res["viE"] = np.concatenate(E1s, axis=0)
+        x0 = np.zeros((ncells, res["N.pred_clusters"]))
+        x0[np.arange(ncells), final - 1] = 1.0
+        res["x0"] = x0
+    return res
 
 
 def _first_int(name: str) -> int:
@@ -1037,14 +1096,24 @@ def SHARP_unlimited3(ndinfo, viewflag=True, n_cores=None, ensize_K=None, rN_seed
             self.dense, self.csc, self.m, self.n = e.dense, e.csc, e.m, e.n
 
         def run_kwargs(self):
-            self._load()
+            if self.dense is None and self.csc is None:
+                self._load()
             kw = super().run_kwargs()
-            self.dense = self.csc = None
+            self.dense = self.csc = None          # rm(mat); gc() (:124-125): the run is the part's last use
             return kw
+
+        def project_kwargs(self):                 # testlog (parts below 1e4 cells, :114 passes no logflag) reads it first
+            if self.dense is None and self.csc is None:
+                self._load()
+            return super().project_kwargs()
+
+        def any_negative(self):
+            return False
 
     ncells_each = ndinfo.get("ncells_each")
     if ncells_each is None:  # one metadata pass, like dim(readRDS(.)) in the reference's first loop
         ncells_each = [Expression.wrap(reader(pth)).n for pth in paths]
     parts = [_Lazy(pth, int(ndinfo["ngenes"]), int(nc)) for pth, nc in zip(paths, ncells_each)]
     return SHARP_unlimited(parts, viewflag=viewflag, n_cores=n_cores, ensize_K=ensize_K, N_cluster=N_cluster,
-                           rN_seed=rN_seed, ctx=ctx, comm=comm, _part_logflag=None, **k)  # :114 passes no logflag
+                           rN_seed=rN_seed, ctx=ctx, comm=comm, _part_logflag=None, _krange_from_part1=True,
+                           **k)  # :114 passes no logflag

@@ -712,6 +712,7 @@ struct PartRun {
     SmBuffers B;
     int *labels_dev = nullptr, *coloff_dev = nullptr, *nc_dev = nullptr;
     int *h_meta = nullptr, *h_wst = nullptr, *h_sst = nullptr, *h_nu = nullptr;  // pinned mirrors
+    bool skipped_smetac = false;
 };
 
 static int part_front(PartRun &R, sharp_ctx *c, const sharp_expr_dev &e, const double *colsum_host,
@@ -774,6 +775,7 @@ static int part_front(PartRun &R, sharp_ctx *c, const sharp_expr_dev &e, const d
     // ---- per-(member, block) problems: parameters and small output tables ----
     sharp_hc_params indp = Q.hc;
     indp.n_cluster = Q.ind_n_cluster;
+    if (Q.block_max_n > 0) indp.max_n = Q.block_max_n; /* SHARP_fpart: `maxN.cluster = 40` inside the worker (R/SHARP_unlimited2.R:421) */
     R.ind = to_dev(indp);
     if (R.ind.n_cluster != 0 && R.ind.n_cluster < 2)
         return set_error(SHARP_E_RSTOP, "The given N.cluster is less than 2, which is not suitable for clustering!");
@@ -979,11 +981,19 @@ static int part_back(PartRun &R) {
         int *corder = b2.take<int>(n);
         int *coff = b2.take<int>(capS + 1);
         SHARP_TRY(launch_sm_codes(c, R.W.A, T, R.coloff_dev, R.nc_dev, st_dev, code, corder, coff));
+        if (Q.skip_smetac) {
+            /* SHARP_fpart (R/SHARP_unlimited2.R:477-531): the part ends after the per-block wMetaC; fColor = "<finalC>en<t>"
+               is returned as the position of the (block, meta-cluster) pair in the blocks' cluster lists -- an injective
+               code, which is all paste() / unique() downstream look at -- un-shuffled like fColor[reind] = fColor */
+            R.skipped_smetac = true;
+            SHARP_TRY(launch_sm_relabel(c, n, code, nullptr, 1, R.src_dev, R.labels_dev));
+        } else {
         sharp_hc_params sp = Q.hc;
         sp.n_cluster = Q.n_cluster;
         SLOW("back smetac_dev", SHARP_TRY(smetac_dev(c, capS, p, R.nc_dev, st_dev, R.E1, corder, coff, nullptr, n, sp, &R.B)));
         SHARP_TRY(d2h(c, R.h_sst, R.B.status, 4));
         SHARP_TRY(launch_sm_relabel(c, n, code, R.B.tf, 0, R.src_dev, R.labels_dev));
+        }
     }
     // viE = enE/K, un-shuffled; kept on the device for sharp_centroids
     SHARP_TRY(c->ws[WS_VIEU].reserve(np * 8));
@@ -1017,7 +1027,11 @@ static int part_finish(PartRun &R, int32_t *labels_out, double *vie_out, double 
     int ncol_x0 = 0;
     std::vector<int> colmap_host;
     if (T == 1) ncol_x0 = R.h_nu[0];
-    else if (x0_out || x0_cols) {
+    else if (R.skipped_smetac) { /* SHARP_fpart returns no x0 (its sx0 stays local, R/SHARP_unlimited2.R:501-514) */
+        if (x0_out) return set_error(SHARP_E_ARG, "skip_smetac: the block-level run has no x0 output");
+        SHARP_TRY(d2h(c, &ncol_x0, R.nc_dev, 4));
+        SHARP_TRY(sync(c));
+    } else if (x0_out || x0_cols) {
         int nC = 0;
         SHARP_TRY(d2h(c, &nC, R.nc_dev, 4));
         SHARP_TRY(sync(c));

@@ -7,6 +7,14 @@ import numpy as np
 import orc
 
 
+def _densify(m, n, csc):
+    cp, ri, v = csc
+    x = np.zeros((m, n), order="F")
+    for c in range(n):
+        x[ri[cp[c]:cp[c + 1]], c] = v[cp[c]:cp[c + 1]]
+    return x
+
+
 class FakeRm:
     def __init__(self, rms):
         self.rms = list(rms)
@@ -68,6 +76,22 @@ class FakeContext:
         oprm = orc.SharpParams(prm.large, prm.logflag, rm.K, rm.p, prm.partition_ncells, prm.n_cluster, prm.enp_n_cluster,
                                prm.ind_n_cluster, _orc_hc(prm.hc), prm.logkind or 2, prm.round_digits)
         kw = dict(dense=dense) if dense is not None else dict(csc=csc)
+        if getattr(prm, "skip_smetac", 0):  # SHARP_fpart: the block stage only (tests/rtrans.py transcribes it)
+            import rtrans
+            x = dense if dense is not None else _densify(m, n, csc)
+            hcb = _orc_hc(prm.hc)
+            hcb.max_n = prm.block_max_n or hcb.max_n
+            re = np.asarray(reind) if reind is not None else np.arange(1, n + 1)
+            fcol, e1, _ = rtrans.fpart_transcribed(np.asarray(x), rm.rms, rm.p, rm.K, prm.partition_ncells, re, hcb,
+                                                   bool(prm.logflag), colsum if prm.normalize else None,
+                                                   enp_hc=orc.hc_params(prm.hc.hmethod, prm.enp_n_cluster, prm.hc.min_n,
+                                                                        prm.hc.max_n, prm.hc.sil_thre, prm.hc.height_ntimes))
+            assert prm.logkind == 10 and prm.round_digits == 1
+            # any injective integer code of the strings will do (the product returns block-order positions)
+            codes = {c: i + 1 for i, c in enumerate(sorted(set(fcol.tolist())))}
+            self._last = {"viE": e1}
+            return {"labels": np.array([codes[c] for c in fcol.tolist()], dtype=np.int32), "viE": e1 if want_vie else None,
+                    "x0": None, "x0_cols": len(codes)}
         r = orc.sharp(m, n, rm.rms, oprm, colsum=colsum if prm.normalize else None, reind=reind, **kw)
         # the oracle returns pred_clusters AFTER the host glue (merge + relabel); relabelling is idempotent, and the
         # merge only applies above 1e4 cells, so feeding it back as the "raw" device labels exercises the same glue

@@ -30,7 +30,7 @@ def test_library_exports_every_declared_symbol():
     missing = [s for s in declared_symbols() if not hasattr(lib, s)]
     assert not missing, missing
     hdr = open(os.path.join(ROOT, "include", "sharp_b200.h")).read()
-    assert lib.sharp_abi_version() == int(re.search(r"#define SHARP_B200_ABI_VERSION (\d+)", hdr).group(1)) == 3
+    assert lib.sharp_abi_version() == int(re.search(r"#define SHARP_B200_ABI_VERSION (\d+)", hdr).group(1)) == 4
 
 
 def test_no_torch_types_in_the_abi():

@@ -2,6 +2,7 @@
 compute calls answered by the CPU oracle (tests/fakectx.py).  What is checked is the glue the reference keeps in R:
 defaults, seeds, dispatch small/large, block layout, merge / relabel rules, SHARP_unlimited's combine."""
 import math
+import os
 
 import numpy as np
 import pytest
@@ -223,3 +224,61 @@ def test_plan_groups_covers_every_part_once():
     assert _lib.plan_groups(26, False)["gstart"] == [0, 3, 7, 11, 15, 19, 23, 26]      # the benchmark, parts in HBM
     assert _lib.plan_groups(26, True)["gstart"] == [0, 2, 6, 10, 14, 18, 22, 26]       # the benchmark, host buffers
     assert _lib.plan_groups(13, True)["gstart"] == [0, 2, 6, 10, 13]                   # one of two ranks
+
+
+def test_sharp_unlimited2_is_two_level_like_the_reference():
+    """R/SHARP_unlimited2.R: SHARP_fpart stops after the per-block wMetaC (log10, round(., 1), block maxN = 40) and ONE
+    global sMetaC merges the block-level clusters of all parts -- against the literal transcription in tests/rtrans.py"""
+    import math
+
+    import rtrans
+    from sharp_b200.rrng import r_sample_perm, ranM2
+    x, truth = synth.make_expression(500, 1500, n_types=4, seed=12, kind="tpm", zero_frac=0.7, sep=2.5, frac=0.5)
+    sizes = [700, 800]
+    parts, o = [], 0
+    for n in sizes:
+        parts.append(np.asfortranarray(x[:, o:o + n]))
+        o += n
+    K, seed, ng = 3, 17, 300
+    ctx = FakeContext()
+    r = api.SHARP_unlimited2(parts, ensize_K=K, partition_ncells=ng, rN_seed=seed, logflag=False, ctx=ctx)
+    p = math.ceil(math.log2(1500) / 0.04)
+    rms = [ranM2(500, p, 50 + seed + k) for k in range(1, K + 1)]
+    pred_t, E1_t = rtrans.unlimited2_transcribed([np.asarray(a) for a in parts], rms, p, K, ng,
+                                                 [np.asarray(r_sample_perm(n, 50)) for n in sizes])
+    assert np.array_equal(r["pred_clusters"], pred_t)
+    assert np.array_equal(r["viE"], E1_t) and r["reduced.ndim"] == p and r["N.pred_clusters"] == len(np.unique(pred_t))
+    assert r["x0"].shape == (1500, r["N.pred_clusters"]) and np.all(r["x0"].sum(1) == 1)
+    assert all(c[0] == "run" and c[2] == 1 for c in ctx.calls) and len(ctx.calls) == 2
+    # SHARP_fpart alone: block-level ids, un-shuffled folds
+    f = api.SHARP_fpart(parts[0], K, p, ng, rN_seed=seed, ctx=FakeContext())
+    fc_t, e1_t, folds_t = rtrans.fpart_transcribed(np.asarray(parts[0]), rms, p, K, ng, np.asarray(r_sample_perm(700, 50)),
+                                                   orc.hc_params(max_n=40))
+    assert synth.ari(f["fColor"], np.unique(fc_t, return_inverse=True)[1]) == 1.0
+    assert np.array_equal(f["folds"], folds_t) and f["nmcluster"] == len(set(fc_t.tolist())) and f["ncells"] == 700
+    assert synth.ari(r["pred_clusters"], truth) > 0.5   # round(., 1) of log10 values costs accuracy; parity is what is tested
+
+
+def test_sharp_unlimited3_reads_parts_lazily_and_uses_part_one_k_range(tmp_path):
+    """R/SHARP_unlimited3.R:59-61 (files ordered by the first integer in their names), :105/:124 (one part in memory at a
+    time), :165-166 (the global sMetaC takes y[[1]]$paras$minN.cluster / maxN.cluster)"""
+    x, _ = synth.make_expression(400, 3 * 260, n_types=3, seed=4, sep=2.5, frac=0.5)
+    names = ["part10.npz", "part2.npz", "part1.npz"]   # numeric order: 1, 2, 10
+    order = [2, 1, 0]
+    plist = [np.asfortranarray(x[:, i * 260:(i + 1) * 260]) for i in range(3)]
+    for nm, i in zip(names, order):
+        cp, ri, v = synth.to_csc(plist[i])
+        np.savez(tmp_path / nm, p=cp, i=ri, x=v, Dim=np.array(plist[i].shape))
+    seen = []
+
+    def reader(path):
+        seen.append(os.path.basename(path))
+        z = np.load(path)
+        return {"p": z["p"], "i": z["i"], "x": z["x"], "Dim": tuple(int(q) for q in z["Dim"])}
+
+    r = api.SHARP_unlimited3({"dir": str(tmp_path), "ncells": 780, "ngenes": 400, "ncells_each": [260, 260, 260]},
+                             viewflag=False, rN_seed=3, ensize_K=2, reader=reader, ctx=FakeContext(), n_streams=1,
+                             logflag=False)
+    ref = api.SHARP_unlimited(plist, viewflag=False, rN_seed=3, ensize_K=2, ctx=FakeContext(), n_streams=1)
+    assert seen == ["part1.npz", "part2.npz", "part10.npz"]
+    assert np.array_equal(r["pred_clusters"], ref["pred_clusters"])
