@@ -178,6 +178,13 @@ class Expression:
         return Expression(int(keep.sum()), self.n, csc=(np.cumsum(ncp), newidx[ri[sel]].astype(np.int32), v[sel]),
                           normalize=self.normalize)
 
+    def with_normalize(self) -> "Expression":
+        """the same matrix with the CPM scaling pending (a shallow copy: subclasses that load lazily stay lazy)"""
+        import copy
+        c = copy.copy(self)
+        c.normalize = True
+        return c
+
     def run_kwargs(self) -> dict:
         if self.dev is not None:
             return {"expr": self.dev}
@@ -618,7 +625,7 @@ def SHARP(scExp, exp_type=None, ensize_K=None, reduced_ndim=None, base_ncells=No
             e = e.clamp_negative()
         e = e.keep_rows(e.row_sums() != 0)
     if exp_type is not None and exp_type not in ("CPM", "TPM"):
-        e = Expression(e.m, e.n, e.dense, e.csc, e.dev, normalize=True)
+        e = e.with_normalize()
     if reduced_ndim is None:
         reduced_ndim = math.ceil(math.log2(ncells) / 0.2 ** 2)
     reduced_ndim = int(reduced_ndim)

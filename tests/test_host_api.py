@@ -278,7 +278,7 @@ def test_sharp_unlimited3_reads_parts_lazily_and_uses_part_one_k_range(tmp_path)
 
     r = api.SHARP_unlimited3({"dir": str(tmp_path), "ncells": 780, "ngenes": 400, "ncells_each": [260, 260, 260]},
                              viewflag=False, rN_seed=3, ensize_K=2, reader=reader, ctx=FakeContext(), n_streams=1,
-                             logflag=False)
-    ref = api.SHARP_unlimited(plist, viewflag=False, rN_seed=3, ensize_K=2, ctx=FakeContext(), n_streams=1)
+                             logflag=False, exp_type="UMI")
+    ref = api.SHARP_unlimited(plist, viewflag=False, rN_seed=3, ensize_K=2, ctx=FakeContext(), n_streams=1, exp_type="UMI")
     assert seen == ["part1.npz", "part2.npz", "part10.npz"]
     assert np.array_equal(r["pred_clusters"], ref["pred_clusters"])
