@@ -76,12 +76,17 @@ int sharp_timer_stop_ms(sharp_ctx *ctx, double *ms);
 /* number of kernels this library launched on the context since creation (bench.py's gpu_launches). */
 int64_t sharp_ctx_launch_count(sharp_ctx *ctx);
 
-/* Projection kernel variant: 0 (default) = order-independent fixed-point accumulation with shared-memory integer
- * atomics (exact 64-bit integer sums; non-zeros equal to 1..4 -- most of a UMI matrix -- are counted per output
- * instead of added, which gives the same sum; used whenever K*p <= 32700); 1 = the fp64 read-modify-write kernel that
- * adds every output's terms in ascending gene order (bit-identical to a sequential sparse product).  Both meet the
- * 1e-5 contract by seven orders of magnitude or more; the switch exists so that tests and ncu can compare them. */
-int sharp_ctx_set_rp_variant(sharp_ctx *ctx, int legacy);
+/* Projection kernel variant (all compute the same exact 64-bit fixed-point sums except 1; the switch exists so that tests
+ * and ncu can compare them):
+ *   0 (default) record-gather kernel for CSC input: one fixed-size record per gene fetched by one coalesced request, signed
+ *     16-bit count fields for the non-zeros equal to 1..4, per-cell scale from a streaming pre-pass (rp_project_v3.cu);
+ *     dense input and matrices it does not cover take variant 2;
+ *   1 the fp64 read-modify-write kernel that adds every output's terms in ascending gene order (bit-identical to a
+ *     sequential sparse product);
+ *   2 the round-1 fixed-point kernel (pointer array + padded entry lists, 8-bit count fields);
+ *   3 variant 0 with the cell's (rowidx, val) segments staged in shared memory one cell ahead by cp.async.bulk (TMA).
+ * All meet the 1e-5 contract by seven orders of magnitude or more. */
+int sharp_ctx_set_rp_variant(sharp_ctx *ctx, int variant);
 
 /* per-kernel device-time profile (off by default): while enabled, every launch of this library on the context's
  * stream is bracketed by CUDA events and accumulated per kernel class.  bench.py's roofline object is computed from

@@ -273,9 +273,11 @@ class Context:
     def launch_count(self) -> int:
         return int(load().sharp_ctx_launch_count(self._h))
 
-    def set_rp_variant(self, legacy: bool):
-        """False (default): fixed-point atomic projection kernel; True: fp64 gene-order read-modify-write kernel"""
-        _check(load().sharp_ctx_set_rp_variant(self._h, int(bool(legacy))))
+    def set_rp_variant(self, variant):
+        """projection kernel: 0 / False (default) record-gather fixed point (CSC input; dense input takes 2); 1 / True the
+        fp64 gene-order read-modify-write kernel; 2 the round-1 fixed-point kernel; 3 record-gather with the cell's
+        (rowidx, val) segments staged in shared memory by cp.async.bulk"""
+        _check(load().sharp_ctx_set_rp_variant(self._h, int(variant)))
 
     def prof_enable(self, on=True):
         _check(load().sharp_prof_enable(self._h, int(bool(on))))

@@ -151,7 +151,8 @@ struct sharp_ctx {
     int last_p = 0;
     int last_K = 0;
     bool serial = false;    // sharp_run_parts: every sub-context enqueues on THIS context's stream (isolated kernel timings)
-    bool rp_legacy = false; // force the fp64 read-modify-write projection kernel (tests compare both variants)
+    int rp_variant = 0;     // projection kernel: 0 record-gather fixed point (CSC; default), 1 fp64 read-modify-write, 2 the r1
+                            // fixed-point kernel (also what dense input takes), 3 record-gather with TMA-staged cell segments
     int reserve_pinned(size_t bytes);
     // per-kernel profile: CUDA events around every launch on `stream` while prof_on (off by default)
     bool prof_on = false;
@@ -178,6 +179,10 @@ struct sharp_rm_dev {
     int kpd = 0;                 // K*p rounded up to 32, plus the 32 dummy columns the padding entries point at
     int max_col_nnz = 0;         // largest number of entries in one column of one member (bound on adds per output)
     int vec_per_gene = 0;        // vectors preloaded per gene by the kernel (covers ~99 % of the genes)
+    // fixed-size records of the record-gather kernel (rp_project_v3.cu): rv vectors of {count, 7 entries} per gene, the
+    // gene's entries dealt round-robin over them; entry = byte offset of the output in an accumulator array | sign
+    uint4 *rec = nullptr;        // [m * rv]
+    int rv = 0;                  // vectors per record (2, 4, 8 or 16); 0: no records (K*p too large)
 };
 
 struct sharp_expr_dev {
@@ -204,9 +209,12 @@ void prof_collect(sharp_ctx *c);
 // ---- kernel launchers (each returns after enqueueing on ctx->stream) ---------------------------------
 // rp_project.cu
 int launch_colsum(sharp_ctx *c, const sharp_expr_dev &e, double *colsum);
+// colsum_dev: [n] per source column when normalize != 0.  colsum_ready = false (normalize = 2): the sums have not been
+// computed yet -- the launcher does it (fused into the record-gather kernel's pre-pass where that applies)
 int launch_rp_project(sharp_ctx *c, const sharp_expr_dev &e, const int64_t *cells_dev, int64_t ncell,
-                      const double *colsum_dev, int normalize, double norm_mul, int logkind, int round_digits,
+                      double *colsum_dev, bool colsum_ready, int normalize, double norm_mul, int logkind, int round_digits,
                       const sharp_rm_dev &rm, double *out /* [K][ncell][p] */);
+constexpr int WS_CELLINFO_SLOT = 47;  // workspace slot of the per-cell records of the record-gather kernel (last of ws[48])
 // corrdist.cu
 int launch_unit_rows(sharp_ctx *c, const double *X, int64_t rows, int p, int ldu, double *U);
 struct GemmProb {

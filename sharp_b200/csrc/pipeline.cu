@@ -170,6 +170,7 @@ enum Slot {
     WS_WM_INT, WS_WM_DBL, WS_WM_S, WS_WM_DESC, WS_WM_SCRATCH, WS_SM_INT, WS_SM_DBL, WS_SM_S, WS_SM_SCRATCH, WS_VIEU,
     WS_LABELS, WS_X0, WS_TMP0, WS_TMP1, WS_TMP2, WS_TMP3, WS_START, WS_CEN, WS_EX_A, WS_EX_B, WS_EX_C, WS_GDESC, WS_HC_E, WS_COUNT
 };
+static_assert(WS_COUNT <= WS_CELLINFO_SLOT, "the last workspace slot belongs to the projection kernel");
 
 // bump allocator over a byte region
 struct Bump {
@@ -266,7 +267,7 @@ static int upload_expr(sharp_ctx *c, int m, int64_t n, const double *dense, cons
     e->owned = !staged;
     if (m <= 0 || n < 0) return set_error(SHARP_E_ARG, "expression matrix: bad dimensions %d x %lld", m, (long long)n);
     auto get = [&](int slot, void **ptr, size_t bytes) -> int {
-        bytes = std::max<size_t>(bytes, 8);
+        bytes = std::max<size_t>(bytes, 8) + 64; /* slack: the staged projection kernel widens its bulk copies to 16-byte boundaries */
         if (staged) {
             SHARP_TRY(c->ws[slot].reserve(bytes));
             *ptr = c->ws[slot].ptr;
@@ -756,7 +757,7 @@ static int part_front(PartRun &R, sharp_ctx *c, const sharp_expr_dev &e, const d
         if (Q.normalize == 1) {
             if (!colsum_host) return set_error(SHARP_E_ARG, "normalize = 1 needs the column sums");
             SHARP_TRY(h2d(c, colsum_dev, colsum_host, (size_t)n * 8));
-        } else SHARP_TRY(launch_colsum(c, e, colsum_dev));
+        } /* normalize = 2: the projection launcher computes them */
     }
     const int logkind = Q.logflag ? (Q.logkind ? Q.logkind : 2) : 0;
 
@@ -764,7 +765,7 @@ static int part_front(PartRun &R, sharp_ctx *c, const sharp_expr_dev &e, const d
     const size_t np = (size_t)n * p;
     SHARP_TRY(c->ws[WS_PROJ].reserve((size_t)K * np * 8));
     R.proj = c->ws[WS_PROJ].as<double>();
-    SHARP_TRY(launch_rp_project(c, e, R.src_dev, n, colsum_dev, Q.normalize, Q.norm_mul, logkind, Q.round_digits, rm, R.proj));
+    SHARP_TRY(launch_rp_project(c, e, R.src_dev, n, colsum_dev, Q.normalize != 2, Q.normalize, Q.norm_mul, logkind, Q.round_digits, rm, R.proj));
 
     // ---- K2 input: unit rows ----
     const int ldu = R.ldu = ldu_of(p);
@@ -1090,7 +1091,7 @@ static int make_child(sharp_ctx *parent, sharp_ctx **out) {
     c->device = parent->device;
     c->sm_count = parent->sm_count;
     c->parent = parent;
-    c->rp_legacy = parent->rp_legacy;
+    c->rp_variant = parent->rp_variant;
     c->block_budget_gb = parent->block_budget_gb;
     cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_ready, cudaEventDisableTiming);
@@ -1457,9 +1458,10 @@ int sharp_ctx_set_serial(sharp_ctx *c, int on) {
     return 0;
 }
 
-int sharp_ctx_set_rp_variant(sharp_ctx *c, int legacy) {
+int sharp_ctx_set_rp_variant(sharp_ctx *c, int variant) {
     if (!c) return set_error(SHARP_E_ARG, "null context");
-    c->rp_legacy = legacy != 0;
+    if (variant < 0 || variant > 3) return set_error(SHARP_E_ARG, "set_rp_variant: variant %d (0..3)", variant);
+    c->rp_variant = variant;
     return 0;
 }
 
@@ -1631,6 +1633,33 @@ int sharp_rm_upload(sharp_ctx *c, int m, int p, int K, const int32_t *colptr, co
         if (e3 != cudaSuccess) e1 = e3;
         if (e4 != cudaSuccess) e2 = e4;
     }
+    if (r->kpd > 0 && r->kpd <= 16383 && e16 && e1 == cudaSuccess && e2 == cudaSuccess) {
+        /* records of the record-gather kernel: the smallest record that fewer than 0.2 % of the genes overflow */
+        int rv = 2;
+        for (; rv <= 16; rv *= 2) {
+            int over = 0;
+            for (int i = 0; i < m; i++) over += (int)(rowptr[i + 1] - rowptr[i]) > 7 * rv;
+            if (over <= m / 500) break;
+        }
+        if (rv <= 16) {
+            std::vector<uint16_t> rec((size_t)m * rv * 8, 0);
+            for (int i = 0; i < m; i++) {
+                const uint32_t cnt = rowptr[i + 1] - rowptr[i];
+                uint16_t *R = rec.data() + (size_t)i * rv * 8;
+                if ((int)cnt > 7 * rv) { R[0] = 0xffffu; continue; }
+                for (uint32_t q = 0; q < cnt; q++) {
+                    const uint32_t en = ent[rowptr[i] + q];
+                    const int v = (int)(q % rv), slot = 1 + (int)(q / rv);
+                    R[v * 8 + slot] = (uint16_t)(((en & 0x7fffu) << 2) | ((en & 0x8000u) ? 1u : 0u));
+                    R[v * 8]++;
+                }
+            }
+            cudaError_t e5 = rm_alloc(c->device, (void **)&r->rec, rec.size() * 2);
+            if (e5 == cudaSuccess) e5 = cudaMemcpy(r->rec, rec.data(), rec.size() * 2, cudaMemcpyHostToDevice);
+            if (e5 != cudaSuccess) e1 = e5;
+            r->rv = rv;
+        }
+    }
     if (e1 != cudaSuccess || e2 != cudaSuccess) {
         sharp_rm_free(r);
         return set_error(SHARP_E_CUDA, "rm_upload: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
@@ -1647,6 +1676,7 @@ void sharp_rm_free(sharp_rm_dev *r) {
     rm_release(r->ent32);
     rm_release(r->vecptr);
     rm_release(r->entvec);
+    rm_release(r->rec);
     delete r;
 }
 
@@ -1696,11 +1726,11 @@ int sharp_rp_project(sharp_ctx *c, int m, int64_t n, const double *dense, const 
             if (normalize == 1) {
                 if (!colsum) return set_error(SHARP_E_ARG, "normalize = 1 needs colsum");
                 SHARP_TRY(h2d(c, cs, colsum, (size_t)n * 8));
-            } else SHARP_TRY(launch_colsum(c, e, cs));
+            }
         }
         size_t ob = (size_t)rm->K * ncell * rm->p * 8;
         SHARP_TRY(c->ws[WS_PROJ].reserve(ob));
-        SHARP_TRY(launch_rp_project(c, e, cells_dev, ncell, cs, normalize, norm_mul, logkind, round_digits, *rm, c->ws[WS_PROJ].as<double>()));
+        SHARP_TRY(launch_rp_project(c, e, cells_dev, ncell, cs, normalize != 2, normalize, norm_mul, logkind, round_digits, *rm, c->ws[WS_PROJ].as<double>()));
         SHARP_TRY(d2h(c, out, c->ws[WS_PROJ].ptr, ob));
         return sync(c);
     };
@@ -2019,7 +2049,7 @@ int sharp_run_parts(sharp_ctx *c, int m, int nparts, sharp_part *parts, const sh
     for (sharp_ctx *s : c->subs) {
         if (c->serial) s->pf_part = -1;
         s->prof_on = c->prof_on;
-        s->rp_legacy = c->rp_legacy;
+        s->rp_variant = c->rp_variant;
         s->block_budget_gb = std::max(1, c->block_budget_gb / lanes);
     }
     // serial mode (profiling): all sub-contexts enqueue on the context's own stream, so no two kernels overlap and

@@ -20,32 +20,9 @@
 //     columns -> bank conflicts), not by HBM: ~30 k adds per cell against 44 KB of HBM traffic per cell.
 //   * a dense tcgen05 contraction is not used: with density 1/sqrt(m) it would execute ~150x more MACs than
 //     this kernel does adds (DESIGN.md has the arithmetic).
-#include "devutil.cuh"
-#include "internal.cuh"
+#include "rp_common.cuh"
 
 namespace sharp {
-
-__device__ __forceinline__ double rp_transform(double x, double cs, int normalize, double norm_mul, int logkind) {
-    double v = x;
-    if (normalize) v = __dmul_rn(__ddiv_rn(x, cs), norm_mul);
-    if (logkind == 2) v = log2(v + 1.0);
-    else if (logkind == 10) v = log10(v + 1.0);
-    return v;
-}
-
-// base::round(x, digits) in the R >= 4.0 flavour restated by the oracle (closest candidate, ties to even)
-__device__ __forceinline__ double rp_round(double x, int digits) {
-    if (digits < 0 || x == 0.0 || !isfinite(x)) return x;
-    double p10 = 1.0;
-    for (int i = 0; i < digits; i++) p10 *= 10.0;
-    double xd = __dmul_rn(x, p10);
-    double fl = floor(xd), ce = ceil(xd);
-    double lo = __ddiv_rn(fl, p10), hi = __ddiv_rn(ce, p10);
-    double dl = __dsub_rn(x, lo), dh = __dsub_rn(hi, x);
-    if (dl < dh) return lo;
-    if (dh < dl) return hi;
-    return (fmod(fl, 2.0) == 0.0) ? lo : hi;
-}
 
 // ---- column sums (colSums(x), R/SHARP.R:113) : one warp per cell -------------------------------------------
 __global__ void __launch_bounds__(256)
@@ -76,28 +53,6 @@ int launch_colsum(sharp_ctx *c, const sharp_expr_dev &e, double *colsum) {
 }
 
 // ---- projection ------------------------------------------------------------------------------------
-struct RpArgs {
-    int m;
-    int64_t n;
-    const double *dense;
-    const int64_t *colptr;
-    const int32_t *rowidx;
-    const double *val;
-    const int64_t *cells;   // source column per output cell (or null)
-    int64_t ncell;
-    const double *colsum;
-    int normalize;
-    double norm_mul;
-    int logkind;
-    int round_digits;
-    int p, K, KP;
-    double scale;           // mag / sqrt(p)
-    const uint32_t *rowptr; // [m+1]
-    const uint16_t *ent16;
-    const uint32_t *ent32;
-    double *out;
-};
-
 // one staged non-zero of the current cell: where its ranM entries are and the transformed value
 struct __align__(16) RpGene {
     uint32_t r0, cnt;
@@ -237,15 +192,6 @@ constexpr int RPF_THREADS = 256;
 constexpr int RPF_WARPS = RPF_THREADS / 32;
 constexpr int RPF_STAGE = 64;  // per-warp compaction buffer of the dense path
 constexpr int RPF_MAXCLS = 4;
-
-__device__ __forceinline__ uint32_t atoms_add(uint32_t addr, uint32_t v) {
-    uint32_t old;
-    asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(addr), "r"(v) : "memory");
-    return old;
-}
-__device__ __forceinline__ void reds_add_if(uint32_t addr, uint32_t v, uint32_t pred) {
-    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p red.shared.add.u32 [%0], %1;\n\t}" ::"r"(addr), "r"(v), "r"(pred) : "memory");
-}
 
 // what one lane adds for its gene: `base` = shared address of the array its first atomic goes to (a class counter array
 // or the low limbs), apos / aneg = the addend for a + / - entry; generic lanes also carry the high words
@@ -544,11 +490,16 @@ static int launch_fx_vec(sharp_ctx *c, const RpFxArgs &A, int vec_per_gene, int6
     return launch_fx<2, FB>(c, A, grid, smem);
 }
 
+struct RpArgs;
+int launch_rp_project_v3(sharp_ctx *c, const RpArgs &Ain, const sharp_rm_dev &rm, bool staged, double *colsum_out, void *info_ws);
+size_t rp_cellinfo_bytes(int64_t n);
+
 int launch_rp_project(sharp_ctx *c, const sharp_expr_dev &e, const int64_t *cells_dev, int64_t ncell,
-                      const double *colsum_dev, int normalize, double norm_mul, int logkind, int round_digits,
+                      double *colsum_dev, bool colsum_ready, int normalize, double norm_mul, int logkind, int round_digits,
                       const sharp_rm_dev &rm, double *out) {
     if (ncell <= 0) return 0;
     if (e.m != rm.m) return set_error(SHARP_E_ARG, "rp_project: expression has %d genes but ranM has %d rows", e.m, rm.m);
+    if (normalize && !colsum_dev) return set_error(SHARP_E_ARG, "rp_project: normalisation needs the column sums");
     RpArgs A;
     A.m = e.m; A.n = e.n; A.dense = e.dense; A.colptr = e.colptr; A.rowidx = e.rowidx; A.val = e.val;
     A.cells = cells_dev; A.ncell = ncell; A.colsum = colsum_dev; A.normalize = normalize ? 1 : 0;
@@ -557,7 +508,17 @@ int launch_rp_project(sharp_ctx *c, const sharp_expr_dev &e, const int64_t *cell
     A.scale = (1.0 / sqrt((double)rm.p)) * rm.mag;   /* entry of 1/sqrt(p) * t(rM) */
     A.rowptr = rm.rowptr; A.ent16 = rm.ent16; A.ent32 = rm.ent32;
     A.out = out;
-    if (rm.entvec && !c->rp_legacy && rm.max_col_nnz < 65536) { /* fixed-point variant */
+    if ((c->rp_variant == 0 || c->rp_variant == 3) && !e.dense && rm.rec) { /* record-gather variant (CSC input) */
+        SHARP_TRY(c->ws[WS_CELLINFO_SLOT].reserve(rp_cellinfo_bytes(e.n)));
+        RpArgs B = A;
+        B.normalize = !normalize ? 0 : (colsum_ready ? 1 : 2); /* 2: the pre-pass computes (and stores) the sums */
+        const int rc = launch_rp_project_v3(c, B, rm, c->rp_variant == 3, (normalize && !colsum_ready) ? colsum_dev : nullptr,
+                                            c->ws[WS_CELLINFO_SLOT].ptr);
+        if (rc <= 0) return rc;
+        /* rc == 1: does not apply (very long ranM columns, huge K*p): the kernels below */
+    }
+    if (normalize && !colsum_ready) SHARP_TRY(launch_colsum(c, e, colsum_dev));
+    if (rm.entvec && c->rp_variant != 1 && rm.max_col_nnz < 65536) { /* fixed-point variant */
         RpFxArgs F;
         F.a = A;
         F.vecptr = rm.vecptr;

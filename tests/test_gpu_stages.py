@@ -58,12 +58,15 @@ def test_rp_project_both_variants_agree(ctx, fmt, logkind):
     rm = ctx.upload_rm(rms)
     kw = dict(dense=x) if fmt == "dense" else dict(csc=synth.to_csc(x))
     out = {}
-    for legacy in (False, True):
-        ctx.set_rp_variant(legacy)
-        out[legacy] = ctx.rp_project(m, n, rm, normalize=2, logkind=logkind, **kw)
-    ctx.set_rp_variant(False)
+    for variant in (0, 1, 2, 3):
+        ctx.set_rp_variant(variant)
+        out[variant] = ctx.rp_project(m, n, rm, normalize=2, logkind=logkind, **kw)
+    ctx.set_rp_variant(0)
     again = ctx.rp_project(m, n, rm, normalize=2, logkind=logkind, **kw)
-    assert np.array_equal(again, out[False])      # integer atomics: bit-reproducible whatever the order
+    assert np.array_equal(again, out[0])          # integer atomics: bit-reproducible whatever the order
+    # the record-gather kernel (0), its TMA-staged form (3) and the round-1 fixed-point kernel (2) form the same integers
+    assert np.array_equal(out[0], out[2]) and np.array_equal(out[0], out[3])
+    out = {False: out[0], True: out[1]}
     refs = np.stack([orc.rp_project(m, n, rms[k], colsum=x.sum(0), logkind=logkind, **kw) for k in range(K)])
     # The fp64 kernel is accurate relative to every member's own projection.  The fixed-point kernel's quantum is set
     # per CELL from its largest transformed value (2^-55 of it here), so its error is measured against the cell's
@@ -113,6 +116,45 @@ def test_rp_project_count_classes_exact(ctx):
             ref = orc.rp_project(m, n, rms[k], dense=x, colsum=colsum, logkind=logkind)
             assert relerr(got_csc[k], ref) <= 1e-12 and relerr(legacy[k], ref) <= 1e-12
         assert np.all(got_csc[:, 3, :] == 0.0)
+
+
+@pytest.mark.parametrize("variant", [0, 3])
+def test_rp_project_record_overflow_and_staging_limits(ctx, variant):
+    """record-gather kernel: genes whose entry list overflows the fixed-size record (served from the CSR lists), cells
+    with more non-zeros than one staged buffer holds (2048) and cells starting at every 16-byte misalignment"""
+    m, K, p = 1200, 4, 300                      # ~35 entries per gene: 8-vector records, some genes overflow 56
+    rng = np.random.default_rng(21)
+    n = 37
+    x = np.zeros((m, n))
+    for c in range(n):
+        k = [0, 1, 2, 3, 5, 1199, 1200][c % 7] if c < 14 else int(rng.integers(5, 900))
+        rows = rng.choice(m, size=min(k, m), replace=False)
+        x[rows, c] = rng.integers(1, 9, size=len(rows)).astype(np.float64)
+    x[:, 20] = rng.integers(1, 4, size=m)       # dense cells: more non-zeros than... (m < 2048: see the wide matrix below)
+    rms = [ranM2(m, p, 700 + k) for k in range(K)]
+    per_gene = np.zeros(m, dtype=int)
+    for r in rms:
+        per_gene += np.bincount(r["i"], minlength=m)
+    rm = ctx.upload_rm(rms)
+    ctx.set_rp_variant(variant)
+    try:
+        got = ctx.rp_project(m, n, rm, csc=synth.to_csc(x), normalize=0, logkind=2)
+        # a wide matrix: cells with > 2048 non-zeros
+        m2 = 6000
+        x2 = np.zeros((m2, 9))
+        for c in range(9):
+            rows = rng.choice(m2, size=[2047, 2048, 2049, 4096, 5000, 1, 2050, 3000, 6000][c], replace=False)
+            x2[rows, c] = rng.integers(1, 30, size=len(rows)).astype(np.float64)
+        rms2 = [ranM2(m2, 64, 800 + k) for k in range(3)]
+        rm2 = ctx.upload_rm(rms2)
+        got2 = ctx.rp_project(m2, 9, rm2, csc=synth.to_csc(x2), normalize=2, logkind=2)
+    finally:
+        ctx.set_rp_variant(0)
+    assert per_gene.max() > 56                  # two genes overflow the 8-vector records: the CSR path is exercised
+    for k in range(K):
+        assert relerr(got[k], orc.rp_project(m, n, rms[k], dense=x, logkind=2)) <= 1e-12
+    for k in range(3):
+        assert relerr(got2[k], orc.rp_project(m2, 9, rms2[k], dense=x2, colsum=x2.sum(0), logkind=2)) <= 1e-12
 
 
 def test_rp_project_long_ranm_columns_use_16bit_fields(ctx):
