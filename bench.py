@@ -371,21 +371,31 @@ def run_reference(args):
 def run_ours(args):
     import torch
     import sharp_b200
-    from sharp_b200 import api, dist
+    from sharp_b200 import api
+    from sharp_b200 import comm as sharp_comm
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: sharp_b200 has no CPU fallback")
-    comm = dist.init_from_env()
-    rank, world = (comm.rank, comm.world) if comm else (0, 1)
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    api.set_devices(local)
+    ctx = api.get_context(local)
+    # N > 1: the communicator is NCCL behind the C ABI (sharp_comm_*); torch is only used to generate the synthetic data
+    comm = sharp_comm.init_from_env(ctx)
+    rank, world = (comm.rank, comm.world) if comm else (0, 1)
     wl = workload(args.workload)
     if args.parts:
         wl["parts"] = wl["parts"][:args.parts]
     m, sizes = wl["m"], wl["parts"]
     ncells = int(sum(sizes))
     p = math.ceil(math.log2(ncells) / 0.04)
-    mine = [i for i in range(len(sizes)) if i % world == rank]
+    # whole parts are dealt round-robin while they divide evenly; the left-over parts are block-sharded over all ranks
+    # (every rank holds their data and clusters a share of their blocks; api.SHARP_unlimited makes the same split)
+    nwhole = (len(sizes) // world) * world if (world > 1 and not args.no_fused and not args.no_shard and
+                                                all(-(-sizes[i] // 2000) >= world for i in range((len(sizes) // world) * world, len(sizes)))) \
+        else len(sizes)
+    shared = list(range(nwhole, len(sizes)))
+    mine = [i for i in range(nwhole) if i % world == rank] + shared
 
     t0 = time.time()
     lam = type_profiles(torch, dev, m, wl["types"], wl["nnz_per_cell"])
@@ -396,13 +406,12 @@ def run_ours(args):
     nnz_all = [0] * len(sizes)
     for i in mine:
         nnz_all[i] = int(host_parts[i]["p"][-1])
+    own = [i for i in mine if i not in shared or rank == 0]   # who reports a part in the exchanges below
     if comm:
-        nnz_all = [int(a[0]) for a in comm.allgather_parts({i: np.array([nnz_all[i]], dtype=np.int64) for i in mine}, len(sizes))]
+        nnz_all = [int(a[0]) for a in comm.allgather_parts({i: np.array([nnz_all[i]], dtype=np.int64) for i in own}, len(sizes))]
 
-    api.set_devices(local)
     api._fused_parts = not args.no_fused
     api._fused_group, api._fused_lanes = args.group, args.lanes
-    ctx = api.get_context(local)
     if args.budget_gb:
         ctx.set_block_budget(args.budget_gb)
     ctxs = api.stream_contexts(args.streams, local) if args.no_fused else [ctx]
@@ -489,21 +498,20 @@ def run_ours(args):
     same = bool(np.array_equal(res["pred_clusters"], res_e2e["pred_clusters"]))
     h2d = sum(host_parts[i]["p"].nbytes + host_parts[i]["i"].nbytes + host_parts[i]["x"].nbytes for i in mine)
     d2h = sum(sizes[i] * 4 for i in mine)
-    if comm:  # whole-job bytes per step, like `value`
-        h2d = sum(nnz_all) * 12 + sum((s + 1) * 8 for s in sizes)
-        d2h = ncells * 4
+    if comm:  # whole-job bytes per step, like `value`: every rank copies its own parts and ALL the block-sharded ones
+        import struct
+        h2d = sum(struct.unpack("<q", b)[0] for b in comm.allgather_bytes(struct.pack("<q", int(h2d))))
+        d2h = sum(struct.unpack("<q", b)[0] for b in comm.allgather_bytes(struct.pack("<q", int(d2h))))
 
     # ---- what came out: a hash of the label vector (must be the same on every rank and for every N), and the ARI
     # ---- against the planted cell types of the synthetic data
     import hashlib
     import synth
     label_hash = hashlib.sha1(np.ascontiguousarray(res["pred_clusters"], dtype=np.int32).tobytes()).hexdigest()[:16]
-    types_all = {i: host_parts[i]["types"] for i in mine}
+    types_all = {i: host_parts[i]["types"] for i in own}
     if comm:
         types_all = comm.allgather_parts(types_all, len(sizes))
-        hashes = comm.allgather_parts({rank: np.frombuffer(label_hash.encode(), dtype=np.uint8)}, world) \
-            if world <= len(sizes) else None
-        if hashes is not None and len({h.tobytes() for h in hashes}) != 1:
+        if len(set(comm.allgather_bytes(label_hash.encode()))) != 1:
             raise SystemExit("the ranks returned different label vectors")
     else:
         types_all = [types_all[i] for i in range(len(sizes))]
@@ -511,17 +519,17 @@ def run_ours(args):
     result = {"N.pred_clusters": int(res.get("N.pred_clusters", res.get("N.pred_cluster", 0))), "label_sha1_16": label_hash,
               "ari_vs_planted_types": synth.ari(res["pred_clusters"], truth), "planted_types": wl["types"],
               "ranks_agree": True if comm else None}
-    if comm:  # every exchange is done; leave the process group cleanly on all ranks
-        try:
-            torch.distributed.destroy_process_group()
-        except Exception:
-            pass
+    if comm:  # every exchange is done
+        comm.barrier()
     if rank != 0:
+        if comm:
+            comm.close()
         return
     # ---- roofline of the dominant kernel (live CUDA-event profile over the timed steps, this rank's share) ----
     pk = peaks()
-    my_nnz = [nnz_all[i] for i in mine]
-    my_sizes = [sizes[i] for i in mine]
+    frac = lambda i: (1.0 / world if i in shared else 1.0)   # a rank clusters its share of the blocks of a sharded part
+    my_nnz = [int(nnz_all[i] * frac(i)) for i in mine]
+    my_sizes = [int(sizes[i] * frac(i)) for i in mine]
     work = algorithmic_work(wl, my_nnz, my_sizes, p)
     kernels = {}
     total_kernel_ms = sum(v[0] for v in prof.values())
@@ -592,8 +600,9 @@ def run_ours(args):
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": wl["name"], "cells": ncells, "genes": m, "parts": len(sizes), "K": wl["K"], "p": p,
                        "nnz": int(sum(nnz_all)), "partition": (f"parts round-robin over {world} rank(s); part-by-part, {args.streams} streams per GPU" if args.no_fused else
-                                     f"parts round-robin over {world} rank(s); fused loop over parts (sharp_run_parts), "
-                                     f"group={args.group or 'default'}, lanes={args.lanes or 'default'}"),
+                                     f"{nwhole} whole parts round-robin over {world} rank(s)"
+                                     + (f", the cell blocks of the other {len(shared)} dealt over all ranks (NCCL allgather of block-level labels and enE rows)" if shared else "")
+                                     + f"; fused loop over parts (sharp_run_parts), group={args.group or 'default'}, lanes={args.lanes or 'default'}"),
                        "l2": "inputs larger than L2 (CSC input %.1f GB per step)" % (sum(nnz_all) * 12 / 1e9),
                        "generation_s": t_gen},
             "step_wall_ms": walls_dev, "clocks": clocks, "gpu_launches": int(launches / args.steps),
@@ -618,6 +627,7 @@ def main():
     ap.add_argument("--lanes", type=int, default=0, help="groups in flight (0 = library default)")
     ap.add_argument("--budget-gb", type=int, default=0, help="distance-matrix workspace cap per context in GB (0 = library default)")
     ap.add_argument("--no-fused", action="store_true", help="part-by-part path (one sharp_run per part, --streams host threads)")
+    ap.add_argument("--no-shard", action="store_true", help="N > 1: deal ALL parts round-robin (no block-sharded left-over parts)")
     ap.add_argument("--cpu-sample", type=int, default=20000, help="cells of the CPU baseline / parity sample (0 = one whole part)")
     ap.add_argument("--ref-sample", type=int, default=0, help="--impl reference: cells per step (0 = one whole part, budget permitting)")
     ap.add_argument("--ref-budget-s", type=float, default=270.0, help="--impl reference: time budget of the whole K + W run")

@@ -192,6 +192,12 @@ typedef struct {
                              pair in block order), un-shuffled; no x0.  0 = SHARP_large (sMetaC across the blocks) */
     int block_max_n;      /* > 0: maxN.cluster of the per-(member, block) clusterings only (SHARP_fpart assigns 40 inside its
                              worker, R/SHARP_unlimited2.R:421; its wMetaC keeps the caller's value, :481); 0 = hc.max_n */
+    int shard;            /* large = 1 with a communicator on the context (sharp_comm_init): 1 = the cell blocks of THIS matrix
+                             are dealt over the ranks (the K x T nested loop of R/SHARP.R:554-618 and the per-block wMetaC,
+                             :692-709, run on the rank that owns the block); block-level results and the rows of enE / K are
+                             allgathered and every rank finishes with the whole matrix's labels / viE.  Every rank makes the
+                             same call; no x0.  Un-shuffled host data (n >= 1e5): only the rank's columns are uploaded */
+    int shard_rotate;     /* rotates which ranks get the larger shares when the blocks do not divide evenly */
 } sharp_run_params;
 
 /* reind: 1-based permutation from `set.seed(50); sample(ncells)` or NULL; applied iff ncells < 1e5
@@ -239,6 +245,9 @@ typedef struct {
     int nclust;                /* out */
     double *cen;               /* out (may be NULL) */
     int64_t *counts;           /* out (may be NULL) */
+    int sharded;               /* 1 (needs sharp_comm_init): EVERY rank passes this part, in the same order relative to the other
+                                  sharded parts, and its blocks are dealt over the ranks (sharp_run_params.shard); every rank
+                                  receives its full outputs.  0: the part belongs to the calling rank alone */
 } sharp_part;
 int sharp_run_parts(sharp_ctx *ctx, int m, int nparts, sharp_part *parts, const sharp_rm_dev *rm,
                     const sharp_run_params *prm, int small_thre, int cen_cap, int group, int lanes);
@@ -274,6 +283,25 @@ int sharp_last_vie(sharp_ctx *ctx, int64_t n, int p, double *vie);
  * tf[nC]. */
 int sharp_smetac_centroids(sharp_ctx *ctx, int nC, int p, const double *cen, int64_t ncells_total,
                            const sharp_hc_params *prm, int32_t *tf);
+
+/* ---- multi-GPU: one process -- or one host thread -- per GPU, NCCL over NVLink behind this ABI -----------
+ * Replaces the gather side of foreach / doParallel (`.combine`, R/SHARP.R:554, 627-635, 692; R/SHARP_unlimited3.R:137-147)
+ * across GPUs.  The path shards by parts and cell blocks with no data-path collective; what is exchanged are block-level
+ * labels, cluster counts and reduced-space rows / centroids in front of the meta-clustering steps.  NCCL is loaded at
+ * run time (dlopen), so single-GPU use does not need it.
+ *   rank 0:     sharp_comm_unique_id(id)          -> 128 bytes, carried to the other ranks by the caller (socket, file, MPI ...)
+ *   every rank: sharp_comm_init(ctx, id, rank, world)   attaches an ncclComm_t to the context (and its sub-contexts)
+ * The collectives below work on HOST buffers (staged through the device); the sharded runs use the communicator directly
+ * on device buffers. */
+#define SHARP_COMM_ID_BYTES 128
+int sharp_comm_unique_id(unsigned char *id, int id_len);
+int sharp_comm_init(sharp_ctx *ctx, const unsigned char *id, int rank, int world);
+int sharp_comm_destroy(sharp_ctx *ctx);
+int sharp_comm_info(sharp_ctx *ctx, int *rank, int *world, int *nccl_version);
+/* bytes[r] bytes from rank r (same array on every rank); recv gets the concatenation in rank order */
+int sharp_comm_allgatherv(sharp_ctx *ctx, const void *send, const int64_t *bytes, void *recv);
+int sharp_comm_bcast(sharp_ctx *ctx, void *buf, int64_t bytes, int root);
+int sharp_comm_barrier(sharp_ctx *ctx);
 
 #ifdef __cplusplus
 }

@@ -43,7 +43,7 @@ class RunParams(C.Structure):
     _fields_ = [("large", C.c_int), ("logflag", C.c_int), ("logkind", C.c_int), ("round_digits", C.c_int),
                 ("partition_ncells", C.c_int), ("n_cluster", C.c_int), ("enp_n_cluster", C.c_int),
                 ("ind_n_cluster", C.c_int), ("hc", HcParams), ("normalize", C.c_int), ("norm_mul", C.c_double),
-                ("skip_smetac", C.c_int), ("block_max_n", C.c_int)]
+                ("skip_smetac", C.c_int), ("block_max_n", C.c_int), ("shard", C.c_int), ("shard_rotate", C.c_int)]
 
 
 class Part(C.Structure):
@@ -51,7 +51,7 @@ class Part(C.Structure):
     _fields_ = [("n", C.c_int64), ("dev", C.c_void_p), ("dense", C.POINTER(C.c_double)), ("colptr", C.POINTER(C.c_int64)),
                 ("rowidx", C.POINTER(C.c_int32)), ("val", C.POINTER(C.c_double)), ("reind", C.POINTER(C.c_int64)),
                 ("pred", C.POINTER(C.c_int32)), ("nclust", C.c_int), ("cen", C.POINTER(C.c_double)),
-                ("counts", C.POINTER(C.c_int64))]
+                ("counts", C.POINTER(C.c_int64)), ("sharded", C.c_int)]
 
 
 # every symbol include/sharp_b200.h declares (tests check that the library exports all of them)
@@ -64,6 +64,8 @@ EXPORTS = [
     "sharp_last_member", "sharp_last_vie", "sharp_prof_enable", "sharp_prof_reset", "sharp_prof_kernels", "sharp_prof_name",
     "sharp_prof_get", "sharp_ctx_set_rp_variant", "sharp_r_ranm", "sharp_r_sample_perm", "sharp_run_parts",
     "sharp_ctx_set_block_budget", "sharp_ctx_set_serial", "sharp_parts_prefetch", "sharp_plan_groups",
+    "sharp_comm_unique_id", "sharp_comm_init", "sharp_comm_destroy", "sharp_comm_info", "sharp_comm_allgatherv",
+    "sharp_comm_bcast", "sharp_comm_barrier",
 ]
 
 _lib = None
@@ -451,7 +453,7 @@ class Context:
         return keep
 
     def run_parts(self, rm: RmDev, prm: RunParams, m: int, parts: list, reinds: list, small_thre=10, cen_cap=64,
-                  group=0, lanes=0) -> list:
+                  group=0, lanes=0, sharded=None) -> list:
         """The per-part loop of SHARP_unlimited in one call (sharp_run_parts).  ``parts``: list of ExprDev (device
         resident) or dicts {"n", "dense"} / {"n", "csc": (p, i, x)} (host).  -> per part {"pred_clusters",
         "N.pred_cluster", "cen" (nclust x p), "counts"}."""
@@ -473,6 +475,7 @@ class Context:
             re = _i64(re)
             keep.append(re)
             a.reind = _ptr(re, C.c_int64)
+            a.sharded = int(bool(sharded[i])) if sharded is not None else 0
             pred = np.empty(a.n, dtype=np.int32)
             cen = np.empty((cen_cap, rm.p))
             cnt = np.zeros(cen_cap, dtype=np.int64)

@@ -516,10 +516,10 @@ def testlog(scExp, ncells=None, p=None, sncells=None, n_cores=None, ctx: Context
 # SHARP_small / SHARP_large
 # =====================================================================================================
 def _run(ctx, e: Expression, rm: RmDev, large, flag, ng, N_cluster, enpN, indN, hc, forview, reind, logkind=2,
-         round_digits=-1, skip_smetac=False, block_max_n=0):
+         round_digits=-1, skip_smetac=False, block_max_n=0, shard=False):
     prm = RunParams(int(large), int(bool(flag)), int(logkind), int(round_digits), int(ng), _ncl(N_cluster), _ncl(enpN),
-                    _ncl(indN), hc, 2 if e.normalize else 0, 1e6, int(bool(skip_smetac)), int(block_max_n))
-    return ctx.run(rm, prm, reind=reind, want_vie=bool(forview), want_x0=bool(forview) and not skip_smetac,
+                    _ncl(indN), hc, 2 if e.normalize else 0, 1e6, int(bool(skip_smetac)), int(block_max_n), int(bool(shard)), 0)
+    return ctx.run(rm, prm, reind=reind, want_vie=bool(forview), want_x0=bool(forview) and not skip_smetac and not shard,
                    max_x0_cols=max(64, hc.max_n + 1, _ncl(N_cluster) + 1), **e.run_kwargs())
 
 
@@ -560,7 +560,7 @@ def SHARP_small(scExp, ncells=None, ensize_K=15, reduced_ndim=None, hmethod="war
 def SHARP_large(scExp, ncells=None, ensize_K=5, reduced_dim=None, partition_ncells=2000, hmethod="ward.D",
                 N_cluster=None, enpN_cluster=None, indN_cluster=None, minN_cluster=2, maxN_cluster=40, sil_thre=0.35,
                 height_Ntimes=2, flashmark=False, flag=True, n_cores=None, forview=True, rM=True, rN_seed=0.5,
-                ctx: Context | None = None, _logkind=2, _round_digits=-1, **kwargs) -> dict:
+                ctx: Context | None = None, _logkind=2, _round_digits=-1, comm=None, **kwargs) -> dict:
     """R/SHARP.R:478-851.  Shuffle (iff ncells < 1e5), blocks of ``partition.ncells`` cells, K x T projections and
     block clusterings, per-block wMetaC, sMetaC across blocks, un-shuffle -- all in ONE device call (sharp_run);
     then the host glue: merge of clusters with < 10 cells (ncells > 1e4, no N.cluster), relabel by first appearance."""
@@ -572,11 +572,16 @@ def SHARP_large(scExp, ncells=None, ensize_K=5, reduced_dim=None, partition_ncel
     p = int(reduced_dim if reduced_dim is not None else k.get("reduced_ndim", math.ceil(math.log2(ncells) / 0.2 ** 2)))
     K = int(ensize_K)
     hc = _hc(hmethod, None, minN_cluster, maxN_cluster, sil_thre, height_Ntimes, flashmark)
+    # ``comm`` (sharp_b200.comm.NcclComm on ``ctx``): every rank makes this same call and the cell blocks -- the K x T nested
+    # loop of R/SHARP.R:554-618 and the per-block wMetaC, :692-709 -- are dealt over the ranks; all ranks return the full result
+    shard = comm is not None and comm.world > 1 and math.ceil(ncells / partition_ncells) >= comm.world
+    if shard and rN_seed == 0.5:
+        raise ValueError("a sharded run needs an integer rN.seed (every rank must draw the same ranM matrices and shuffle)")
     reind = _reind(ncells, rN_seed) if ncells < 1e5 else None  # drawn always in R, applied iff ncol(E) < 1e5
     rm, own = _as_rmdev(ctx, rM, e.m, p, K, rN_seed)
     try:
         r = _run(ctx, e, rm, 1, flag, partition_ncells, N_cluster, enpN_cluster, indN_cluster, hc, forview, reind,
-                 _logkind, _round_digits)
+                 _logkind, _round_digits, shard=shard)
     finally:
         if own:
             rm.close()
@@ -586,8 +591,13 @@ def SHARP_large(scExp, ncells=None, ensize_K=5, reduced_dim=None, partition_ncel
         labels = _merge_small(labels)
     res = _finish(labels)
     if forview:
-        res["x0"] = r["x0"]
         res["viE"] = r["viE"]
+        if shard:  # the soft indicator stays on the ranks that clustered the block; the hard one follows from the labels
+            x0 = np.zeros((ncells, res["N.pred_cluster"]))
+            x0[np.arange(ncells), res["pred_clusters"] - 1] = 1.0
+            res["x0"] = x0
+        else:
+            res["x0"] = r["x0"]
     return res
 
 
@@ -597,8 +607,9 @@ def SHARP_large(scExp, ncells=None, ensize_K=5, reduced_dim=None, partition_ncel
 def SHARP(scExp, exp_type=None, ensize_K=None, reduced_ndim=None, base_ncells=None, partition_ncells=None,
           hmethod=None, N_cluster=None, enpN_cluster=None, indN_cluster=None, minN_cluster=None, maxN_cluster=None,
           sil_thre=None, height_Ntimes=None, flashmark=False, logflag=None, sncells=None, n_cores=None, forview=True,
-          prep=None, rM=None, rN_seed=None, rownames=None, ctx: Context | None = None, **kwargs) -> dict:
-    """R/SHARP.R:44-318.  ``n.cores`` is accepted and ignored (the GPU is the unit of parallelism)."""
+          prep=None, rM=None, rN_seed=None, rownames=None, ctx: Context | None = None, comm=None, **kwargs) -> dict:
+    """R/SHARP.R:44-318.  ``n.cores`` is accepted and ignored (the GPU is the unit of parallelism); ``comm``: an optional
+    :class:`sharp_b200.comm.NcclComm` -- the cell blocks of the SHARP_large path are then dealt over its ranks."""
     k = _kw(kwargs)
     g = lambda name, cur: k.get(name, cur)
     exp_type, ensize_K, reduced_ndim = g("exp_type", exp_type), g("ensize_K", ensize_K), g("reduced_ndim", reduced_ndim)
@@ -661,7 +672,7 @@ def SHARP(scExp, exp_type=None, ensize_K=None, reduced_ndim=None, base_ncells=No
             ensize_K = 5
         enresults = SHARP_large(e, ncells, ensize_K, reduced_ndim, partition_ncells, hmethod, N_cluster, enpN_cluster,
                                 indN_cluster, minN_cluster, maxN_cluster, sil_thre, height_Ntimes, flashmark, flag,
-                                n_cores, forview, rM, rN_seed, ctx=ctx)
+                                n_cores, forview, rM, rN_seed, ctx=ctx, comm=comm)
     enresults["N.cells"] = ncells
     enresults["N.genes"] = ngenes
     enresults["reduced.dim"] = reduced_ndim
@@ -768,7 +779,7 @@ def _fused_inputs(parts, mine):
     return ins
 
 
-def _run_parts_fused(ctx, parts, mine, rM, p, K, rN_seed, a, n_cores):
+def _run_parts_fused(ctx, parts, mine, rM, p, K, rN_seed, a, n_cores, shared=frozenset()):
     """What the loop `y[[i]] = SHARP(scExp[[i]], reduced.ndim = p, prep = FALSE, logflag = FALSE, rM = rM, ...)` returns
     for the parts in ``mine`` (R/SHARP_unlimited.R:125-149), computed by ONE sharp_run_parts call."""
     normalize = a["exp_type"] is not None and a["exp_type"] not in ("CPM", "TPM")
@@ -781,7 +792,7 @@ def _run_parts_fused(ctx, parts, mine, rM, p, K, rN_seed, a, n_cores):
         reinds.append(_reind(parts[i].n, rN_seed) if parts[i].n < 1e5 else None)
     start = time.time()
     outs = ctx.run_parts(rM, prm, parts[mine[0]].m, ins, reinds, small_thre=10, cen_cap=max(64, a["maxN_cluster"] + 1),
-                         group=_fused_group, lanes=_fused_lanes)
+                         group=_fused_group, lanes=_fused_lanes, sharded=[i in shared for i in mine])
     res = []
     for i, o in zip(mine, outs):
         cid = o["pred_clusters"]
@@ -806,7 +817,7 @@ def SHARP_unlimited(scExp, viewflag=True, n_cores=None, ensize_K=None, N_cluster
     with the shared ranM matrices; the part-level clusters are merged by one global sMetaC over their centroids
     (computed on the device from the part's viE, which never leaves it unless ``viewflag``).
 
-    ``comm``: optional :class:`sharp_b200.dist.Comm` -- the parts are then sharded over the ranks (one process per
+    ``comm``: optional :class:`sharp_b200.comm.NcclComm` -- the parts are then sharded over the ranks (one process per
     GPU) and only centroids, counts and labels are exchanged (allgather); every rank returns the full result."""
     k = _kw(kwargs)
     rN_seed, ensize_K = k.pop("rN_seed", rN_seed), k.pop("ensize_K", ensize_K)
@@ -842,8 +853,26 @@ def SHARP_unlimited(scExp, viewflag=True, n_cores=None, ensize_K=None, N_cluster
     if _part_logflag is None and "logflag" in k:   # SHARP_unlimited3 passes no logflag itself (:114), so `...` may
         _part_logflag = k.pop("logflag")
     rank, world = (comm.rank, comm.world) if comm is not None else (0, 1)
-    mine = [i for i in range(nnp) if i % world == rank]
+    # Several ranks: whole parts are dealt round-robin while they divide evenly; the parts that are left
+    # over -- 26 parts on 8 ranks leave 2 -- are BLOCK-sharded: every rank clusters a share of their cell blocks and the
+    # library allgathers the block-level results (sharp_part.sharded), so that all ranks carry the same load.  That needs
+    # the fused path, an integer seed, the left-over parts' data on every rank and at least `world` blocks per part.
+    nwhole = nnp
+    shared: list = []
+    if world > 1 and nnp % world:
+        cand = list(range((nnp // world) * world, nnp))
+        ng = 2000 if k.get("partition_ncells") is None else int(k["partition_ncells"])
+        ok = (rN_seed != 0.5 and getattr(comm, "backend", "") == "nccl" and
+              all(parts[i].dev is not None or parts[i].dense is not None or parts[i].csc is not None for i in cand) and
+              all(math.ceil(parts[i].n / ng) >= world for i in cand) and
+              _parts_fast_path(parts, cand, k, viewflag, _part_logflag, n_streams) is not None)
+        ok = all(b == b"1" for b in comm.allgather_bytes(b"1" if ok else b"0"))   # the same decision on every rank
+        if ok:
+            nwhole, shared = cand[0], cand
+    mine = [i for i in range(nwhole) if i % world == rank] + shared
     fast = _parts_fast_path(parts, mine, k, viewflag, _part_logflag, n_streams)
+    if shared and fast is None:
+        raise ValueError("the block-sharded parts need the fused path on every rank (same parameters as the rank's own parts)")
     # host buffers: the copy of the first parts starts now and runs while the ranM matrices are drawn on the host
     _pf_keep = None
     if fast is not None and mine and parts[mine[0]].dev is None:
@@ -880,7 +909,7 @@ def SHARP_unlimited(scExp, viewflag=True, n_cores=None, ensize_K=None, N_cluster
     try:
         if fast is not None:  # every part takes the SHARP_large path with the same parameters: one fused device call
             t0 = time.time()
-            outs = _run_parts_fused(ctx, parts, mine, rM, p, ensize_K, rN_seed, fast, n_cores)
+            outs = _run_parts_fused(ctx, parts, mine, rM, p, ensize_K, rN_seed, fast, n_cores, set(shared))
             for i, o in zip(mine, outs):
                 y[i], cens[i], viEs[i] = o, o.pop("cen"), None
             if _TRACE:
@@ -909,11 +938,12 @@ def SHARP_unlimited(scExp, viewflag=True, n_cores=None, ensize_K=None, N_cluster
         rM.close()
     _mark("parts")
     if comm is not None:
-        preds_all = comm.allgather_parts({i: y[i]["pred_clusters"] for i in mine}, nnp)
-        cens_all = comm.allgather_parts(cens, nnp)
+        own = [i for i in mine if i not in shared or rank == 0]   # a block-sharded part is complete on every rank: rank 0 contributes it
+        preds_all = comm.allgather_parts({i: y[i]["pred_clusters"] for i in own}, nnp)
+        cens_all = comm.allgather_parts({i: cens[i] for i in own}, nnp)
         y0 = comm.bcast_obj({kk: y[0][kk] for kk in ("reduced.dim", "ensize.K", "paras")} if 0 in y else None, 0)
         if viewflag:
-            viEs = comm.allgather_parts(viEs, nnp)
+            viEs = comm.allgather_parts({i: viEs[i] for i in own}, nnp)
     else:
         preds_all = [y[i]["pred_clusters"] for i in range(nnp)]
         cens_all = [cens[i] for i in range(nnp)]

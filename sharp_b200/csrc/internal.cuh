@@ -30,7 +30,7 @@ int set_error(int code, const char *fmt, ...);
 // Dynamic shared memory opt-in of every kernel: always the sm_100 maximum (227 KB), never the per-launch size -- host
 // threads driving different contexts set it concurrently, and a smaller value set by one thread between another
 // thread's attribute call and its launch would make that launch fail.
-constexpr int SHARP_SMEM_OPTIN = 223 * 1024;  /* 227 KB minus room for the kernels' small static arrays */
+constexpr int SHARP_SMEM_OPTIN = 222 * 1024;  /* 227 KB minus room for the kernels' small static arrays */
 
 // The opt-in is set ONCE per kernel and device, not per launch: cudaFuncSetAttribute is not a cheap host-side setter --
 // under SHARP_B200_TRACE it was seen blocking the enqueueing thread for hundreds of ms while other streams were
@@ -110,7 +110,7 @@ namespace sharp {
 // kernel classes of the per-kernel device-time profile (sharp_prof_*; bench.py's roofline object)
 enum KernelId { KID_RP_PROJECT = 0, KID_COLSUM, KID_UNIT_ROWS, KID_CORRDIST, KID_HCLUST, KID_HCLUST_SMALL,
                 KID_SWEEP_NESTED, KID_SWEEP_EXACT, KID_WM_WEIGHTS, KID_WM_SIMILARITY, KID_WMETAC, KID_SM_CENTROIDS,
-                KID_SMETAC, KID_ENE, KID_MISC, KID_H2D, KID_COUNT };
+                KID_SMETAC, KID_ENE, KID_MISC, KID_H2D, KID_COMM, KID_COUNT };
 struct ProfPending { int kid; cudaEvent_t a, b; };
 }  // namespace sharp
 
@@ -151,6 +151,9 @@ struct sharp_ctx {
     int last_p = 0;
     int last_K = 0;
     bool serial = false;    // sharp_run_parts: every sub-context enqueues on THIS context's stream (isolated kernel timings)
+    // multi-GPU: an NCCL communicator (ncclComm_t) attached by sharp_comm_init; sub-contexts share their parent's
+    void *comm = nullptr;
+    int comm_rank = 0, comm_world = 1;
     int rp_variant = 0;     // projection kernel: 0 record-gather fixed point (CSC; default), 1 fp64 read-modify-write, 2 the r1
                             // fixed-point kernel (also what dense input takes), 3 record-gather with TMA-staged cell segments
     int reserve_pinned(size_t bytes);
@@ -195,6 +198,9 @@ struct sharp_expr_dev {
     double *val = nullptr;
     int64_t nnz = 0;
     bool owned = true;
+    // a column slice of a larger matrix (sharded runs on un-shuffled host data upload only the rank's columns):
+    // column 0 of this matrix is column col0 of the whole one, which has n_total columns (0: this IS the whole matrix)
+    int64_t col0 = 0, n_total = 0;
 };
 
 namespace sharp {
@@ -206,6 +212,10 @@ void prof_begin(sharp_ctx *c, int kid);
 void prof_end(sharp_ctx *c);
 void prof_collect(sharp_ctx *c);
 
+// comm.cu: allgather of per-rank device segments (bytes[r] from rank r, concatenated in rank order at recv) on stream st
+int comm_allgatherv_dev(sharp_ctx *c, const void *send, void *recv, const int64_t *bytes, cudaStream_t st);
+void comm_destroy(sharp_ctx *c);
+
 // ---- kernel launchers (each returns after enqueueing on ctx->stream) ---------------------------------
 // rp_project.cu
 int launch_colsum(sharp_ctx *c, const sharp_expr_dev &e, double *colsum);
@@ -214,6 +224,7 @@ int launch_colsum(sharp_ctx *c, const sharp_expr_dev &e, double *colsum);
 int launch_rp_project(sharp_ctx *c, const sharp_expr_dev &e, const int64_t *cells_dev, int64_t ncell,
                       double *colsum_dev, bool colsum_ready, int normalize, double norm_mul, int logkind, int round_digits,
                       const sharp_rm_dev &rm, double *out /* [K][ncell][p] */);
+constexpr int WS_COMM_SLOT = 46;      // staging of the host-buffer collectives (comm.cu)
 constexpr int WS_CELLINFO_SLOT = 47;  // workspace slot of the per-cell records of the record-gather kernel (last of ws[48])
 // corrdist.cu
 int launch_unit_rows(sharp_ctx *c, const double *X, int64_t rows, int p, int ldu, double *U);

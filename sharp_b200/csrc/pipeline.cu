@@ -170,7 +170,7 @@ enum Slot {
     WS_WM_INT, WS_WM_DBL, WS_WM_S, WS_WM_DESC, WS_WM_SCRATCH, WS_SM_INT, WS_SM_DBL, WS_SM_S, WS_SM_SCRATCH, WS_VIEU,
     WS_LABELS, WS_X0, WS_TMP0, WS_TMP1, WS_TMP2, WS_TMP3, WS_START, WS_CEN, WS_EX_A, WS_EX_B, WS_EX_C, WS_GDESC, WS_HC_E, WS_COUNT
 };
-static_assert(WS_COUNT <= WS_CELLINFO_SLOT, "the last workspace slot belongs to the projection kernel");
+static_assert(WS_COUNT <= WS_COMM_SLOT, "the last two workspace slots belong to comm.cu and the projection kernel");
 
 // bump allocator over a byte region
 struct Bump {
@@ -714,7 +714,26 @@ struct PartRun {
     int *labels_dev = nullptr, *coloff_dev = nullptr, *nc_dev = nullptr;
     int *h_meta = nullptr, *h_wst = nullptr, *h_sst = nullptr, *h_nu = nullptr;  // pinned mirrors
     bool skipped_smetac = false;
+    // block-sharded run (sharp_run_params.shard / sharp_part.sharded with a communicator on the context): this rank
+    // clusters blocks [t0, t0 + T) of the T_all blocks; n / start / enrp / proj ... above are LOCAL (its own cells, in
+    // shuffled order), na / start_all are the whole matrix.  The per-block wMetaC results and the rows of enE / K are
+    // allgathered, after which every rank runs the cross-block stage (sMetaC, relabel, un-shuffle) on the whole matrix.
+    bool sharded = false;
+    int64_t na = 0, pos0 = 0;
+    int t0 = 0, T_all = 0;
+    std::vector<int64_t> start_all;
+    int64_t *src_all_dev = nullptr, *start_all_dev = nullptr;
+    double *E1_all = nullptr;
 };
+
+// blocks [t0, t1) of T for one rank: as even as possible, the larger shares rotated by `rotate` (successive sharded
+// matrices give their extra blocks to different ranks)
+static void shard_range(int T, int rank, int world, int rotate, int *t0, int *t1) {
+    const int r = ((rank + rotate) % world + world) % world;
+    const int base = T / world, extra = T % world;
+    *t0 = r * base + std::min(r, extra);
+    *t1 = *t0 + base + (r < extra ? 1 : 0);
+}
 
 static int part_front(PartRun &R, sharp_ctx *c, const sharp_expr_dev &e, const double *colsum_host,
                       const sharp_rm_dev &rm, const int64_t *reind, const sharp_run_params &Q) {
@@ -722,27 +741,51 @@ static int part_front(PartRun &R, sharp_ctx *c, const sharp_expr_dev &e, const d
     R.e = e;
     R.rm = &rm;
     R.Q = Q;
-    const int64_t n = R.n = e.n;
+    const int64_t na = R.na = e.n_total ? e.n_total : e.n;   /* cells of the whole matrix (e may hold a column slice of it) */
     const int p = R.p = rm.p, K = R.K = rm.K;
-    if (n < 2) return set_error(SHARP_E_ARG, "need at least 2 cells");
-    if (n > 2000000000LL / std::max(1, K)) return set_error(SHARP_E_LIMIT, "too many cells for one call (%lld); split into parts", (long long)n);
-    make_blocks(n, Q.large, Q.partition_ncells, R.start);
-    const int T = R.T = (int)R.start.size() - 1;
+    if (na < 2) return set_error(SHARP_E_ARG, "need at least 2 cells");
+    if (na > 2000000000LL / std::max(1, K)) return set_error(SHARP_E_LIMIT, "too many cells for one call (%lld); split into parts", (long long)na);
+    make_blocks(na, Q.large, Q.partition_ncells, R.start_all);
+    R.T_all = (int)R.start_all.size() - 1;
+    R.shuffle = Q.large && reind && na < 100000;
+    R.sharded = Q.large && Q.shard && c->comm && c->comm_world > 1;
+    R.t0 = 0;
+    int t1 = R.T_all;
+    if (R.sharded) {
+        if (R.T_all < c->comm_world) return set_error(SHARP_E_ARG, "sharded run: %d blocks cannot be dealt over %d ranks", R.T_all, c->comm_world);
+        shard_range(R.T_all, c->comm_rank, c->comm_world, Q.shard_rotate, &R.t0, &t1);
+    } else if (e.n_total && e.n_total != e.n) return set_error(SHARP_E_ARG, "a column slice needs a sharded run");
+    const int T = R.T = t1 - R.t0;
+    R.pos0 = R.start_all[R.t0];
+    R.start.resize((size_t)T + 1);
+    for (int t = 0; t <= T; t++) R.start[t] = R.start_all[R.t0 + t] - R.pos0;
+    const int64_t n = R.n = R.start[T];
     R.max_bn = 0;
     for (int t = 0; t < T; t++) R.max_bn = std::max<int>(R.max_bn, (int)(R.start[t + 1] - R.start[t]));
-    R.shuffle = Q.large && reind && n < 100000;
+    if (R.shuffle && e.col0 != 0) return set_error(SHARP_E_ARG, "a shuffled matrix cannot be given as a column slice");
+    if (!R.shuffle && R.sharded && (e.col0 > R.pos0 || e.col0 + e.n < R.pos0 + n))
+        return set_error(SHARP_E_ARG, "the column slice does not cover this rank's blocks");
 
     // ---- inputs: source column per position, block boundaries, column sums ----
     R.src_dev = nullptr;
+    R.src_all_dev = nullptr;
     if (R.shuffle) {
+        SHARP_TRY(c->ws[WS_SRC].reserve((size_t)na * 8));
+        R.src_all_dev = c->ws[WS_SRC].as<int64_t>();
+        SHARP_TRY(c->reserve_pinned((size_t)na * 8));
+        int64_t *hp = reinterpret_cast<int64_t *>(c->pinned);
+        for (int64_t i = 0; i < na; i++) {
+            if (reind[i] < 1 || reind[i] > na) return set_error(SHARP_E_ARG, "reind is not a permutation of 1..n");
+            hp[i] = reind[i] - 1;
+        }
+        SHARP_TRY(h2d_staged(c, R.src_all_dev, hp, (size_t)na * 8));
+        R.src_dev = R.src_all_dev + R.pos0;   /* this rank's cells: positions pos0 .. pos0 + n of the shuffled order */
+    } else if (R.sharded && R.pos0 != e.col0) { /* un-shuffled, not starting at the matrix's first column: explicit source list */
         SHARP_TRY(c->ws[WS_SRC].reserve((size_t)n * 8));
         R.src_dev = c->ws[WS_SRC].as<int64_t>();
         SHARP_TRY(c->reserve_pinned((size_t)n * 8));
         int64_t *hp = reinterpret_cast<int64_t *>(c->pinned);
-        for (int64_t i = 0; i < n; i++) {
-            if (reind[i] < 1 || reind[i] > n) return set_error(SHARP_E_ARG, "reind is not a permutation of 1..n");
-            hp[i] = reind[i] - 1;
-        }
+        for (int64_t i = 0; i < n; i++) hp[i] = R.pos0 - e.col0 + i;
         SHARP_TRY(h2d_staged(c, R.src_dev, hp, (size_t)n * 8));
     }
     SHARP_TRY(c->ws[WS_START].reserve((size_t)(T + 1) * 8));
@@ -752,11 +795,11 @@ static int part_front(PartRun &R, sharp_ctx *c, const sharp_expr_dev &e, const d
     SHARP_TRY(h2d_staged(c, R.start_dev, c->pinned, (size_t)(T + 1) * 8));
     double *colsum_dev = nullptr;
     if (Q.normalize) {
-        SHARP_TRY(c->ws[WS_COLSUM].reserve((size_t)n * 8));
+        SHARP_TRY(c->ws[WS_COLSUM].reserve((size_t)e.n * 8));
         colsum_dev = c->ws[WS_COLSUM].as<double>();
         if (Q.normalize == 1) {
             if (!colsum_host) return set_error(SHARP_E_ARG, "normalize = 1 needs the column sums");
-            SHARP_TRY(h2d(c, colsum_dev, colsum_host, (size_t)n * 8));
+            SHARP_TRY(h2d(c, colsum_dev, colsum_host + e.col0, (size_t)e.n * 8));
         } /* normalize = 2: the projection launcher computes them */
     }
     const int logkind = Q.logflag ? (Q.logkind ? Q.logkind : 2) : 0;
@@ -843,7 +886,8 @@ static int run_blocks(sharp_ctx *g, PartRun *const *parts, int np_parts) {
            The agglomeration kernel could keep two problems per SM resident, but a lone problem already streams at the
            per-SM share of HBM bandwidth (ncu: 0.13 ms per problem at 125 per launch, 0.15 ms at 297), and the shorter
            launches let the other lane's stages slot in between them: the whole job ran 4 % faster on B200 this way. */
-        wave_probs = std::min(wave_probs, std::max(1, g->sm_count));
+        static const int per_sm = getenv("SHARP_WAVE_PER_SM") ? std::max(1, atoi(getenv("SHARP_WAVE_PER_SM"))) : 1; /* development switch */
+        wave_probs = std::min(wave_probs, std::max(1, g->sm_count * per_sm));
         const int nw = (nprob + wave_probs - 1) / wave_probs;
         wave_probs = (nprob + nw - 1) / nw;
     }
@@ -961,48 +1005,107 @@ static int part_back(PartRun &R) {
     wp.n_cluster = Q.large ? Q.enp_n_cluster : Q.n_cluster;
     SLOW("back wmetac_dev", SHARP_TRY(wmetac_dev(c, R.enrp, n, K, T, R.start.data(), R.start_dev, 40, wp, &R.W)));
     SHARP_TRY(d2h(c, R.h_wst, R.W.A.status, (size_t)T * 4));
+    // ---- sharded run: the cross-block stage sees the whole matrix on every rank ----
+    const int64_t na = R.na;
+    const int T_all = R.T_all;
+    WmArgs Afull = R.W.A;            /* what launch_sm_codes reads: start, ucount, status, fcode */
+    const double *E1x = R.E1;
+    if (R.sharded) {
+        const int W = c->comm_world;
+        std::vector<int64_t> bcell((size_t)W), bblk((size_t)W), brow((size_t)W);
+        for (int r = 0; r < W; r++) { /* the same deterministic split on every rank */
+            int a0, a1;
+            shard_range(T_all, r, W, Q.shard_rotate, &a0, &a1);
+            bcell[r] = (R.start_all[a1] - R.start_all[a0]) * 4;
+            bblk[r] = (int64_t)(a1 - a0) * 4;
+            brow[r] = (R.start_all[a1] - R.start_all[a0]) * (int64_t)p * 8;
+        }
+        /* ranks own contiguous block ranges, but a rotated split starts at another rank than 0: segments are gathered in
+           RANK order into staging and copied to their BLOCK position */
+        size_t ib3 = bump_size({(size_t)na * 4, (size_t)T_all * 4, (size_t)T_all * 4, (size_t)(T_all + 1) * 8, (size_t)na * 4,
+                                (size_t)T_all * 4, (size_t)T_all * 4});
+        SHARP_TRY(c->ws[WS_TMP2].reserve(ib3));
+        Bump b3(c->ws[WS_TMP2].ptr, ib3);
+        int *fcode_all = b3.take<int>(na), *ucount_all = b3.take<int>(T_all), *status_all = b3.take<int>(T_all);
+        R.start_all_dev = b3.take<int64_t>(T_all + 1);
+        int *g_fcode = b3.take<int>(na), *g_ucount = b3.take<int>(T_all), *g_status = b3.take<int>(T_all);
+        SHARP_TRY(c->ws[WS_TMP3].reserve((size_t)na * p * 8 * 2));
+        R.E1_all = c->ws[WS_TMP3].as<double>();
+        double *g_rows = R.E1_all + (size_t)na * p;
+        SHARP_TRY(c->reserve_pinned((size_t)(T_all + 1) * 8));
+        memcpy(c->pinned, R.start_all.data(), (size_t)(T_all + 1) * 8);
+        SHARP_TRY(h2d_staged(c, R.start_all_dev, c->pinned, (size_t)(T_all + 1) * 8));
+        prof_begin(c, KID_COMM);
+        int rc = comm_allgatherv_dev(c, R.W.A.fcode, g_fcode, bcell.data(), c->stream);
+        if (!rc) rc = comm_allgatherv_dev(c, R.W.A.ucount, g_ucount, bblk.data(), c->stream);
+        if (!rc) rc = comm_allgatherv_dev(c, R.W.A.status, g_status, bblk.data(), c->stream);
+        if (!rc) rc = comm_allgatherv_dev(c, R.E1, g_rows, brow.data(), c->stream);
+        prof_end(c);
+        c->launches--; /* collectives, not kernels of this library */
+        SHARP_TRY(rc);
+        int64_t oc = 0, ob = 0;
+        for (int r = 0; r < W; r++) { /* rank order -> block order */
+            int a0, a1;
+            shard_range(T_all, r, W, Q.shard_rotate, &a0, &a1);
+            const int64_t cells = R.start_all[a1] - R.start_all[a0];
+            SHARP_CUDA(cudaMemcpyAsync(fcode_all + R.start_all[a0], g_fcode + oc, (size_t)cells * 4, cudaMemcpyDeviceToDevice, c->stream));
+            SHARP_CUDA(cudaMemcpyAsync(R.E1_all + (size_t)R.start_all[a0] * p, g_rows + (size_t)oc * p, (size_t)cells * p * 8, cudaMemcpyDeviceToDevice, c->stream));
+            SHARP_CUDA(cudaMemcpyAsync(ucount_all + a0, g_ucount + ob, (size_t)(a1 - a0) * 4, cudaMemcpyDeviceToDevice, c->stream));
+            SHARP_CUDA(cudaMemcpyAsync(status_all + a0, g_status + ob, (size_t)(a1 - a0) * 4, cudaMemcpyDeviceToDevice, c->stream));
+            oc += cells;
+            ob += a1 - a0;
+        }
+        Afull.start = R.start_all_dev;
+        Afull.ucount = ucount_all;
+        Afull.status = status_all;
+        Afull.fcode = fcode_all;
+        Afull.ncells = na;
+        E1x = R.E1_all;
+    }
+    const int Tx = R.sharded ? T_all : T;
+    const int64_t *out_row = R.sharded ? R.src_all_dev : R.src_dev;
     // ---- labels / sMetaC ----
-    SHARP_TRY(c->ws[WS_LABELS].reserve((size_t)n * 4));
+    SHARP_TRY(c->ws[WS_LABELS].reserve((size_t)na * 4));
     R.labels_dev = c->ws[WS_LABELS].as<int>();
     R.coloff_dev = nullptr;
     R.nc_dev = nullptr;
-    if (T == 1) {
+    if (Tx == 1) {
         if (!Q.large) SHARP_TRY(launch_sm_relabel(c, n, R.W.A.finalc, nullptr, 0, R.src_dev, R.labels_dev)); /* finalC ids */
         else SHARP_TRY(launch_sm_relabel(c, n, R.W.A.fcode, nullptr, 1, R.src_dev, R.labels_dev)); /* position in unique(fColor) */
         SHARP_TRY(d2h(c, R.h_nu, R.W.A.ucount, 4));
     } else {
-        const int capS = T * R.W.A.capU;
-        size_t ib2 = bump_size({(size_t)(T + 1) * 4, 64, 64, (size_t)n * 4, (size_t)n * 4, (size_t)(capS + 1) * 4});
+        const int capS = Tx * R.W.A.capU;
+        size_t ib2 = bump_size({(size_t)(Tx + 1) * 4, 64, 64, (size_t)na * 4, (size_t)na * 4, (size_t)(capS + 1) * 4});
         SHARP_TRY(c->ws[WS_TMP0].reserve(ib2));
         Bump b2(c->ws[WS_TMP0].ptr, ib2);
-        R.coloff_dev = b2.take<int>(T + 1);
+        R.coloff_dev = b2.take<int>(Tx + 1);
         R.nc_dev = b2.take<int>(1);
         int *st_dev = b2.take<int>(1);
-        int *code = b2.take<int>(n);
-        int *corder = b2.take<int>(n);
+        int *code = b2.take<int>(na);
+        int *corder = b2.take<int>(na);
         int *coff = b2.take<int>(capS + 1);
-        SHARP_TRY(launch_sm_codes(c, R.W.A, T, R.coloff_dev, R.nc_dev, st_dev, code, corder, coff));
+        SHARP_TRY(launch_sm_codes(c, Afull, Tx, R.coloff_dev, R.nc_dev, st_dev, code, corder, coff));
         if (Q.skip_smetac) {
             /* SHARP_fpart (R/SHARP_unlimited2.R:477-531): the part ends after the per-block wMetaC; fColor = "<finalC>en<t>"
                is returned as the position of the (block, meta-cluster) pair in the blocks' cluster lists -- an injective
                code, which is all paste() / unique() downstream look at -- un-shuffled like fColor[reind] = fColor */
             R.skipped_smetac = true;
-            SHARP_TRY(launch_sm_relabel(c, n, code, nullptr, 1, R.src_dev, R.labels_dev));
+            SHARP_TRY(launch_sm_relabel(c, na, code, nullptr, 1, out_row, R.labels_dev));
         } else {
-        sharp_hc_params sp = Q.hc;
-        sp.n_cluster = Q.n_cluster;
-        SLOW("back smetac_dev", SHARP_TRY(smetac_dev(c, capS, p, R.nc_dev, st_dev, R.E1, corder, coff, nullptr, n, sp, &R.B)));
-        SHARP_TRY(d2h(c, R.h_sst, R.B.status, 4));
-        SHARP_TRY(launch_sm_relabel(c, n, code, R.B.tf, 0, R.src_dev, R.labels_dev));
+            sharp_hc_params sp = Q.hc;
+            sp.n_cluster = Q.n_cluster;
+            SLOW("back smetac_dev", SHARP_TRY(smetac_dev(c, capS, p, R.nc_dev, st_dev, E1x, corder, coff, nullptr, na, sp, &R.B)));
+            SHARP_TRY(d2h(c, R.h_sst, R.B.status, 4));
+            SHARP_TRY(launch_sm_relabel(c, na, code, R.B.tf, 0, out_row, R.labels_dev));
         }
     }
     // viE = enE/K, un-shuffled; kept on the device for sharp_centroids
-    SHARP_TRY(c->ws[WS_VIEU].reserve(np * 8));
+    SHARP_TRY(c->ws[WS_VIEU].reserve((size_t)na * p * 8));
     R.vieu = c->ws[WS_VIEU].as<double>();
     prof_begin(c, KID_ENE);
-    scatter_rows_kernel<<<(unsigned)n, 128, 0, c->stream>>>(R.E1, n, p, R.src_dev, R.vieu);
+    scatter_rows_kernel<<<(unsigned)na, 128, 0, c->stream>>>(E1x, na, p, out_row, R.vieu);
     prof_end(c);
-    c->last_n = n;
+    c->last_n = na;
     c->last_p = p;
     c->last_K = K;
     return 0;
@@ -1020,8 +1123,9 @@ static int part_status(const PartRun &R) {
 
 static int part_finish(PartRun &R, int32_t *labels_out, double *vie_out, double *x0_out, int *x0_cols, int max_x0_cols) {
     sharp_ctx *c = R.c;
-    const int64_t n = R.n;
-    const int p = R.p, T = R.T;
+    const int64_t n = R.na;
+    const int p = R.p, T = R.sharded ? R.T_all : R.T;
+    if (R.sharded && x0_out) return set_error(SHARP_E_ARG, "a sharded run does not produce x0 (call with forview = FALSE)");
     SHARP_TRY(d2h(c, labels_out, R.labels_dev, (size_t)n * 4));
     SHARP_TRY(sync(c));
     SHARP_TRY(part_status(R));
@@ -1092,6 +1196,7 @@ static int make_child(sharp_ctx *parent, sharp_ctx **out) {
     c->sm_count = parent->sm_count;
     c->parent = parent;
     c->rp_variant = parent->rp_variant;
+    c->comm = parent->comm; c->comm_rank = parent->comm_rank; c->comm_world = parent->comm_world;
     c->block_budget_gb = parent->block_budget_gb;
     cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_ready, cudaEventDisableTiming);
@@ -1230,7 +1335,10 @@ static int group_issue(GroupRun &G, sharp_part *parts, int m, const sharp_rm_dev
         }
         if (e.m != rm.m) return set_error(SHARP_E_ARG, "run_parts: part %d has %d genes but ranM has %d rows", G.idx[j], e.m, rm.m);
         lap(t_up, tl);
-        SHARP_TRY(part_front(G.runs[j], s, e, nullptr, rm, P.reind, Q));
+        sharp_run_params Qp = Q;
+        Qp.shard = P.sharded ? 1 : 0;          /* the blocks of a sharded part are dealt over the ranks of the communicator */
+        Qp.shard_rotate = G.idx[j];
+        SHARP_TRY(part_front(G.runs[j], s, e, nullptr, rm, P.reind, Qp));
         lap(t_front, tl);
         SHARP_CUDA(cudaEventRecord(s->ev_ready, s->stream));
     }
@@ -1245,15 +1353,15 @@ static int group_issue(GroupRun &G, sharp_part *parts, int m, const sharp_rm_dev
         PartRun &R = G.runs[j];
         SHARP_CUDA(cudaStreamWaitEvent(s->stream, G.blocks->ev_blocks, 0));
         SHARP_TRY(part_back(R));
-        if ((size_t)R.n * 4 > s->h_labels_cap) {
+        if ((size_t)R.na * 4 > s->h_labels_cap) {
             if (s->h_labels) cudaFreeHost(s->h_labels);
             s->h_labels = nullptr;
             s->h_labels_cap = 0;
-            size_t want = ((size_t)R.n * 4 * 9 / 8 + 4095) & ~(size_t)4095;
+            size_t want = ((size_t)R.na * 4 * 9 / 8 + 4095) & ~(size_t)4095;
             SHARP_CUDA(cudaMallocHost((void **)&s->h_labels, want));
             s->h_labels_cap = want;
         }
-        SHARP_TRY(d2h(s, s->h_labels, R.labels_dev, (size_t)R.n * 4));
+        SHARP_TRY(d2h(s, s->h_labels, R.labels_dev, (size_t)R.na * 4));
         SHARP_CUDA(cudaEventRecord(s->ev_done, s->stream));
     }
     lap(t_back, tl);
@@ -1307,28 +1415,28 @@ static int group_complete(GroupRun &G, sharp_part *parts, int small_thre, int ce
         PartRun &R = G.runs[j];
         SHARP_CUDA(cudaEventSynchronize(s->ev_done));
         SHARP_TRY(part_status(R));
-        memcpy(P.pred, s->h_labels, (size_t)R.n * 4);
-        const int thre = (R.Q.n_cluster == 0 && R.n > 10000) ? small_thre : 0;
-        const int nclust = host_merge_relabel(P.pred, R.n, thre, coff, corder);
+        memcpy(P.pred, s->h_labels, (size_t)R.na * 4);
+        const int thre = (R.Q.n_cluster == 0 && R.na > 10000) ? small_thre : 0;
+        const int nclust = host_merge_relabel(P.pred, R.na, thre, coff, corder);
         G.nclust[j] = nclust;
         P.nclust = nclust;
         if (!P.cen) continue;
         if (nclust > cen_cap) return set_error(SHARP_E_NOMEM, "run_parts: part %d has %d clusters but cen has room for %d", G.idx[j], nclust, cen_cap);
         // centroids of viE per final cluster (colMeans of R/sMetaC.R:58-63 for the global sMetaC)
-        const size_t ib = bump_size({(size_t)R.n * 4, (size_t)(nclust + 1) * 4, 64, (size_t)nclust * 8});
+        const size_t ib = bump_size({(size_t)R.na * 4, (size_t)(nclust + 1) * 4, 64, (size_t)nclust * 8});
         SHARP_TRY(s->ws[WS_TMP0].reserve(ib));
         Bump b(s->ws[WS_TMP0].ptr, ib);
-        int *corder_d = b.take<int>(R.n), *coff_d = b.take<int>(nclust + 1), *nc_d = b.take<int>(1);
+        int *corder_d = b.take<int>(R.na), *coff_d = b.take<int>(nclust + 1), *nc_d = b.take<int>(1);
         int64_t *cnt_d = b.take<int64_t>(nclust);
         SHARP_TRY(s->ws[WS_CEN].reserve((size_t)nclust * R.p * 8));
-        SHARP_TRY(s->reserve_pinned((size_t)R.n * 4 + (size_t)(nclust + 2) * 4));
+        SHARP_TRY(s->reserve_pinned((size_t)R.na * 4 + (size_t)(nclust + 2) * 4));
         int *hp = reinterpret_cast<int *>(s->pinned);
-        memcpy(hp, corder.data(), (size_t)R.n * 4);
-        memcpy(hp + R.n, coff.data(), (size_t)(nclust + 1) * 4);
-        hp[R.n + nclust + 1] = nclust;
-        SHARP_TRY(h2d_staged(s, corder_d, hp, (size_t)R.n * 4));
-        SHARP_TRY(h2d_staged(s, coff_d, hp + R.n, (size_t)(nclust + 1) * 4));
-        SHARP_TRY(h2d_staged(s, nc_d, hp + R.n + nclust + 1, 4));
+        memcpy(hp, corder.data(), (size_t)R.na * 4);
+        memcpy(hp + R.na, coff.data(), (size_t)(nclust + 1) * 4);
+        hp[R.na + nclust + 1] = nclust;
+        SHARP_TRY(h2d_staged(s, corder_d, hp, (size_t)R.na * 4));
+        SHARP_TRY(h2d_staged(s, coff_d, hp + R.na, (size_t)(nclust + 1) * 4));
+        SHARP_TRY(h2d_staged(s, nc_d, hp + R.na + nclust + 1, 4));
         SHARP_TRY(launch_sm_centroids(s, R.vieu, R.p, corder_d, coff_d, nc_d, nclust, s->ws[WS_CEN].as<double>(), cnt_d));
         SHARP_TRY(s->reserve_pinned((size_t)nclust * R.p * 8 + (size_t)nclust * 8));
         G.h_cen[j] = reinterpret_cast<double *>(s->pinned);
@@ -1413,6 +1521,7 @@ void sharp_ctx_destroy(sharp_ctx *c) {
     if (!c) return;
     g_live_ctx--;
     cudaSetDevice(c->device);
+    if (c->comm) { cudaStreamSynchronize(c->stream); comm_destroy(c); }
     destroy_ctx_resources(c);
     delete c;
 }
@@ -1450,7 +1559,7 @@ int sharp_ctx_set_block_budget(sharp_ctx *c, int gigabytes) {
 
 static const char *const g_kernel_names[KID_COUNT] = {
     "rp_project", "colsum", "unit_rows", "corrdist", "hclust", "hclust_small", "sweep_nested", "sweep_exact",
-    "wm_weights", "wm_similarity", "wmetac_misc", "sm_centroids", "smetac_misc", "ene_scatter", "misc", "h2d_expr"};
+    "wm_weights", "wm_similarity", "wmetac_misc", "sm_centroids", "smetac_misc", "ene_scatter", "misc", "h2d_expr", "nccl_allgather"};
 
 int sharp_ctx_set_serial(sharp_ctx *c, int on) {
     if (!c) return set_error(SHARP_E_ARG, "null context");
@@ -1633,7 +1742,7 @@ int sharp_rm_upload(sharp_ctx *c, int m, int p, int K, const int32_t *colptr, co
         if (e3 != cudaSuccess) e1 = e3;
         if (e4 != cudaSuccess) e2 = e4;
     }
-    if (r->kpd > 0 && r->kpd <= 16383 && e16 && e1 == cudaSuccess && e2 == cudaSuccess) {
+    if (r->kpd > 0 && r->kpd <= 8191 && r->max_col_nnz <= 255 && e16 && e1 == cudaSuccess && e2 == cudaSuccess) {
         /* records of the record-gather kernel: the smallest record that fewer than 0.2 % of the genes overflow */
         int rv = 2;
         for (; rv <= 16; rv *= 2) {
@@ -1650,7 +1759,7 @@ int sharp_rm_upload(sharp_ctx *c, int m, int p, int K, const int32_t *colptr, co
                 for (uint32_t q = 0; q < cnt; q++) {
                     const uint32_t en = ent[rowptr[i] + q];
                     const int v = (int)(q % rv), slot = 1 + (int)(q / rv);
-                    R[v * 8 + slot] = (uint16_t)(((en & 0x7fffu) << 2) | ((en & 0x8000u) ? 1u : 0u));
+                    R[v * 8 + slot] = (uint16_t)(((en & 0x7fffu) << 2) + ((en & 0x8000u) ? (uint32_t)r->kpd * 4u : 0u)); /* offset into [+ | -] */
                     R[v * 8]++;
                 }
             }
@@ -1989,7 +2098,31 @@ int sharp_run(sharp_ctx *c, int m, int64_t n, const double *dense, const int64_t
     SHARP_TRY(use(c));
     if (!rm || !prm || !labels) return set_error(SHARP_E_ARG, "run: null argument");
     sharp_expr_dev e;
-    int rc = upload_expr(c, m, n, dense, colptr, rowidx, val, &e, true);
+    int rc;
+    const bool shuffled = prm->large && reind && n < 100000;
+    if (prm->large && prm->shard && c->comm && c->comm_world > 1 && !shuffled && n >= 2) {
+        /* a sharded run on un-shuffled host data: this rank's blocks are a contiguous range of columns -- upload only those */
+        std::vector<int64_t> start;
+        make_blocks(n, 1, prm->partition_ncells, start);
+        const int T = (int)start.size() - 1;
+        if (T < c->comm_world) return set_error(SHARP_E_ARG, "sharded run: %d blocks cannot be dealt over %d ranks", T, c->comm_world);
+        int t0, t1;
+        shard_range(T, c->comm_rank, c->comm_world, prm->shard_rotate, &t0, &t1);
+        const int64_t c0 = start[t0], nc = start[t1] - start[t0];
+        if (dense) rc = upload_expr(c, m, nc, dense + (size_t)c0 * m, nullptr, nullptr, nullptr, &e, true);
+        else {
+            if (!colptr) return set_error(SHARP_E_ARG, "expression matrix: neither dense nor complete CSC slots given");
+            rc = c->reserve_pinned((size_t)(nc + 1) * 8);
+            if (!rc) {
+                int64_t *cp = reinterpret_cast<int64_t *>(c->pinned);
+                const int64_t base = colptr[c0];
+                for (int64_t i = 0; i <= nc; i++) cp[i] = colptr[c0 + i] - base;
+                rc = upload_expr(c, m, nc, nullptr, cp, rowidx + base, val + base, &e, true);
+            }
+        }
+        e.col0 = c0;
+        e.n_total = n;
+    } else rc = upload_expr(c, m, n, dense, colptr, rowidx, val, &e, true);
     if (!rc) rc = sharp_run_dev(c, &e, colsum, rm, reind, prm, labels, vie, x0, x0_cols, max_x0_cols);
     cudaStreamSynchronize(c->stream);
     free_expr(&e);
@@ -2050,6 +2183,7 @@ int sharp_run_parts(sharp_ctx *c, int m, int nparts, sharp_part *parts, const sh
         if (c->serial) s->pf_part = -1;
         s->prof_on = c->prof_on;
         s->rp_variant = c->rp_variant;
+        s->comm = c->comm; s->comm_rank = c->comm_rank; s->comm_world = c->comm_world;
         s->block_budget_gb = std::max(1, c->block_budget_gb / lanes);
     }
     // serial mode (profiling): all sub-contexts enqueue on the context's own stream, so no two kernels overlap and

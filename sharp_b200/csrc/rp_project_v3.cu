@@ -10,11 +10,13 @@
 //   * RECORDS.  Every gene owns one fixed-size, 16*RV-byte aligned record of RV 16-byte vectors (no pointer array, no
 //     dependent lookup: the address follows from the gene index).  A vector is {count, 7 entries}; the gene's entries are
 //     dealt round-robin over its vectors, so the RV lanes that fetch one record -- ONE coalesced request per gene, all
-//     lanes of a gene in the same line -- each get an equal share of the adds.  An entry is the byte offset of its
-//     output inside an accumulator array (col * 4) with the sign in bit 0: address = array base + (entry & ~3).
+//     lanes of a gene in the same line -- each get an equal share of the adds.  An entry is a byte offset into the PAIR
+//     of count arrays [+ counts | - counts]: col * 4 for a +entry, col * 4 + (bytes of one array) for a -entry, so the
+//     sign costs no instruction on the count path: address = base + entry, addend = 1 << (8 * class).
 //     Records are sized so that < 0.2 % of the genes overflow; those are served from the gene-major CSR lists.
-//   * SIGNED 16-bit count fields (two classes per word): a -entry adds -(1 << shift), decoding is sign extension; one
-//     code path for every matrix with columns of fewer than 32768 entries (the r1 kernel had an 8-bit and a 16-bit variant).
+//   * COUNT WORDS: one word per output and sign, four 8-bit fields (classes 1..4); a field counts the entries of one
+//     ranM column with that sign that met that class in this cell, so it cannot overflow while the longest column has
+//     <= 255 entries (m up to ~65 000 genes; longer columns take the r1 kernel's 16-bit path).
 //   * PER-CELL RECORD.  colSums(x), the value range, the fixed-point scale and the four class values are produced by
 //     one streaming pre-pass (cellprep_kernel, which replaces colsum_kernel on this path), so the scatter kernel makes a
 //     single pass over a cell's non-zeros and needs two barriers per cell instead of nine.
@@ -104,34 +106,43 @@ __device__ __forceinline__ void rpv_entries(const uint4 &w, uint32_t e[7]) {
     e[5] = w.w & 0xffffu; e[6] = w.w >> 16;
 }
 
-// count-class lanes: one non-returning atomic per entry (+-(1 << shift) on the class's counter word)
-__device__ __forceinline__ void rpv_scatter_class(const uint4 &w, uint32_t n, uint32_t nmax, uint32_t base, uint32_t addp) {
+// predicated shared-memory atomics (no branch around the instruction: the slots of a vector are straight-line code)
+__device__ __forceinline__ void reds_add_lt(uint32_t addr, uint32_t v, uint32_t s, uint32_t n) { /* if (s < n) */
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.lt.u32 p, %2, %3;\n\t@p red.shared.add.u32 [%0], %1;\n\t}" ::"r"(addr), "r"(v), "r"(s), "r"(n) : "memory");
+}
+__device__ __forceinline__ uint32_t atoms_add_lt(uint32_t addr, uint32_t v, uint32_t s, uint32_t n) { /* if (s < n); else returns 0 */
+    uint32_t old = 0;
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.lt.u32 p, %3, %4;\n\t@p atom.shared.add.u32 %0, [%1], %2;\n\t}" : "+r"(old) : "r"(addr), "r"(v), "r"(s), "r"(n) : "memory");
+    return old;
+}
+
+// count-class lanes: one non-returning atomic per entry; the entry IS the byte offset into [+ counts | - counts]
+__device__ __forceinline__ void rpv_scatter_class(const uint4 &w, uint32_t n, uint32_t base, uint32_t addc) {
     uint32_t e[7];
     rpv_entries(w, e);
-    const uint32_t addn = 0u - addp;
 #pragma unroll
-    for (int s = 0; s < 7; s++) {
-        if ((uint32_t)s >= nmax) break; /* warp-uniform */
-        if ((uint32_t)s < n) reds_add(base + (e[s] & 0xfffcu), (e[s] & 1u) ? addn : addp);
-    }
+    for (int s = 0; s < 7; s++) reds_add_lt(base + e[s], addc, (uint32_t)s, n);
 }
 
 // generic lanes: 64-bit add as two 32-bit limbs (the returning atomic on the low limb yields the carry)
-__device__ __forceinline__ void rpv_scatter_generic(const uint4 &w, uint32_t n, uint32_t nmax, uint32_t lo_base, uint32_t arr,
+__device__ __forceinline__ void rpv_scatter_generic(const uint4 &w, uint32_t n, uint32_t lo_base, uint32_t arr,
                                                     uint32_t apos, uint32_t hpos, uint32_t aneg, uint32_t hneg) {
     uint32_t e[7];
     rpv_entries(w, e);
+    uint32_t addr[7], old[7], negm = 0u;
+#pragma unroll
+    for (int s = 0; s < 7; s++) { /* all low-limb atomics are issued before the first carry is consumed */
+        const bool neg = e[s] >= arr;
+        negm |= neg ? (1u << s) : 0u;
+        addr[s] = lo_base + (neg ? e[s] - arr : e[s]);
+        old[s] = atoms_add_lt(addr[s], neg ? aneg : apos, (uint32_t)s, n);
+    }
 #pragma unroll
     for (int s = 0; s < 7; s++) {
-        if ((uint32_t)s >= nmax) break; /* warp-uniform */
-        if ((uint32_t)s < n) {
-            const uint32_t addr = lo_base + (e[s] & 0xfffcu);
-            const bool neg = e[s] & 1u;
-            const uint32_t av = neg ? aneg : apos;
-            const uint32_t old = atoms_add(addr, av);
-            const uint32_t hv = (neg ? hneg : hpos) + (((uint32_t)(old + av) < av) ? 1u : 0u);
-            if (hv) reds_add(addr + arr, hv);
-        }
+        const bool neg = (negm >> s) & 1u;
+        const uint32_t av = neg ? aneg : apos;
+        const uint32_t hv = (neg ? hneg : hpos) + (((uint32_t)(old[s] + av) < av) ? 1u : 0u);
+        reds_add_lt(addr[s] + arr, hv, (uint32_t)s, hv ? n : 0u);
     }
 }
 
@@ -145,7 +156,7 @@ __device__ __forceinline__ void rpv_overflow(const RpV3Args &A, uint32_t g, int 
         const unsigned ent = __ldg(A.a.ent16 + q);
         const uint32_t addr = base + ((ent & 0x7fffu) << 2);
         const bool neg = ent & 0x8000u;
-        if (!generic) reds_add(addr, neg ? (0u - apos) : apos);
+        if (!generic) reds_add(addr + (neg ? arr : 0u), apos); /* base = the + count array, apos = 1 << (8 * class) */
         else {
             const uint32_t av = neg ? aneg : apos;
             const uint32_t old = atoms_add(addr, av);
@@ -177,15 +188,12 @@ __device__ __forceinline__ void rpv_class_chunk(const RpV3Args &A, uint32_t s_ba
             uint32_t n = w[b].x & 0xffffu;
             const bool ovf = n == 0xffffu;
             if (ovf) n = 0;
-            const uint32_t c = (pk[b] >> 28) & 3u;
-            const uint32_t base = s_base + (c >> 1) * arr;
-            const uint32_t addp = 1u << ((c & 1u) * 16);
-            const uint32_t nmax = __reduce_max_sync(0xffffffffu, n);
-            rpv_scatter_class(w[b], n, nmax, base, addp);
+            const uint32_t addc = 1u << ((pk[b] >> 25) & 24u); /* 1 << (8 * class): the class sits in bits 28..29 */
+            rpv_scatter_class(w[b], n, s_base, addc);
             if (__any_sync(0xffffffffu, ovf)) {
                 /* vector 0 of the record carries the marker: tell the gene's other lanes */
                 const bool govf = __shfl_sync(0xffffffffu, ovf ? 1 : 0, lane & ~(RV - 1)) != 0;
-                if (govf && pk[b]) rpv_overflow<RV>(A, pk[b] & 0x0fffffffu, v, false, base, arr, addp, 0u, 0u, 0u);
+                if (govf && pk[b]) rpv_overflow<RV>(A, pk[b] & 0x0fffffffu, v, false, s_base, arr, addc, 0u, 0u, 0u);
             }
         }
     }
@@ -211,8 +219,7 @@ __device__ __forceinline__ void rpv_generic_chunk(const RpV3Args &A, uint32_t s_
         uint32_t n = w.x & 0xffffu;
         const bool ovf = n == 0xffffu;
         if (ovf) n = 0;
-        const uint32_t nmax = __reduce_max_sync(0xffffffffu, n);
-        rpv_scatter_generic(w, n, nmax, lo_base, arr, apos, hpos, aneg, hneg);
+        rpv_scatter_generic(w, n, lo_base, arr, apos, hpos, aneg, hneg);
         if (__any_sync(0xffffffffu, ovf)) {
             const bool govf = __shfl_sync(0xffffffffu, ovf ? 1 : 0, lane & ~(RV - 1)) != 0;
             if (govf && pk) rpv_overflow<RV>(A, pk & 0x0fffffffu, v, true, lo_base, arr, apos, hpos, aneg, hneg);
@@ -248,7 +255,7 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t
 constexpr int RPV_LIST = 64;       // per-warp list of generic non-zeros waiting for an all-generic pass
 constexpr int RPV_STAGE_NNZ = 2048; // staged variant: non-zeros of a cell held per buffer (the rest is read from global)
 
-// dynamic shared memory: [4][kpd] words (class counters 1|2, class counters 3|4, low limbs, high limbs); per-warp generic
+// dynamic shared memory: [4][kpd] words (+ counts, - counts, low limbs, high limbs); per-warp generic
 // lists (position in the column); staged variant: 2 buffers of {rowidx[STAGE + 8], val[STAGE + 4]}
 template <int RV, int NT, int MINB, bool TMA>
 __global__ void __launch_bounds__(NT, MINB) rp_project_v3_kernel(RpV3Args A) {
@@ -376,14 +383,12 @@ __global__ void __launch_bounds__(NT, MINB) rp_project_v3_kernel(RpV3Args A) {
                 long long tot = (long long)(((unsigned long long)hi[i] << 32) | (unsigned long long)lo[i]);
                 lo[i] = 0u;
                 hi[i] = 0u;
+                const uint32_t wp = cw[i], wn = cw[kpd + i];   /* + counts, - counts: four 8-bit class fields each */
+                cw[i] = 0u;
+                cw[kpd + i] = 0u;
 #pragma unroll
-                for (int a = 0; a < 2; a++) {
-                    const uint32_t w = cw[a * kpd + i];
-                    cw[a * kpd + i] = 0u;
-                    const int d0 = (int)(short)(w & 0xffffu);          /* signed 16-bit fields: decode by sign extension */
-                    const int d1 = ((int)(w - (uint32_t)d0)) >> 16;
-                    tot += qc[2 * a] * (long long)d0 + qc[2 * a + 1] * (long long)d1;
-                }
+                for (int c = 0; c < 4; c++)
+                    tot += qc[c] * (long long)((int)((wp >> (8 * c)) & 255u) - (int)((wn >> (8 * c)) & 255u));
                 double r = __dmul_rn(__dmul_rn((double)tot, unscale), A.a.scale);
                 if (A.a.round_digits >= 0) r = rp_round(r, A.a.round_digits);
                 if (bad) r = __longlong_as_double(0x7ff8000000000000LL);
@@ -423,7 +428,7 @@ static int launch_v3_rv(sharp_ctx *c, const RpV3Args &A, int64_t ncell, bool sta
 
 // CSC input only.  Returns 1 when this variant does not apply (the caller falls back to rp_project_fx_kernel).
 int launch_rp_project_v3(sharp_ctx *c, const RpArgs &Ain, const sharp_rm_dev &rm, bool staged, double *colsum_out, void *info_ws) {
-    if (!rm.rec || Ain.dense || !rm.ent16 || rm.max_col_nnz > 32767) return 1;
+    if (!rm.rec || Ain.dense || !rm.ent16 || rm.max_col_nnz > 255) return 1;
     RpV3Args A;
     A.a = Ain;
     A.a.normalize = Ain.normalize ? 1 : 0; /* the scatter kernel divides by the record's cs */

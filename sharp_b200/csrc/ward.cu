@@ -630,30 +630,22 @@ __global__ void __launch_bounds__(RNN_THREADS, 2) hclust_rnn_kernel(HcProb *prob
 }
 
 // =====================================================================================================
-// K3, round-parallel variant on TRIANGULAR storage (n <= 2048): half the bytes of hclust_rnn_kernel
+// K3, round-parallel variant on TRIANGULAR storage: half the bytes and half the arithmetic of hclust_rnn_kernel
 // =====================================================================================================
 // Same rounds as hclust_rnn_kernel (all reciprocal-nearest-neighbour pairs of a reducible linkage merge at once, the
 // reference's merge order is recovered by sorting the merges by height, any tie hands the problem to the exact
 // kernel), but the dissimilarities are symmetric and this kernel reads and writes each of them ONCE per round:
 //   * the working matrices hold the strict upper triangle only, row i = columns tri_c0(i) .. nrp-1 (rows start on
 //     16-byte boundaries); round 1 reads the upper triangle of the pristine full matrix P.D;
-//   * the n x n value v(i', j'), i' < j', is computed once and serves both clusters: it is a candidate for the
-//     nearest neighbour of ROW i' (reduced over the columns by the warps, combined per band of rows) and of COLUMN j'.
-//     Columns are OWNED: lane l of warp w handles the same old columns j = 32 (NW s + w) + l in every row, so the
-//     running column minimum lives in that lane's registers, as do the column's kind / new index / size -- no
-//     shared-memory lookups per element and no atomics;
-//   * this round's pairs are owned the same way (pair q belongs to one lane for the whole round), and a merged row
-//     (a, b) reads row a contiguously, row b contiguously right of b and as a column gather between a and b;
-//   * rows are taken in bands of 16, eight from the top and eight from the bottom of the triangle, so every band is
-//     the same amount of work for every warp.
-// Traffic per problem (simulation of the benchmark's blocks): ~3.6 n^2 x 8 B streamed + ~1 n^2 x 8 B of gathers,
-// against 11.7 n^2 x 8 B measured for the full-matrix kernel.
-constexpr int TRI_THREADS = 512;
-constexpr int TRI_NW = TRI_THREADS / 32;
-constexpr int TRI_MAXN = 2048;
-constexpr int TRI_CH = TRI_MAXN / (32 * TRI_NW);        // chunk slots per lane (4)
-constexpr int TRI_PS = TRI_MAXN / 2 / (32 * TRI_NW);    // pair slots per lane (2)
-constexpr int TRI_BAND = 16;
+//   * one warp per row of the next partition's matrix, as before, but only the columns RIGHT of the row: the value
+//     v(i', j'), i' < j', is computed once.  It is a candidate for the nearest neighbour of row i' -- reduced by the warp,
+//     "upper" minimum and its index, like hclust.f's NN list -- and of COLUMN j': column minima are kept as 64-bit
+//     order-preserving keys in shared memory, lowered with atomicMin behind a plain-read filter (a few updates per column);
+//   * the reciprocal pairs follow from the two: (k, x), k < x, merges iff x is the upper nearest neighbour of k, that
+//     distance beats k's column minimum, EQUALS x's column minimum and beats x's upper minimum.  Equal candidates
+//     anywhere (a key that meets its own value) raise the tie flag: the problem is redone by the exact kernel;
+//   * a merged row (a, b) reads row a contiguously, row b contiguously right of b and as a column gather between a and b;
+//   * rows are dealt to the warps in (top, bottom) pairs of the triangle: the same amount of work for every warp.
 
 __device__ __forceinline__ int tri_c0(int i) { return (i + 1) & ~1; }
 __device__ __forceinline__ size_t tri_rowoff(int i, int nrp) {
@@ -675,17 +667,29 @@ struct TriSrc {
     }
 };
 
-__host__ __device__ inline size_t hclust_tri_part_offset(int n) { /* bytes of the round state, 16-byte aligned */
-    size_t rounds = (size_t)n * (16 + 8 + 4) + (size_t)n * 2 * 9 + ((size_t)n / 2 + 1) * 2 + (size_t)n + 16;
-    return (rounds + 15) & ~(size_t)15;
+__device__ __forceinline__ unsigned long long tri_key(double v) { /* unsigned order == numeric order; -0.0 == +0.0 */
+    unsigned long long b = (unsigned long long)__double_as_longlong(v + 0.0);
+    return b ^ ((b >> 63) ? ~0ull : 0x8000000000000000ull);
+}
+__device__ __forceinline__ double tri_unkey(unsigned long long k) {
+    k ^= (k >> 63) ? 0x8000000000000000ull : ~0ull;
+    return __longlong_as_double((long long)k);
+}
+constexpr unsigned long long TRI_KEY_INF = 0xfff0000000000000ull; /* tri_key(+inf) */
+
+// candidate v for the nearest neighbour of column jp (shared-memory key array); *tie is raised when v meets an equal value
+__device__ __forceinline__ void tri_col_consider(unsigned long long *colkey, int jp, double v, int *tie) {
+    if (!(v == v)) { *tie = 1; return; } /* NaN: the exact kernel reports it like the reference */
+    const unsigned long long k = tri_key(v);
+    const unsigned long long cur = *reinterpret_cast<volatile unsigned long long *>(colkey + jp);
+    if (k < cur) {
+        if (atomicMin(colkey + jp, k) == k) *tie = 1;
+    } else if (k == cur) *tie = 1;
 }
 
-struct TriCol { /* running minimum of one owned column */
-    double d;
-    int i;
-};
-
-__global__ void __launch_bounds__(TRI_THREADS, 1) hclust_tri_kernel(HcProb *probs, int method) {
+template <int TRI_THREADS, int TRI_MINB>
+__global__ void __launch_bounds__(TRI_THREADS, TRI_MINB) hclust_tri_kernel(HcProb *probs, int method) {
+    constexpr int TRI_NW = TRI_THREADS / 32;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ int s_tie, s_nm;
     __shared__ int tmp_scan[TRI_THREADS];
@@ -696,22 +700,20 @@ __global__ void __launch_bounds__(TRI_THREADS, 1) hclust_tri_kernel(HcProb *prob
     if (n < 2) return;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
-    double *dnn0 = reinterpret_cast<double *>(smem_raw);   // [2][n] distance to the nearest neighbour
+    // [2][n] doubles: half `cur` holds the upper minimum of every row of the current partition, the other half the
+    // column minima (as keys); both are dead once the round's setup is done and swap roles for the next partition
+    double *dnn0 = reinterpret_cast<double *>(smem_raw);
     double *hrow = dnn0 + 2 * (size_t)n;                    // [n] height of the merge that built new cluster i'
     int *rank = reinterpret_cast<int *>(hrow + n);          // [n] scan scratch
-    u16 *nn0 = reinterpret_cast<u16 *>(rank + n);           // [2][n] nearest neighbour
+    u16 *nn0 = reinterpret_cast<u16 *>(rank + n);           // [2][n] half `cur`: upper nearest neighbour; other half: partner scratch
     u16 *size0 = nn0 + 2 * (size_t)n;                       // [2][n] cluster sizes
     u16 *orig0 = size0 + 2 * (size_t)n;                     // [2][n] representative (smallest original index)
     u16 *sA = orig0 + 2 * (size_t)n;                        // [n] first source cluster of new cluster i'
     u16 *sB = sA + n;                                       // [n] second source (RNN_NONE: not merged this round)
     u16 *cmap = sB + n;                                     // [n] old cluster -> index of its cluster in the next partition
-    u16 *pl = cmap + n;                                     // [n/2 + 1] kept members of this round's pairs
+    u16 *partner = cmap + n;                                // [n] this round's partner of every current cluster, or RNN_NONE
+    u16 *pl = partner + n;                                  // [n/2 + 1] kept members of this round's pairs
     unsigned char *kind = reinterpret_cast<unsigned char *>(pl + (n / 2 + 1));  // [n] 0 not merging, 1 kept member, 2 retired member
-    // per-band partial row minima of the warps, behind the arrays above AND behind the sort scratch of the epilogue
-    typedef double PartD[TRI_NW][TRI_BAND];
-    typedef int PartI[TRI_NW][TRI_BAND];
-    PartD *part_d = reinterpret_cast<PartD *>(smem_raw + hclust_tri_part_offset(n));                 // [2]
-    PartI *part_i = reinterpret_cast<PartI *>(reinterpret_cast<unsigned char *>(part_d) + 2 * sizeof(PartD));  // [2]
 
     int cur = 0;
     for (int i = tid; i < n; i += THREADS) {
@@ -731,10 +733,11 @@ __global__ void __launch_bounds__(TRI_THREADS, 1) hclust_tri_kernel(HcProb *prob
     int base = 0;
     while (nr > 1) {
         const bool first = (round == 0);
-        const u16 *nn = nn0 + (size_t)cur * n, *size = size0 + (size_t)cur * n, *orig = orig0 + (size_t)cur * n;
-        const double *dnn = dnn0 + (size_t)cur * n;
-        u16 *nn2 = nn0 + (size_t)(cur ^ 1) * n, *size2 = size0 + (size_t)(cur ^ 1) * n, *orig2 = orig0 + (size_t)(cur ^ 1) * n;
-        double *dnn2 = dnn0 + (size_t)(cur ^ 1) * n;
+        const u16 *size = size0 + (size_t)cur * n, *orig = orig0 + (size_t)cur * n;
+        const u16 *nnu = nn0 + (size_t)cur * n;                             /* upper nearest neighbour of the current rows */
+        const double *dup = dnn0 + (size_t)cur * n;                         /* upper minimum of the current rows */
+        const unsigned long long *ckey = reinterpret_cast<const unsigned long long *>(dnn0 + (size_t)(cur ^ 1) * n);
+        u16 *size2 = size0 + (size_t)(cur ^ 1) * n, *orig2 = orig0 + (size_t)(cur ^ 1) * n;
         int nnew = nr, m = 0;
         if (first) {
             for (int i = tid; i < nr; i += THREADS) {
@@ -744,10 +747,23 @@ __global__ void __launch_bounds__(TRI_THREADS, 1) hclust_tri_kernel(HcProb *prob
             __syncthreads();
         } else {
             if (s_tie) { failed = true; break; }
-            // ---- survivors: every cluster except the larger-indexed member of a reciprocal pair ----
+            // ---- this round's pairs (k, x), k < x: x = nnu[k], d = dup[k] < column minimum of k, == column minimum of x,
+            //      < upper minimum of x.  Equalities that would make the choice ambiguous have raised s_tie already. ----
+            for (int i = tid; i < nr; i += THREADS) partner[i] = RNN_NONE;
+            __syncthreads();
+            for (int k = tid; k < nr; k += THREADS) {
+                const double d = dup[k];
+                if (!(d < SHARP_INF)) continue;
+                const int x = nnu[k];
+                const unsigned long long kd = tri_key(d);
+                if (kd == ckey[k]) s_tie = 1; /* the nearest neighbour of k is not unique (one above, one below) */
+                if (kd < ckey[k] && kd == ckey[x] && d < dup[x]) { partner[k] = (u16)x; partner[x] = (u16)k; }
+            }
+            __syncthreads();
+            if (s_tie) { failed = true; break; }
             for (int i = tid; i < nr; i += THREADS) {
-                const int j = nn[i];
-                rank[i] = (nn[j] == i && j < i) ? 0 : 1;
+                const int j = partner[i];
+                rank[i] = (j != RNN_NONE && j < i) ? 0 : 1;
             }
             __syncthreads();
             nnew = block_exclusive_scan<THREADS>(rank, nr, tmp_scan);
@@ -755,13 +771,13 @@ __global__ void __launch_bounds__(TRI_THREADS, 1) hclust_tri_kernel(HcProb *prob
             if (m == 0) { failed = true; break; }
             base = s_nm;
             for (int i = tid; i < nr; i += THREADS) {
-                const int j = nn[i];
-                const bool paired = nn[j] == i;
+                const int j = partner[i];
+                const bool paired = j != RNN_NONE;
                 if (paired && j < i) { /* retired: i - rank[i] = number of retired clusters before i, a dense numbering */
                     const int q = base + (i - rank[i]);
                     P.ia[q] = (int)orig[j] + 1;
                     P.ib[q] = (int)orig[i] + 1;
-                    P.crit[q] = dnn[i];
+                    P.crit[q] = dup[j];
                     cmap[i] = (u16)rank[j];
                     kind[i] = 2;
                     pl[i - rank[i]] = (u16)j;
@@ -774,7 +790,7 @@ __global__ void __launch_bounds__(TRI_THREADS, 1) hclust_tri_kernel(HcProb *prob
                 orig2[ip] = orig[i];
                 if (paired) {
                     sB[ip] = (u16)j;
-                    hrow[ip] = dnn[i];
+                    hrow[ip] = dup[i];
                     size2[ip] = (u16)(size[i] + size[j]);
                 } else {
                     sB[ip] = RNN_NONE;
@@ -791,174 +807,130 @@ __global__ void __launch_bounds__(TRI_THREADS, 1) hclust_tri_kernel(HcProb *prob
             }
         }
         double *B = nullptr;
-        int nrpB = (nnew + 1) & ~1;
+        const int nrpB = (nnew + 1) & ~1;
         if (!first) {
             B = (round & 1) ? P.Dw : P.E;
             const size_t capB = (round & 1) ? (size_t)n * P.ld : (size_t)P.ecap;
             work += (double)nr * nr;
             if (tri_elems(nnew) > capB || !B || (work > 16.0 * n * n && nr > 256)) { failed = true; break; }
         }
-        // ---- this lane's columns and pairs for the whole round (registers) ----
-        int cj[TRI_CH];            /* old column index, -1: none / not a plain column */
-        int ccm[TRI_CH];           /* its index in the next partition */
-        double csz[TRI_CH];
-        TriCol cbest[TRI_CH];
-        unsigned ctie = 0u;        /* bit s: the minimum of chunk slot s is attained twice; bit 8 + t: pair slot t */
-#pragma unroll
-        for (int s = 0; s < TRI_CH; s++) {
-            const int j = 32 * (NW * s + warp) + lane;
-            cj[s] = (j < nr && kind[j] == 0) ? j : -1;
-            ccm[s] = (j < nr) ? (int)cmap[j] : 0;
-            csz[s] = (j < nr) ? (double)size[j] : 1.0;
-            cbest[s].d = SHARP_INF; cbest[s].i = INT_MAX;
-        }
-        int pc[TRI_PS], pd[TRI_PS], pjp[TRI_PS];   /* pair (c, d), c < d, and its new index; pc = -1: none */
-        double pmc[TRI_PS], pmd[TRI_PS], phj[TRI_PS];
-        TriCol pbest[TRI_PS];
-#pragma unroll
-        for (int t = 0; t < TRI_PS; t++) {
-            const int q = warp + NW * (lane + 32 * t);
-            pc[t] = -1; pd[t] = 0; pjp[t] = 0; pmc[t] = pmd[t] = 1.0; phj[t] = 0.0;
-            if (q < m) {
-                const int c = pl[q], d = nn[c];
-                pc[t] = c; pd[t] = d; pjp[t] = cmap[c];
-                pmc[t] = (double)size[c]; pmd[t] = (double)size[d]; phj[t] = hrow[pjp[t]];
-            }
-            pbest[t].d = SHARP_INF; pbest[t].i = INT_MAX;
-        }
-        // ---- rows in bands of 16 (8 from the top, 8 from the bottom of the triangle) ----
-        const int nbands = (nnew + TRI_BAND - 1) / TRI_BAND;
-        for (int band = 0; band < nbands; band++) {
-            const int pb = band & 1;
-            for (int r = 0; r < TRI_BAND; r++) {
-                const int rr = band * TRI_BAND + r;
-                if (rr >= nnew) break;
-                const int ip = (rr & 1) ? nnew - 1 - (rr >> 1) : (rr >> 1);
+        // the halves of dnn0 / nn0 swap roles: upper minima of the NEXT partition go where this round's column keys were
+        // (consumed by the setup above), the next column keys where this round's upper minima were
+        double *dup2 = dnn0 + (size_t)(cur ^ 1) * n;
+        u16 *nnu2 = nn0 + (size_t)(cur ^ 1) * n;
+        unsigned long long *ckey2 = reinterpret_cast<unsigned long long *>(dnn0 + (size_t)cur * n);
+        for (int i = tid; i < nnew; i += THREADS) ckey2[i] = TRI_KEY_INF;
+        __syncthreads();
+        // ---- one warp per row of the next partition's matrix, columns right of the row only; rows in (top, bottom) pairs ----
+        const int half = (nnew + 1) / 2;
+        for (int rr = warp; rr < half; rr += NW) {
+#pragma unroll 1
+            for (int side = 0; side < 2; side++) {
+                const int ip = side ? nnew - 1 - rr : rr;
+                if (side && ip == rr) break;
                 const int a = sA[ip];
                 const u16 b16 = sB[ip];
                 const bool im = b16 != RNN_NONE;
-                const int b = im ? (int)b16 : a;
-                const double ma = (double)size[a], mb = (double)size[b], hi = hrow[ip];
                 const double *rowa = A.row(a);
-                const double *rowb = A.row(b);
                 double *out = B ? B + tri_rowoff(ip, nrpB) - tri_c0(ip) : nullptr;
+                const double ma = (double)size[a];
                 RnnBest best;
                 best.d = SHARP_INF; best.i = INT_MAX; best.tie = false;
-                // plain columns right of a
-                double x[TRI_CH], y[TRI_CH];
+                int tie_seen = 0;
+                const int jstart = (a + 1) & ~31; /* aligned start: full sectors */
+                if (!im) {
+                    for (int jb = jstart; jb < nr; jb += 32 * RNN_UC) {
+                        double x[RNN_UC];
 #pragma unroll
-                for (int s = 0; s < TRI_CH; s++) {
-                    const int j = cj[s];
-                    x[s] = 0.0; y[s] = 0.0;
-                    if (j > a) {
-                        x[s] = rowa[j];
-                        if (im) y[s] = (j > b) ? rowb[j] : A.row(j)[b];
-                    }
-                }
-#pragma unroll
-                for (int s = 0; s < TRI_CH; s++) {
-                    const int j = cj[s];
-                    if (j > a) {
-                        double v = sq ? __dmul_rn(x[s], x[s]) : x[s];
-                        if (im) { /* new cluster (a, b) against c = j: I2 = a, J2 = b, K = c */
-                            const double y1 = sq ? __dmul_rn(y[s], y[s]) : y[s];
-                            v = lance_williams(method, v, y1, hi, ma, mb, csz[s]);
+                        for (int u = 0; u < RNN_UC; u++) {
+                            const int j = jb + u * 32 + lane;
+                            x[u] = (j > a && j < nr) ? rowa[j] : 0.0;
                         }
-                        const int jp = ccm[s];
+#pragma unroll
+                        for (int u = 0; u < RNN_UC; u++) {
+                            const int j = jb + u * 32 + lane;
+                            if (j <= a || j >= nr || kind[j] != 0) continue;
+                            const int jp = cmap[j];
+                            const double v = sq ? __dmul_rn(x[u], x[u]) : x[u];
+                            if (out) out[jp] = v;
+                            rnn_consider(best, v, jp);
+                            tri_col_consider(ckey2, jp, v, &tie_seen);
+                        }
+                    }
+                    for (int q = lane; q < m; q += 32) { /* this row's cluster a against the new cluster (c, d): I2 = c, J2 = d, K = a */
+                        const int c = pl[q];
+                        if (c <= a) continue;
+                        const int d = partner[c], jp = cmap[c];
+                        double xc = rowa[c], xd = rowa[d];
+                        if (sq) { xc = __dmul_rn(xc, xc); xd = __dmul_rn(xd, xd); }
+                        const double v = lance_williams(method, xc, xd, hrow[jp], (double)size[c], (double)size[d], ma);
                         if (out) out[jp] = v;
                         rnn_consider(best, v, jp);
-                        if (v < cbest[s].d) { cbest[s].d = v; cbest[s].i = ip; ctie &= ~(1u << s); }
-                        else if (v == cbest[s].d) ctie |= 1u << s;
+                        tri_col_consider(ckey2, jp, v, &tie_seen);
                     }
-                }
-                // this round's pairs right of a: the new cluster (c, d)
+                } else {
+                    const int b = (int)b16;
+                    const double *rowb = A.row(b);
+                    const double mb = (double)size[b], hi = hrow[ip];
+                    for (int jb = jstart; jb < nr; jb += 32 * RNN_UM) {
+                        double x[RNN_UM], y[RNN_UM];
 #pragma unroll
-                for (int t = 0; t < TRI_PS; t++) {
-                    const int c = pc[t];
-                    if (c > a) {
-                        const int d = pd[t], jp = pjp[t];
+                        for (int u = 0; u < RNN_UM; u++) {
+                            const int j = jb + u * 32 + lane;
+                            const bool ok = j > a && j < nr && j != b;
+                            x[u] = ok ? rowa[j] : 0.0;
+                            y[u] = ok ? ((j > b) ? rowb[j] : A.row(j)[b]) : 0.0; /* between a and b: column b of row j */
+                        }
+#pragma unroll
+                        for (int u = 0; u < RNN_UM; u++) {
+                            const int j = jb + u * 32 + lane;
+                            if (j <= a || j >= nr || kind[j] != 0) continue;
+                            const int jp = cmap[j];
+                            double x1 = x[u], y1 = y[u];
+                            if (sq) { x1 = __dmul_rn(x1, x1); y1 = __dmul_rn(y1, y1); }
+                            /* new cluster (a, b) against c = j: I2 = a, J2 = b, K = c */
+                            const double v = lance_williams(method, x1, y1, hi, ma, mb, (double)size[j]);
+                            if (out) out[jp] = v;
+                            rnn_consider(best, v, jp);
+                            tri_col_consider(ckey2, jp, v, &tie_seen);
+                        }
+                    }
+                    for (int q = lane; q < m; q += 32) { /* both are new: the two updates in the order of their heights, like the reference */
+                        const int c = pl[q];
+                        if (c <= a) continue;
+                        const int d = partner[c], jp = cmap[c];
                         double x1 = rowa[c], x2 = rowa[d];
-                        if (sq) { x1 = __dmul_rn(x1, x1); x2 = __dmul_rn(x2, x2); }
-                        double v;
-                        if (!im) { /* this row's cluster a against (c, d): I2 = c, J2 = d, K = a */
-                            v = lance_williams(method, x1, x2, phj[t], pmc[t], pmd[t], ma);
-                        } else {   /* both are new: the two updates in the order of their heights, like the reference */
-                            double y1 = (c > b) ? rowb[c] : A.row(c)[b];
-                            double y2 = (d > b) ? rowb[d] : A.row(d)[b];
-                            if (sq) { y1 = __dmul_rn(y1, y1); y2 = __dmul_rn(y2, y2); }
-                            const double hj = phj[t], mc = pmc[t], md = pmd[t];
-                            if (hi == hj) s_tie = 1;
-                            const bool fst = hi < hj; /* this row's pair merges first */
-                            const double h1 = fst ? hi : hj, h2 = fst ? hj : hi;
-                            const double p1 = fst ? ma : mc, p2 = fst ? mb : md; /* sizes of the pair merging first */
-                            const double r1 = fst ? mc : ma, r2 = fst ? md : mb; /* sizes of the other pair's members */
-                            const double t1 = lance_williams(method, x1, fst ? y1 : x2, h1, p1, p2, r1);
-                            const double t2 = lance_williams(method, fst ? x2 : y1, y2, h1, p1, p2, r2);
-                            v = lance_williams(method, t1, t2, h2, r1, r2, p1 + p2);
+                        double y1 = (c > b) ? rowb[c] : A.row(c)[b];
+                        double y2 = (d > b) ? rowb[d] : A.row(d)[b];
+                        if (sq) {
+                            x1 = __dmul_rn(x1, x1); y1 = __dmul_rn(y1, y1);
+                            x2 = __dmul_rn(x2, x2); y2 = __dmul_rn(y2, y2);
                         }
+                        const double hj = hrow[jp], mc = (double)size[c], md = (double)size[d];
+                        if (hi == hj) tie_seen = 1;
+                        const bool fst = hi < hj; /* this row's pair merges first */
+                        const double h1 = fst ? hi : hj, h2 = fst ? hj : hi;
+                        const double p1 = fst ? ma : mc, p2 = fst ? mb : md; /* sizes of the pair merging first */
+                        const double r1 = fst ? mc : ma, r2 = fst ? md : mb; /* sizes of the other pair's members */
+                        /* first merge: (I2, J2) of the earlier pair against each member of the later pair */
+                        const double t1 = lance_williams(method, x1, fst ? y1 : x2, h1, p1, p2, r1);
+                        const double t2 = lance_williams(method, fst ? x2 : y1, y2, h1, p1, p2, r2);
+                        /* second merge: the later pair (I2 = its kept member, J2 = retired) against the merged earlier pair */
+                        const double v = lance_williams(method, t1, t2, h2, r1, r2, p1 + p2);
                         if (out) out[jp] = v;
                         rnn_consider(best, v, jp);
-                        if (v < pbest[t].d) { pbest[t].d = v; pbest[t].i = ip; ctie &= ~(256u << t); }
-                        else if (v == pbest[t].d) ctie |= 256u << t;
+                        tri_col_consider(ckey2, jp, v, &tie_seen);
                     }
                 }
                 bool tie;
                 const DI w = rnn_finish(best, &tie);
+                if (w.i == INT_MAX) tie = false; /* the last row has no column to its right: no upper neighbour, not a tie */
+                if (__any_sync(0xffffffffu, tie_seen != 0)) tie = true;
                 if (lane == 0) {
-                    part_d[pb][warp][r] = w.d;
-                    part_i[pb][warp][r] = (tie && w.i != INT_MAX) ? -1 - w.i : w.i; /* negative: attained twice inside this warp's share */
+                    nnu2[ip] = (u16)(w.i == INT_MAX ? 0 : w.i);
+                    dup2[ip] = w.d;
+                    if (tie) s_tie = 1;
                 }
-            }
-            __syncthreads();
-            if (tid < TRI_BAND) { /* row part of the nearest neighbour of every row of the band */
-                const int rr = band * TRI_BAND + tid;
-                if (rr < nnew) {
-                    const int ip = (rr & 1) ? nnew - 1 - (rr >> 1) : (rr >> 1);
-                    double bd = SHARP_INF;
-                    int bi = INT_MAX;
-                    bool tie = false;
-                    for (int w2 = 0; w2 < NW; w2++) {
-                        const double d = part_d[pb][w2][tid];
-                        int i = part_i[pb][w2][tid];
-                        if (i == INT_MAX) continue;
-                        bool t2 = false;
-                        if (i < 0) { i = -1 - i; t2 = true; }
-                        if (d < bd) { bd = d; bi = i; tie = t2; }
-                        else if (d == bd) tie = true;
-                    }
-                    dnn2[ip] = bd;
-                    nn2[ip] = (u16)(bi == INT_MAX ? 0 : bi);
-                    rank[ip] = (bi == INT_MAX) ? 2 : (tie ? 1 : 0); /* scratch: 2 no candidate in the row part, 1 tie */
-                }
-            }
-            /* part_[pb] is rewritten two bands later, behind the next band's barrier */
-        }
-        __syncthreads();
-        // ---- column part: the owner of every column folds its running minimum into the row part ----
-#pragma unroll
-        for (int s = 0; s < TRI_CH; s++) {
-            if (cj[s] >= 0) {
-                const int jp = ccm[s];
-                const int st = rank[jp];
-                bool tie = (ctie >> s) & 1u;
-                if (cbest[s].i == INT_MAX) { if (st == 2) s_tie = 1; else if (st == 1) s_tie = 1; continue; }
-                if (st == 2 || cbest[s].d < dnn2[jp]) { dnn2[jp] = cbest[s].d; nn2[jp] = (u16)cbest[s].i; }
-                else if (cbest[s].d == dnn2[jp]) tie = true;
-                else tie = (st == 1);
-                if (tie) s_tie = 1;
-            }
-        }
-#pragma unroll
-        for (int t = 0; t < TRI_PS; t++) {
-            if (pc[t] >= 0) {
-                const int jp = pjp[t];
-                const int st = rank[jp];
-                bool tie = (ctie >> (8 + t)) & 1u;
-                if (pbest[t].i == INT_MAX) { if (st != 0) s_tie = 1; continue; }
-                if (st == 2 || pbest[t].d < dnn2[jp]) { dnn2[jp] = pbest[t].d; nn2[jp] = (u16)pbest[t].i; }
-                else if (pbest[t].d == dnn2[jp]) tie = true;
-                else tie = (st == 1);
-                if (tie) s_tie = 1;
             }
         }
         if (tid == 0 && !first) s_nm = base + m;
@@ -1017,14 +989,17 @@ static size_t hclust_rnn_smem_bytes(int n) {
 }
 
 static size_t hclust_tri_smem_bytes(int n) {
-    const size_t rounds = hclust_tri_part_offset(n) + 2 * (size_t)TRI_NW * TRI_BAND * 12;
-    return std::max(rounds, hclust_rnn_smem_bytes(n));
+    size_t rounds = (size_t)n * (16 + 8 + 4) + (size_t)n * 2 * 10 + ((size_t)n / 2 + 1) * 2 + (size_t)n + 16;
+    size_t p2 = 1;
+    while ((int)p2 < n - 1) p2 <<= 1;
+    size_t sort = p2 * 12 + (size_t)n * 8;
+    return (std::max(rounds, sort) + 31) & ~(size_t)15;
 }
 
 bool hclust_fast_ok(int max_n, int method) {
     static const bool no_rnn = getenv("SHARP_HCLUST_EXACT") != nullptr; /* development switch */
     const bool reducible = method != SHARP_MEDIAN && method != SHARP_CENTROID;
-    return reducible && !no_rnn && max_n > 384 && max_n < 65535 && hclust_rnn_smem_bytes(max_n) <= (size_t)SHARP_SMEM_OPTIN - 4096;
+    return reducible && !no_rnn && max_n > 384 && max_n < 65535 && hclust_tri_smem_bytes(max_n) <= (size_t)SHARP_SMEM_OPTIN - 4096;
 }
 
 static size_t hclust_smem_bytes(int n) {
@@ -1056,9 +1031,15 @@ int launch_hclust(sharp_ctx *c, HcProb *probs_dev, int nprob, int max_n, int met
     if (fast && hclust_fast_ok(max_n, method)) {
         static const bool no_tri = getenv("SHARP_HCLUST_FULL") != nullptr; /* development switch: the full-matrix kernel */
         prof_begin(c, KID_HCLUST);
-        if (max_n <= TRI_MAXN && !no_tri) {
-            SHARP_SMEM_OPTIN_ONCE((hclust_tri_kernel), c->device);
-            hclust_tri_kernel<<<nprob, TRI_THREADS, hclust_tri_smem_bytes(max_n), c->stream>>>(probs_dev, method);
+        if (!no_tri) {
+            static const int tri_threads = getenv("SHARP_TRI_THREADS") ? atoi(getenv("SHARP_TRI_THREADS")) : 512; /* development switch */
+            if (tri_threads == 1024) {
+                SHARP_SMEM_OPTIN_ONCE((hclust_tri_kernel<1024, 1>), c->device);
+                hclust_tri_kernel<1024, 1><<<nprob, 1024, hclust_tri_smem_bytes(max_n), c->stream>>>(probs_dev, method);
+            } else {
+                SHARP_SMEM_OPTIN_ONCE((hclust_tri_kernel<512, 2>), c->device);
+                hclust_tri_kernel<512, 2><<<nprob, 512, hclust_tri_smem_bytes(max_n), c->stream>>>(probs_dev, method);
+            }
         } else {
             SHARP_SMEM_OPTIN_ONCE((hclust_rnn_kernel), c->device);
             hclust_rnn_kernel<<<nprob, RNN_THREADS, hclust_rnn_smem_bytes(max_n), c->stream>>>(probs_dev, method);

@@ -13,7 +13,8 @@ for p in (HERE, os.path.dirname(HERE)):
 def main(rank, world, port, outdir):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
                       LOCAL_RANK=str(rank))
-    from sharp_b200 import api, dist
+    from sharp_b200 import api
+    import torchcomm as dist
     comm = dist.init_from_env("gloo")
     assert comm.rank == rank and comm.world == world
     # collectives

@@ -1,4 +1,4 @@
-"""The N > 1 path on CPU: world_size 2, gloo backend (127.0.0.1 rendezvous).  Collectives of sharp_b200/dist.py and
+"""The N > 1 path on CPU: world_size 2, gloo backend (127.0.0.1 rendezvous).  Collectives of tests/torchcomm.py (the gloo stand-in of sharp_b200.comm.NcclComm) and
 the sharded SHARP_unlimited driver (compute answered by the oracle through tests/fakectx.py): both ranks must return
 the result of the single-process run."""
 import os

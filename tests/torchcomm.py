@@ -1,10 +1,8 @@
-"""One-process-per-GPU plumbing for the sharded drivers (SHARP_unlimited over parts).
-
-The path shards naturally: parts (and the cell blocks inside them) are independent until the global sMetaC,
-which needs only the part-level cluster centroids (nC x p fp64, a few MB) and the per-part label vectors
-(int32, ncells in total) from every rank -- one allgather each (NCCL over NVLink on the GPU box, gloo in the
-CPU tests).  torch.distributed is used for the rendezvous and the collectives only.
-"""
+"""TEST INFRASTRUCTURE: a torch.distributed (gloo) stand-in for sharp_b200.comm.NcclComm, so that the N > 1 HOST logic of the
+sharded drivers (which parts / blocks a rank owns, what is exchanged, that every rank returns the full result) runs on a
+machine without GPUs: world_size 2, backend "gloo".  Same interface as NcclComm (rank, world, barrier, bcast_obj,
+allgather_parts, max_float).  The product package does not import torch: its communicator is NCCL behind the C ABI
+(sharp_comm_*, sharp_b200/comm.py)."""
 from __future__ import annotations
 
 import os
