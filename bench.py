@@ -60,9 +60,16 @@ def workload(name: str) -> dict:
         return dict(name="SHARP_unlimited, synthetic UMI 27998 genes x 1306127 cells (10x brain shape), 26 CSC parts "
                          "(25 x 50000 + 56127), exp.type=UMI, K=5, p=508, rN.seed=2103, viewflag=FALSE",
                     m=27998, parts=[50000] * 25 + [56127], K=5, types=20, nnz_per_cell=2000, exp_type="UMI")
-    if name == "cfg3":
-        return dict(name="SHARP_unlimited-style, synthetic UMI 20000 genes x 100000 cells, 2 CSC parts, K=15",
-                    m=20000, parts=[50000] * 2, K=15, types=10, nnz_per_cell=1400, exp_type="UMI")
+    if name == "cfg2":  # BASELINE.json configs[1]: the default ensemble of SHARP() on one GPU (SHARP_large: 10 000 >= base.ncells)
+        return dict(name="SHARP(), synthetic TPM 20000 genes x 10000 cells, dense fp64 (70 % zeros), default ensemble "
+                         "(SHARP_large, K=5, p=333, 5 blocks of 2000), rN.seed=2103",
+                    single=True, m=20000, parts=[10000], K=5, types=8, nnz_per_cell=6000, exp_type="TPM", dense=True,
+                    metric="cells/sec end-to-end SHARP at 10k cells (config 2)")
+    if name == "cfg3":  # BASELINE.json configs[2]: 15-member ensemble, cell blocks dealt over the GPUs
+        return dict(name="SHARP(exp.type=UMI, ensize.K=15), synthetic UMI 20000 genes x 100000 cells (CSC, ~93 % zeros), "
+                         "p=416, 50 blocks of 2000 dealt over the ranks, rN.seed=2103",
+                    single=True, m=20000, parts=[100000], K=15, types=10, nnz_per_cell=1400, exp_type="UMI", dense=False,
+                    metric="cells/sec end-to-end SHARP at 100k cells, K=15 (config 3)")
     if name == "dev":  # development / CPU-side dry runs
         return dict(name="dev: 3000 genes x 3 parts of 2600 cells", m=3000, parts=[2600] * 3, K=3, types=5,
                     nnz_per_cell=300, exp_type="UMI")
@@ -277,6 +284,9 @@ def cpu_baseline_run(wl, part, p, sample_cells, rms, reind):
     import orc
     n, csc = sample_of(part, sample_cells)
     colsum = np.add.reduceat(csc[2], csc[0][:-1]) if wl["exp_type"] == "UMI" else None
+    if wl.get("dense"):  # config 2 is TPM: the synthetic counts scaled to 1e6 per cell (the same numbers the dense matrix holds)
+        cs = np.add.reduceat(csc[2], csc[0][:-1])
+        csc = (csc[0], csc[1], csc[2] / np.repeat(cs, np.diff(csc[0])) * 1e6)
     prm = orc.SharpParams(1, 1, wl["K"], p, 2000, 0, 0, 0, orc.hc_params(max_n=max(40, -(-n // 5000))), 2, -1)
     t0 = time.time()
     ref = orc.sharp(wl["m"], n, rms, prm, csc=csc, colsum=colsum, reind=reind, want_vie=True, want_x0=False)
@@ -368,7 +378,183 @@ def run_reference(args):
                       "e2e": {"value": val, "unit": "cells/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 
 
+def run_single(args, wl):
+    """configs 2 and 3: ONE expression matrix through SHARP() (-> SHARP_large).  N > 1: every rank makes the same call with
+    the communicator and the cell blocks are dealt over the ranks (sharp_run_params.shard)."""
+    import hashlib
+    import torch
+    import synth
+    from sharp_b200 import api
+    from sharp_b200 import comm as sharp_comm
+    from sharp_b200.rrng import r_sample_perm, ranM2
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    api.set_devices(local)
+    ctx = api.get_context(local)
+    comm = sharp_comm.init_from_env(ctx)
+    rank, world = (comm.rank, comm.world) if comm else (0, 1)
+    m, n, K = wl["m"], wl["parts"][0], wl["K"]
+    p = math.ceil(math.log2(n) / 0.04)
+    t0 = time.time()
+    lam = type_profiles(torch, dev, m, wl["types"], wl["nnz_per_cell"])
+    part = gen_part(torch, dev, lam, n, 0, True)            # every rank generates the same matrix (seeded)
+    del lam
+    truth = part["types"]
+    if wl["dense"]:  # TPM-like: columns scaled to 1e6, dense column-major fp64 in pinned host memory
+        cp, ri, xv = part["p"], part["i"], part["x"]
+        hd = torch.zeros((n, m), dtype=torch.float64, pin_memory=True)  # row c = column c of the genes x cells matrix
+        x = hd.numpy()
+        cols = np.repeat(np.arange(n), np.diff(cp))
+        x[cols, ri] = xv
+        x /= x.sum(1, keepdims=True) / 1e6
+        host = x.T                                           # (m, n) Fortran-ordered view of the pinned buffer
+        in_bytes = x.nbytes
+        dev_expr = ctx.upload_expr(m, n, dense=host)
+    else:
+        host = (part["p"], part["i"], part["x"], (m, n))
+        in_bytes = part["p"].nbytes + part["i"].nbytes + part["x"].nbytes
+        dev_expr = ctx.upload_expr(m, n, csc=host[:3])
+    torch.cuda.empty_cache()
+    t_gen = time.time() - t0
+    kw = dict(exp_type=wl["exp_type"], rN_seed=SEED, logflag=False, ctx=ctx, comm=comm, forview=world == 1)
+    if K != 5:
+        kw["ensize_K"] = K
+
+    def barrier():
+        ctx.sync()
+        torch.cuda.synchronize()
+        if comm:
+            comm.barrier()
+
+    def timed(data, steps, profile):
+        barrier()
+        if profile:
+            ctx.prof_reset()
+            ctx.prof_enable(True)
+        l0 = ctx.launch_count()
+        ctx.timer_start()
+        res = None
+        for _ in range(steps):
+            res = api.SHARP(data, **kw)
+        ms = ctx.timer_stop_ms()
+        barrier()
+        if profile:
+            ctx.prof_enable(False)
+        return (comm.max_float(ms) if comm else ms), res, ctx.launch_count() - l0
+
+    for _ in range(args.warmup):
+        api.SHARP(dev_expr, **kw)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ms, res, launches = timed(dev_expr, args.steps, True)
+    clocks = sampler.stop() if rank == 0 else None
+    prof = ctx.prof_get()
+    dev_expr.close()
+    h2d_gbs = h2d_bandwidth(torch, dev)
+    api.SHARP(host, **kw)
+    ms_e2e, res_e2e, _ = timed(host, args.steps, False)
+    same = bool(np.array_equal(res["pred_clusters"], res_e2e["pred_clusters"]))
+    label_hash = hashlib.sha1(np.ascontiguousarray(res["pred_clusters"], dtype=np.int32).tobytes()).hexdigest()[:16]
+    if comm and len(set(comm.allgather_bytes(label_hash.encode()))) != 1:
+        raise SystemExit("the ranks returned different label vectors")
+    # ---- parity + CPU baseline (N = 1): the oracle on the whole matrix (config 2) or its first 8000 cells (config 3) ----
+    cpu = parity = None
+    if world == 1 and not args.no_cpu_baseline:
+        import orc
+        ns = n if wl["dense"] else min(n, 8000)
+        rms = [ranM2(m, p if ns == n else math.ceil(math.log2(ns) / 0.04), 50 + SEED + k) for k in range(1, K + 1)]
+        ps = rms[0]["Dim"][1]
+        reind = np.asarray(r_sample_perm(ns, 50))
+        oprm = orc.SharpParams(1, 1, K, ps, 2000, 0, 0, 0, orc.hc_params(max_n=max(40, -(-ns // 5000))), 2, -1)
+        if wl["dense"]:
+            sub, okw, colsum = host, dict(dense=np.asfortranarray(host)), None
+        else:
+            _, csc = sample_of(part, ns)
+            sub, okw = csc + ((m, ns),), dict(csc=csc)
+            colsum = np.add.reduceat(csc[2], csc[0][:-1])
+        t1 = time.time()
+        ref = orc.sharp(m, ns, rms, oprm, colsum=colsum, reind=reind, want_x0=False, **okw)
+        dt = time.time() - t1
+        got = res if ns == n else api.SHARP(sub, exp_type=wl["exp_type"], rN_seed=SEED, logflag=False, ctx=ctx, ensize_K=K)
+        rel = float(np.max(np.abs(got["viE"] - ref["viE"])) / np.max(np.abs(ref["viE"])))
+        parity = {"cells": int(ns), "m": m, "p": int(ps), "K": K, "ari": synth.ari(got["pred_clusters"], ref["pred_clusters"]),
+                  "equal": bool(np.array_equal(got["pred_clusters"], ref["pred_clusters"])), "proj_max_rel": rel,
+                  "what": "SHARP() (C ABI) vs the oracle on " + ("the whole matrix" if ns == n else f"the first {ns} cells as their own SHARP_large job")}
+        cpu = {"value": ns / dt, "unit": "cells/s", "cores": orc.num_threads(), "kind": "port", "seconds": dt,
+               "sample": ("the whole configuration" if ns == n else f"first {ns} cells (4 blocks x K={K})") + " through the oracle port (OpenMP over (member, block) tasks)"}
+        if not parity["equal"] or not rel <= 1e-5:
+            print(json.dumps({"parity": parity}), file=sys.stderr)
+            raise SystemExit("PARITY FAILURE: the GPU path and the oracle disagree on the benchmark's own data")
+    if comm:
+        comm.barrier()
+    if rank != 0:
+        if comm:
+            comm.close()
+        return
+    pk = peaks()
+    ldu = (p + 15) // 16 * 16
+    nloc = n / world
+    blocks = block_sizes(n)
+    bl = [b for i, b in enumerate(blocks) if world == 1 or True]
+    share = 1.0 / world
+    in_cell = (m * 8) if wl["dense"] else (in_bytes / n)
+    work = {"rp_project": ("hbm", nloc * (in_cell + K * p * 8)),
+            "corrdist": ("tensor", sum(1.0 * b * (b + 1) * ldu for b in bl) * K * share),
+            "hclust": ("hbm", sum(b * b * 8 + (b - 1) * b * 8 * 3 for b in bl) * K * share),
+            "sweep_nested": ("hbm", sum(b * b * 8 + b * ldu * 8 for b in bl) * K * share),
+            "unit_rows": ("hbm", nloc * K * (p + ldu) * 8)}
+    kernels, dgemm = {}, None
+    total_ms = sum(v[0] for v in prof.values())
+    for name, (kms, kn) in sorted(prof.items(), key=lambda kv: -kv[1][0]):
+        ent = {"ms_per_step": kms / args.steps, "launches_per_step": kn / args.steps, "share_of_kernel_time": kms / total_ms}
+        if name in work:
+            bound, amount = work[name]
+            per_s = amount * args.steps / (kms * 1e-3)
+            if bound == "hbm":
+                ent.update(bound="hbm", achieved=per_s / 1e9, peak=pk["hbm_gbs"], unit="GB/s", frac=per_s / 1e9 / pk["hbm_gbs"])
+            else:
+                dgemm = dgemm or dgemm_peak_tflops(torch, dev)
+                ent.update(bound="tensor", achieved=per_s / 1e12, peak=dgemm, unit="TFLOP/s", frac=per_s / 1e12 / dgemm,
+                           peak_source="cuBLAS DGEMM 4096^3 measured in this run (fp64 DMMA pipe)")
+        kernels[name] = ent
+    dom = next((k for k in kernels if "bound" in kernels[k]), None)
+    TR = load_traffic()
+    roofline = None
+    if dom:
+        e = kernels[dom]
+        roofline = {"kernel": dom, "bound": e["bound"], "achieved": e["achieved"], "peak": e["peak"], "unit": e["unit"], "frac": e["frac"],
+                    "traffic": None, "peak_source": e.get("peak_source", pk["source"]),
+                    "ms_per_launch": e["ms_per_step"] / max(e["launches_per_step"], 1e-9),
+                    "timing": "CUDA events around every launch during the timed steps (one stream: no two kernels overlap)",
+                    "traffic_note": "the committed ncu capture is of the config-4 launches (profiles/traffic.json: " + str(TR.get("source")) + ")"}
+        rp = kernels.get("rp_project")
+        if rp and "frac" in rp:
+            roofline["rp_project"] = {k: rp[k] for k in ("bound", "achieved", "peak", "unit", "frac")}
+    line = {"metric": wl["metric"], "value": n * args.steps / (ms * 1e-3), "unit": "cells/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": wl["name"], "cells": n, "genes": m, "K": K, "p": p, "input_bytes": int(in_bytes),
+                       "partition": "one GPU" if world == 1 else f"{len(blocks)} cell blocks dealt over {world} ranks (contiguous ranges); NCCL allgather of block-level labels and enE rows; every rank returns the full labels",
+                       "l2": "flushed between steps by the run itself: every step streams %.1f GB of distance matrices" % (sum(b * b * 8 for b in blocks) * K / 1e9),
+                       "generation_s": t_gen},
+            "clocks": clocks, "gpu_launches": int(launches / args.steps),
+            "e2e": {"value": n * args.steps / (ms_e2e * 1e-3), "unit": "cells/s", "h2d_bytes_per_step": int(in_bytes),
+                    "d2h_bytes_per_step": int(n * 4 + (n * p * 8 + n * 41 * 8 if world == 1 else n * 4)), "ms_per_step": ms_e2e / args.steps,
+                    "labels_equal_device_resident_run": same, "h2d_gbs_measured": h2d_gbs},
+            "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu, "parity": parity,
+            "result": {"N.pred_cluster": int(res["N.pred_cluster"]), "label_sha1_16": label_hash,
+                       "ari_vs_planted_types": synth.ari(res["pred_clusters"], truth), "planted_types": wl["types"],
+                       "ranks_agree": True if comm else None}}
+    print(json.dumps(line))
+    if comm:
+        comm.close()
+
+
 def run_ours(args):
+    if workload(args.workload).get("single"):
+        return run_single(args, workload(args.workload))
     import torch
     import sharp_b200
     from sharp_b200 import api

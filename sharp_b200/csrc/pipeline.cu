@@ -11,6 +11,8 @@
 #include <cstring>
 #include <numeric>
 
+#include <nvtx3/nvToolsExt.h>
+
 #include "internal.cuh"
 #include "metac.cuh"
 
@@ -163,6 +165,13 @@ void prof_collect(sharp_ctx *c) {
     c->prof_pending.clear();
     cudaGetLastError();
 }
+
+// NVTX ranges around the host-side stages of a run (front / blocks / back / complete, per part and group): they cost
+// nothing without a profiler attached and give nsys / ncu timelines the structure of the pipeline
+struct NvtxRange {
+    explicit NvtxRange(const char *name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+};
 
 // workspace slots
 enum Slot {
@@ -1175,13 +1184,14 @@ static int run_core(sharp_ctx *c, const sharp_expr_dev &e, const double *colsum_
                     int *x0_cols, int max_x0_cols) {
     Trace tr(c);
     PartRun R;
-    SHARP_TRY(part_front(R, c, e, colsum_host, rm, reind, Q));
+    { NvtxRange r("sharp front (colSums, projection, unit rows)"); SHARP_TRY(part_front(R, c, e, colsum_host, rm, reind, Q)); }
     tr.mark("front", true);
     PartRun *one = &R;
-    SHARP_TRY(run_blocks(c, &one, 1));
+    { NvtxRange r("sharp blocks (distances, agglomeration, sweep)"); SHARP_TRY(run_blocks(c, &one, 1)); }
     tr.mark("blocks", true);
-    SHARP_TRY(part_back(R));
+    { NvtxRange r("sharp back (wMetaC, sMetaC, relabel)"); SHARP_TRY(part_back(R)); }
     tr.mark("back", true);
+    NvtxRange rf("sharp finish (outputs)");
     SHARP_TRY(part_finish(R, labels_out, vie_out, x0_out, x0_cols, max_x0_cols));
     tr.mark("finish");
     return 0;
@@ -1338,6 +1348,7 @@ static int group_issue(GroupRun &G, sharp_part *parts, int m, const sharp_rm_dev
         sharp_run_params Qp = Q;
         Qp.shard = P.sharded ? 1 : 0;          /* the blocks of a sharded part are dealt over the ranks of the communicator */
         Qp.shard_rotate = G.idx[j];
+        NvtxRange rfront("sharp_run_parts: front of a part");
         SHARP_TRY(part_front(G.runs[j], s, e, nullptr, rm, P.reind, Qp));
         lap(t_front, tl);
         SHARP_CUDA(cudaEventRecord(s->ev_ready, s->stream));
@@ -1345,13 +1356,14 @@ static int group_issue(GroupRun &G, sharp_part *parts, int m, const sharp_rm_dev
     for (int j = 0; j < np; j++) SHARP_CUDA(cudaStreamWaitEvent(G.blocks->stream, G.subs[j]->ev_ready, 0));
     std::vector<PartRun *> ptrs(np);
     for (int j = 0; j < np; j++) ptrs[j] = &G.runs[j];
-    SHARP_TRY(run_blocks(G.blocks, ptrs.data(), np));
+    { NvtxRange rb("sharp_run_parts: blocks of a group"); SHARP_TRY(run_blocks(G.blocks, ptrs.data(), np)); }
     SHARP_CUDA(cudaEventRecord(G.blocks->ev_blocks, G.blocks->stream));
     lap(t_blocks, tl);
     for (int j = 0; j < np; j++) {
         sharp_ctx *s = G.subs[j];
         PartRun &R = G.runs[j];
         SHARP_CUDA(cudaStreamWaitEvent(s->stream, G.blocks->ev_blocks, 0));
+        NvtxRange rback("sharp_run_parts: back of a part");
         SHARP_TRY(part_back(R));
         if ((size_t)R.na * 4 > s->h_labels_cap) {
             if (s->h_labels) cudaFreeHost(s->h_labels);
@@ -1404,6 +1416,7 @@ static int group_prefetch(const std::vector<int> &idx, const std::vector<sharp_c
 }
 
 static int group_complete(GroupRun &G, sharp_part *parts, int small_thre, int cen_cap) {
+    NvtxRange rc("sharp_run_parts: complete a group (merge, relabel, centroids)");
     const int np = (int)G.idx.size();
     G.nclust.assign(np, 0);
     G.h_cen.assign(np, nullptr);

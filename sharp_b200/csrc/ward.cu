@@ -667,27 +667,59 @@ struct TriSrc {
     }
 };
 
-__device__ __forceinline__ unsigned long long tri_key(double v) { /* unsigned order == numeric order; -0.0 == +0.0 */
-    unsigned long long b = (unsigned long long)__double_as_longlong(v + 0.0);
-    return b ^ ((b >> 63) ? ~0ull : 0x8000000000000000ull);
-}
-__device__ __forceinline__ double tri_unkey(unsigned long long k) {
-    k ^= (k >> 63) ? 0x8000000000000000ull : ~0ull;
-    return __longlong_as_double((long long)k);
-}
-constexpr unsigned long long TRI_KEY_INF = 0xfff0000000000000ull; /* tri_key(+inf) */
+// Running minimum of a row (registers of one lane) and the per-element update, written without branches around the
+// common path: the r2 profile of the first version showed ~130 warp instructions per element slot, most of them
+// divergence bookkeeping (BSSY / BRA / BSYNC around `continue`s and nested ifs).
+struct TriRow {
+    double d;
+    int i;
+    int tie;   /* the running minimum has been met twice */
+};
 
-// candidate v for the nearest neighbour of column jp (shared-memory key array); *tie is raised when v meets an equal value
-__device__ __forceinline__ void tri_col_consider(unsigned long long *colkey, int jp, double v, int *tie) {
-    if (!(v == v)) { *tie = 1; return; } /* NaN: the exact kernel reports it like the reference */
-    const unsigned long long k = tri_key(v);
-    const unsigned long long cur = *reinterpret_cast<volatile unsigned long long *>(colkey + jp);
-    if (k < cur) {
-        if (atomicMin(colkey + jp, k) == k) *tie = 1;
-    } else if (k == cur) *tie = 1;
+// Column minima live in shared memory as plain doubles and are lowered with a 64-bit integer atomicMin on their bit
+// patterns -- the order of the patterns is the numeric order for non-negative values.  A negative value or a NaN
+// (impossible for Ward / single / complete / average / mcquitty on proper dissimilarities) raises the flag, and the
+// problem is redone by the exact kernel like any tie.
+__device__ __forceinline__ void tri_elem(bool valid, double v, int jp, double *out, TriRow &r, double *colmin, int &flag) {
+    if (out && valid) out[jp] = v;
+    const bool lt = valid && v < r.d;
+    const bool eq = valid && v == r.d;
+    r.tie = lt ? 0 : (r.tie | (int)eq);
+    r.i = lt ? jp : r.i;
+    r.d = lt ? v : r.d;
+    const double cur = *reinterpret_cast<volatile double *>(colmin + (valid ? jp : 0));
+    flag |= (int)(valid && (!(v >= 0.0) || v == cur));
+    if (valid && v < cur) {
+        const unsigned long long k = (unsigned long long)__double_as_longlong(v + 0.0);
+        if (atomicMin(reinterpret_cast<unsigned long long *>(colmin + jp), k) == k) flag |= 1;
+    }
 }
 
-template <int TRI_THREADS, int TRI_MINB>
+__device__ __forceinline__ DI tri_row_finish(const TriRow &b, bool *tie) { /* warp-wide (value, index) minimum, all lanes */
+    DI mine;
+    mine.d = b.d;
+    mine.i = b.i;
+    const DI w = warp_argmin_redux(mine);
+    const bool dup = b.i != INT_MAX && b.d == w.d && (b.i != w.i || b.tie);
+    *tie = __any_sync(0xffffffffu, dup);
+    return w;
+}
+
+// Lance-Williams update with the method fixed at compile time for Ward (METHOD = SHARP_WARD_D; 0 = run-time switch)
+template <int METHOD>
+__device__ __forceinline__ double tri_lw(int method, double d1, double d2, double d12, double mi, double mj, double mk) {
+    if (METHOD == SHARP_WARD_D) {
+        const double t1 = __dmul_rn(mi + mk, d1);
+        const double t2 = __dmul_rn(mj + mk, d2);
+        const double t3 = __dmul_rn(mk, d12);
+        return __ddiv_rn(__dsub_rn(__dadd_rn(t1, t2), t3), mi + mj + mk);
+    }
+    return lance_williams(method, d1, d2, d12, mi, mj, mk);
+}
+
+constexpr u16 TRI_MERGING = 0x8000u; /* flag in the column map: the old cluster merges this round (handled by the pair pass) */
+
+template <int TRI_THREADS, int TRI_MINB, int METHOD>
 __global__ void __launch_bounds__(TRI_THREADS, TRI_MINB) hclust_tri_kernel(HcProb *probs, int method) {
     constexpr int TRI_NW = TRI_THREADS / 32;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -701,19 +733,18 @@ __global__ void __launch_bounds__(TRI_THREADS, TRI_MINB) hclust_tri_kernel(HcPro
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
     // [2][n] doubles: half `cur` holds the upper minimum of every row of the current partition, the other half the
-    // column minima (as keys); both are dead once the round's setup is done and swap roles for the next partition
+    // column minima; both are dead once the round's setup is done and swap roles for the next partition
     double *dnn0 = reinterpret_cast<double *>(smem_raw);
     double *hrow = dnn0 + 2 * (size_t)n;                    // [n] height of the merge that built new cluster i'
     int *rank = reinterpret_cast<int *>(hrow + n);          // [n] scan scratch
-    u16 *nn0 = reinterpret_cast<u16 *>(rank + n);           // [2][n] half `cur`: upper nearest neighbour; other half: partner scratch
+    u16 *nn0 = reinterpret_cast<u16 *>(rank + n);           // [2][n] upper nearest neighbour (current / next partition)
     u16 *size0 = nn0 + 2 * (size_t)n;                       // [2][n] cluster sizes
     u16 *orig0 = size0 + 2 * (size_t)n;                     // [2][n] representative (smallest original index)
     u16 *sA = orig0 + 2 * (size_t)n;                        // [n] first source cluster of new cluster i'
     u16 *sB = sA + n;                                       // [n] second source (RNN_NONE: not merged this round)
-    u16 *cmap = sB + n;                                     // [n] old cluster -> index of its cluster in the next partition
+    u16 *cmap = sB + n;                                     // [n] old cluster -> index in the next partition | TRI_MERGING
     u16 *partner = cmap + n;                                // [n] this round's partner of every current cluster, or RNN_NONE
     u16 *pl = partner + n;                                  // [n/2 + 1] kept members of this round's pairs
-    unsigned char *kind = reinterpret_cast<unsigned char *>(pl + (n / 2 + 1));  // [n] 0 not merging, 1 kept member, 2 retired member
 
     int cur = 0;
     for (int i = tid; i < n; i += THREADS) {
@@ -736,28 +767,27 @@ __global__ void __launch_bounds__(TRI_THREADS, TRI_MINB) hclust_tri_kernel(HcPro
         const u16 *size = size0 + (size_t)cur * n, *orig = orig0 + (size_t)cur * n;
         const u16 *nnu = nn0 + (size_t)cur * n;                             /* upper nearest neighbour of the current rows */
         const double *dup = dnn0 + (size_t)cur * n;                         /* upper minimum of the current rows */
-        const unsigned long long *ckey = reinterpret_cast<const unsigned long long *>(dnn0 + (size_t)(cur ^ 1) * n);
+        const double *cmin = dnn0 + (size_t)(cur ^ 1) * n;                  /* column minimum of the current clusters */
         u16 *size2 = size0 + (size_t)(cur ^ 1) * n, *orig2 = orig0 + (size_t)(cur ^ 1) * n;
         int nnew = nr, m = 0;
         if (first) {
             for (int i = tid; i < nr; i += THREADS) {
-                cmap[i] = (u16)i; kind[i] = 0; sA[i] = (u16)i; sB[i] = RNN_NONE; hrow[i] = 0.0;
+                cmap[i] = (u16)i; sA[i] = (u16)i; sB[i] = RNN_NONE; hrow[i] = 0.0;
                 size2[i] = 1; orig2[i] = (u16)i;
             }
             __syncthreads();
         } else {
             if (s_tie) { failed = true; break; }
             // ---- this round's pairs (k, x), k < x: x = nnu[k], d = dup[k] < column minimum of k, == column minimum of x,
-            //      < upper minimum of x.  Equalities that would make the choice ambiguous have raised s_tie already. ----
+            //      < upper minimum of x.  Equalities that would make the choice ambiguous raise s_tie. ----
             for (int i = tid; i < nr; i += THREADS) partner[i] = RNN_NONE;
             __syncthreads();
             for (int k = tid; k < nr; k += THREADS) {
                 const double d = dup[k];
                 if (!(d < SHARP_INF)) continue;
                 const int x = nnu[k];
-                const unsigned long long kd = tri_key(d);
-                if (kd == ckey[k]) s_tie = 1; /* the nearest neighbour of k is not unique (one above, one below) */
-                if (kd < ckey[k] && kd == ckey[x] && d < dup[x]) { partner[k] = (u16)x; partner[x] = (u16)k; }
+                if (d == cmin[k]) s_tie = 1; /* the nearest neighbour of k is not unique (one above, one below) */
+                if (d < cmin[k] && d == cmin[x] && d < dup[x]) { partner[k] = (u16)x; partner[x] = (u16)k; }
             }
             __syncthreads();
             if (s_tie) { failed = true; break; }
@@ -778,14 +808,12 @@ __global__ void __launch_bounds__(TRI_THREADS, TRI_MINB) hclust_tri_kernel(HcPro
                     P.ia[q] = (int)orig[j] + 1;
                     P.ib[q] = (int)orig[i] + 1;
                     P.crit[q] = dup[j];
-                    cmap[i] = (u16)rank[j];
-                    kind[i] = 2;
+                    cmap[i] = (u16)(rank[j] | TRI_MERGING);
                     pl[i - rank[i]] = (u16)j;
                     continue;
                 }
                 const int ip = rank[i];
-                cmap[i] = (u16)ip;
-                kind[i] = paired ? 1 : 0;
+                cmap[i] = (u16)(ip | (paired ? TRI_MERGING : 0));
                 sA[ip] = (u16)i;
                 orig2[ip] = orig[i];
                 if (paired) {
@@ -814,12 +842,12 @@ __global__ void __launch_bounds__(TRI_THREADS, TRI_MINB) hclust_tri_kernel(HcPro
             work += (double)nr * nr;
             if (tri_elems(nnew) > capB || !B || (work > 16.0 * n * n && nr > 256)) { failed = true; break; }
         }
-        // the halves of dnn0 / nn0 swap roles: upper minima of the NEXT partition go where this round's column keys were
-        // (consumed by the setup above), the next column keys where this round's upper minima were
+        // the halves of dnn0 / nn0 swap roles: upper minima of the NEXT partition go where this round's column minima were
+        // (consumed by the setup above), the next column minima where this round's upper minima were
         double *dup2 = dnn0 + (size_t)(cur ^ 1) * n;
         u16 *nnu2 = nn0 + (size_t)(cur ^ 1) * n;
-        unsigned long long *ckey2 = reinterpret_cast<unsigned long long *>(dnn0 + (size_t)cur * n);
-        for (int i = tid; i < nnew; i += THREADS) ckey2[i] = TRI_KEY_INF;
+        double *cmin2 = dnn0 + (size_t)cur * n;
+        for (int i = tid; i < nnew; i += THREADS) cmin2[i] = SHARP_INF;
         __syncthreads();
         // ---- one warp per row of the next partition's matrix, columns right of the row only; rows in (top, bottom) pairs ----
         const int half = (nnew + 1) / 2;
@@ -834,39 +862,36 @@ __global__ void __launch_bounds__(TRI_THREADS, TRI_MINB) hclust_tri_kernel(HcPro
                 const double *rowa = A.row(a);
                 double *out = B ? B + tri_rowoff(ip, nrpB) - tri_c0(ip) : nullptr;
                 const double ma = (double)size[a];
-                RnnBest best;
-                best.d = SHARP_INF; best.i = INT_MAX; best.tie = false;
-                int tie_seen = 0;
+                TriRow best;
+                best.d = SHARP_INF; best.i = INT_MAX; best.tie = 0;
+                int flag = 0;
                 const int jstart = (a + 1) & ~31; /* aligned start: full sectors */
                 if (!im) {
                     for (int jb = jstart; jb < nr; jb += 32 * RNN_UC) {
                         double x[RNN_UC];
+                        unsigned cm[RNN_UC];
 #pragma unroll
                         for (int u = 0; u < RNN_UC; u++) {
                             const int j = jb + u * 32 + lane;
-                            x[u] = (j > a && j < nr) ? rowa[j] : 0.0;
+                            const bool in = j > a && j < nr;
+                            x[u] = in ? rowa[j] : 0.0;
+                            cm[u] = in ? (unsigned)cmap[j] : (unsigned)TRI_MERGING;
                         }
 #pragma unroll
                         for (int u = 0; u < RNN_UC; u++) {
-                            const int j = jb + u * 32 + lane;
-                            if (j <= a || j >= nr || kind[j] != 0) continue;
-                            const int jp = cmap[j];
                             const double v = sq ? __dmul_rn(x[u], x[u]) : x[u];
-                            if (out) out[jp] = v;
-                            rnn_consider(best, v, jp);
-                            tri_col_consider(ckey2, jp, v, &tie_seen);
+                            tri_elem(!(cm[u] & TRI_MERGING), v, (int)(cm[u] & 0x7fffu), out, best, cmin2, flag);
                         }
                     }
-                    for (int q = lane; q < m; q += 32) { /* this row's cluster a against the new cluster (c, d): I2 = c, J2 = d, K = a */
-                        const int c = pl[q];
-                        if (c <= a) continue;
-                        const int d = partner[c], jp = cmap[c];
-                        double xc = rowa[c], xd = rowa[d];
+                    for (int q0 = 0; q0 < m; q0 += 32) { /* this row's cluster a against the new cluster (c, d): I2 = c, J2 = d, K = a */
+                        const int q = q0 + lane;
+                        const int c = q < m ? (int)pl[q] : 0;
+                        const bool valid = q < m && c > a;
+                        const int d = valid ? (int)partner[c] : 0, jp = valid ? (int)(cmap[c] & 0x7fffu) : 0;
+                        double xc = valid ? rowa[c] : 0.0, xd = valid ? rowa[d] : 0.0;
                         if (sq) { xc = __dmul_rn(xc, xc); xd = __dmul_rn(xd, xd); }
-                        const double v = lance_williams(method, xc, xd, hrow[jp], (double)size[c], (double)size[d], ma);
-                        if (out) out[jp] = v;
-                        rnn_consider(best, v, jp);
-                        tri_col_consider(ckey2, jp, v, &tie_seen);
+                        const double v = tri_lw<METHOD>(method, xc, xd, hrow[jp], (double)size[c], (double)size[d], ma);
+                        tri_elem(valid, v, jp, out, best, cmin2, flag);
                     }
                 } else {
                     const int b = (int)b16;
@@ -874,58 +899,55 @@ __global__ void __launch_bounds__(TRI_THREADS, TRI_MINB) hclust_tri_kernel(HcPro
                     const double mb = (double)size[b], hi = hrow[ip];
                     for (int jb = jstart; jb < nr; jb += 32 * RNN_UM) {
                         double x[RNN_UM], y[RNN_UM];
+                        unsigned cm[RNN_UM];
 #pragma unroll
                         for (int u = 0; u < RNN_UM; u++) {
                             const int j = jb + u * 32 + lane;
-                            const bool ok = j > a && j < nr && j != b;
-                            x[u] = ok ? rowa[j] : 0.0;
-                            y[u] = ok ? ((j > b) ? rowb[j] : A.row(j)[b]) : 0.0; /* between a and b: column b of row j */
+                            const bool in = j > a && j < nr && j != b;
+                            x[u] = in ? rowa[j] : 0.0;
+                            y[u] = in ? ((j > b) ? rowb[j] : A.row(j)[b]) : 0.0; /* between a and b: column b of row j */
+                            cm[u] = in ? (unsigned)cmap[j] : (unsigned)TRI_MERGING;
                         }
 #pragma unroll
                         for (int u = 0; u < RNN_UM; u++) {
                             const int j = jb + u * 32 + lane;
-                            if (j <= a || j >= nr || kind[j] != 0) continue;
-                            const int jp = cmap[j];
                             double x1 = x[u], y1 = y[u];
                             if (sq) { x1 = __dmul_rn(x1, x1); y1 = __dmul_rn(y1, y1); }
                             /* new cluster (a, b) against c = j: I2 = a, J2 = b, K = c */
-                            const double v = lance_williams(method, x1, y1, hi, ma, mb, (double)size[j]);
-                            if (out) out[jp] = v;
-                            rnn_consider(best, v, jp);
-                            tri_col_consider(ckey2, jp, v, &tie_seen);
+                            const double v = tri_lw<METHOD>(method, x1, y1, hi, ma, mb, (double)size[j < nr ? j : 0]);
+                            tri_elem(!(cm[u] & TRI_MERGING), v, (int)(cm[u] & 0x7fffu), out, best, cmin2, flag);
                         }
                     }
-                    for (int q = lane; q < m; q += 32) { /* both are new: the two updates in the order of their heights, like the reference */
-                        const int c = pl[q];
-                        if (c <= a) continue;
-                        const int d = partner[c], jp = cmap[c];
-                        double x1 = rowa[c], x2 = rowa[d];
-                        double y1 = (c > b) ? rowb[c] : A.row(c)[b];
-                        double y2 = (d > b) ? rowb[d] : A.row(d)[b];
+                    for (int q0 = 0; q0 < m; q0 += 32) { /* both are new: the two updates in the order of their heights, like the reference */
+                        const int q = q0 + lane;
+                        const int c = q < m ? (int)pl[q] : 0;
+                        const bool valid = q < m && c > a;
+                        const int d = valid ? (int)partner[c] : b + 1, jp = valid ? (int)(cmap[c] & 0x7fffu) : 0;
+                        const int cc = valid ? c : b + 1; /* any index right of b keeps the loads of idle lanes in bounds */
+                        double x1 = valid ? rowa[cc] : 0.0, x2 = valid ? rowa[d] : 0.0;
+                        double y1 = valid ? ((cc > b) ? rowb[cc] : A.row(cc)[b]) : 0.0;
+                        double y2 = valid ? ((d > b) ? rowb[d] : A.row(d)[b]) : 0.0;
                         if (sq) {
                             x1 = __dmul_rn(x1, x1); y1 = __dmul_rn(y1, y1);
                             x2 = __dmul_rn(x2, x2); y2 = __dmul_rn(y2, y2);
                         }
-                        const double hj = hrow[jp], mc = (double)size[c], md = (double)size[d];
-                        if (hi == hj) tie_seen = 1;
+                        const double hj = hrow[jp], mc = (double)size[cc < nr ? cc : 0], md = (double)size[d < nr ? d : 0];
+                        flag |= (int)(valid && hi == hj);
                         const bool fst = hi < hj; /* this row's pair merges first */
                         const double h1 = fst ? hi : hj, h2 = fst ? hj : hi;
                         const double p1 = fst ? ma : mc, p2 = fst ? mb : md; /* sizes of the pair merging first */
                         const double r1 = fst ? mc : ma, r2 = fst ? md : mb; /* sizes of the other pair's members */
                         /* first merge: (I2, J2) of the earlier pair against each member of the later pair */
-                        const double t1 = lance_williams(method, x1, fst ? y1 : x2, h1, p1, p2, r1);
-                        const double t2 = lance_williams(method, fst ? x2 : y1, y2, h1, p1, p2, r2);
+                        const double t1 = tri_lw<METHOD>(method, x1, fst ? y1 : x2, h1, p1, p2, r1);
+                        const double t2 = tri_lw<METHOD>(method, fst ? x2 : y1, y2, h1, p1, p2, r2);
                         /* second merge: the later pair (I2 = its kept member, J2 = retired) against the merged earlier pair */
-                        const double v = lance_williams(method, t1, t2, h2, r1, r2, p1 + p2);
-                        if (out) out[jp] = v;
-                        rnn_consider(best, v, jp);
-                        tri_col_consider(ckey2, jp, v, &tie_seen);
+                        const double v = tri_lw<METHOD>(method, t1, t2, h2, r1, r2, p1 + p2);
+                        tri_elem(valid, v, jp, out, best, cmin2, flag);
                     }
                 }
                 bool tie;
-                const DI w = rnn_finish(best, &tie);
-                if (w.i == INT_MAX) tie = false; /* the last row has no column to its right: no upper neighbour, not a tie */
-                if (__any_sync(0xffffffffu, tie_seen != 0)) tie = true;
+                const DI w = tri_row_finish(best, &tie); /* no candidate at all (the last row): no upper neighbour, not a tie */
+                if (__any_sync(0xffffffffu, flag != 0)) tie = true;
                 if (lane == 0) {
                     nnu2[ip] = (u16)(w.i == INT_MAX ? 0 : w.i);
                     dup2[ip] = w.d;
@@ -989,7 +1011,7 @@ static size_t hclust_rnn_smem_bytes(int n) {
 }
 
 static size_t hclust_tri_smem_bytes(int n) {
-    size_t rounds = (size_t)n * (16 + 8 + 4) + (size_t)n * 2 * 10 + ((size_t)n / 2 + 1) * 2 + (size_t)n + 16;
+    size_t rounds = (size_t)n * (16 + 8 + 4) + (size_t)n * 2 * 10 + ((size_t)n / 2 + 1) * 2 + 16;
     size_t p2 = 1;
     while ((int)p2 < n - 1) p2 <<= 1;
     size_t sort = p2 * 12 + (size_t)n * 8;
@@ -999,7 +1021,7 @@ static size_t hclust_tri_smem_bytes(int n) {
 bool hclust_fast_ok(int max_n, int method) {
     static const bool no_rnn = getenv("SHARP_HCLUST_EXACT") != nullptr; /* development switch */
     const bool reducible = method != SHARP_MEDIAN && method != SHARP_CENTROID;
-    return reducible && !no_rnn && max_n > 384 && max_n < 65535 && hclust_tri_smem_bytes(max_n) <= (size_t)SHARP_SMEM_OPTIN - 4096;
+    return reducible && !no_rnn && max_n > 384 && max_n < 32768 && hclust_tri_smem_bytes(max_n) <= (size_t)SHARP_SMEM_OPTIN - 4096;
 }
 
 static size_t hclust_smem_bytes(int n) {
@@ -1032,13 +1054,22 @@ int launch_hclust(sharp_ctx *c, HcProb *probs_dev, int nprob, int max_n, int met
         static const bool no_tri = getenv("SHARP_HCLUST_FULL") != nullptr; /* development switch: the full-matrix kernel */
         prof_begin(c, KID_HCLUST);
         if (!no_tri) {
-            static const int tri_threads = getenv("SHARP_TRI_THREADS") ? atoi(getenv("SHARP_TRI_THREADS")) : 512; /* development switch */
-            if (tri_threads == 1024) {
-                SHARP_SMEM_OPTIN_ONCE((hclust_tri_kernel<1024, 1>), c->device);
-                hclust_tri_kernel<1024, 1><<<nprob, 1024, hclust_tri_smem_bytes(max_n), c->stream>>>(probs_dev, method);
+            /* 32 warps per problem, one problem per SM: measured on B200 1.4x faster than 16 warps (one or two problems per SM
+               made no difference: the kernel sits at the DRAM efficiency of many concurrent 2 KB row streams, ~2.5 TB/s) */
+            static const int tri_threads = getenv("SHARP_TRI_THREADS") ? atoi(getenv("SHARP_TRI_THREADS")) : 1024; /* development switch */
+            const size_t tsm = hclust_tri_smem_bytes(max_n);
+            if (tri_threads == 1024 && method == SHARP_WARD_D) {
+                SHARP_SMEM_OPTIN_ONCE((hclust_tri_kernel<1024, 1, SHARP_WARD_D>), c->device);
+                hclust_tri_kernel<1024, 1, SHARP_WARD_D><<<nprob, 1024, tsm, c->stream>>>(probs_dev, method);
+            } else if (tri_threads == 1024) {
+                SHARP_SMEM_OPTIN_ONCE((hclust_tri_kernel<1024, 1, 0>), c->device);
+                hclust_tri_kernel<1024, 1, 0><<<nprob, 1024, tsm, c->stream>>>(probs_dev, method);
+            } else if (method == SHARP_WARD_D) {
+                SHARP_SMEM_OPTIN_ONCE((hclust_tri_kernel<512, 2, SHARP_WARD_D>), c->device);
+                hclust_tri_kernel<512, 2, SHARP_WARD_D><<<nprob, 512, tsm, c->stream>>>(probs_dev, method);
             } else {
-                SHARP_SMEM_OPTIN_ONCE((hclust_tri_kernel<512, 2>), c->device);
-                hclust_tri_kernel<512, 2><<<nprob, 512, hclust_tri_smem_bytes(max_n), c->stream>>>(probs_dev, method);
+                SHARP_SMEM_OPTIN_ONCE((hclust_tri_kernel<512, 2, 0>), c->device);
+                hclust_tri_kernel<512, 2, 0><<<nprob, 512, tsm, c->stream>>>(probs_dev, method);
             }
         } else {
             SHARP_SMEM_OPTIN_ONCE((hclust_rnn_kernel), c->device);
