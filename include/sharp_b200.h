@@ -284,6 +284,17 @@ int sharp_last_vie(sharp_ctx *ctx, int64_t n, int p, double *vie);
 int sharp_smetac_centroids(sharp_ctx *ctx, int nC, int p, const double *cen, int64_t ncells_total,
                            const sharp_hc_params *prm, int32_t *tf);
 
+/* ---- streaming ingestion for SHARP_unlimited3 -------------------------------------------------------
+ * Replaces  mat = readRDS(allfiles[i])  (R/SHARP_unlimited3.R:105, freed at :124-125) for parts kept in the raw dgCMatrix
+ * container SHCSC001 (64-byte header: "SHCSC001", int32 m, int32 0, int64 n, int64 nnz; then the slots p (int64[n+1]),
+ * i (int32[nnz]), x (double[nnz]), every section padded to 64 bytes, little-endian).  The reader fills caller buffers --
+ * pinned ones from sharp_host_alloc make the following H2D copy asynchronous -- with pread() from `threads` threads, so a
+ * host thread can read part i + 1 while sharp_run_parts works on part i.  Pure host code apart from the pinned allocator. */
+int sharp_host_alloc(void **ptr, size_t bytes);
+void sharp_host_free(void *ptr);
+int sharp_csc_file_info(const char *path, int *m, int64_t *n, int64_t *nnz);
+int sharp_csc_file_read(const char *path, int64_t *colptr, int32_t *rowidx, double *val, int threads);
+
 /* ---- multi-GPU: one process -- or one host thread -- per GPU, NCCL over NVLink behind this ABI -----------
  * Replaces the gather side of foreach / doParallel (`.combine`, R/SHARP.R:554, 627-635, 692; R/SHARP_unlimited3.R:137-147)
  * across GPUs.  The path shards by parts and cell blocks with no data-path collective; what is exchanged are block-level

@@ -697,6 +697,8 @@ double cor_vec(int n, const double *x, const double *y) {
 }
 
 /* sMetaC (R/sMetaC.R:17-210).  labels: arbitrary int codes; R = unique() by first appearance. */
+int smetac_from_centroids(int nC, int p, const std::vector<double> &aG, int64_t ncells, orc_hc_params P, std::vector<int32_t> &tf);
+
 int smetac_core(int64_t ncells, int p, const int32_t *labels, const double *se1, orc_hc_params P,
                 std::vector<int32_t> &finalcolor, std::vector<int32_t> &tf) {
     /* R = unique(rerowColor) */
@@ -731,6 +733,15 @@ int smetac_core(int64_t ncells, int p, const int32_t *labels, const double *se1,
         for (int c = 0; c < nC; c++)
             for (int j = 0; j < p; j++) aG[(size_t)c * p + j] = (double)(sum[(size_t)c * p + j] / cnt[c]);
     }
+    int rc0 = smetac_from_centroids(nC, p, aG, ncells, P, tf);
+    if (rc0) return rc0;
+    finalcolor.resize(ncells);
+    for (int64_t i = 0; i < ncells; i++) finalcolor[i] = tf[code[i]];
+    return 0;
+}
+
+/* everything of sMetaC after the centroids (R/sMetaC.R:67-182); ncells drives the k-range tweak (:101-119) */
+int smetac_from_centroids(int nC, int p, const std::vector<double> &aG, int64_t ncells, orc_hc_params P, std::vector<int32_t> &tf) {
     /* S[i,j] = cor(aG[i,], aG[j,])  (R/sMetaC.R:67-85) */
     std::vector<double> S((size_t)nC * nC, 0.0);
 #pragma omp parallel for schedule(dynamic, 4)
@@ -774,8 +785,6 @@ int smetac_core(int64_t ncells, int p, const int32_t *labels, const double *se1,
     } else {
         tf = H.f;
     }
-    finalcolor.resize(ncells);
-    for (int64_t i = 0; i < ncells; i++) finalcolor[i] = tf[code[i]];
     return 0;
 }
 
@@ -950,6 +959,17 @@ int oracle_smetac(int64_t ncells, int p, const int32_t *labels, const double *se
     std::copy(fc.begin(), fc.end(), finalcolor);
     if (tf) std::copy(t.begin(), t.end(), tf);
     if (nc_out) *nc_out = (int)t.size();
+    return 0;
+}
+
+/* sMetaC given the cluster centroids (what SHARP_unlimited's global step looks like when the parts live elsewhere) */
+int oracle_smetac_centroids(int nC, int p, const double *cen, int64_t ncells_total, const orc_hc_params *prm, int32_t *tf) {
+    if (nC < 2) return fail(-24, "sMetaC: combn(nC, 2) needs at least 2 clusters");
+    std::vector<double> aG(cen, cen + (size_t)nC * p);
+    std::vector<int32_t> t;
+    int rc = smetac_from_centroids(nC, p, aG, ncells_total, *prm, t);
+    if (rc) return rc;
+    std::copy(t.begin(), t.end(), tf);
     return 0;
 }
 

@@ -105,6 +105,10 @@ int oracle_wmetac(int N, int C, const int32_t *labels, const orc_hc_params *prm,
 int oracle_smetac(int64_t ncells, int p, const int32_t *labels, const double *se1, const orc_hc_params *prm,
                   int32_t *finalcolor, int32_t *tf, int *nc_out);
 
+/* sMetaC from precomputed centroids (cen rowmajor nC x p, unique(rerowColor) order); ncells_total drives the k-range
+ * tweak of R/sMetaC.R:101-119.  tf[nC]. */
+int oracle_smetac_centroids(int nC, int p, const double *cen, int64_t ncells_total, const orc_hc_params *prm, int32_t *tf);
+
 /* ---- SHARP_small / SHARP_large compute for ONE expression matrix  (R/SHARP.R:339-454, 478-851)
  * Everything the R drivers decide up front is an input: `large` (0 = SHARP_small, 1 = SHARP_large), the log flag,
  * K ranM matrices (dgCMatrix slots, concatenated; rm_nnz_off[K+1] offsets into rm_rowidx/rm_x, rm_colptr K x (p+1)),

@@ -65,7 +65,8 @@ EXPORTS = [
     "sharp_prof_get", "sharp_ctx_set_rp_variant", "sharp_r_ranm", "sharp_r_sample_perm", "sharp_run_parts",
     "sharp_ctx_set_block_budget", "sharp_ctx_set_serial", "sharp_parts_prefetch", "sharp_plan_groups",
     "sharp_comm_unique_id", "sharp_comm_init", "sharp_comm_destroy", "sharp_comm_info", "sharp_comm_allgatherv",
-    "sharp_comm_bcast", "sharp_comm_barrier",
+    "sharp_comm_bcast", "sharp_comm_barrier", "sharp_host_alloc", "sharp_host_free", "sharp_csc_file_info",
+    "sharp_csc_file_read",
 ]
 
 _lib = None
@@ -92,6 +93,8 @@ def load():
                  "sharp_ctx_launch_count", "sharp_rm_free", "sharp_expr_free"):
         getattr(lib, name).argtypes = [C.c_void_p]
     lib.sharp_timer_stop_ms.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
+    lib.sharp_host_free.restype = None
+    lib.sharp_host_free.argtypes = [C.c_void_p]
     _lib = lib
     return lib
 

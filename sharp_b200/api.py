@@ -1119,6 +1119,7 @@ def SHARP_unlimited3(ndinfo, viewflag=True, n_cores=None, ensize_K=None, rN_seed
         z = np.load(path)
         return {"p": z["p"], "i": z["i"], "x": z["x"], "Dim": tuple(int(v) for v in z["Dim"])}
 
+    _user_reader = reader
     reader = reader or default_reader
 
     class _Lazy(Expression):
@@ -1147,6 +1148,10 @@ def SHARP_unlimited3(ndinfo, viewflag=True, n_cores=None, ensize_K=None, rN_seed
         def any_negative(self):
             return False
 
+    if _user_reader is None and paths and all(pth.endswith(".csc") for pth in paths):
+        # raw dgCMatrix files: the streamed path -- batches of parts go through the fused loop over parts while the
+        # native reader loads the next batch into pinned buffers
+        return _unlimited3_streamed(paths, ndinfo, viewflag, n_cores, ensize_K, rN_seed, N_cluster, ctx, comm, k)
     ncells_each = ndinfo.get("ncells_each")
     if ncells_each is None:  # one metadata pass, like dim(readRDS(.)) in the reference's first loop
         ncells_each = [Expression.wrap(reader(pth)).n for pth in paths]
@@ -1154,3 +1159,61 @@ def SHARP_unlimited3(ndinfo, viewflag=True, n_cores=None, ensize_K=None, rN_seed
     return SHARP_unlimited(parts, viewflag=viewflag, n_cores=n_cores, ensize_K=ensize_K, N_cluster=N_cluster,
                            rN_seed=rN_seed, ctx=ctx, comm=comm, _part_logflag=None, _krange_from_part1=True,
                            **k)  # :114 passes no logflag
+
+
+def _unlimited3_streamed(paths, ndinfo, viewflag, n_cores, ensize_K, rN_seed, N_cluster, ctx, comm, k) -> dict:
+    """SHARP_unlimited3 over SHCSC001 files (sharp_b200/io.py): R/SHARP_unlimited3.R:103-131 with the per-part SHARP() calls
+    fused (sharp_run_parts) batch by batch, reading batch b + 1 from disk while batch b is uploaded and clustered; then
+    the global sMetaC with part 1's k-range (:165-166), merge, relabel by size.  Parts that would not take the SHARP_large
+    path (fewer than 1e4 cells) fall back to the generic driver with a reader callback."""
+    from . import io as sio
+    start = time.time()
+    ctx = ctx or get_context()
+    infos = [sio.file_info(pth) for pth in paths]               # headers only
+    nnp = len(paths)
+    nnc = [i[1] for i in infos]
+    m = infos[0][0]
+    ncells = int(sum(nnc))
+    if min(nnc) < 1e4 or viewflag or len({max(40, math.ceil(n / 5000)) for n in nnc}) != 1:
+        def reader(pth):
+            mm, n, (cp, ri, v) = sio.PartSlot(*sio.file_info(pth)[1:], pinned=False).load(pth)
+            return {"p": cp, "i": ri, "x": v, "Dim": (mm, n)}
+        return SHARP_unlimited3(dict(ndinfo, ncells_each=nnc), viewflag, n_cores, ensize_K, rN_seed, N_cluster, reader=reader,
+                                ctx=ctx, comm=comm, **k)
+    p = math.ceil(math.log2(ncells) / 0.2 ** 2)
+    rN_seed = _check_seed(rN_seed, allow_half=False)
+    ensize_K = 5 if ensize_K is None else int(ensize_K)
+    rank, world = (comm.rank, comm.world) if comm is not None else (0, 1)
+    mine = [i for i in range(nnp) if i % world == rank]        # files are dealt round-robin: a rank reads only its own
+    kk = dict(k)
+    kk.pop("logflag", None)
+    batch = max(1, int(kk.pop("_batch", 8)))
+    parts_meta = [Expression(m, n, csc=()) for n in nnc]        # shapes only (the fast-path test looks at sizes and data presence)
+    fast = _parts_fast_path(parts_meta, list(range(nnp)), kk, False, False, None)
+    if fast is None:
+        raise ValueError("SHARP_unlimited3 (streamed): unsupported argument for the fused path: " + ", ".join(sorted(set(kk) - _FUSED_KEYS)))
+    rM = ctx.upload_rm(_rm_list(m, p, ensize_K, rN_seed, comm))
+    rd = sio.BatchReader([paths[i] for i in mine], [infos[i] for i in mine], batch, pinned=_lib.device_count() > 0)
+    y, cens = {}, {}
+    try:
+        for b, loaded in rd:
+            idx = mine[b * batch:(b + 1) * batch]
+            plist = list(parts_meta)
+            for i, (mm, n, csc) in zip(idx, loaded):
+                plist[i] = Expression(mm, n, csc=csc)
+            for i, o in zip(idx, _run_parts_fused(ctx, plist, idx, rM, p, ensize_K, rN_seed, fast, n_cores)):
+                y[i], cens[i] = o, o.pop("cen")
+    finally:
+        rd.close()
+        rM.close()
+    if comm is not None:
+        preds_all = comm.allgather_parts({i: y[i]["pred_clusters"] for i in mine}, nnp)
+        cens_all = comm.allgather_parts(cens, nnp)
+        y0 = comm.bcast_obj({q: y[0][q] for q in ("reduced.dim", "ensize.K", "paras")} if 0 in y else None, 0)
+    else:
+        preds_all, cens_all, y0 = [y[i]["pred_clusters"] for i in range(nnp)], [cens[i] for i in range(nnp)], y[0]
+    cen = np.ascontiguousarray(np.concatenate(cens_all, axis=0))
+    final = _unlimited_combine(ctx, cen, [c.shape[0] for c in cens_all], preds_all, ncells, y0["paras"]["hmethod"], N_cluster,
+                               y0["paras"]["minN.cluster"], y0["paras"]["maxN.cluster"], y0["paras"]["sil.thre"],
+                               y0["paras"]["height.Ntimes"])
+    return _unlimited_result(final, ncells, m, y0, start)

@@ -63,10 +63,7 @@ class FakeContext:
         return orc.smetac(labels, se1, _orc_hc(prm))
 
     def smetac_centroids(self, cen, ncells_total, prm):
-        # every centroid as a one-cell cluster: colMeans of one row is the row.  (The k-range tweak of
-        # R/sMetaC.R:101-119 depends on ncells; the fake is only used below 1e4 cells where it is inactive.)
-        assert ncells_total < 10000
-        return orc.smetac(np.arange(1, cen.shape[0] + 1), cen, _orc_hc(prm))["tf"]
+        return orc.smetac_centroids(cen, ncells_total, _orc_hc(prm))
 
     def run(self, rm, prm, m=None, n=None, dense=None, csc=None, expr=None, colsum=None, reind=None, want_vie=True,
             want_x0=True, max_x0_cols=None):
@@ -98,6 +95,25 @@ class FakeContext:
         self._last = r
         return {"labels": r["pred_clusters"].copy(), "viE": r["viE"] if want_vie else None,
                 "x0": r.get("x0") if want_x0 else None, "x0_cols": 0}
+
+    def parts_prefetch(self, m, parts, group=0, lanes=0):
+        return None
+
+    def run_parts(self, rm, prm, m, parts, reinds, small_thre=10, cen_cap=64, group=0, lanes=0, sharded=None):
+        """sharp_run_parts: per part SHARP_large + merge of small clusters (n > 1e4) + first-appearance relabel + centroids"""
+        from sharp_b200.api import _first_appearance_codes, _merge_small
+        out = []
+        for pt, re in zip(parts, reinds):
+            n = int(pt["n"])
+            r = self.run(rm, prm, m=m, n=n, dense=pt.get("dense"), csc=pt.get("csc"), reind=re, want_x0=False)
+            lab = r["labels"]
+            if prm.n_cluster == 0 and n > 10000:
+                lab = _merge_small(lab, small_thre)
+            cid, _ = _first_appearance_codes(lab)
+            nc = int(cid.max())
+            cen, cnt = self.centroids(cid, nc, rm.p)
+            out.append({"pred_clusters": cid, "N.pred_cluster": nc, "cen": cen, "counts": cnt})
+        return out
 
     def centroids(self, labels, nclust, p):
         vie = self._last["viE"]

@@ -202,6 +202,16 @@ def smetac(labels, se1, prm=None):
     return {"finalColor": fc, "tf": tf}
 
 
+def smetac_centroids(cen, ncells_total, prm=None):
+    cen = _f64(cen)
+    nC, p = cen.shape
+    prm = prm or hc_params()
+    tf = np.empty(nC, dtype=np.int32)
+    _chk(lib().oracle_smetac_centroids(nC, p, _p(cen, C.c_double), C.c_int64(int(ncells_total)), C.byref(prm),
+                                       _p(tf, C.c_int32)))
+    return tf
+
+
 def pack_rms(rms):
     """list of dgCMatrix dicts -> (colptr K x (p+1) int32, rowidx, x, nnz_off int64[K+1])"""
     colptr = np.ascontiguousarray(np.stack([r["p"] for r in rms]), dtype=np.int32)

@@ -282,3 +282,39 @@ def test_sharp_unlimited3_reads_parts_lazily_and_uses_part_one_k_range(tmp_path)
     ref = api.SHARP_unlimited(plist, viewflag=False, rN_seed=3, ensize_K=2, ctx=FakeContext(), n_streams=1, exp_type="UMI")
     assert seen == ["part1.npz", "part2.npz", "part10.npz"]
     assert np.array_equal(r["pred_clusters"], ref["pred_clusters"])
+
+
+def test_shcsc_files_and_the_streamed_unlimited3(tmp_path):
+    """SHCSC001 container: writer (python) <-> native reader (sharp_csc_file_*), the double-buffered batch reader, and
+    SHARP_unlimited3 over a directory of .csc files (batches through the fused loop over parts) against the in-memory
+    driver with part 1's k-range"""
+    from sharp_b200 import io as sio
+    m, sizes = 300, [10050, 10000, 10200]
+    x, _ = synth.make_expression(m, sum(sizes), n_types=3, seed=14, kind="umi", zero_frac=0.6, sep=2.5, frac=0.5)
+    plist, o = [], 0
+    for n in sizes:
+        plist.append(np.asfortranarray(x[:, o:o + n]))
+        o += n
+    for name, a in zip(["p3.csc", "p1.csc", "p2.csc"], [plist[2], plist[0], plist[1]]):
+        cp, ri, v = synth.to_csc(a)
+        sio.write_csc(tmp_path / name, m, a.shape[1], cp, ri, v)
+    assert sio.file_info(tmp_path / "p1.csc")[:2] == (m, sizes[0])
+    slot = sio.PartSlot(max(sizes), int((x != 0).sum()), pinned=False)
+    mm, n, (cp, ri, v) = slot.load(str(tmp_path / "p2.csc"))
+    cp0, ri0, v0 = synth.to_csc(plist[1])
+    assert (mm, n) == (m, sizes[1]) and np.array_equal(cp, cp0) and np.array_equal(ri, ri0) and np.array_equal(v, v0)
+    with pytest.raises(api.SharpError):
+        (tmp_path / "bad.csc").write_bytes(b"not a matrix" * 10)
+        sio.file_info(tmp_path / "bad.csc")
+    os.remove(tmp_path / "bad.csc")
+    paths = [str(tmp_path / f"p{i}.csc") for i in (1, 2, 3)]
+    rd = sio.BatchReader(paths, [sio.file_info(p) for p in paths], batch=2, pinned=False)
+    seen = [(b, [q[1] for q in loaded]) for b, loaded in rd]
+    rd.close()
+    assert seen == [(0, sizes[:2]), (1, sizes[2:])]
+    ctx = FakeContext()
+    r = api.SHARP_unlimited3({"dir": str(tmp_path), "ncells": sum(sizes), "ngenes": m}, viewflag=False, rN_seed=3, ensize_K=2,
+                             exp_type="UMI", ctx=ctx, _batch=2)
+    ref = api.SHARP_unlimited([synth.to_csc(a) + (a.shape,) for a in plist], viewflag=False, rN_seed=3, ensize_K=2, exp_type="UMI",
+                              ctx=FakeContext(), n_streams=1, _krange_from_part1=True)
+    assert np.array_equal(r["pred_clusters"], ref["pred_clusters"]) and r["N.pred_clusters"] == ref["N.pred_clusters"]
