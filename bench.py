@@ -477,7 +477,7 @@ def run_single(args, wl):
         t1 = time.time()
         ref = orc.sharp(m, ns, rms, oprm, colsum=colsum, reind=reind, want_x0=False, **okw)
         dt = time.time() - t1
-        got = res if ns == n else api.SHARP(sub, exp_type=wl["exp_type"], rN_seed=SEED, logflag=False, ctx=ctx, ensize_K=K)
+        got = res if ns == n else api.SHARP(sub, exp_type=wl["exp_type"], rN_seed=SEED, logflag=False, prep=False, ctx=ctx, ensize_K=K)
         rel = float(np.max(np.abs(got["viE"] - ref["viE"])) / np.max(np.abs(ref["viE"])))
         parity = {"cells": int(ns), "m": m, "p": int(ps), "K": K, "ari": synth.ari(got["pred_clusters"], ref["pred_clusters"]),
                   "equal": bool(np.array_equal(got["pred_clusters"], ref["pred_clusters"])), "proj_max_rel": rel,

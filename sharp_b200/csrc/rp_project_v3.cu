@@ -106,22 +106,15 @@ __device__ __forceinline__ void rpv_entries(const uint4 &w, uint32_t e[7]) {
     e[5] = w.w & 0xffffu; e[6] = w.w >> 16;
 }
 
-// predicated shared-memory atomics (no branch around the instruction: the slots of a vector are straight-line code)
-__device__ __forceinline__ void reds_add_lt(uint32_t addr, uint32_t v, uint32_t s, uint32_t n) { /* if (s < n) */
-    asm volatile("{\n\t.reg .pred p;\n\tsetp.lt.u32 p, %2, %3;\n\t@p red.shared.add.u32 [%0], %1;\n\t}" ::"r"(addr), "r"(v), "r"(s), "r"(n) : "memory");
-}
-__device__ __forceinline__ uint32_t atoms_add_lt(uint32_t addr, uint32_t v, uint32_t s, uint32_t n) { /* if (s < n); else returns 0 */
-    uint32_t old = 0;
-    asm volatile("{\n\t.reg .pred p;\n\tsetp.lt.u32 p, %3, %4;\n\t@p atom.shared.add.u32 %0, [%1], %2;\n\t}" : "+r"(old) : "r"(addr), "r"(v), "r"(s), "r"(n) : "memory");
-    return old;
-}
-
-// count-class lanes: one non-returning atomic per entry; the entry IS the byte offset into [+ counts | - counts]
+// count-class lanes: one non-returning atomic per entry; the entry IS the byte offset into [+ counts | - counts].
+// (ptxas turns predicated shared atomics into branches anyway; the plain form below measured 11 % faster on B200 than
+// explicit per-slot predicates with all low-limb atomics hoisted.)
 __device__ __forceinline__ void rpv_scatter_class(const uint4 &w, uint32_t n, uint32_t base, uint32_t addc) {
     uint32_t e[7];
     rpv_entries(w, e);
 #pragma unroll
-    for (int s = 0; s < 7; s++) reds_add_lt(base + e[s], addc, (uint32_t)s, n);
+    for (int s = 0; s < 7; s++)
+        if ((uint32_t)s < n) reds_add(base + e[s], addc);
 }
 
 // generic lanes: 64-bit add as two 32-bit limbs (the returning atomic on the low limb yields the carry)
@@ -129,20 +122,16 @@ __device__ __forceinline__ void rpv_scatter_generic(const uint4 &w, uint32_t n, 
                                                     uint32_t apos, uint32_t hpos, uint32_t aneg, uint32_t hneg) {
     uint32_t e[7];
     rpv_entries(w, e);
-    uint32_t addr[7], old[7], negm = 0u;
-#pragma unroll
-    for (int s = 0; s < 7; s++) { /* all low-limb atomics are issued before the first carry is consumed */
-        const bool neg = e[s] >= arr;
-        negm |= neg ? (1u << s) : 0u;
-        addr[s] = lo_base + (neg ? e[s] - arr : e[s]);
-        old[s] = atoms_add_lt(addr[s], neg ? aneg : apos, (uint32_t)s, n);
-    }
 #pragma unroll
     for (int s = 0; s < 7; s++) {
-        const bool neg = (negm >> s) & 1u;
-        const uint32_t av = neg ? aneg : apos;
-        const uint32_t hv = (neg ? hneg : hpos) + (((uint32_t)(old[s] + av) < av) ? 1u : 0u);
-        reds_add_lt(addr[s] + arr, hv, (uint32_t)s, hv ? n : 0u);
+        if ((uint32_t)s < n) {
+            const bool neg = e[s] >= arr;
+            const uint32_t addr = lo_base + (neg ? e[s] - arr : e[s]);
+            const uint32_t av = neg ? aneg : apos;
+            const uint32_t old = atoms_add(addr, av);
+            const uint32_t hv = (neg ? hneg : hpos) + (((uint32_t)(old + av) < av) ? 1u : 0u);
+            if (hv) reds_add(addr + arr, hv);
+        }
     }
 }
 
