@@ -290,3 +290,26 @@ def test_unlimited_viewflag_above_1e5_cells_uses_the_reprojection(ctx):
     assert r["viE"].shape == (ncells, 50) and r["x0"].shape == (ncells, r["N.pred_clusters"])
     r2 = api.SHARP_unlimited(parts, viewflag=False, rN_seed=seed, ensize_K=K, exp_type="UMI", ctx=ctx)
     assert np.array_equal(r["pred_clusters"], r2["pred_clusters"])
+
+
+def test_unlimited3_streamed_from_shcsc_files(ctx, tmp_path):
+    """SHARP_unlimited3 over a directory of SHCSC001 files: batches of parts through the fused loop over parts while the
+    native reader (pread into pinned buffers) loads the next batch -- same labels as the in-memory driver with part 1's
+    k-range, for several batch sizes"""
+    from sharp_b200 import io as sio
+    m, K, seed = 900, 3, 31
+    sizes = [10000, 10650, 11200, 10100, 10300]
+    x, truth = synth.make_expression(m, sum(sizes), n_types=5, seed=22, kind="umi", zero_frac=0.8, sep=2.0, frac=0.4)
+    parts, o = [], 0
+    for i, n in enumerate(sizes):
+        a = np.asfortranarray(x[:, o:o + n])
+        parts.append(synth.to_csc(a) + (a.shape,))
+        sio.write_csc(tmp_path / f"part_{i + 1}.csc", m, n, *parts[-1][:3])
+        o += n
+    ref = api.SHARP_unlimited(parts, viewflag=False, rN_seed=seed, ensize_K=K, exp_type="UMI", ctx=ctx, _krange_from_part1=True)
+    for batch in (2, 5, 1):
+        got = api.SHARP_unlimited3({"dir": str(tmp_path), "ncells": sum(sizes), "ngenes": m}, viewflag=False, rN_seed=seed,
+                                   ensize_K=K, exp_type="UMI", ctx=ctx, _batch=batch)
+        assert np.array_equal(got["pred_clusters"], ref["pred_clusters"]), batch
+        assert got["N.pred_clusters"] == ref["N.pred_clusters"]
+    assert synth.ari(ref["pred_clusters"], truth) > 0.8
