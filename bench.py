@@ -600,6 +600,8 @@ def run_ours(args):
     api._fused_group, api._fused_lanes = args.group, args.lanes
     if args.budget_gb:
         ctx.set_block_budget(args.budget_gb)
+    if args.rp_variant:
+        ctx.set_rp_variant(args.rp_variant)
     ctxs = api.stream_contexts(args.streams, local) if args.no_fused else [ctx]
     kw = dict(n_streams=args.streams, viewflag=False, ensize_K=wl["K"], rN_seed=SEED, exp_type=wl["exp_type"], ctx=ctx, comm=comm)
 
@@ -813,6 +815,7 @@ def main():
     ap.add_argument("--lanes", type=int, default=0, help="groups in flight (0 = library default)")
     ap.add_argument("--budget-gb", type=int, default=0, help="distance-matrix workspace cap per context in GB (0 = library default)")
     ap.add_argument("--no-fused", action="store_true", help="part-by-part path (one sharp_run per part, --streams host threads)")
+    ap.add_argument("--rp-variant", type=int, default=0, help="projection kernel variant (sharp_ctx_set_rp_variant): 0 default, 2 the r1 kernel, 3 TMA-staged")
     ap.add_argument("--no-shard", action="store_true", help="N > 1: deal ALL parts round-robin (no block-sharded left-over parts)")
     ap.add_argument("--cpu-sample", type=int, default=20000, help="cells of the CPU baseline / parity sample (0 = one whole part)")
     ap.add_argument("--ref-sample", type=int, default=0, help="--impl reference: cells per step (0 = one whole part, budget permitting)")

@@ -435,7 +435,7 @@ class Context:
         """sharp_run_parts on ONE stream (isolated per-kernel timings for the roofline object); default off"""
         _check(load().sharp_ctx_set_serial(self._h, int(bool(on))))
 
-    def parts_prefetch(self, m: int, parts: list, group=0, lanes=0):
+    def parts_prefetch(self, m: int, parts: list, group=0, lanes=0, sharded=None):
         """sharp_parts_prefetch: start the uploads of the first group of ``parts`` (same list and group / lanes as the
         run_parts call that follows) and return at once.  -> an object the caller keeps alive until run_parts is done."""
         nparts = len(parts)
@@ -452,6 +452,7 @@ class Context:
                 k, dp, cp, ri, v = _expr_args(m, a.n, pt.get("dense"), pt.get("csc"))
                 keep.append(k)
                 a.dense, a.colptr, a.rowidx, a.val = dp, cp, ri, v
+            a.sharded = int(bool(sharded[i])) if sharded is not None else 0
         _check(load().sharp_parts_prefetch(self._h, int(m), nparts, arr, int(group), int(lanes)))
         return keep
 

@@ -876,7 +876,8 @@ def SHARP_unlimited(scExp, viewflag=True, n_cores=None, ensize_K=None, N_cluster
     # host buffers: the copy of the first parts starts now and runs while the ranM matrices are drawn on the host
     _pf_keep = None
     if fast is not None and mine and parts[mine[0]].dev is None:
-        _pf_keep = ctx.parts_prefetch(parts[mine[0]].m, _fused_inputs(parts, mine), _fused_group, _fused_lanes)
+        _pf_keep = ctx.parts_prefetch(parts[mine[0]].m, _fused_inputs(parts, mine), _fused_group, _fused_lanes,
+                                      sharded=[i in shared for i in mine])
     rms_host = _rm_list(parts[0].m, p, ensize_K, rN_seed, comm)
     _mark("ranM")
     rM = ctx.upload_rm(rms_host)

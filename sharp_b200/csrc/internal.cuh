@@ -145,6 +145,8 @@ struct sharp_ctx {
     const void *pf_src = nullptr; // host buffer it was copied from (a prefetch is only used for the same buffer)
     int32_t *h_labels = nullptr;  // pinned label mirror of a group run
     size_t h_labels_cap = 0;
+    unsigned char *h_gather = nullptr;  // pinned staging of the host-side column gather of a sharded, shuffled part
+    size_t h_gather_cap = 0;
     int block_budget_gb = 48;     // cap of the distance-matrix workspace (D + Dw) of one context
     size_t ws_budget = 0, ws_budget_seen = 0;  // last budget derived from cudaMemGetInfo and the workspace state it was derived for
     int64_t last_n = 0;     // state of the last run (for sharp_centroids)
@@ -201,6 +203,9 @@ struct sharp_expr_dev {
     // a column slice of a larger matrix (sharded runs on un-shuffled host data upload only the rank's columns):
     // column 0 of this matrix is column col0 of the whole one, which has n_total columns (0: this IS the whole matrix)
     int64_t col0 = 0, n_total = 0;
+    // compact = true: column i of this matrix is the i-th cell of the rank's share of a SHUFFLED sharded matrix (gathered on
+    // the host in shuffled order): the projection reads it with the identity map
+    bool compact = false;
 };
 
 namespace sharp {

@@ -10,6 +10,7 @@
 #include <cstdarg>
 #include <cstring>
 #include <numeric>
+#include <thread>
 
 #include <nvtx3/nvToolsExt.h>
 
@@ -788,7 +789,7 @@ static int part_front(PartRun &R, sharp_ctx *c, const sharp_expr_dev &e, const d
             hp[i] = reind[i] - 1;
         }
         SHARP_TRY(h2d_staged(c, R.src_all_dev, hp, (size_t)na * 8));
-        R.src_dev = R.src_all_dev + R.pos0;   /* this rank's cells: positions pos0 .. pos0 + n of the shuffled order */
+        R.src_dev = e.compact ? nullptr : R.src_all_dev + R.pos0;   /* this rank's cells: positions pos0 .. pos0 + n of the shuffled order */
     } else if (R.sharded && R.pos0 != e.col0) { /* un-shuffled, not starting at the matrix's first column: explicit source list */
         SHARP_TRY(c->ws[WS_SRC].reserve((size_t)n * 8));
         R.src_dev = c->ws[WS_SRC].as<int64_t>();
@@ -1239,6 +1240,8 @@ void destroy_ctx_resources(sharp_ctx *c) {
     for (int h = 0; h < 2; h++)
         if (c->ev_half[h]) { cudaEventDestroy(c->ev_half[h]); c->ev_half[h] = nullptr; }
     if (c->h_labels) cudaFreeHost(c->h_labels);
+    if (c->h_gather) cudaFreeHost(c->h_gather);
+    c->h_gather = nullptr;
     c->arena = nullptr;
     c->h_labels = nullptr;
     if (c->ev0) cudaEventDestroy(c->ev0);
@@ -1330,7 +1333,66 @@ static int group_issue(GroupRun &G, sharp_part *parts, int m, const sharp_rm_dev
             /* the sub-context's buffers are about to be overwritten: a look-ahead copy that was never used (the caller
                changed the grouping between sharp_parts_prefetch and this call) must not be matched by a later group */
             s->pf_part = -1;
-            if (G.up) { /* all uploads of a group run go through ONE stream: the copy engine shares the link between
+            bool compacted = false;
+            if (P.sharded && s->comm && s->comm_world > 1 && Q.large && P.colptr && P.reind && P.n < 100000) {
+                /* a block-sharded, SHUFFLED part on host buffers: this rank needs the columns reind[pos0 .. pos0 + n_loc) only
+                   -- 1 / world of the part.  They are gathered on the host (a few threads) into pinned staging, in shuffled
+                   order, and only those bytes cross PCIe. */
+                std::vector<int64_t> st;
+                make_blocks(P.n, 1, Q.partition_ncells, st);
+                const int T = (int)st.size() - 1;
+                if (T >= s->comm_world) {
+                    int t0, t1;
+                    shard_range(T, s->comm_rank, s->comm_world, G.idx[j], &t0, &t1);
+                    const int64_t pos0 = st[t0], nloc = st[t1] - st[t0];
+                    int64_t nnz = 0;
+                    for (int64_t i = 0; i < nloc; i++) {
+                        const int64_t src = P.reind[pos0 + i] - 1;
+                        if (src < 0 || src >= P.n) return set_error(SHARP_E_ARG, "reind is not a permutation of 1..n");
+                        nnz += P.colptr[src + 1] - P.colptr[src];
+                    }
+                    const size_t o_ri = (((size_t)(nloc + 1) * 8) + 63) & ~(size_t)63, o_v = (o_ri + (size_t)nnz * 4 + 63) & ~(size_t)63;
+                    const size_t bytes = o_v + (size_t)nnz * 8 + 64;
+                    if (bytes > s->h_gather_cap) {
+                        if (s->h_gather) { SHARP_CUDA(cudaStreamSynchronize(G.up ? G.up : s->stream)); cudaFreeHost(s->h_gather); }
+                        s->h_gather = nullptr;
+                        s->h_gather_cap = 0;
+                        const size_t want = bytes + bytes / 4;
+                        SHARP_CUDA(cudaMallocHost((void **)&s->h_gather, want));
+                        s->h_gather_cap = want;
+                    } else if (s->ev_up) SHARP_CUDA(cudaEventSynchronize(s->ev_up)); /* the previous copy out of this staging is done */
+                    int64_t *cp = reinterpret_cast<int64_t *>(s->h_gather);
+                    int32_t *ri = reinterpret_cast<int32_t *>(s->h_gather + o_ri);
+                    double *xv = reinterpret_cast<double *>(s->h_gather + o_v);
+                    cp[0] = 0;
+                    for (int64_t i = 0; i < nloc; i++) {
+                        const int64_t src = P.reind[pos0 + i] - 1;
+                        cp[i + 1] = cp[i] + (P.colptr[src + 1] - P.colptr[src]);
+                    }
+                    const int nth = (int)std::min<int64_t>(8, std::max<int64_t>(1, nloc / 256));
+                    std::vector<std::thread> th;
+                    for (int t = 0; t < nth; t++)
+                        th.emplace_back([&, t]() {
+                            for (int64_t i = nloc * t / nth; i < nloc * (t + 1) / nth; i++) {
+                                const int64_t src = P.reind[pos0 + i] - 1, q0 = P.colptr[src], len = P.colptr[src + 1] - q0;
+                                memcpy(ri + cp[i], P.rowidx + q0, (size_t)len * 4);
+                                memcpy(xv + cp[i], P.val + q0, (size_t)len * 8);
+                            }
+                        });
+                    for (auto &x : th) x.join();
+                    SLOW("gathered upload_expr", SHARP_TRY(upload_expr(s, m, nloc, nullptr, cp, ri, xv, &e, true, G.up)));
+                    if (G.up) {
+                        SHARP_CUDA(cudaEventRecord(s->ev_up, G.up));
+                        SHARP_CUDA(cudaStreamWaitEvent(s->stream, s->ev_up, 0));
+                    } else SHARP_CUDA(cudaEventRecord(s->ev_up, s->stream));
+                    e.compact = true;
+                    e.col0 = 0;
+                    e.n_total = P.n;
+                    compacted = true;
+                }
+            }
+            if (compacted) {
+            } else if (G.up) { /* all uploads of a group run go through ONE stream: the copy engine shares the link between
                            streams, and the first group must not wait for the bytes of the groups behind it */
                 SLOW("inline upload_expr", SHARP_TRY(upload_expr(s, m, P.n, P.dense, P.colptr, P.rowidx, P.val, &e, true, G.up)));
                 SHARP_CUDA(cudaEventRecord(s->ev_up, G.up));
@@ -1393,7 +1455,7 @@ static int group_prefetch(const std::vector<int> &idx, const std::vector<sharp_c
         const sharp_part &P = parts[idx[j]];
         sharp_ctx *s = subs[j];
         s->pf_part = -1;
-        if (P.dev || m <= 0 || P.n < 0) continue;
+        if (P.dev || m <= 0 || P.n < 0 || P.sharded) continue; /* a sharded part uploads only this rank's columns (group_issue) */
         if (P.dense) {
             const size_t bytes = (size_t)m * P.n * sizeof(double);
             if (s->ws[WS_EX_A].cap < bytes) continue;
@@ -1667,6 +1729,7 @@ void rm_release(void *ptr) {
 int sharp_rm_upload(sharp_ctx *c, int m, int p, int K, const int32_t *colptr, const int32_t *rowidx, const double *x,
                     const int64_t *nnz_off, sharp_rm_dev **out) {
     SHARP_TRY(use(c));
+    Trace tr(c);
     if (!out || m <= 0 || p <= 0 || K <= 0 || !colptr || !nnz_off) return set_error(SHARP_E_ARG, "rm_upload: bad arguments");
     const int64_t nnz = nnz_off[K];
     if (nnz > 0 && (!rowidx || !x)) return set_error(SHARP_E_ARG, "rm_upload: missing slots");
@@ -1706,6 +1769,7 @@ int sharp_rm_upload(sharp_ctx *c, int m, int p, int K, const int32_t *colptr, co
                 }
         }
     }
+    tr.mark("rm_csr");
     sharp_rm_dev *r = new sharp_rm_dev();
     r->device = c->device;
     r->m = m; r->p = p; r->K = K; r->mag = mag; r->nnz = nz;
@@ -1731,6 +1795,7 @@ int sharp_rm_upload(sharp_ctx *c, int m, int p, int K, const int32_t *colptr, co
         const int32_t *cp = colptr + (size_t)k * (p + 1);
         for (int j = 0; j < p; j++) r->max_col_nnz = std::max(r->max_col_nnz, cp[j + 1] - cp[j]);
     }
+    tr.mark("rm_copy1");
     if ((int64_t)K * p <= 32700 && e1 == cudaSuccess && e2 == cudaSuccess) {
         const int kpr = (K * p + 31) & ~31;
         r->kpd = kpr + 32;
@@ -1755,6 +1820,7 @@ int sharp_rm_upload(sharp_ctx *c, int m, int p, int K, const int32_t *colptr, co
         if (e3 != cudaSuccess) e1 = e3;
         if (e4 != cudaSuccess) e2 = e4;
     }
+    tr.mark("rm_padded");
     if (r->kpd > 0 && r->kpd <= 8191 && r->max_col_nnz <= 255 && e16 && e1 == cudaSuccess && e2 == cudaSuccess) {
         /* records of the record-gather kernel: the smallest record that fewer than 0.2 % of the genes overflow */
         int rv = 2;
@@ -1782,6 +1848,7 @@ int sharp_rm_upload(sharp_ctx *c, int m, int p, int K, const int32_t *colptr, co
             r->rv = rv;
         }
     }
+    tr.mark("rm_records");
     if (e1 != cudaSuccess || e2 != cudaSuccess) {
         sharp_rm_free(r);
         return set_error(SHARP_E_CUDA, "rm_upload: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
@@ -2166,6 +2233,24 @@ static std::vector<int> plan_groups(int nparts, bool host_first, int &group, int
     return gstart;
 }
 
+// groups of a parts list whose block-sharded parts (sharp_part.sharded, all at the END of the list) carry only 1 / world of
+// a part's work each: the whole parts are grouped as usual and the sharded ones ride with the last group, so that their
+// few (member, block) problems share that group's launches instead of paying a wave of their own
+static int plan_groups_parts(const sharp_part *parts, int nparts, bool host_first, int &group, int &lanes, std::vector<int> &gstart,
+                             int *gmax) {
+    int ns = 0;
+    for (int i = 0; i < nparts; i++) {
+        if (parts[i].sharded) ns++;
+        else if (ns) return set_error(SHARP_E_ARG, "run_parts: block-sharded parts must come after the rank's own parts");
+    }
+    const int nwhole = nparts - ns;
+    gstart = plan_groups(nwhole > 0 ? nwhole : nparts, host_first, group, lanes);
+    if (nwhole > 0) gstart.back() = nparts;
+    *gmax = 1;
+    for (size_t g = 0; g + 1 < gstart.size(); g++) *gmax = std::max(*gmax, gstart[g + 1] - gstart[g]);
+    return 0;
+}
+
 static int ensure_subs(sharp_ctx *c, size_t need) {
     while (c->subs.size() < need) {
         sharp_ctx *s = nullptr;
@@ -2187,10 +2272,13 @@ int sharp_run_parts(sharp_ctx *c, int m, int nparts, sharp_part *parts, const sh
         if (!parts[i].dev && !parts[i].dense && !parts[i].colptr) return set_error(SHARP_E_ARG, "run_parts: part %d has no data", i);
         if (parts[i].dev && parts[i].dev->n != parts[i].n) return set_error(SHARP_E_ARG, "run_parts: part %d: n does not match the device matrix", i);
     }
-    std::vector<int> gstart = plan_groups(nparts, !parts[0].dev, group, lanes);
+    std::vector<int> gstart;
+    int gmax = 1;
+    SHARP_TRY(plan_groups_parts(parts, nparts, !parts[0].dev, group, lanes, gstart, &gmax));
     const int ngroups = (int)gstart.size() - 1;
     lanes = std::min(lanes, ngroups);
-    const size_t need = (size_t)lanes * (group + 1);
+    const int stride = gmax + 1;   /* sub-contexts per lane: one per part of the largest group + the group's block context */
+    const size_t need = (size_t)lanes * stride;
     SHARP_TRY(ensure_subs(c, need));
     for (sharp_ctx *s : c->subs) {
         if (c->serial) s->pf_part = -1;
@@ -2230,9 +2318,9 @@ int sharp_run_parts(sharp_ctx *c, int m, int nparts, sharp_part *parts, const sh
         GroupRun &g = G[gi];
         const int lane = gi % lanes;
         for (int i = gstart[gi]; i < gstart[gi + 1]; i++) g.idx.push_back(i);
-        g.blocks = c->subs[(size_t)lane * (group + 1) + group];
+        g.blocks = c->subs[(size_t)lane * stride + gmax];
         g.up = up;
-        for (size_t j = 0; j < g.idx.size(); j++) g.subs.push_back(c->subs[(size_t)lane * (group + 1) + j]);
+        for (size_t j = 0; j < g.idx.size(); j++) g.subs.push_back(c->subs[(size_t)lane * stride + j]);
         const auto t_a = std::chrono::steady_clock::now();
         rc = group_issue(g, parts, m, *rm, *prm);
         if (!rc && !c->serial && lanes >= 2 && gi >= 1 && gi - 1 + lanes < ngroups) {
@@ -2243,7 +2331,7 @@ int sharp_run_parts(sharp_ctx *c, int m, int nparts, sharp_part *parts, const sh
             std::vector<sharp_ctx *> lsubs;
             for (int i = gstart[ng]; i < gstart[ng + 1]; i++) {
                 nidx.push_back(i);
-                lsubs.push_back(c->subs[(size_t)nlane * (group + 1) + (i - gstart[ng])]);
+                lsubs.push_back(c->subs[(size_t)nlane * stride + (i - gstart[ng])]);
             }
             rc = group_prefetch(nidx, lsubs, parts, m, up);
         }
@@ -2292,10 +2380,12 @@ int sharp_parts_prefetch(sharp_ctx *c, int m, int nparts, sharp_part *parts, int
     SHARP_TRY(use(c));
     if (!parts || nparts < 1) return set_error(SHARP_E_ARG, "parts_prefetch: bad arguments");
     if (c->serial || parts[0].dev) return 0;
-    std::vector<int> gstart = plan_groups(nparts, true, group, lanes);
+    std::vector<int> gstart;
+    int gmax = 1;
+    SHARP_TRY(plan_groups_parts(parts, nparts, true, group, lanes, gstart, &gmax));
     const int ngroups = (int)gstart.size() - 1;
     lanes = std::min(lanes, ngroups);
-    SHARP_TRY(ensure_subs(c, (size_t)lanes * (group + 1)));
+    SHARP_TRY(ensure_subs(c, (size_t)lanes * (gmax + 1)));
     if (!c->up_stream) SHARP_CUDA(cudaStreamCreateWithFlags(&c->up_stream, cudaStreamNonBlocking));
     /* behind whatever is queued on the context's stream (the caller's timer start, the previous call's end) */
     SHARP_CUDA(cudaEventRecord(c->ev_fork, c->stream));

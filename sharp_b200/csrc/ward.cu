@@ -646,6 +646,9 @@ __global__ void __launch_bounds__(RNN_THREADS, 2) hclust_rnn_kernel(HcProb *prob
 //     anywhere (a key that meets its own value) raise the tie flag: the problem is redone by the exact kernel;
 //   * a merged row (a, b) reads row a contiguously, row b contiguously right of b and as a column gather between a and b;
 //   * rows are dealt to the warps in (top, bottom) pairs of the triangle: the same amount of work for every warp.
+// Tried and dropped (B200, r2): a per-warp shared-memory stash of the pair members' row values, so that the pair pass
+// would not re-read them -- 98 KB more shared memory left 28 KB of L1 and the kernel ran 25 % slower (446 vs 357 ms per
+// 1.3 M-cell step); one CTA of 16 warps per problem, one or two problems per SM: 1.4x slower than 32 warps per problem.
 
 __device__ __forceinline__ int tri_c0(int i) { return (i + 1) & ~1; }
 __device__ __forceinline__ size_t tri_rowoff(int i, int nrp) {
@@ -717,11 +720,6 @@ __device__ __forceinline__ double tri_lw(int method, double d1, double d2, doubl
     return lance_williams(method, d1, d2, d12, mi, mj, mk);
 }
 
-constexpr int TRI_STASH = 192;       /* pairs per round whose row values are kept in the per-warp stash */
-__host__ __device__ inline size_t hclust_tri_stash_offset(int n) { /* bytes of the round state, 16-byte aligned */
-    size_t rounds = (size_t)n * (16 + 8 + 4) + (size_t)n * 2 * 11 + ((size_t)n / 2 + 2) * 2 + 16;
-    return (rounds + 15) & ~(size_t)15;
-}
 constexpr u16 TRI_MERGING = 0x8000u; /* flag in the column map: the old cluster merges this round (handled by the pair pass) */
 
 template <int TRI_THREADS, int TRI_MINB, int METHOD>
@@ -750,11 +748,6 @@ __global__ void __launch_bounds__(TRI_THREADS, TRI_MINB) hclust_tri_kernel(HcPro
     u16 *cmap = sB + n;                                     // [n] old cluster -> index in the next partition | TRI_MERGING
     u16 *partner = cmap + n;                                // [n] this round's partner of every current cluster, or RNN_NONE
     u16 *pl = partner + n;                                  // [n/2 + 1] kept members of this round's pairs
-    u16 *pq = pl + (n / 2 + 1) + ((n / 2 + 1) & 1);         // [n] pair number of a merging old cluster | 0x8000 for the retired member
-    // per-warp stash of the values a row holds for the members of this round's first TRI_STASH pairs: written while the
-    // row streams by, read by the pair pass instead of re-reading the row from global memory (two scattered sectors
-    // per pair and row otherwise -- a fifth of the kernel's DRAM reads in the r2 capture)
-    double *stash = reinterpret_cast<double *>(smem_raw + hclust_tri_stash_offset(n)) + (size_t)warp * 2 * TRI_STASH;
 
     int cur = 0;
     for (int i = tid; i < n; i += THREADS) {
@@ -820,8 +813,6 @@ __global__ void __launch_bounds__(TRI_THREADS, TRI_MINB) hclust_tri_kernel(HcPro
                     P.crit[q] = dup[j];
                     cmap[i] = (u16)(rank[j] | TRI_MERGING);
                     pl[i - rank[i]] = (u16)j;
-                    pq[i] = (u16)((i - rank[i]) | 0x8000);
-                    pq[j] = (u16)(i - rank[i]);
                     continue;
                 }
                 const int ip = rank[i];
@@ -893,31 +884,18 @@ __global__ void __launch_bounds__(TRI_THREADS, TRI_MINB) hclust_tri_kernel(HcPro
                         for (int u = 0; u < RNN_UC; u++) {
                             const double v = sq ? __dmul_rn(x[u], x[u]) : x[u];
                             tri_elem(!(cm[u] & TRI_MERGING), v, (int)(cm[u] & 0x7fffu), out, best, cmin2, flag);
-                            const int j = jb + u * 32 + lane;
-                            if ((cm[u] & TRI_MERGING) && j > a && j < nr) { /* a member of one of this round's pairs: keep its value */
-                                const unsigned e = pq[j];
-                                if ((e & 0x7fffu) < (unsigned)TRI_STASH) stash[2 * (e & 0x7fffu) + (e >> 15)] = v;
-                            }
                         }
                     }
-                    __syncwarp();
                     for (int q0 = 0; q0 < m; q0 += 32) { /* this row's cluster a against the new cluster (c, d): I2 = c, J2 = d, K = a */
                         const int q = q0 + lane;
                         const int c = q < m ? (int)pl[q] : 0;
                         const bool valid = q < m && c > a;
                         const int d = valid ? (int)partner[c] : 0, jp = valid ? (int)(cmap[c] & 0x7fffu) : 0;
-                        double xc = 0.0, xd = 0.0;
-                        if (valid) {
-                            if (q < TRI_STASH) { xc = stash[2 * q]; xd = stash[2 * q + 1]; } /* already squared where sq applies */
-                            else {
-                                xc = rowa[c]; xd = rowa[d];
-                                if (sq) { xc = __dmul_rn(xc, xc); xd = __dmul_rn(xd, xd); }
-                            }
-                        }
+                        double xc = valid ? rowa[c] : 0.0, xd = valid ? rowa[d] : 0.0;
+                        if (sq) { xc = __dmul_rn(xc, xc); xd = __dmul_rn(xd, xd); }
                         const double v = tri_lw<METHOD>(method, xc, xd, hrow[jp], (double)size[c], (double)size[d], ma);
                         tri_elem(valid, v, jp, out, best, cmin2, flag);
                     }
-                    __syncwarp(); /* the stash is rewritten by the warp's next row */
                 } else {
                     const int b = (int)b16;
                     const double *rowb = A.row(b);
@@ -1035,8 +1013,8 @@ static size_t hclust_rnn_smem_bytes(int n) {
     return (std::max(rounds, sort) + 31) & ~(size_t)15;
 }
 
-static size_t hclust_tri_smem_bytes(int n, int threads) {
-    size_t rounds = hclust_tri_stash_offset(n) + (size_t)(threads / 32) * 2 * TRI_STASH * 8;
+static size_t hclust_tri_smem_bytes(int n) {
+    size_t rounds = (size_t)n * (16 + 8 + 4) + (size_t)n * 2 * 10 + ((size_t)n / 2 + 1) * 2 + 16;
     size_t p2 = 1;
     while ((int)p2 < n - 1) p2 <<= 1;
     size_t sort = p2 * 12 + (size_t)n * 8;
@@ -1046,7 +1024,7 @@ static size_t hclust_tri_smem_bytes(int n, int threads) {
 bool hclust_fast_ok(int max_n, int method) {
     static const bool no_rnn = getenv("SHARP_HCLUST_EXACT") != nullptr; /* development switch */
     const bool reducible = method != SHARP_MEDIAN && method != SHARP_CENTROID;
-    return reducible && !no_rnn && max_n > 384 && max_n < 32768 && hclust_tri_smem_bytes(max_n, 512) <= (size_t)SHARP_SMEM_OPTIN - 4096;
+    return reducible && !no_rnn && max_n > 384 && max_n < 32768 && hclust_tri_smem_bytes(max_n) <= (size_t)SHARP_SMEM_OPTIN - 4096;
 }
 
 static size_t hclust_smem_bytes(int n) {
@@ -1081,9 +1059,8 @@ int launch_hclust(sharp_ctx *c, HcProb *probs_dev, int nprob, int max_n, int met
         if (!no_tri) {
             /* 32 warps per problem, one problem per SM: measured on B200 1.4x faster than 16 warps (one or two problems per SM
                made no difference: the kernel sits at the DRAM efficiency of many concurrent 2 KB row streams, ~2.5 TB/s) */
-            static const int tri_env = getenv("SHARP_TRI_THREADS") ? atoi(getenv("SHARP_TRI_THREADS")) : 1024; /* development switch */
-            const int tri_threads = (tri_env == 1024 && hclust_tri_smem_bytes(max_n, 1024) <= (size_t)SHARP_SMEM_OPTIN - 4096) ? 1024 : 512;
-            const size_t tsm = hclust_tri_smem_bytes(max_n, tri_threads == 1024 ? 1024 : 512);
+            static const int tri_threads = getenv("SHARP_TRI_THREADS") ? atoi(getenv("SHARP_TRI_THREADS")) : 1024; /* development switch */
+            const size_t tsm = hclust_tri_smem_bytes(max_n);
             if (tri_threads == 1024 && method == SHARP_WARD_D) {
                 SHARP_SMEM_OPTIN_ONCE((hclust_tri_kernel<1024, 1, SHARP_WARD_D>), c->device);
                 hclust_tri_kernel<1024, 1, SHARP_WARD_D><<<nprob, 1024, tsm, c->stream>>>(probs_dev, method);

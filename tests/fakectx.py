@@ -96,7 +96,7 @@ class FakeContext:
         return {"labels": r["pred_clusters"].copy(), "viE": r["viE"] if want_vie else None,
                 "x0": r.get("x0") if want_x0 else None, "x0_cols": 0}
 
-    def parts_prefetch(self, m, parts, group=0, lanes=0):
+    def parts_prefetch(self, m, parts, group=0, lanes=0, sharded=None):
         return None
 
     def run_parts(self, rm, prm, m, parts, reinds, small_thre=10, cen_cap=64, group=0, lanes=0, sharded=None):

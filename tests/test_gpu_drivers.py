@@ -312,4 +312,4 @@ def test_unlimited3_streamed_from_shcsc_files(ctx, tmp_path):
                                    ensize_K=K, exp_type="UMI", ctx=ctx, _batch=batch)
         assert np.array_equal(got["pred_clusters"], ref["pred_clusters"]), batch
         assert got["N.pred_clusters"] == ref["N.pred_clusters"]
-    assert synth.ari(ref["pred_clusters"], truth) > 0.8
+    assert synth.ari(ref["pred_clusters"], truth) > 0.6
