@@ -150,7 +150,10 @@ SEXP sharp_R_rp_project(SEXP E, SEXP rm_ptr, SEXP cells, SEXP normalize, SEXP lo
  * replaces the compute of SHARP_small (R/SHARP.R:343-416) / SHARP_large (R/SHARP.R:502-783) / SHARP_fpart. */
 SEXP sharp_R_run(SEXP E, SEXP rm_ptr, SEXP reind, SEXP large, SEXP flag, SEXP logkind, SEXP round_digits, SEXP ng,
                  SEXP Ncl, SEXP enpN, SEXP indN, SEXP hmethod, SEXP minN, SEXP maxN, SEXP silthre, SEXP heightN,
-                 SEXP normalize, SEXP forview, SEXP device, SEXP p_) {
+                 SEXP normalize, SEXP forview, SEXP device, SEXP p_, SEXP opts) {
+    /* opts: NULL or integer(4) = c(skip_smetac, block_max_n, shard, shard_rotate) -- SHARP_fpart's two-level scheme
+     * (R/SHARP_unlimited2.R:421, 477-494: per-block maxN.cluster = 40, no cross-block sMetaC) and block-sharded runs on
+     * a context that carries a communicator (sharp_R_comm_init) */
     expr_t e = expr_from(E);
     sharp_rm_dev *rm = (sharp_rm_dev *)R_ExternalPtrAddr(rm_ptr);
     if (!rm) Rf_error("rm handle was freed");
@@ -167,6 +170,12 @@ SEXP sharp_R_run(SEXP E, SEXP rm_ptr, SEXP reind, SEXP large, SEXP flag, SEXP lo
     q.hc = hc_from(hmethod, R_NilValue, minN, maxN, silthre, heightN);
     q.normalize = Rf_asInteger(normalize);
     q.norm_mul = 1e6;
+    if (!Rf_isNull(opts) && Rf_length(opts) >= 4) {
+        q.skip_smetac = INTEGER(opts)[0];
+        q.block_max_n = INTEGER(opts)[1];
+        q.shard = INTEGER(opts)[2];
+        q.shard_rotate = INTEGER(opts)[3];
+    }
     const int p = Rf_asInteger(p_), view = Rf_asLogical(forview);
     int64_t *re = NULL;
     if (!Rf_isNull(reind)) {
@@ -372,17 +381,89 @@ SEXP sharp_R_smetac_centroids(SEXP cen, SEXP ncells, SEXP hmethod, SEXP Ncl, SEX
     return tf;
 }
 
+/* ---- multi-GPU: one R process per GPU; the NCCL communicator lives on the context ------------------------------ */
+/* .Call("sharp_R_comm_unique_id") -> raw(128); rank 0 calls it and hands the bytes to the other processes (socket,
+ * file, MPI -- the library never does the rendezvous itself) */
+SEXP sharp_R_comm_unique_id(void) {
+    SEXP id = PROTECT(Rf_allocVector(RAWSXP, SHARP_COMM_ID_BYTES));
+    if (sharp_comm_unique_id(RAW(id), SHARP_COMM_ID_BYTES) != SHARP_OK) { UNPROTECT(1); Rf_error("%s", sharp_last_error()); }
+    UNPROTECT(1);
+    return id;
+}
+
+/* .Call("sharp_R_comm_init", id, rank, world, device): every process, same id; replaces registerDoParallel(n.cores) */
+SEXP sharp_R_comm_init(SEXP id, SEXP rank, SEXP world, SEXP device) {
+    if (TYPEOF(id) != RAWSXP || Rf_length(id) < SHARP_COMM_ID_BYTES) Rf_error("sharp_R_comm_init: id must be raw(128)");
+    if (sharp_comm_init(ctx_for(Rf_asInteger(device)), RAW(id), Rf_asInteger(rank), Rf_asInteger(world)) != SHARP_OK)
+        Rf_error("%s", sharp_last_error());
+    return R_NilValue;
+}
+
+/* .Call("sharp_R_comm_allgather", x, device): x raw vector (serialize() of this rank's labels / centroids) -> list of
+ * raw vectors, one per rank: the `.combine` of foreach (R/SHARP_unlimited3.R:137-147) across processes */
+SEXP sharp_R_comm_allgather(SEXP x, SEXP device) {
+    sharp_ctx *c = ctx_for(Rf_asInteger(device));
+    int rank = 0, world = 1;
+    sharp_comm_info(c, &rank, &world, NULL);
+    int64_t *sizes = (int64_t *)R_alloc((size_t)world, sizeof(int64_t));
+    int64_t *eight = (int64_t *)R_alloc((size_t)world, sizeof(int64_t));
+    for (int r = 0; r < world; r++) eight[r] = 8;
+    int64_t mine = (int64_t)XLENGTH(x);
+    if (sharp_comm_allgatherv(c, &mine, eight, sizes) != SHARP_OK) Rf_error("%s", sharp_last_error());
+    int64_t total = 0;
+    for (int r = 0; r < world; r++) total += sizes[r];
+    unsigned char *all = (unsigned char *)R_alloc((size_t)(total > 0 ? total : 1), 1);
+    if (sharp_comm_allgatherv(c, RAW(x), sizes, all) != SHARP_OK) Rf_error("%s", sharp_last_error());
+    SEXP out = PROTECT(Rf_allocVector(VECSXP, world));
+    int64_t off = 0;
+    for (int r = 0; r < world; r++) {
+        SEXP v = PROTECT(Rf_allocVector(RAWSXP, (R_xlen_t)sizes[r]));
+        memcpy(RAW(v), all + off, (size_t)sizes[r]);
+        SET_VECTOR_ELT(out, r, v);
+        UNPROTECT(1);
+        off += sizes[r];
+    }
+    UNPROTECT(1);
+    return out;
+}
+
+/* ---- streaming ingestion (SHARP_unlimited3, R/SHARP_unlimited3.R:103-131: readRDS per part) ----------------------- */
+/* .Call("sharp_R_csc_read", path) -> list(Dim, p, i, x): the slots of the dgCMatrix stored in an SHCSC001 file (written
+ * once with writeBin -- INTEGRATION.md 5), read by the library's threaded pread.  `p` comes back as doubles (a part
+ * can hold more than 2^31 non-zeros); new("dgCMatrix", ...) takes as.integer(p) when it fits. */
+SEXP sharp_R_csc_read(SEXP path) {
+    const char *f = CHAR(STRING_ELT(path, 0));
+    int m = 0;
+    int64_t n = 0, nnz = 0;
+    if (sharp_csc_file_info(f, &m, &n, &nnz) != SHARP_OK) Rf_error("%s", sharp_last_error());
+    int64_t *cp = (int64_t *)R_alloc((size_t)(n + 1), sizeof(int64_t));
+    SEXP ri = PROTECT(Rf_allocVector(INTSXP, (R_xlen_t)nnz)), xv = PROTECT(Rf_allocVector(REALSXP, (R_xlen_t)nnz));
+    if (sharp_csc_file_read(f, cp, INTEGER(ri), REAL(xv), 4) != SHARP_OK) { UNPROTECT(2); Rf_error("%s", sharp_last_error()); }
+    SEXP pp = PROTECT(Rf_allocVector(REALSXP, (R_xlen_t)(n + 1)));
+    for (int64_t j = 0; j <= n; j++) REAL(pp)[j] = (double)cp[j];
+    SEXP dim = PROTECT(Rf_allocVector(INTSXP, 2));
+    INTEGER(dim)[0] = m; INTEGER(dim)[1] = (int)n;
+    SEXP out = PROTECT(Rf_allocVector(VECSXP, 4));
+    SET_VECTOR_ELT(out, 0, dim); SET_VECTOR_ELT(out, 1, pp); SET_VECTOR_ELT(out, 2, ri); SET_VECTOR_ELT(out, 3, xv);
+    UNPROTECT(5);
+    return out;
+}
+
 static const R_CallMethodDef call_methods[] = {
     {"sharp_R_device_info", (DL_FUNC)&sharp_R_device_info, 1},
     {"sharp_R_rm_upload", (DL_FUNC)&sharp_R_rm_upload, 2},
     {"sharp_R_rp_project", (DL_FUNC)&sharp_R_rp_project, 9},
-    {"sharp_R_run", (DL_FUNC)&sharp_R_run, 20},
+    {"sharp_R_run", (DL_FUNC)&sharp_R_run, 21},
     {"sharp_R_run_parts", (DL_FUNC)&sharp_R_run_parts, 14},
     {"sharp_R_opt_hclust", (DL_FUNC)&sharp_R_opt_hclust, 9},
     {"sharp_R_wmetac", (DL_FUNC)&sharp_R_wmetac, 8},
     {"sharp_R_smetac", (DL_FUNC)&sharp_R_smetac, 9},
     {"sharp_R_centroids", (DL_FUNC)&sharp_R_centroids, 4},
     {"sharp_R_smetac_centroids", (DL_FUNC)&sharp_R_smetac_centroids, 9},
+    {"sharp_R_comm_unique_id", (DL_FUNC)&sharp_R_comm_unique_id, 0},
+    {"sharp_R_comm_init", (DL_FUNC)&sharp_R_comm_init, 4},
+    {"sharp_R_comm_allgather", (DL_FUNC)&sharp_R_comm_allgather, 2},
+    {"sharp_R_csc_read", (DL_FUNC)&sharp_R_csc_read, 1},
     {NULL, NULL, 0}};
 
 void R_init_SHARP(DllInfo *dll) {

@@ -145,6 +145,9 @@ struct sharp_ctx {
     const void *pf_src = nullptr; // host buffer it was copied from (a prefetch is only used for the same buffer)
     int32_t *h_labels = nullptr;  // pinned label mirror of a group run
     size_t h_labels_cap = 0;
+    cudaStream_t rm_stream = nullptr;   // copies of the projection matrices (sharp_rm_upload)
+    unsigned char *rm_stage = nullptr;  // their pinned staging blob
+    size_t rm_stage_cap = 0;
     unsigned char *h_gather = nullptr;  // pinned staging of the host-side column gather of a sharded, shuffled part
     size_t h_gather_cap = 0;
     int block_budget_gb = 48;     // cap of the distance-matrix workspace (D + Dw) of one context
@@ -187,6 +190,7 @@ struct sharp_rm_dev {
     // fixed-size records of the record-gather kernel (rp_project_v3.cu): rv vectors of {count, 7 entries} per gene, the
     // gene's entries dealt round-robin over them; entry = byte offset of the output in an accumulator array | sign
     uint4 *rec = nullptr;        // [m * rv]
+    unsigned char *blob = nullptr;  // the one device allocation all of the above point into
     int rv = 0;                  // vectors per record (2, 4, 8 or 16); 0: no records (K*p too large)
 };
 

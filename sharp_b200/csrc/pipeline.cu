@@ -1252,6 +1252,9 @@ void destroy_ctx_resources(sharp_ctx *c) {
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
     if (c->ev_up) cudaEventDestroy(c->ev_up);
     if (c->up_stream) { cudaStreamSynchronize(c->up_stream); cudaStreamDestroy(c->up_stream); }
+    if (c->rm_stream) { cudaStreamSynchronize(c->rm_stream); cudaStreamDestroy(c->rm_stream); }
+    if (c->rm_stage) cudaFreeHost(c->rm_stage);
+    c->rm_stage = nullptr;
     cudaStreamDestroy(c->stream);
 }
 
@@ -1689,6 +1692,17 @@ int sharp_prof_get(sharp_ctx *c, int kid, double *ms, int64_t *launches) {
 // matrices on every call and frees it at the end, and cudaMalloc / cudaFree are device-wide synchronisations whose cost
 // is unbounded on a busy 180 GB device (hundreds of ms were measured between two steps).  A released buffer is kept
 // (up to 64 of them, a few MB in all) and handed to the next request of at most its size and at least half of it.
+// fn(t) for t = 0..nt-1 on nt host threads (the caller runs t = 0)
+extern "C++" {
+template <class F>
+static void host_parallel(int nt, F fn) {
+    std::vector<std::thread> th;
+    for (int t = 1; t < nt; t++) th.emplace_back([&fn, t]() { fn(t); });
+    fn(0);
+    for (auto &x : th) x.join();
+}
+}
+
 namespace {
 struct RmCacheEnt { int device; size_t cap; void *ptr; };
 std::mutex g_rm_mu;
@@ -1726,6 +1740,11 @@ void rm_release(void *ptr) {
 }
 }  // namespace
 
+// The K ranM matrices (dgCMatrix slots, concatenated) in the layouts of the projection kernels: gene-major CSR (fp64
+// variant, overflow genes of the records), the padded vectors of the r1 fixed-point kernel (dense input) and the
+// fixed-size records of rp_project_v3.cu.  Built by a few host threads (members, then gene ranges) into ONE pinned
+// blob and copied with ONE cudaMemcpyAsync on a stream of its own, so the copy does not queue behind a look-ahead
+// upload of expression data that is already in flight.
 int sharp_rm_upload(sharp_ctx *c, int m, int p, int K, const int32_t *colptr, const int32_t *rowidx, const double *x,
                     const int64_t *nnz_off, sharp_rm_dev **out) {
     SHARP_TRY(use(c));
@@ -1734,124 +1753,200 @@ int sharp_rm_upload(sharp_ctx *c, int m, int p, int K, const int32_t *colptr, co
     const int64_t nnz = nnz_off[K];
     if (nnz > 0 && (!rowidx || !x)) return set_error(SHARP_E_ARG, "rm_upload: missing slots");
     if ((int64_t)K * p > 0x7fffffffLL) return set_error(SHARP_E_LIMIT, "K*p too large");
-    double mag = 0.0;
-    for (int64_t q = 0; q < nnz; q++) {
-        double a = std::fabs(x[q]);
-        if (a == 0.0) continue;
-        if (mag == 0.0) mag = a;
-        else if (a != mag)
-            return set_error(SHARP_E_LIMIT, "rm_upload: the projection matrices are not ternary (|x| = %g and %g); only ranM()-style matrices are supported", mag, a);
-    }
+    for (int k = 0; k < K; k++)
+        if (colptr[(size_t)k * (p + 1) + p] != nnz_off[k + 1] - nnz_off[k])
+            return set_error(SHARP_E_ARG, "rm_upload: colptr/nnz_off mismatch for matrix %d", k);
     const bool e16 = (int64_t)K * p <= 32768;
-    std::vector<uint32_t> rowptr((size_t)m + 1, 0);
+    const int NT = std::max(1, std::min(K, 8));
+    // ---- per member: entries per gene, magnitude check, widest column ----
+    std::vector<uint32_t> cntk((size_t)K * m, 0);
+    std::vector<double> magk((size_t)K, 0.0), mag2k((size_t)K, 0.0);
+    std::vector<int> badk((size_t)K, 0), colk((size_t)K, 0);
+    host_parallel(NT, [&](int t) {
+        for (int k = t; k < K; k += NT) {
+            uint32_t *cnt = cntk.data() + (size_t)k * m;
+            double mag = 0.0, other = 0.0;
+            for (int64_t q = nnz_off[k]; q < nnz_off[k + 1]; q++) {
+                if (rowidx[q] < 0 || rowidx[q] >= m) { badk[k] = 1; break; }
+                const double a = std::fabs(x[q]);
+                if (a == 0.0) continue;
+                cnt[rowidx[q]]++;
+                if (mag == 0.0) mag = a;
+                else if (a != mag) other = a;
+            }
+            magk[k] = mag; mag2k[k] = other;
+            const int32_t *cp = colptr + (size_t)k * (p + 1);
+            int w = 0;
+            for (int j = 0; j < p; j++) w = std::max(w, cp[j + 1] - cp[j]);
+            colk[k] = w;
+        }
+    });
+    double mag = 0.0;
+    int max_col_nnz = 0;
     for (int k = 0; k < K; k++) {
-        const int32_t *cp = colptr + (size_t)k * (p + 1);
-        if (cp[p] != nnz_off[k + 1] - nnz_off[k]) return set_error(SHARP_E_ARG, "rm_upload: colptr/nnz_off mismatch for matrix %d", k);
-        for (int64_t q = nnz_off[k]; q < nnz_off[k + 1]; q++) {
-            if (rowidx[q] < 0 || rowidx[q] >= m) return set_error(SHARP_E_ARG, "rm_upload: row index out of range");
-            if (x[q] != 0.0) rowptr[rowidx[q] + 1]++;
+        if (badk[k]) return set_error(SHARP_E_ARG, "rm_upload: row index out of range");
+        double other = mag2k[k];
+        if (magk[k] != 0.0) {
+            if (mag == 0.0) mag = magk[k];
+            else if (magk[k] != mag) other = magk[k];
+        }
+        if (other != 0.0)
+            return set_error(SHARP_E_LIMIT, "rm_upload: the projection matrices are not ternary (|x| = %g and %g); only ranM()-style matrices are supported", mag, other);
+        max_col_nnz = std::max(max_col_nnz, colk[k]);
+    }
+    // rowptr, and cntk[k][i] becomes the position of member k's first entry of gene i (members in order inside a gene)
+    std::vector<uint32_t> rowptr((size_t)m + 1, 0);
+    {
+        uint32_t run = 0;
+        for (int i = 0; i < m; i++) {
+            for (int k = 0; k < K; k++) {
+                uint32_t &cv = cntk[(size_t)k * m + i];
+                const uint32_t t = cv;
+                cv = run;
+                run += t;
+            }
+            rowptr[i + 1] = run;
         }
     }
-    for (int i = 0; i < m; i++) rowptr[i + 1] += rowptr[i];
     const int64_t nz = rowptr[m];
     std::vector<uint32_t> ent((size_t)nz + 8, 0);
-    {
-        std::vector<uint32_t> fill(rowptr.begin(), rowptr.end() - 1);
-        for (int k = 0; k < K; k++) {
+    host_parallel(NT, [&](int t) {
+        for (int k = t; k < K; k += NT) {
+            uint32_t *fill = cntk.data() + (size_t)k * m;
             const int32_t *cp = colptr + (size_t)k * (p + 1);
             for (int j = 0; j < p; j++)
                 for (int32_t q = cp[j]; q < cp[j + 1]; q++) {
-                    int64_t g = nnz_off[k] + q;
+                    const int64_t g = nnz_off[k] + q;
                     if (x[g] == 0.0) continue;
-                    uint32_t col = (uint32_t)(k * p + j);
-                    uint32_t v = e16 ? (col | (x[g] < 0 ? 0x8000u : 0u)) : (col | (x[g] < 0 ? 0x80000000u : 0u));
-                    ent[fill[rowidx[g]]++] = v;
+                    const uint32_t col = (uint32_t)(k * p + j);
+                    ent[fill[rowidx[g]]++] = e16 ? (col | (x[g] < 0 ? 0x8000u : 0u)) : (col | (x[g] < 0 ? 0x80000000u : 0u));
                 }
         }
-    }
+    });
     tr.mark("rm_csr");
     sharp_rm_dev *r = new sharp_rm_dev();
     r->device = c->device;
     r->m = m; r->p = p; r->K = K; r->mag = mag; r->nnz = nz;
+    r->max_col_nnz = max_col_nnz;
     r->tile_genes = RP_TILE_GENES_HOST;
     r->ntiles = (m + r->tile_genes - 1) / r->tile_genes;
     for (int t = 0; t < r->ntiles; t++) {
         int g0 = t * r->tile_genes, g1 = std::min(m, g0 + r->tile_genes);
         r->max_tile_entries = std::max<int>(r->max_tile_entries, (int)(rowptr[g1] - rowptr[g0]));
     }
-    cudaError_t e1 = rm_alloc(c->device, (void **)&r->rowptr, (size_t)(m + 1) * 4);
-    cudaError_t e2;
-    if (e16) {
-        std::vector<uint16_t> e16v((size_t)nz + 16, 0);
-        for (int64_t q = 0; q < nz; q++) e16v[q] = (uint16_t)ent[q];
-        e2 = rm_alloc(c->device, (void **)&r->ent16, e16v.size() * 2);
-        if (e1 == cudaSuccess && e2 == cudaSuccess) e2 = cudaMemcpy(r->ent16, e16v.data(), e16v.size() * 2, cudaMemcpyHostToDevice);
-    } else {
-        e2 = rm_alloc(c->device, (void **)&r->ent32, ent.size() * 4);
-        if (e1 == cudaSuccess && e2 == cudaSuccess) e2 = cudaMemcpy(r->ent32, ent.data(), ent.size() * 4, cudaMemcpyHostToDevice);
-    }
-    if (e1 == cudaSuccess) e1 = cudaMemcpy(r->rowptr, rowptr.data(), (size_t)(m + 1) * 4, cudaMemcpyHostToDevice);
-    for (int k = 0; k < K; k++) {
-        const int32_t *cp = colptr + (size_t)k * (p + 1);
-        for (int j = 0; j < p; j++) r->max_col_nnz = std::max(r->max_col_nnz, cp[j + 1] - cp[j]);
-    }
-    tr.mark("rm_copy1");
-    if ((int64_t)K * p <= 32700 && e1 == cudaSuccess && e2 == cudaSuccess) {
+    // ---- layout of the blob ----
+    const bool want_padded = (int64_t)K * p <= 32700;
+    std::vector<uint32_t> vecptr;
+    int rv = 0;
+    if (want_padded) {
         const int kpr = (K * p + 31) & ~31;
         r->kpd = kpr + 32;
-        std::vector<uint32_t> vecptr((size_t)m + 1, 0);
-        for (int i = 0; i < m; i++) vecptr[i + 1] = vecptr[i] + (rowptr[i + 1] - rowptr[i] + 7) / 8;
-        std::vector<uint16_t> padded((size_t)vecptr[m] * 8 + 8, (uint16_t)kpr);
+        vecptr.assign((size_t)m + 1, 0);
         double mean = 0, sq = 0;
         for (int i = 0; i < m; i++) {
-            const uint32_t c = rowptr[i + 1] - rowptr[i];
-            for (uint32_t q = c; q < ((c + 7) & ~7u); q++) padded[(size_t)vecptr[i] * 8 + q] = (uint16_t)(kpr + (i & 31));
-            for (uint32_t q = 0; q < c; q++) padded[(size_t)vecptr[i] * 8 + q] = (uint16_t)ent[rowptr[i] + q];
-            mean += c;
-            sq += (double)c * c;
+            const uint32_t cn = rowptr[i + 1] - rowptr[i];
+            vecptr[i + 1] = vecptr[i] + (cn + 7) / 8;
+            mean += cn;
+            sq += (double)cn * cn;
         }
         mean /= m;
         const double sd = std::sqrt(std::max(0.0, sq / m - mean * mean));
         r->vec_per_gene = std::min(6, std::max(1, (int)std::ceil((mean + 2.5 * sd) / 8.0)));
-        cudaError_t e3 = rm_alloc(c->device, (void **)&r->vecptr, (size_t)(m + 1) * 4);
-        cudaError_t e4 = rm_alloc(c->device, (void **)&r->entvec, padded.size() * 2);
-        if (e3 == cudaSuccess) e3 = cudaMemcpy(r->vecptr, vecptr.data(), (size_t)(m + 1) * 4, cudaMemcpyHostToDevice);
-        if (e4 == cudaSuccess) e4 = cudaMemcpy(r->entvec, padded.data(), padded.size() * 2, cudaMemcpyHostToDevice);
-        if (e3 != cudaSuccess) e1 = e3;
-        if (e4 != cudaSuccess) e2 = e4;
-    }
-    tr.mark("rm_padded");
-    if (r->kpd > 0 && r->kpd <= 8191 && r->max_col_nnz <= 255 && e16 && e1 == cudaSuccess && e2 == cudaSuccess) {
-        /* records of the record-gather kernel: the smallest record that fewer than 0.2 % of the genes overflow */
-        int rv = 2;
-        for (; rv <= 16; rv *= 2) {
-            int over = 0;
-            for (int i = 0; i < m; i++) over += (int)(rowptr[i + 1] - rowptr[i]) > 7 * rv;
-            if (over <= m / 500) break;
+        if (r->kpd <= 8191 && max_col_nnz <= 255 && e16) {
+            /* records of the record-gather kernel: the smallest record that fewer than 0.2 % of the genes overflow */
+            for (rv = 2; rv <= 16; rv *= 2) {
+                int over = 0;
+                for (int i = 0; i < m; i++) over += (int)(rowptr[i + 1] - rowptr[i]) > 7 * rv;
+                if (over <= m / 500) break;
+            }
+            if (rv > 16) rv = 0;
         }
-        if (rv <= 16) {
-            std::vector<uint16_t> rec((size_t)m * rv * 8, 0);
-            for (int i = 0; i < m; i++) {
-                const uint32_t cnt = rowptr[i + 1] - rowptr[i];
-                uint16_t *R = rec.data() + (size_t)i * rv * 8;
-                if ((int)cnt > 7 * rv) { R[0] = 0xffffu; continue; }
-                for (uint32_t q = 0; q < cnt; q++) {
+    }
+    auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
+    const size_t o_rowptr = 0;
+    const size_t o_ent = al(o_rowptr + (size_t)(m + 1) * 4);
+    const size_t ent_bytes = e16 ? ((size_t)nz + 16) * 2 : ((size_t)nz + 8) * 4;
+    const size_t o_vecptr = al(o_ent + ent_bytes);
+    const size_t o_entvec = al(o_vecptr + (want_padded ? (size_t)(m + 1) * 4 : 0));
+    const size_t entvec_bytes = want_padded ? ((size_t)vecptr[m] * 8 + 8) * 2 : 0;
+    const size_t o_rec = al(o_entvec + entvec_bytes);
+    const size_t rec_bytes = (size_t)m * rv * 16;
+    const size_t total = al(o_rec + rec_bytes);
+    if (c->rm_stage_cap < total) {
+        if (c->rm_stage) cudaFreeHost(c->rm_stage);
+        c->rm_stage = nullptr;
+        c->rm_stage_cap = 0;
+        const size_t cap = total + total / 4;
+        cudaError_t eh = cudaHostAlloc((void **)&c->rm_stage, cap, cudaHostAllocDefault);
+        if (eh != cudaSuccess) { delete r; return set_error(SHARP_E_CUDA, "rm_upload: pinned staging of %zu bytes: %s", cap, cudaGetErrorString(eh)); }
+        c->rm_stage_cap = cap;
+    }
+    unsigned char *H = c->rm_stage;
+    memcpy(H + o_rowptr, rowptr.data(), (size_t)(m + 1) * 4);
+    if (want_padded) memcpy(H + o_vecptr, vecptr.data(), (size_t)(m + 1) * 4);
+    const int kpr = r->kpd - 32;
+    const uint32_t kpd4 = (uint32_t)r->kpd * 4u;
+    const int GT = 4; /* gene ranges */
+    host_parallel(GT, [&](int t) {
+        const int g0 = (int)((int64_t)m * t / GT), g1 = (int)((int64_t)m * (t + 1) / GT);
+        if (e16) {
+            uint16_t *E = reinterpret_cast<uint16_t *>(H + o_ent);
+            for (uint32_t q = rowptr[g0]; q < rowptr[g1]; q++) E[q] = (uint16_t)ent[q];
+            if (t == GT - 1) for (int64_t q = nz; q < nz + 16; q++) E[q] = 0;
+        } else {
+            uint32_t *E = reinterpret_cast<uint32_t *>(H + o_ent);
+            for (uint32_t q = rowptr[g0]; q < rowptr[g1]; q++) E[q] = ent[q];
+            if (t == GT - 1) for (int64_t q = nz; q < nz + 8; q++) E[q] = 0;
+        }
+        if (want_padded) {
+            uint16_t *Pd = reinterpret_cast<uint16_t *>(H + o_entvec);
+            for (int i = g0; i < g1; i++) {
+                const uint32_t cn = rowptr[i + 1] - rowptr[i];
+                uint16_t *dst = Pd + (size_t)vecptr[i] * 8;
+                for (uint32_t q = 0; q < cn; q++) dst[q] = (uint16_t)ent[rowptr[i] + q];
+                for (uint32_t q = cn; q < ((cn + 7) & ~7u); q++) dst[q] = (uint16_t)(kpr + (i & 31));
+            }
+            if (t == GT - 1) for (int q = 0; q < 8; q++) Pd[(size_t)vecptr[m] * 8 + q] = (uint16_t)kpr;
+        }
+        if (rv) {
+            uint16_t *R0 = reinterpret_cast<uint16_t *>(H + o_rec);
+            memset(R0 + (size_t)g0 * rv * 8, 0, (size_t)(g1 - g0) * rv * 16);
+            for (int i = g0; i < g1; i++) {
+                const uint32_t cn = rowptr[i + 1] - rowptr[i];
+                uint16_t *R = R0 + (size_t)i * rv * 8;
+                if ((int)cn > 7 * rv) { R[0] = 0xffffu; continue; }
+                for (uint32_t q = 0; q < cn; q++) {
                     const uint32_t en = ent[rowptr[i] + q];
                     const int v = (int)(q % rv), slot = 1 + (int)(q / rv);
-                    R[v * 8 + slot] = (uint16_t)(((en & 0x7fffu) << 2) + ((en & 0x8000u) ? (uint32_t)r->kpd * 4u : 0u)); /* offset into [+ | -] */
+                    R[v * 8 + slot] = (uint16_t)(((en & 0x7fffu) << 2) + ((en & 0x8000u) ? kpd4 : 0u)); /* offset into [+ | -] */
                     R[v * 8]++;
                 }
             }
-            cudaError_t e5 = rm_alloc(c->device, (void **)&r->rec, rec.size() * 2);
-            if (e5 == cudaSuccess) e5 = cudaMemcpy(r->rec, rec.data(), rec.size() * 2, cudaMemcpyHostToDevice);
-            if (e5 != cudaSuccess) e1 = e5;
-            r->rv = rv;
         }
+    });
+    tr.mark("rm_layouts");
+    unsigned char *dev = nullptr;
+    cudaError_t e1 = rm_alloc(c->device, (void **)&dev, total);
+    if (e1 == cudaSuccess && !c->rm_stream) e1 = cudaStreamCreateWithFlags(&c->rm_stream, cudaStreamNonBlocking);
+    if (e1 == cudaSuccess) e1 = cudaMemcpyAsync(dev, H, total, cudaMemcpyHostToDevice, c->rm_stream);
+    if (e1 == cudaSuccess) e1 = cudaStreamSynchronize(c->rm_stream);
+    tr.mark("rm_copy");
+    if (e1 != cudaSuccess) {
+        if (dev) rm_release(dev);
+        delete r;
+        return set_error(SHARP_E_CUDA, "rm_upload: %s", cudaGetErrorString(e1));
     }
-    tr.mark("rm_records");
-    if (e1 != cudaSuccess || e2 != cudaSuccess) {
-        sharp_rm_free(r);
-        return set_error(SHARP_E_CUDA, "rm_upload: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
+    r->blob = dev;
+    r->rowptr = reinterpret_cast<uint32_t *>(dev + o_rowptr);
+    if (e16) r->ent16 = reinterpret_cast<uint16_t *>(dev + o_ent);
+    else r->ent32 = reinterpret_cast<uint32_t *>(dev + o_ent);
+    if (want_padded) {
+        r->vecptr = reinterpret_cast<uint32_t *>(dev + o_vecptr);
+        r->entvec = reinterpret_cast<uint4 *>(dev + o_entvec);
+    }
+    if (rv) {
+        r->rec = reinterpret_cast<uint4 *>(dev + o_rec);
+        r->rv = rv;
     }
     *out = r;
     return 0;
@@ -1860,12 +1955,7 @@ int sharp_rm_upload(sharp_ctx *c, int m, int p, int K, const int32_t *colptr, co
 void sharp_rm_free(sharp_rm_dev *r) {
     if (!r) return;
     cudaSetDevice(r->device);
-    rm_release(r->rowptr);
-    rm_release(r->ent16);
-    rm_release(r->ent32);
-    rm_release(r->vecptr);
-    rm_release(r->entvec);
-    rm_release(r->rec);
+    rm_release(r->blob); /* every layout lives in the one blob */
     delete r;
 }
 

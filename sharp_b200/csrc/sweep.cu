@@ -114,32 +114,46 @@ __device__ int select_rule(int n, int nlev, const double *msil, const double *ch
 // =====================================================================================================
 // nested sweep (feature problems)
 // =====================================================================================================
+// One CTA of NT threads per problem; thread t owns point x = c0 + t of the current chunk of NT points.
+//   * the rows are visited CLUSTER BY CLUSTER of the finest cut (counting sort `order`, ascending y inside a cluster --
+//     the order cluster::sildist adds in), so the distance sum of (x, cluster) is a register accumulation, stored once
+//     per cluster: no shared-memory read-modify-write per element (r2 profile: 30 % of the stalls of the first version);
+//   * shared memory holds the MEANS q[c][t] = sum / count of every live cluster (dead clusters: +Inf), the sums live in
+//     an L2-resident scratch: a level touches two sums, and a rescan for the nearest other cluster is NT-uniform loads
+//     and compares instead of kmax fp64 divisions in a handful of divergent lanes (23 % of the stalls);
+//   * the medians are radix selections (one warp per level) instead of 39 block-wide bitonic sorts (18 %).
 // dynamic shared memory layout (bytes):
-//   acc      [kcap][SW_THREADS] double   (also: sort buffer P2 doubles; Gram matrix kcap*kcap doubles; the scan
-//            scratch rank [n] int of cutree, which runs before and after the passes that use the accumulators)
-//   cidf [n] int, step_of [n] u16, link [n] u16   -- 105 KB at n = 2000, kmax = 40: TWO problems per SM
-//   small tables: cnt_lv [nlevcap][kcap] int, own map slot_lv [nlevcap][kcap] uint8, mergeA/B [nlevcap] int
+//   q        [kcap][NT] double   (also: Gram matrix kcap*kcap doubles; the scan scratch rank [n] int of cutree, which
+//            runs before and after the passes that use q; the radix histograms [NT/32][256] int)
+//   cidf [n] int, step_of [n] u16, link [n] u16, order [n] u16
+//   small tables: cnt_lv [nlevcap][kcap] int, own map slot_lv [nlevcap][kcap] uint8, mergeA/B [nlevcap] int, cstart
 struct NestedLayout {
-    size_t acc_off, ints_off, cnt_off, slot_off, merge_off, msil_off, total;
+    size_t acc_off, ints_off, cnt_off, slot_off, merge_off, msil_off, cstart_off, total;
 };
-__host__ __device__ inline NestedLayout nested_layout(int n, int kcap, int nlevcap) {
+__host__ __device__ inline NestedLayout nested_layout(int n, int kcap, int nlevcap, int nt) {
     NestedLayout L;
-    size_t acc_bytes = (size_t)kcap * SW_THREADS * 8;
-    int p2 = 1;
-    while (p2 < n) p2 <<= 1;
-    size_t sort_bytes = (size_t)p2 * 8;
+    size_t acc_bytes = (size_t)kcap * nt * 8;
     size_t gram_bytes = (size_t)kcap * kcap * 8;
-    size_t a = acc_bytes > sort_bytes ? acc_bytes : sort_bytes;
-    a = a > gram_bytes ? a : gram_bytes;
+    size_t hist_bytes = (size_t)(nt / 32) * 256 * 4;
+    size_t a = acc_bytes > gram_bytes ? acc_bytes : gram_bytes;
+    a = a > hist_bytes ? a : hist_bytes;
     a = a > (size_t)n * 4 ? a : (size_t)n * 4;
     L.acc_off = 0;
     L.ints_off = (a + 15) & ~(size_t)15;
-    L.cnt_off = (L.ints_off + (size_t)n * 4 + (size_t)2 * n * 2 + 15) & ~(size_t)15;
+    L.cnt_off = (L.ints_off + (size_t)n * 4 + (size_t)3 * n * 2 + 15) & ~(size_t)15;
     L.slot_off = L.cnt_off + (size_t)nlevcap * kcap * 4;
     L.merge_off = (L.slot_off + (size_t)nlevcap * kcap + 15) & ~(size_t)15;
     L.msil_off = (L.merge_off + (size_t)nlevcap * 2 * 4 + 15) & ~(size_t)15;
-    L.total = L.msil_off + (size_t)nlevcap * 2 * 8;
+    L.cstart_off = L.msil_off + (size_t)nlevcap * 2 * 8;
+    L.total = L.cstart_off + (size_t)(kcap + 1) * 4;
     return L;
+}
+
+constexpr int NESTED_NT_MAX = 512;
+constexpr size_t NESTED_SMEM_MAX = 216 * 1024;
+
+static int nested_threads(int max_n, int kcap, int nlevcap) {
+    return nested_layout(max_n, kcap, nlevcap, 512).total <= NESTED_SMEM_MAX ? 512 : 256;
 }
 
 size_t sweep_nested_scratch_bytes(int max_n, int max_p, HcParamsDev prm) {
@@ -147,21 +161,104 @@ size_t sweep_nested_scratch_bytes(int max_n, int max_p, HcParamsDev prm) {
     if (nlev < 1) nlev = 1;
     size_t sil = (size_t)nlev * max_n * 8;
     size_t csum = (size_t)NESTED_MAXK * max_p * 8;
-    return ((sil + csum) + 255) & ~(size_t)255;
+    size_t sums = (size_t)NESTED_MAXK * NESTED_NT_MAX * 8;
+    return ((sil + csum + sums) + 255) & ~(size_t)255;
 }
 
-__global__ void __launch_bounds__(SW_THREADS, 2)
+// order-preserving 64-bit key of a double (NaN excluded by the caller), and back
+__device__ __forceinline__ unsigned long long sil_key(double v) {
+    const long long b = __double_as_longlong(v + 0.0); /* -0 -> +0 */
+    return b < 0 ? ~(unsigned long long)b : ((unsigned long long)b | 0x8000000000000000ull);
+}
+__device__ __forceinline__ double sil_unkey(unsigned long long k) {
+    return __longlong_as_double((long long)((k & 0x8000000000000000ull) ? (k & 0x7fffffffffffffffull) : ~k));
+}
+
+// stats::median of a[0..n) by one warp: radix selection of the element of rank (n + 1) / 2 - 1, eight 8-bit passes over
+// the (L2-resident) values with a 256-bin histogram in shared memory; for even n the next element is either the same
+// value or the smallest larger one.  Returns the same bits as median_sorted() on the sorted array.
+__device__ double warp_median_select(const double *__restrict__ a, int n, int *hist, int lane) {
+    const int r0 = (n + 1) / 2 - 1;
+    int r = r0, less = 0, eq = 0;
+    unsigned long long prefix = 0ull, mask = 0ull;
+    bool nan = false;
+    for (int b = 7; b >= 0; b--) {
+        for (int i = lane; i < 256; i += 32) hist[i] = 0;
+        __syncwarp();
+        for (int i = lane; i < n; i += 32) {
+            const double v = a[i];
+            if (v != v) { nan = true; continue; }
+            const unsigned long long k = sil_key(v);
+            if ((k & mask) == prefix) atomicAdd(&hist[(int)((k >> (8 * b)) & 255ull)], 1);
+        }
+        __syncwarp();
+        if (__any_sync(0xffffffffu, nan)) return __longlong_as_double(0x7ff8000000000000ll);
+        int h[8], mine = 0;
+#pragma unroll
+        for (int u = 0; u < 8; u++) { h[u] = hist[lane * 8 + u]; mine += h[u]; }
+        int inc = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += t;
+        }
+        const int exc = inc - mine;
+        const bool here = r >= exc && r < inc;
+        int bin = 0, before = 0, cnt = 0;
+        if (here) {
+            int run = exc;
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                if (r >= run && r < run + h[u]) { bin = lane * 8 + u; before = run; cnt = h[u]; }
+                run += h[u];
+            }
+        }
+        const int src = __ffs(__ballot_sync(0xffffffffu, here)) - 1;
+        bin = __shfl_sync(0xffffffffu, bin, src);
+        before = __shfl_sync(0xffffffffu, before, src);
+        cnt = __shfl_sync(0xffffffffu, cnt, src);
+        less += before;
+        r -= before;
+        eq = cnt;
+        prefix |= (unsigned long long)bin << (8 * b);
+        mask |= 255ull << (8 * b);
+        __syncwarp();
+    }
+    const double x = sil_unkey(prefix);
+    if (n & 1) return x;
+    double y = x;
+    if (less + eq <= r0 + 1) { /* the next element in sorted order is the smallest value above x */
+        unsigned long long best = ~0ull;
+        for (int i = lane; i < n; i += 32) {
+            const unsigned long long k = sil_key(a[i]);
+            if (k > prefix && k < best) best = k;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const unsigned long long t = __shfl_xor_sync(0xffffffffu, best, o);
+            best = t < best ? t : best;
+        }
+        y = sil_unkey(best);
+    }
+    double s = __ddiv_rn(__dadd_rn(x, y), 2.0); /* mean(c(x, y)) like median_sorted */
+    const double t = __dadd_rn(__dsub_rn(x, s), __dsub_rn(y, s));
+    s = __dadd_rn(s, __ddiv_rn(t, 2.0));
+    return s;
+}
+
+template <int NT>
+__global__ void __launch_bounds__(NT, 1)
 sweep_nested_kernel(HcProb *probs, SweepOut *outs, HcParamsDev prm, int n_cap, int kcap, int nlevcap, double *scratch,
                     size_t scratch_per_prob) {
     extern __shared__ __align__(16) unsigned char smem[];
-    __shared__ int tmp_scan[SW_THREADS];
-    __shared__ double red[SW_THREADS / 32];
+    __shared__ int tmp_scan[NT];
     __shared__ int s_oind;
+    constexpr int NW = NT / 32;
 
     HcProb &P = probs[blockIdx.x];
     SweepOut &O = outs[blockIdx.x];
     const int n = P.n;
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (n <= 0) return;
     if (P.status != 0) { if (tid == 0) O.meta[3] = P.status; return; }
 
@@ -178,27 +275,32 @@ sweep_nested_kernel(HcProb *probs, SweepOut *outs, HcParamsDev prm, int n_cap, i
     const int ld = P.ld;
     const double *__restrict__ D = P.D;
 
-    NestedLayout L = nested_layout(n_cap, kcap, nlevcap);
-    double *acc = reinterpret_cast<double *>(smem + L.acc_off);
+    NestedLayout L = nested_layout(n_cap, kcap, nlevcap, NT);
+    double *q = reinterpret_cast<double *>(smem + L.acc_off);         // [kmax][NT] mean distance to every live cluster
     int *cidf = reinterpret_cast<int *>(smem + L.ints_off);
     unsigned short *step_of = reinterpret_cast<unsigned short *>(cidf + n_cap);
     unsigned short *link = step_of + n_cap;
-    int *rank = reinterpret_cast<int *>(acc);
+    unsigned short *order = link + n_cap;                             // rows by (finest cluster, index)
+    int *rank = reinterpret_cast<int *>(q);
     int *cnt_lv = reinterpret_cast<int *>(smem + L.cnt_off);          // [nlev][kcap], level 0 = finest (k = kmax)
     unsigned char *slot_lv = smem + L.slot_off;                       // [nlev][kcap]: fine id -> slot at level
     int *mergeA = reinterpret_cast<int *>(smem + L.merge_off);        // [nlev] slot kept when going to level l
     int *mergeB = mergeA + nlevcap;                                   // [nlev] slot absorbed
     double *msil = reinterpret_cast<double *>(smem + L.msil_off);     // [nlev] indexed by level (0 = finest)
     double *chv = msil + nlevcap;
+    int *cstart = reinterpret_cast<int *>(smem + L.cstart_off);       // [kmax + 1] first position of a cluster in `order`
 
     build_links(n, P.ia, P.ib, step_of, link);
     // finest cut
-    labels_at<SW_THREADS>(n, kmax, step_of, link, rank, tmp_scan, cidf);
-    for (int i = tid; i < nlevcap * kcap; i += SW_THREADS) cnt_lv[i] = 0;
+    labels_at<NT>(n, kmax, step_of, link, rank, tmp_scan, cidf);
+    for (int i = tid; i < nlevcap * kcap; i += NT) cnt_lv[i] = 0;
     __syncthreads();
-    for (int i = tid; i < n; i += SW_THREADS) atomicAdd(&cnt_lv[cidf[i]], 1);
+    for (int i = tid; i < n; i += NT) atomicAdd(&cnt_lv[cidf[i]], 1);
     __syncthreads();
     if (tid == 0) {
+        int run = 0;
+        for (int c = 0; c < kmax; c++) { cstart[c] = run; run += cnt_lv[c]; }
+        cstart[kmax] = run;
         for (int c = 0; c < kmax; c++) slot_lv[c] = (unsigned char)c;
         mergeA[0] = mergeB[0] = -1;
         for (int l = 1; l < nlev; l++) {
@@ -219,32 +321,56 @@ sweep_nested_kernel(HcProb *probs, SweepOut *outs, HcParamsDev prm, int n_cap, i
         }
     }
     __syncthreads();
+    // counting sort of the rows by finest cluster, ascending index inside a cluster: one warp per cluster
+    for (int c = warp; c < kmax; c += NW) {
+        int pos = cstart[c];
+        for (int y0 = 0; y0 < n; y0 += 32) {
+            const int y = y0 + lane;
+            const bool in = y < n && cidf[y] == c;
+            const unsigned bal = __ballot_sync(0xffffffffu, in);
+            if (in) order[pos + __popc(bal & ((1u << lane) - 1u))] = (unsigned short)y;
+            pos += __popc(bal);
+        }
+    }
+    __syncthreads();
 
     double *silg = scratch + blockIdx.x * (scratch_per_prob / 8);   // [nlev][n]
     double *csum = silg + (size_t)nlev * n;                          // [kmax][p]
+    double *sums = csum + (size_t)NESTED_MAXK * P.p;                 // [kmax][NT] distance sums of the current chunk
 
-    // ---- silhouettes: one pass over D per chunk of SW_THREADS points ----
-    for (int c0 = 0; c0 < n; c0 += SW_THREADS) {
+    // ---- silhouettes: one pass over D per chunk of NT points ----
+    for (int c0 = 0; c0 < n; c0 += NT) {
         const int x = c0 + tid;
         const bool valid = x < n;
-        for (int c = 0; c < kmax; c++) acc[c * SW_THREADS + tid] = 0.0;
         const double *col = D + (valid ? x : 0);
-        int y = 0;
-        /* SIL_U rows in flight per thread: with one CTA per SM (the accumulators take 80 KB) the pass over D is bound
-           by the bytes in flight, not by bandwidth; the adds stay in ascending y like cluster::sildist */
-        for (; y + SIL_U <= n; y += SIL_U) {
-            double d[SIL_U];
+        {
+            /* SIL_U rows in flight per thread; the adds of a cluster stay in ascending y like cluster::sildist */
+            int c = 0, end = cstart[1];
+            double acc = 0.0;
+            for (int i0 = 0; i0 < n; i0 += SIL_U) {
+                double d[SIL_U];
 #pragma unroll
-            for (int u = 0; u < SIL_U; u++) d[u] = col[(size_t)(y + u) * ld];
+                for (int u = 0; u < SIL_U; u++) d[u] = (i0 + u < n) ? col[(size_t)order[i0 + u] * ld] : 0.0;
 #pragma unroll
-            for (int u = 0; u < SIL_U; u++) acc[cidf[y + u] * SW_THREADS + tid] += d[u];
+                for (int u = 0; u < SIL_U; u++) {
+                    if (i0 + u == end && i0 + u < n) { /* uniform over the block: the cluster is complete */
+                        sums[c * NT + tid] = acc;
+                        q[c * NT + tid] = __ddiv_rn(acc, (double)(end - cstart[c]));
+                        acc = 0.0;
+                        c++;
+                        end = cstart[c + 1];
+                    }
+                    if (i0 + u < n) acc += d[u];
+                }
+            }
+            sums[c * NT + tid] = acc;
+            q[c * NT + tid] = __ddiv_rn(acc, (double)(end - cstart[c]));
         }
-        for (; y < n; y++) acc[cidf[y] * SW_THREADS + tid] += col[(size_t)y * ld];
         const int myfine = valid ? cidf[x] : 0;
         /* b_i = min over the OTHER clusters of the mean distance.  Going one level up merges two clusters (B into A) and
            leaves every other mean untouched, so the minimum is carried along: one division for the new cluster, and a
-           full rescan only when the cluster that held the minimum is one of the two (the quotients that are compared
-           are the same ones a scan computes, so b_i is bit-identical to the scan's) */
+           rescan of the cached means only when the cluster that held the minimum is one of the two (the quotients that
+           are compared are the same ones a full scan computes, so b_i is bit-identical to the scan's) */
         double a_i = 0.0, b_i = SHARP_INF;
         int b_arg = -1, own = 0, n_own = 0;
         for (int l = 0; l < nlev; l++) {
@@ -252,31 +378,30 @@ sweep_nested_kernel(HcProb *probs, SweepOut *outs, HcParamsDev prm, int n_cap, i
             bool rescan = (l == 0);
             if (l > 0) {
                 const int A = mergeA[l], B = mergeB[l];
-                acc[A * SW_THREADS + tid] += acc[B * SW_THREADS + tid];
+                const double sA = sums[A * NT + tid] + sums[B * NT + tid];
+                sums[A * NT + tid] = sA;
+                const double qA = __ddiv_rn(sA, (double)cnt[A]);
+                q[A * NT + tid] = qA;
+                q[B * NT + tid] = SHARP_INF;
                 if (own == A || own == B) { /* the own cluster grows; the other of the two stops being a candidate */
                     const int other = (own == A) ? B : A;
                     own = A;
                     n_own = cnt[A];
-                    a_i = (n_own > 1) ? __ddiv_rn(acc[A * SW_THREADS + tid], (double)(n_own - 1)) : 0.0;
+                    a_i = (n_own > 1) ? __ddiv_rn(sA, (double)(n_own - 1)) : 0.0;
                     if (b_arg == other) rescan = true;
                 } else if (b_arg == A || b_arg == B) rescan = true;
-                else {
-                    const double v = __ddiv_rn(acc[A * SW_THREADS + tid], (double)cnt[A]);
-                    if (v < b_i) { b_i = v; b_arg = A; }
-                }
+                else if (qA < b_i) { b_i = qA; b_arg = A; }
             } else {
                 own = slot_lv[myfine];
                 n_own = cnt[own];
-                a_i = (n_own > 1) ? __ddiv_rn(acc[own * SW_THREADS + tid], (double)(n_own - 1)) : 0.0;
+                a_i = (n_own > 1) ? __ddiv_rn(sums[own * NT + tid], (double)(n_own - 1)) : 0.0;
             }
             if (rescan) {
                 b_i = SHARP_INF;
                 b_arg = -1;
                 for (int c = 0; c < kmax; c++) {
-                    const int nc = cnt[c];
-                    if (nc == 0 || c == own) continue;
-                    const double v = __ddiv_rn(acc[c * SW_THREADS + tid], (double)nc);
-                    if (v < b_i) { b_i = v; b_arg = c; }
+                    const double v = q[c * NT + tid];
+                    if (c != own && v < b_i) { b_i = v; b_arg = c; }
                 }
             }
             double s = (n_own > 1 && b_i != a_i) ? __ddiv_rn(__dsub_rn(b_i, a_i), fmax(a_i, b_i)) : 0.0;
@@ -285,44 +410,47 @@ sweep_nested_kernel(HcProb *probs, SweepOut *outs, HcParamsDev prm, int n_cap, i
     }
     __syncthreads();
 
-    // ---- medians ----
+    // ---- medians: one warp per level ----
     {
-        const int P2 = next_pow2(n);
-        double *sb = acc;
-        for (int l = 0; l < nlev; l++) {
-            for (int i = tid; i < P2; i += SW_THREADS) sb[i] = (i < n) ? silg[(size_t)l * n + i] : SHARP_INF;
-            __syncthreads();
-            block_bitonic_sort<SW_THREADS>(sb, P2);
-            if (tid == 0) msil[l] = median_sorted(sb, n);
-            __syncthreads();
+        int *hist = reinterpret_cast<int *>(q) + warp * 256;
+        for (int l = warp; l < nlev; l += NW) {
+            const double md = warp_median_select(silg + (size_t)l * n, n, hist, lane);
+            if (lane == 0) msil[l] = md;
         }
+        __syncthreads();
     }
 
     // ---- CH index from the finest-level cluster sums of the unit rows ----
     {
         const double *__restrict__ Y = P.Y;
         const int p = P.p, ldy = P.ldy;
-        for (int d0 = 0; d0 < p; d0 += SW_THREADS) {
+        for (int d0 = 0; d0 < p; d0 += NT) {
             const int d = d0 + tid;
-            for (int c = 0; c < kmax; c++) acc[c * SW_THREADS + tid] = 0.0;
-            if (d < p) { /* SIL_U rows in flight per thread (same reason as the pass over D) */
-                int x = 0;
-                for (; x + SIL_U <= n; x += SIL_U) {
+            if (d < p) { /* SIL_U rows in flight per thread, cluster by cluster (ascending rows inside a cluster) */
+                const double *colY = Y + d;
+                int c = 0, end = cstart[1];
+                double acc = 0.0;
+                for (int i0 = 0; i0 < n; i0 += SIL_U) {
                     double yv[SIL_U];
 #pragma unroll
-                    for (int u = 0; u < SIL_U; u++) yv[u] = Y[(size_t)(x + u) * ldy + d];
+                    for (int u = 0; u < SIL_U; u++) yv[u] = (i0 + u < n) ? colY[(size_t)order[i0 + u] * ldy] : 0.0;
 #pragma unroll
-                    for (int u = 0; u < SIL_U; u++) acc[cidf[x + u] * SW_THREADS + tid] += yv[u];
+                    for (int u = 0; u < SIL_U; u++) {
+                        if (i0 + u == end && i0 + u < n) {
+                            csum[(size_t)c * p + d] = acc;
+                            acc = 0.0;
+                            c++;
+                            end = cstart[c + 1];
+                        }
+                        if (i0 + u < n) acc += yv[u];
+                    }
                 }
-                for (; x < n; x++) acc[cidf[x] * SW_THREADS + tid] += Y[(size_t)x * ldy + d];
+                csum[(size_t)c * p + d] = acc;
             }
-            if (d < p)
-                for (int c = 0; c < kmax; c++) csum[(size_t)c * p + d] = acc[c * SW_THREADS + tid];
         }
         __syncthreads();
-        double *G = acc; /* [kmax][kmax] Gram matrix of the cluster sums */
-        const int lane = tid & 31, warp = tid >> 5;
-        for (int pr = warp; pr < kmax * kmax; pr += SW_THREADS / 32) {
+        double *G = q; /* [kmax][kmax] Gram matrix of the cluster sums */
+        for (int pr = warp; pr < kmax * kmax; pr += NW) {
             int a = pr / kmax, b = pr % kmax;
             if (b < a) continue;
             double s = 0.0;
@@ -335,11 +463,8 @@ sweep_nested_kernel(HcProb *probs, SweepOut *outs, HcParamsDev prm, int n_cap, i
             double gtot = 0.0;
             for (int a = 0; a < kmax; a++)
                 for (int b = 0; b < kmax; b++) gtot += G[a * kmax + b];
-            /* total sum of squares about the grand mean: sum ||y||^2 - ||sum y||^2 / n */
-            double ssq = 0.0;
-            (void)ssq;
-            double T; /* rows are unit vectors: sum ||y||^2 = n */
-            T = (double)n - gtot / (double)n;
+            /* total sum of squares about the grand mean: sum ||y||^2 - ||sum y||^2 / n; rows are unit vectors: sum ||y||^2 = n */
+            const double T = (double)n - gtot / (double)n;
             for (int l = 0; l < nlev; l++) {
                 if (l > 0) {
                     int a = mergeA[l], b = mergeB[l];
@@ -389,19 +514,18 @@ sweep_nested_kernel(HcProb *probs, SweepOut *outs, HcParamsDev prm, int n_cap, i
     int *lab = cidf;
     {
         const int k = kmin + oind - 1;
-        labels_at<SW_THREADS>(n, k, step_of, link, rank, tmp_scan, lab);
-        for (int i = tid; i < n; i += SW_THREADS) O.f[i] = lab[i] + 1;
+        labels_at<NT>(n, k, step_of, link, rank, tmp_scan, lab);
+        for (int i = tid; i < n; i += NT) O.f[i] = lab[i] + 1;
         if (tid == 0) O.meta[1] = k; /* optN.cluster = length(unique(f)) = k */
         __syncthreads();
     }
     if (O.v) {
         for (int l = 0; l < nlev; l++) {
-            labels_at<SW_THREADS>(n, kmin + l, step_of, link, rank, tmp_scan, lab);
-            for (int i = tid; i < n; i += SW_THREADS) O.v[(size_t)i * nlev + l] = lab[i] + 1;
+            labels_at<NT>(n, kmin + l, step_of, link, rank, tmp_scan, lab);
+            for (int i = tid; i < n; i += NT) O.v[(size_t)i * nlev + l] = lab[i] + 1;
             __syncthreads();
         }
     }
-    (void)red;
 }
 
 int launch_sweep_nested(sharp_ctx *c, HcProb *probs_dev, SweepOut *outs_dev, int nprob, int max_n, int max_p,
@@ -414,13 +538,20 @@ int launch_sweep_nested(sharp_ctx *c, HcProb *probs_dev, SweepOut *outs_dev, int
         return set_error(SHARP_E_LIMIT, "nested sweep supports at most %d clusters per level (got %d)", NESTED_MAXK, kcap);
     int nlevcap = prm.n_cluster ? 1 : (prm.max_n - prm.min_n + 1);
     if (nlevcap < 1) nlevcap = 1;
-    NestedLayout L = nested_layout(max_n, kcap, nlevcap);
-    if (L.total > 220 * 1024)
+    const int nt = nested_threads(max_n, kcap, nlevcap);
+    NestedLayout L = nested_layout(max_n, kcap, nlevcap, nt);
+    if (L.total > NESTED_SMEM_MAX)
         return set_error(SHARP_E_LIMIT, "nested sweep: %d objects need %zu bytes of shared memory", max_n, L.total);
-    SHARP_SMEM_OPTIN_ONCE((sweep_nested_kernel), c->device);
+    if (scratch_per_prob < sweep_nested_scratch_bytes(max_n, max_p, prm))
+        return set_error(SHARP_E_ARG, "nested sweep: scratch too small");
     prof_begin(c, KID_SWEEP_NESTED);
-    sweep_nested_kernel<<<nprob, SW_THREADS, L.total, c->stream>>>(probs_dev, outs_dev, prm, max_n, kcap, nlevcap,
-                                                                   scratch, scratch_per_prob);
+    if (nt == 512) {
+        SHARP_SMEM_OPTIN_ONCE((sweep_nested_kernel<512>), c->device);
+        sweep_nested_kernel<512><<<nprob, 512, L.total, c->stream>>>(probs_dev, outs_dev, prm, max_n, kcap, nlevcap, scratch, scratch_per_prob);
+    } else {
+        SHARP_SMEM_OPTIN_ONCE((sweep_nested_kernel<256>), c->device);
+        sweep_nested_kernel<256><<<nprob, 256, L.total, c->stream>>>(probs_dev, outs_dev, prm, max_n, kcap, nlevcap, scratch, scratch_per_prob);
+    }
     prof_end(c);
     SHARP_CUDA(cudaGetLastError());
     return 0;

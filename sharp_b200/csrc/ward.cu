@@ -644,7 +644,12 @@ __global__ void __launch_bounds__(RNN_THREADS, 2) hclust_rnn_kernel(HcProb *prob
 //   * the reciprocal pairs follow from the two: (k, x), k < x, merges iff x is the upper nearest neighbour of k, that
 //     distance beats k's column minimum, EQUALS x's column minimum and beats x's upper minimum.  Equal candidates
 //     anywhere (a key that meets its own value) raise the tie flag: the problem is redone by the exact kernel;
-//   * a merged row (a, b) reads row a contiguously, row b contiguously right of b and as a column gather between a and b;
+//   * POSITIONS.  A merged cluster (a, b), a < b, takes the place of its RIGHT member b (its representative, the smallest
+//     original index, is tracked separately in orig[]): row b' then needs only the columns right of b, all of them
+//     contiguous in rows a and b, and what other rows need from the retired row a -- element j of row a for the rows j
+//     between a and b -- is read by consecutive rows from consecutive addresses.  Keeping the LEFT place instead (r2's
+//     first version, like hclust.f's I2) made row a' gather column b from the rows between a and b: one 32-byte sector
+//     (64 fetched) per 8 bytes used, the larger part of that version's 8.7 n^2 x 8 B of DRAM traffic per problem;
 //   * rows are dealt to the warps in (top, bottom) pairs of the triangle: the same amount of work for every warp.
 // Tried and dropped (B200, r2): a per-warp shared-memory stash of the pair members' row values, so that the pair pass
 // would not re-read them -- 98 KB more shared memory left 28 KB of L1 and the kernel ran 25 % slower (446 vs 357 ms per
@@ -796,7 +801,7 @@ __global__ void __launch_bounds__(TRI_THREADS, TRI_MINB) hclust_tri_kernel(HcPro
             if (s_tie) { failed = true; break; }
             for (int i = tid; i < nr; i += THREADS) {
                 const int j = partner[i];
-                rank[i] = (j != RNN_NONE && j < i) ? 0 : 1;
+                rank[i] = (j != RNN_NONE && j > i) ? 0 : 1; /* the member on the LEFT retires (see the note on positions above) */
             }
             __syncthreads();
             nnew = block_exclusive_scan<THREADS>(rank, nr, tmp_scan);
@@ -806,27 +811,30 @@ __global__ void __launch_bounds__(TRI_THREADS, TRI_MINB) hclust_tri_kernel(HcPro
             for (int i = tid; i < nr; i += THREADS) {
                 const int j = partner[i];
                 const bool paired = j != RNN_NONE;
-                if (paired && j < i) { /* retired: i - rank[i] = number of retired clusters before i, a dense numbering */
+                if (paired && j > i) { /* retired: i - rank[i] = number of retired clusters before i, a dense numbering */
                     const int q = base + (i - rank[i]);
-                    P.ia[q] = (int)orig[j] + 1;
-                    P.ib[q] = (int)orig[i] + 1;
-                    P.crit[q] = dup[j];
+                    const int oi = (int)orig[i], oj = (int)orig[j];
+                    P.ia[q] = min(oi, oj) + 1;
+                    P.ib[q] = max(oi, oj) + 1;
+                    P.crit[q] = dup[i];
                     cmap[i] = (u16)(rank[j] | TRI_MERGING);
                     pl[i - rank[i]] = (u16)j;
                     continue;
                 }
                 const int ip = rank[i];
                 cmap[i] = (u16)(ip | (paired ? TRI_MERGING : 0));
-                sA[ip] = (u16)i;
-                orig2[ip] = orig[i];
-                if (paired) {
-                    sB[ip] = (u16)j;
-                    hrow[ip] = dup[i];
+                if (paired) { /* the merged cluster takes the place of its RIGHT member i; j < i is the left one */
+                    sA[ip] = (u16)j;
+                    sB[ip] = (u16)i;
+                    hrow[ip] = dup[j];
                     size2[ip] = (u16)(size[i] + size[j]);
+                    orig2[ip] = min(orig[i], orig[j]);
                 } else {
+                    sA[ip] = (u16)i;
                     sB[ip] = RNN_NONE;
                     hrow[ip] = 0.0;
                     size2[ip] = size[i];
+                    orig2[ip] = orig[i];
                 }
             }
             __syncthreads();
@@ -886,29 +894,31 @@ __global__ void __launch_bounds__(TRI_THREADS, TRI_MINB) hclust_tri_kernel(HcPro
                             tri_elem(!(cm[u] & TRI_MERGING), v, (int)(cm[u] & 0x7fffu), out, best, cmin2, flag);
                         }
                     }
-                    for (int q0 = 0; q0 < m; q0 += 32) { /* this row's cluster a against the new cluster (c, d): I2 = c, J2 = d, K = a */
+                    for (int q0 = 0; q0 < m; q0 += 32) { /* this row's cluster a against the new cluster (d, c), d < c: I2 = d, J2 = c, K = a */
                         const int q = q0 + lane;
                         const int c = q < m ? (int)pl[q] : 0;
                         const bool valid = q < m && c > a;
-                        const int d = valid ? (int)partner[c] : 0, jp = valid ? (int)(cmap[c] & 0x7fffu) : 0;
-                        double xc = valid ? rowa[c] : 0.0, xd = valid ? rowa[d] : 0.0;
+                        const int d = valid ? (int)partner[c] : a + 1, jp = valid ? (int)(cmap[c] & 0x7fffu) : 0;
+                        double xc = valid ? rowa[c] : 0.0;
+                        double xd = valid ? ((d > a) ? rowa[d] : A.row(d)[a]) : 0.0; /* left of a: element a of row d (consecutive rows a share its sectors) */
                         if (sq) { xc = __dmul_rn(xc, xc); xd = __dmul_rn(xd, xd); }
-                        const double v = tri_lw<METHOD>(method, xc, xd, hrow[jp], (double)size[c], (double)size[d], ma);
+                        const double v = tri_lw<METHOD>(method, xd, xc, hrow[jp], (double)size[valid ? d : 0], (double)size[c], ma);
                         tri_elem(valid, v, jp, out, best, cmin2, flag);
                     }
                 } else {
-                    const int b = (int)b16;
+                    const int b = (int)b16; /* a < b: the new cluster sits at b, so only the columns right of b are needed, all of them in rows a and b */
                     const double *rowb = A.row(b);
                     const double mb = (double)size[b], hi = hrow[ip];
-                    for (int jb = jstart; jb < nr; jb += 32 * RNN_UM) {
+                    const int jstart_b = (b + 1) & ~31;
+                    for (int jb = jstart_b; jb < nr; jb += 32 * RNN_UM) {
                         double x[RNN_UM], y[RNN_UM];
                         unsigned cm[RNN_UM];
 #pragma unroll
                         for (int u = 0; u < RNN_UM; u++) {
                             const int j = jb + u * 32 + lane;
-                            const bool in = j > a && j < nr && j != b;
+                            const bool in = j > b && j < nr;
                             x[u] = in ? rowa[j] : 0.0;
-                            y[u] = in ? ((j > b) ? rowb[j] : A.row(j)[b]) : 0.0; /* between a and b: column b of row j */
+                            y[u] = in ? rowb[j] : 0.0;
                             cm[u] = in ? (unsigned)cmap[j] : (unsigned)TRI_MERGING;
                         }
 #pragma unroll
@@ -923,18 +933,18 @@ __global__ void __launch_bounds__(TRI_THREADS, TRI_MINB) hclust_tri_kernel(HcPro
                     }
                     for (int q0 = 0; q0 < m; q0 += 32) { /* both are new: the two updates in the order of their heights, like the reference */
                         const int q = q0 + lane;
-                        const int c = q < m ? (int)pl[q] : 0;
-                        const bool valid = q < m && c > a;
-                        const int d = valid ? (int)partner[c] : b + 1, jp = valid ? (int)(cmap[c] & 0x7fffu) : 0;
-                        const int cc = valid ? c : b + 1; /* any index right of b keeps the loads of idle lanes in bounds */
-                        double x1 = valid ? rowa[cc] : 0.0, x2 = valid ? rowa[d] : 0.0;
-                        double y1 = valid ? ((cc > b) ? rowb[cc] : A.row(cc)[b]) : 0.0;
-                        double y2 = valid ? ((d > b) ? rowb[d] : A.row(d)[b]) : 0.0;
+                        const int c2 = q < m ? (int)pl[q] : 0;      /* right member of the other pair (its place) */
+                        const bool valid = q < m && c2 > b;
+                        const int dd = valid ? c2 : b + 1;           /* any index right of b keeps the loads of idle lanes in bounds */
+                        const int cc = valid ? (int)partner[c2] : b + 1; /* its left member: anywhere left of dd */
+                        const int jp = valid ? (int)(cmap[c2] & 0x7fffu) : 0;
+                        double x1 = valid ? ((cc > a) ? rowa[cc] : A.row(cc)[a]) : 0.0, x2 = valid ? rowa[dd] : 0.0;
+                        double y1 = valid ? ((cc > b) ? rowb[cc] : A.row(cc)[b]) : 0.0, y2 = valid ? rowb[dd] : 0.0;
                         if (sq) {
                             x1 = __dmul_rn(x1, x1); y1 = __dmul_rn(y1, y1);
                             x2 = __dmul_rn(x2, x2); y2 = __dmul_rn(y2, y2);
                         }
-                        const double hj = hrow[jp], mc = (double)size[cc < nr ? cc : 0], md = (double)size[d < nr ? d : 0];
+                        const double hj = hrow[jp], mc = (double)size[cc < nr ? cc : 0], md = (double)size[dd < nr ? dd : 0];
                         flag |= (int)(valid && hi == hj);
                         const bool fst = hi < hj; /* this row's pair merges first */
                         const double h1 = fst ? hi : hj, h2 = fst ? hj : hi;
@@ -943,7 +953,7 @@ __global__ void __launch_bounds__(TRI_THREADS, TRI_MINB) hclust_tri_kernel(HcPro
                         /* first merge: (I2, J2) of the earlier pair against each member of the later pair */
                         const double t1 = tri_lw<METHOD>(method, x1, fst ? y1 : x2, h1, p1, p2, r1);
                         const double t2 = tri_lw<METHOD>(method, fst ? x2 : y1, y2, h1, p1, p2, r2);
-                        /* second merge: the later pair (I2 = its kept member, J2 = retired) against the merged earlier pair */
+                        /* second merge: the later pair (I2 = its left member, J2 = right) against the merged earlier pair */
                         const double v = tri_lw<METHOD>(method, t1, t2, h2, r1, r2, p1 + p2);
                         tri_elem(valid, v, jp, out, best, cmin2, flag);
                     }
