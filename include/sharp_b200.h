@@ -284,6 +284,14 @@ int sharp_last_vie(sharp_ctx *ctx, int64_t n, int p, double *vie);
 int sharp_smetac_centroids(sharp_ctx *ctx, int nC, int p, const double *cen, int64_t ncells_total,
                            const sharp_hc_params *prm, int32_t *tf);
 
+/* The label tail of SHARP_unlimited on the host (R/SHARP_unlimited.R:166-183), pure host code: part t's cells are
+ * pred[part_start[t] .. part_start[t+1]) with 1-based part-level cluster ids; out[i] = tf[part_off[t] + pred[i] - 1];
+ * clusters with fewer than merge_thre cells are merged into the smallest such id (:168-176; merge_thre <= 0: skipped);
+ * ids are renumbered 1.. by decreasing size, ties in the string order of the ids (:180-183).  counts (optional, ntf
+ * entries) receives the sizes of the new ids 1..*n_labels. */
+int sharp_labels_combine(int nparts, const int64_t *part_start, const int32_t *part_off, const int32_t *pred,
+                         const int32_t *tf, int ntf, int merge_thre, int32_t *out, int64_t *counts, int *n_labels);
+
 /* ---- streaming ingestion for SHARP_unlimited3 -------------------------------------------------------
  * Replaces  mat = readRDS(allfiles[i])  (R/SHARP_unlimited3.R:105, freed at :124-125) for parts kept in the raw dgCMatrix
  * container SHCSC001 (64-byte header: "SHCSC001", int32 m, int32 0, int64 n, int64 nnz; then the slots p (int64[n+1]),

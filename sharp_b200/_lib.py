@@ -62,7 +62,7 @@ EXPORTS = [
     "sharp_hclust", "sharp_opt_hclust", "sharp_getrowcolor", "sharp_wmetac", "sharp_smetac", "sharp_run",
     "sharp_expr_upload", "sharp_expr_free", "sharp_run_dev", "sharp_centroids", "sharp_smetac_centroids",
     "sharp_last_member", "sharp_last_vie", "sharp_prof_enable", "sharp_prof_reset", "sharp_prof_kernels", "sharp_prof_name",
-    "sharp_prof_get", "sharp_ctx_set_rp_variant", "sharp_r_ranm", "sharp_r_sample_perm", "sharp_run_parts",
+    "sharp_prof_get", "sharp_ctx_set_rp_variant", "sharp_r_ranm", "sharp_r_sample_perm", "sharp_labels_combine", "sharp_run_parts",
     "sharp_ctx_set_block_budget", "sharp_ctx_set_serial", "sharp_parts_prefetch", "sharp_plan_groups",
     "sharp_comm_unique_id", "sharp_comm_init", "sharp_comm_destroy", "sharp_comm_info", "sharp_comm_allgatherv",
     "sharp_comm_bcast", "sharp_comm_barrier", "sharp_host_alloc", "sharp_host_free", "sharp_csc_file_info",
@@ -180,6 +180,27 @@ def r_sample_perm_native(n: int, seed: int) -> np.ndarray:
     if rc != 0:
         raise SharpError(rc, "sharp_r_sample_perm failed")
     return out
+
+
+def labels_combine(preds: list, counts_per_part: list, tf: np.ndarray, merge_thre: int) -> tuple[np.ndarray, np.ndarray]:
+    """sharp_labels_combine: (final labels 1.. by decreasing size, their sizes) from the per-part cluster ids and the
+    global sMetaC's tf (R/SHARP_unlimited.R:166-183) -- pure host code"""
+    nparts = len(preds)
+    start = np.zeros(nparts + 1, dtype=np.int64)
+    start[1:] = np.cumsum([len(p) for p in preds])
+    off = np.zeros(nparts, dtype=np.int32)
+    off[1:] = np.cumsum(counts_per_part[:-1])
+    pred = np.ascontiguousarray(np.concatenate(preds), dtype=np.int32)
+    tf = np.ascontiguousarray(tf, dtype=np.int32)
+    out = np.empty(int(start[-1]), dtype=np.int32)
+    counts = np.zeros(len(tf), dtype=np.int64)
+    nl = C.c_int()
+    rc = load().sharp_labels_combine(nparts, _ptr(start, C.c_int64), _ptr(off, C.c_int32), _ptr(pred, C.c_int32),
+                                     _ptr(tf, C.c_int32), len(tf), int(merge_thre), _ptr(out, C.c_int32),
+                                     _ptr(counts, C.c_int64), C.byref(nl))
+    if rc != 0:
+        raise SharpError(rc, "sharp_labels_combine: inconsistent cluster ids")
+    return out, counts[:nl.value]
 
 
 def plan_groups(nparts: int, host_data: bool, group=0, lanes=0) -> dict:

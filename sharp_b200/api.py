@@ -709,24 +709,66 @@ def _relabel_by_size(labels: np.ndarray) -> np.ndarray:
     return lut[np.asarray(labels, dtype=np.int64)]
 
 
+def _exchange_parts(comm, own, y, cens, nnp):
+    """ONE allgather for everything the global step needs from the other ranks: the labels and centroids of the parts in
+    `own`, and part 1's parameter list from the rank that holds it (the `.combine` of R/SHARP_unlimited3.R:137-147)"""
+    import pickle
+    payload = {i: y[i]["pred_clusters"] for i in own}
+    payload.update({nnp + i: cens[i] for i in own})
+    if 0 in own:
+        head = pickle.dumps({q: y[0][q] for q in ("reduced.dim", "ensize.K", "paras")})
+        payload[2 * nnp] = np.frombuffer(head, dtype=np.uint8)
+    got = comm.allgather_parts(payload, 2 * nnp + 1)
+    return got[:nnp], got[nnp:2 * nnp], pickle.loads(got[2 * nnp].tobytes())
+
+
 def _unlimited_combine(ctx, cen, counts_per_part, preds, ncells, hmethod, N_cluster, minN, maxN, sil_thre,
                        height_Ntimes) -> np.ndarray:
-    """global sMetaC on the part-level cluster centroids + merge + relabel (R/SHARP_unlimited.R:151-183)"""
+    """global sMetaC on the part-level cluster centroids + merge + relabel (R/SHARP_unlimited.R:151-183); the label
+    tail (tf[fColor], clusters under 10 cells merged, ids by decreasing size) is one native host pass
+    (sharp_labels_combine; `_combine_labels_py` is the same thing in numpy, kept as its test oracle)"""
     hc = _hc(hmethod, N_cluster, minN, maxN, sil_thre, height_Ntimes)
+    t0 = time.time()
     tf = ctx.smetac_centroids(cen, ncells, hc)
+    t1 = time.time()
+    merge = 10 if (_ncl(N_cluster) == 0 and ncells > 1e4) else 0
+    final, sizes = _lib.labels_combine(preds, counts_per_part, tf, merge)
+    if _TRACE:
+        print(f"[sharp trace py] global sMetaC on {cen.shape[0]} centroids {1e3 * (t1 - t0):.2f} ms, label tail "
+              f"{1e3 * (time.time() - t1):.2f} ms", file=sys.stderr)
+    return _SizedLabels(final, sizes)
+
+
+class _SizedLabels(np.ndarray):
+    """an int32 label vector that carries the sizes of its labels 1..L (saves a counting pass over 1.3 M cells)"""
+    def __new__(cls, arr, sizes):
+        obj = np.asarray(arr).view(cls)
+        obj.sizes = sizes
+        return obj
+
+    def __array_finalize__(self, obj):
+        self.sizes = getattr(obj, "sizes", None)
+
+
+def _combine_labels_py(tf, counts_per_part, preds, ncells, merge: bool) -> np.ndarray:
     final = np.empty(ncells, dtype=np.int32)
     pos, off = 0, 0
     for pred, nk in zip(preds, counts_per_part):
         final[pos:pos + len(pred)] = tf[off + pred - 1]
         pos += len(pred)
         off += nk
-    if _ncl(N_cluster) == 0 and ncells > 1e4:
+    if merge:
         final = _merge_small(final)
     return _relabel_by_size(final)
 
 
 def _unlimited_result(final, ncells, ngenes, y0, start):
-    uf, ufc = _counts(final)
+    sizes = getattr(final, "sizes", None)
+    if sizes is not None:
+        final = np.asarray(final)
+        uf, ufc = np.arange(1, len(sizes) + 1, dtype=np.int32), sizes
+    else:
+        uf, ufc = _counts(final)
     return {"pred_clusters": final, "unique_pred_clusters": uf.astype(np.int64),
             "distr_pred_clusters": {int(v): int(c) for v, c in zip(uf, ufc)},
             "N.pred_clusters": int(len(uf)), "N.cells": int(ncells), "N.genes": int(ngenes),
@@ -940,9 +982,7 @@ def SHARP_unlimited(scExp, viewflag=True, n_cores=None, ensize_K=None, N_cluster
     _mark("parts")
     if comm is not None:
         own = [i for i in mine if i not in shared or rank == 0]   # a block-sharded part is complete on every rank: rank 0 contributes it
-        preds_all = comm.allgather_parts({i: y[i]["pred_clusters"] for i in own}, nnp)
-        cens_all = comm.allgather_parts({i: cens[i] for i in own}, nnp)
-        y0 = comm.bcast_obj({kk: y[0][kk] for kk in ("reduced.dim", "ensize.K", "paras")} if 0 in y else None, 0)
+        preds_all, cens_all, y0 = _exchange_parts(comm, own, y, cens, nnp)
         if viewflag:
             viEs = comm.allgather_parts({i: viEs[i] for i in own}, nnp)
     else:
@@ -1208,9 +1248,7 @@ def _unlimited3_streamed(paths, ndinfo, viewflag, n_cores, ensize_K, rN_seed, N_
         rd.close()
         rM.close()
     if comm is not None:
-        preds_all = comm.allgather_parts({i: y[i]["pred_clusters"] for i in mine}, nnp)
-        cens_all = comm.allgather_parts(cens, nnp)
-        y0 = comm.bcast_obj({q: y[0][q] for q in ("reduced.dim", "ensize.K", "paras")} if 0 in y else None, 0)
+        preds_all, cens_all, y0 = _exchange_parts(comm, list(mine), y, cens, nnp)
     else:
         preds_all, cens_all, y0 = [y[i]["pred_clusters"] for i in range(nnp)], [cens[i] for i in range(nnp)], y[0]
     cen = np.ascontiguousarray(np.concatenate(cens_all, axis=0))

@@ -104,10 +104,16 @@ __global__ void __launch_bounds__(MT) wm_enumerate_kernel(WmArgs A) {
         }
         __syncthreads();
         if (fits) {
-            for (int c = tid; c < nk; c += MT) { /* stable: ascending scan per cluster */
+            for (int c = tid >> 5; c < nk; c += MT / 32) { /* stable: one warp per cluster, ascending ballots */
                 int pos = moff[base + c];
-                for (int i = 0; i < N; i++)
-                    if (gid[(size_t)k * N + i] == base + c) members[pos++] = i;
+                const int lane = tid & 31;
+                for (int i0 = 0; i0 < N; i0 += 32) {
+                    const int i = i0 + lane;
+                    const bool in = i < N && gid[(size_t)k * N + i] == base + c;
+                    const unsigned bal = __ballot_sync(0xffffffffu, in);
+                    if (in) members[pos + __popc(bal & ((1u << lane) - 1u))] = i;
+                    pos += __popc(bal);
+                }
             }
         }
         __syncthreads();
@@ -128,19 +134,21 @@ __global__ void __launch_bounds__(MT) wm_weights_kernel(WmArgs A) {
     const int64_t s0 = A.start[t];
     const int N = (int)(A.start[t + 1] - s0);
     const int i = blockIdx.x * MT + threadIdx.x;
-    if (i >= N) return;
     const int K = A.K;
+    __shared__ double term[WM_MAXK + 1]; /* x (1 - x) for x = cnt / K: the K + 1 values an entry of AA can take */
+    if (threadIdx.x <= K) {
+        const double x = __ddiv_rn((double)threadIdx.x, (double)K);
+        term[threadIdx.x] = __dmul_rn(x, __dsub_rn(1.0, x));
+    }
+    __syncthreads();
+    if (i >= N) return;
     int mine[WM_MAXK];
     for (int k = 0; k < K; k++) mine[k] = A.labels[(size_t)k * A.ncells + s0 + i];
     double rs = 0.0;
-    const double Cd = (double)K;
     for (int j = 0; j < N; j++) {
         int cnt = 0;
         for (int k = 0; k < K; k++) cnt += (A.labels[(size_t)k * A.ncells + s0 + j] == mine[k]);
-        if (cnt != 0) {
-            double x = __ddiv_rn((double)cnt, Cd);
-            rs = __dadd_rn(rs, __dmul_rn(x, __dsub_rn(1.0, x)));
-        }
+        rs = __dadd_rn(rs, term[cnt]); /* term[0] = +0: the sum is the one over the pairs that share a cluster */
     }
     double w0 = __dmul_rn(__ddiv_rn(4.0, (double)N), rs);
     A.w1[s0 + i] = __ddiv_rn(__dadd_rn(w0, 0.01), __dadd_rn(1.0, 0.01));
@@ -444,10 +452,16 @@ sm_codes_kernel(WmArgs A, const int *coloff, int *code, int *corder, int *coff) 
         if (t == gridDim.x - 1) coff[off + nu] = run;
     }
     __syncthreads();
-    for (int q = tid; q < nu; q += MT) {
+    for (int q = tid >> 5; q < nu; q += MT / 32) { /* one warp per cluster, ascending ballots */
         int pos = coff[off + q];
-        for (int i = 0; i < N; i++)
-            if (A.fcode[s0 + i] == q) corder[pos++] = (int)(s0 + i);
+        const int lane = tid & 31;
+        for (int i0 = 0; i0 < N; i0 += 32) {
+            const int i = i0 + lane;
+            const bool in = i < N && A.fcode[s0 + i] == q;
+            const unsigned bal = __ballot_sync(0xffffffffu, in);
+            if (in) corder[pos + __popc(bal & ((1u << lane) - 1u))] = (int)(s0 + i);
+            pos += __popc(bal);
+        }
     }
 }
 
@@ -460,7 +474,15 @@ sm_centroids_kernel(const double *__restrict__ E1, int p, const int *__restrict_
     const int q0 = coff[c], q1 = coff[c + 1];
     for (int d = threadIdx.x; d < p; d += MT) {
         double s = 0.0;
-        for (int q = q0; q < q1; q++) s = __dadd_rn(s, E1[(size_t)corder[q] * p + d]);
+        int q = q0;
+        for (; q + 8 <= q1; q += 8) { /* eight rows in flight; the adds stay in ascending row order */
+            double v[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) v[u] = E1[(size_t)corder[q + u] * p + d];
+#pragma unroll
+            for (int u = 0; u < 8; u++) s = __dadd_rn(s, v[u]);
+        }
+        for (; q < q1; q++) s = __dadd_rn(s, E1[(size_t)corder[q] * p + d]);
         cen[(size_t)c * p + d] = __ddiv_rn(s, (double)(q1 - q0));
     }
     if (counts && threadIdx.x == 0) counts[c] = q1 - q0;

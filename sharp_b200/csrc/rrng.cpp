@@ -12,6 +12,7 @@
 #include <cmath>
 #include <cstdint>
 #include <cstring>
+#include <string>
 #include <vector>
 
 #include "../../include/sharp_b200.h"
@@ -257,6 +258,63 @@ int sharp_r_sample_perm(int64_t seed, int64_t n, int64_t *out) {
         out[i] = (int64_t)x[j] + 1;
         x[j] = x[--remaining];
     }
+    return SHARP_OK;
+}
+
+
+// The label tail of SHARP_unlimited (R/SHARP_unlimited.R:166-183), one pass each instead of R's table()/match() on
+// 1.3 M-element vectors: final = tf[fColor code]; clusters with fewer than `merge_thre` cells take the smallest such id
+// (:168-176, skipped for merge_thre <= 0); ids renumbered 1.. by decreasing size, ties in the STRING order of the ids
+// (names(sort(table(f), decreasing = TRUE)): table() orders its names as character, the sort is stable).
+int sharp_labels_combine(int nparts, const int64_t *part_start, const int32_t *part_off, const int32_t *pred,
+                         const int32_t *tf, int ntf, int merge_thre, int32_t *out, int64_t *counts, int *n_labels) {
+    if (nparts < 1 || !part_start || !part_off || !pred || !tf || ntf < 1 || !out || !n_labels) return SHARP_E_ARG;
+    const int64_t n = part_start[nparts];
+    int mx = 0;
+    for (int q = 0; q < ntf; q++) {
+        if (tf[q] < 1) return SHARP_E_ARG;
+        mx = std::max(mx, tf[q]);
+    }
+    std::vector<int64_t> cnt((size_t)mx + 1, 0);
+    for (int t = 0; t < nparts; t++) {
+        const int32_t *lut = tf + part_off[t];
+        const int lim = ntf - part_off[t];
+        for (int64_t i = part_start[t]; i < part_start[t + 1]; i++) {
+            const int c = pred[i];
+            if (c < 1 || c > lim) return SHARP_E_ARG;
+            const int v = lut[c - 1];
+            out[i] = v;
+            cnt[v]++;
+        }
+    }
+    std::vector<int32_t> map((size_t)mx + 1, 0);
+    for (int v = 0; v <= mx; v++) map[v] = v;
+    if (merge_thre > 0) {
+        int smallest = 0;
+        for (int v = 1; v <= mx; v++)
+            if (cnt[v] > 0 && cnt[v] < merge_thre) { smallest = v; break; }
+        if (smallest) {
+            int64_t moved = 0;
+            for (int v = smallest + 1; v <= mx; v++)
+                if (cnt[v] > 0 && cnt[v] < merge_thre) { map[v] = smallest; moved += cnt[v]; cnt[v] = 0; }
+            cnt[smallest] += moved;
+        }
+    }
+    std::vector<int> ids;
+    for (int v = 1; v <= mx; v++)
+        if (cnt[v] > 0) ids.push_back(v);
+    std::vector<std::string> name((size_t)mx + 1);
+    for (int v : ids) name[v] = std::to_string(v);
+    std::sort(ids.begin(), ids.end(), [&](int a, int b) { return name[a] < name[b]; });
+    std::stable_sort(ids.begin(), ids.end(), [&](int a, int b) { return cnt[a] > cnt[b]; });
+    std::vector<int32_t> code((size_t)mx + 1, 0);
+    for (size_t r = 0; r < ids.size(); r++) {
+        code[ids[r]] = (int32_t)(r + 1);
+        if (counts) counts[r] = cnt[ids[r]];
+    }
+    for (int v = 0; v <= mx; v++) map[v] = code[map[v]];
+    for (int64_t i = 0; i < n; i++) out[i] = map[out[i]];
+    *n_labels = (int)ids.size();
     return SHARP_OK;
 }
 

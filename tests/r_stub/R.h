@@ -9,7 +9,7 @@ typedef int Rboolean;
 #define TRUE 1
 #define FALSE 0
 extern SEXP R_NilValue;
-enum { INTSXP = 13, REALSXP = 14, VECSXP = 19 };
+enum { INTSXP = 13, REALSXP = 14, VECSXP = 19, RAWSXP = 24 };
 void Rf_error(const char *, ...);
 char *R_alloc(size_t, int);
 #endif

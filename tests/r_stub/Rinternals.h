@@ -10,6 +10,10 @@ void Rf_unprotect(int);
 #define UNPROTECT(n) Rf_unprotect(n)
 int *INTEGER(SEXP);
 double *REAL(SEXP);
+typedef unsigned char Rbyte;
+Rbyte *RAW(SEXP);
+R_xlen_t XLENGTH(SEXP);
+int TYPEOF(SEXP);
 SEXP VECTOR_ELT(SEXP, R_xlen_t);
 SEXP SET_VECTOR_ELT(SEXP, R_xlen_t, SEXP);
 SEXP STRING_ELT(SEXP, R_xlen_t);

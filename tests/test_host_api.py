@@ -318,3 +318,37 @@ def test_shcsc_files_and_the_streamed_unlimited3(tmp_path):
     ref = api.SHARP_unlimited([synth.to_csc(a) + (a.shape,) for a in plist], viewflag=False, rN_seed=3, ensize_K=2, exp_type="UMI",
                               ctx=FakeContext(), n_streams=1, _krange_from_part1=True)
     assert np.array_equal(r["pred_clusters"], ref["pred_clusters"]) and r["N.pred_clusters"] == ref["N.pred_clusters"]
+
+
+def test_labels_combine_native_equals_numpy_tail():
+    """sharp_labels_combine (host C++) == tf[fColor] + _merge_small + _relabel_by_size, including the string order of
+    equal-sized ids (R/SHARP_unlimited.R:166-183)"""
+    from sharp_b200 import _lib
+    rng = np.random.default_rng(5)
+    for trial in range(6):
+        nparts = int(rng.integers(1, 6))
+        counts = [int(rng.integers(2, 9)) for _ in range(nparts)]
+        ntf = sum(counts)
+        tf = rng.integers(1, 14 if trial % 2 else 120, size=ntf).astype(np.int32)
+        preds = []
+        for t in range(nparts):
+            n = int(rng.integers(40, 3000))
+            pr = rng.integers(1, counts[t] + 1, size=n).astype(np.int32)
+            if trial >= 3:                       # a few tiny clusters, and equal sizes (ties resolved in string order)
+                pr[:n // 2] = 1
+                pr[n // 2:n // 2 + 3] = min(2, counts[t])
+            preds.append(pr)
+        ncells = sum(len(p) for p in preds)
+        for merge in (0, 10):
+            want = api._combine_labels_py(tf, counts, preds, ncells, bool(merge))
+            got, sizes = _lib.labels_combine(preds, counts, tf, merge)
+            assert np.array_equal(got, want)
+            assert np.array_equal(sizes, np.bincount(want)[1:])
+    # ties between ids 2, 10, 3: string order "10" < "2" < "3"
+    tf = np.array([2, 10, 3], dtype=np.int32)
+    preds = [np.array([1, 2, 3, 1, 2, 3], dtype=np.int32)]
+    got, _ = _lib.labels_combine(preds, [3], tf, 0)
+    assert np.array_equal(got, api._combine_labels_py(tf, [3], preds, 6, False))
+    assert got.tolist() == [2, 1, 3, 2, 1, 3]
+    with pytest.raises(Exception):
+        _lib.labels_combine([np.array([4], dtype=np.int32)], [3], tf, 0)
