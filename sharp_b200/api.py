@@ -324,13 +324,31 @@ def _member_seeds(K, rN_seed, comm=None):
 
 def _rm_list(m, p, K, rN_seed, comm=None):
     """K x ranM(E, p, 50 + rN.seed + k) (R/SHARP.R:539-549) with R's RNG stream, one host thread per member (the
-    native generator releases the GIL)."""
+    native generator releases the GIL).  With several ranks on one host the members are dealt over the ranks and the
+    slots exchanged (a draw is one sequential MT19937 stream of m * p numbers: K threads per rank on every rank would
+    only fight for the cores -- 20 ms instead of 8 at 8 ranks)."""
     from concurrent.futures import ThreadPoolExecutor
     seeds = _member_seeds(K, rN_seed, comm)
-    if K == 1:
-        return [_lib.r_ranm(m, p, seeds[0])]
-    with ThreadPoolExecutor(max_workers=min(K, 16)) as ex:
-        return list(ex.map(lambda sd: _lib.r_ranm(m, p, sd), seeds))
+    world = comm.world if comm is not None else 1
+    mine = [k for k in range(K) if k % world == (comm.rank if comm is not None else 0)]
+
+    def draw(k):
+        return _lib.r_ranm(m, p, seeds[k])
+
+    if len(mine) <= 1:
+        got = {k: draw(k) for k in mine}
+    else:
+        with ThreadPoolExecutor(max_workers=min(len(mine), 16)) as ex:
+            got = dict(zip(mine, ex.map(draw, mine)))
+    if world == 1:
+        return [got[k] for k in range(K)]
+    payload = {}
+    for k, r in got.items():
+        payload[3 * k] = np.ascontiguousarray(r["p"], dtype=np.int32)
+        payload[3 * k + 1] = np.ascontiguousarray(r["i"], dtype=np.int32)
+        payload[3 * k + 2] = np.ascontiguousarray(r["x"], dtype=np.float64)
+    allv = comm.allgather_parts(payload, 3 * K)
+    return [{"Dim": (m, p), "p": allv[3 * k], "i": allv[3 * k + 1], "x": allv[3 * k + 2]} for k in range(K)]
 
 
 def _as_rmdev(ctx: Context, rM, m, p, K, rN_seed) -> tuple[RmDev, bool]:

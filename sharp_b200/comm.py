@@ -111,23 +111,35 @@ class NcclComm:
         self.ctx = None
 
     # -- collectives on host buffers -----------------------------------------------------------------
-    def allgather_bytes(self, payload: bytes) -> list[bytes]:
+    def allgather_arrays(self, payload: np.ndarray) -> list[np.ndarray]:
+        """payload: a uint8 array (any length) per rank -> the list of every rank's array (views into ONE receive
+        buffer; segments start on 8-byte boundaries)"""
         lib = _lib.load()
+        payload = np.ascontiguousarray(payload, dtype=np.uint8)
+        padded = (len(payload) + 7) & ~7
         one = np.array([len(payload)], dtype=np.int64)
         sizes = np.zeros(self.world, dtype=np.int64)
         eight = np.full(self.world, 8, dtype=np.int64)
         _lib._check(lib.sharp_comm_allgatherv(self.ctx._h, one.ctypes.data_as(C.c_void_p), eight.ctypes.data_as(C.POINTER(C.c_int64)),
                                               sizes.ctypes.data_as(C.c_void_p)))
-        total = int(sizes.sum())
-        send = np.frombuffer(payload, dtype=np.uint8) if payload else np.zeros(1, dtype=np.uint8)
-        recv = np.zeros(max(total, 1), dtype=np.uint8)
-        _lib._check(lib.sharp_comm_allgatherv(self.ctx._h, send.ctypes.data_as(C.c_void_p), sizes.ctypes.data_as(C.POINTER(C.c_int64)),
+        seg = (sizes + 7) & ~7
+        total = int(seg.sum())
+        if padded != len(payload) or padded == 0:
+            send = np.zeros(max(padded, 8), dtype=np.uint8)
+            send[:len(payload)] = payload
+        else:
+            send = payload
+        recv = np.empty(max(total, 8), dtype=np.uint8)
+        _lib._check(lib.sharp_comm_allgatherv(self.ctx._h, send.ctypes.data_as(C.c_void_p), seg.ctypes.data_as(C.POINTER(C.c_int64)),
                                               recv.ctypes.data_as(C.c_void_p)))
         out, off = [], 0
         for r in range(self.world):
-            out.append(recv[off:off + int(sizes[r])].tobytes())
-            off += int(sizes[r])
+            out.append(recv[off:off + int(sizes[r])])
+            off += int(seg[r])
         return out
+
+    def allgather_bytes(self, payload: bytes) -> list[bytes]:
+        return [a.tobytes() for a in self.allgather_arrays(np.frombuffer(payload, dtype=np.uint8))]
 
     def barrier(self):
         _lib._check(_lib.load().sharp_comm_barrier(self.ctx._h))
@@ -145,7 +157,7 @@ class NcclComm:
     def allgather_parts(self, mine: dict, nparts: int) -> list:
         """every rank contributes the arrays of the parts it owns ({part index: ndarray}); returns the list of all
         ``nparts`` arrays on every rank.  Fixed binary layout per array: index, dtype code, ndim, shape, bytes."""
-        return unpack_parts(self.allgather_bytes(pack_parts(mine)), nparts)
+        return unpack_parts(self.allgather_arrays(pack_parts(mine)), nparts)
 
     def max_float(self, x: float) -> float:
         vals = [struct.unpack("<d", b)[0] for b in self.allgather_bytes(struct.pack("<d", float(x)))]
@@ -156,28 +168,38 @@ _DT = {"<f8": 0, "<i4": 1, "<i8": 2, "|u1": 3, "<f4": 4}
 _DT_INV = {v: k for k, v in _DT.items()}
 
 
-def pack_parts(mine: dict) -> bytes:
-    out = bytearray()
+def pack_parts(mine: dict) -> np.ndarray:
+    """{index: ndarray} -> one uint8 array.  Per array: int32 index, dtype code, ndim, 0; int64 shape[ndim]; the data,
+    padded to 8 bytes -- so every array starts on an 8-byte boundary of the blob and unpacking needs no copy."""
+    pieces = []
     for i in sorted(mine):
         a = np.ascontiguousarray(mine[i])
-        code = _DT[a.dtype.str]
-        out += struct.pack("<iii", int(i), code, a.ndim) + struct.pack(f"<{a.ndim}q", *a.shape) + a.tobytes()
-    return bytes(out)
+        head = struct.pack("<iiii", int(i), _DT[a.dtype.str], a.ndim, 0) + struct.pack(f"<{a.ndim}q", *a.shape)
+        pieces.append(np.frombuffer(head, dtype=np.uint8))
+        pieces.append(a.reshape(-1).view(np.uint8))
+        tail = (-a.nbytes) & 7
+        if tail:
+            pieces.append(np.zeros(tail, dtype=np.uint8))
+    return np.concatenate(pieces) if pieces else np.zeros(0, dtype=np.uint8)
 
 
 def unpack_parts(blobs: list, nparts: int) -> list:
+    """the arrays of all ranks (views into the blobs, which stay alive with them)"""
     out = [None] * nparts
     for blob in blobs:
+        blob = np.frombuffer(blob, dtype=np.uint8) if isinstance(blob, (bytes, bytearray)) else blob
         off = 0
         while off < len(blob):
-            i, code, nd = struct.unpack_from("<iii", blob, off)
-            off += 12
+            i, code, nd, _ = struct.unpack_from("<iiii", blob, off)
+            off += 16
             shape = struct.unpack_from(f"<{nd}q", blob, off)
             off += 8 * nd
             dt = np.dtype(_DT_INV[code])
             cnt = int(np.prod(shape)) if nd else 1
-            out[i] = np.frombuffer(blob, dtype=dt, count=cnt, offset=off).reshape(shape).copy()
-            off += cnt * dt.itemsize
+            nb = cnt * dt.itemsize
+            seg = blob[off:off + nb]
+            out[i] = (seg.view(dt) if seg.ctypes.data % dt.itemsize == 0 else np.frombuffer(seg.tobytes(), dtype=dt)).reshape(shape)
+            off += (nb + 7) & ~7
     missing = [i for i, a in enumerate(out) if a is None]
     if missing:
         raise RuntimeError(f"allgather_parts: no rank contributed parts {missing}")

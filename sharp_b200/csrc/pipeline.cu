@@ -2482,7 +2482,10 @@ int sharp_parts_prefetch(sharp_ctx *c, int m, int nparts, sharp_part *parts, int
     SHARP_CUDA(cudaStreamWaitEvent(c->up_stream, c->ev_fork, 0));
     std::vector<int> idx;
     std::vector<sharp_ctx *> subs;
-    for (int i = gstart[0]; i < gstart[1]; i++) {
+    /* only the FIRST part of group 0: this call is made before the projection matrices exist (their draw takes about as
+       long as one part's copy), and the copy of those matrices must not queue behind a whole group of parts -- the
+       first kernels need both.  The other parts of the group are copied by the run itself, behind the matrices. */
+    for (int i = gstart[0]; i < gstart[1] && i < gstart[0] + 1; i++) {
         idx.push_back(i);
         subs.push_back(c->subs[(size_t)(i - gstart[0])]); /* lane 0 */
     }
