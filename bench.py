@@ -70,6 +70,12 @@ def workload(name: str) -> dict:
                          "p=416, 50 blocks of 2000 dealt over the ranks, rN.seed=2103",
                     single=True, m=20000, parts=[100000], K=15, types=10, nnz_per_cell=1400, exp_type="UMI", dense=False,
                     metric="cells/sec end-to-end SHARP at 100k cells, K=15 (config 3)")
+    if name == "cfg5":  # BASELINE.json configs[4], bounded: the parts live in SHCSC001 files and are streamed (read ->
+        # pinned -> H2D -> cluster); 20 files of 50 000 cells per rank-set by default (--parts bounds it)
+        return dict(name="SHARP_unlimited3 on SHCSC001 files (streaming ingestion), synthetic UMI 20000 genes x 1000000 cells "
+                         "(config 5's shape, bounded from 1e7 cells), 20 files of 50000 cells, exp.type=UMI, K=5, rN.seed=2103",
+                    streamed=True, m=20000, parts=[50000] * 20, K=5, types=15, nnz_per_cell=1000, exp_type="UMI",
+                    metric="cells/sec end-to-end SHARP_unlimited3, parts streamed from files (config 5, bounded)")
     if name == "dev":  # development / CPU-side dry runs
         return dict(name="dev: 3000 genes x 3 parts of 2600 cells", m=3000, parts=[2600] * 3, K=3, types=5,
                     nnz_per_cell=300, exp_type="UMI")
@@ -552,9 +558,107 @@ def run_single(args, wl):
         comm.close()
 
 
+def run_streamed(args, wl):
+    """config 5 (bounded): SHARP_unlimited3 over a directory of SHCSC001 files -- the reference reads one .rds per part
+    (R/SHARP_unlimited3.R:103-131); here a reader thread fills pinned buffers with pread() while the previous batch of
+    parts is copied and clustered.  Both numbers of the line are end to end FROM THE FILES (page cache warm after the
+    warm-up steps); `value` and `e2e` are the same measurement, there is no device-resident variant of this path."""
+    import shutil
+    import torch
+    from sharp_b200 import api, io as sio
+    from sharp_b200 import comm as sharp_comm
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    api.set_devices(local)
+    ctx = api.get_context(local)
+    comm = sharp_comm.init_from_env(ctx)
+    rank, world = (comm.rank, comm.world) if comm else (0, 1)
+    if args.parts:
+        wl["parts"] = wl["parts"][:args.parts]
+    m, sizes = wl["m"], wl["parts"]
+    ncells = int(sum(sizes))
+    root = os.environ.get("SHARP_BENCH_TMP") or ("/dev/shm" if os.path.isdir("/dev/shm") else tempfile.gettempdir())
+    d = os.path.join(root, "sharp_b200_cfg5")
+    t0 = time.time()
+    nbytes = 0
+    if rank == 0:
+        shutil.rmtree(d, ignore_errors=True)
+        os.makedirs(d)
+        lam = type_profiles(torch, dev, m, wl["types"], wl["nnz_per_cell"])
+        for i, n in enumerate(sizes):
+            part = gen_part(torch, dev, lam, n, i, False)
+            path = os.path.join(d, f"part{i + 1}.csc")
+            sio.write_csc(path, m, n, part["p"], part["i"], part["x"])
+            nbytes += os.path.getsize(path)
+            del part
+        del lam
+        torch.cuda.empty_cache()
+    if comm:
+        comm.barrier()
+    t_gen = time.time() - t0
+    nd = {"dir": d, "ncells": ncells, "ngenes": m}
+    kw = dict(viewflag=False, ensize_K=wl["K"], rN_seed=SEED, exp_type=wl["exp_type"], ctx=ctx, comm=comm)
+
+    def barrier():
+        ctx.sync()
+        torch.cuda.synchronize()
+        if comm:
+            comm.barrier()
+
+    try:
+        for _ in range(args.warmup):
+            api.SHARP_unlimited3(nd, **kw)
+        sampler = ClockSampler(local)
+        if rank == 0:
+            sampler.start()
+        barrier()
+        ctx.prof_reset()
+        l0 = ctx.launch_count()
+        ctx.timer_start()
+        walls = []
+        for _ in range(args.steps):
+            w0 = time.perf_counter()
+            res = api.SHARP_unlimited3(nd, **kw)
+            walls.append(round(1e3 * (time.perf_counter() - w0), 1))
+        ms = ctx.timer_stop_ms()
+        barrier()
+        ms = comm.max_float(ms) if comm else ms
+        launches = ctx.launch_count() - l0
+        clocks = sampler.stop() if rank == 0 else None
+    finally:
+        if comm:
+            comm.barrier()
+        if rank == 0:
+            shutil.rmtree(d, ignore_errors=True)
+    import hashlib
+    label_hash = hashlib.sha1(np.ascontiguousarray(res["pred_clusters"], dtype=np.int32).tobytes()).hexdigest()[:16]
+    if comm and len(set(comm.allgather_bytes(label_hash.encode()))) != 1:
+        raise SystemExit("the ranks returned different label vectors")
+    if rank == 0:
+        value = ncells * args.steps / (ms * 1e-3)
+        line = {"metric": wl["metric"], "value": value, "unit": "cells/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+                "data": "synthetic",
+                "config": {"workload": wl["name"], "cells": ncells, "genes": m, "files": len(sizes), "file_bytes": int(nbytes),
+                           "file_dir": root, "K": wl["K"], "p": int(math.ceil(math.log2(ncells) / 0.04)),
+                           "l2": "inputs larger than L2 (%.1f GB of files per step)" % (nbytes / 1e9), "generation_s": t_gen},
+                "step_wall_ms": walls, "clocks": clocks, "gpu_launches": int(launches / args.steps),
+                "e2e": {"value": value, "unit": "cells/s", "h2d_bytes_per_step": int(nbytes), "d2h_bytes_per_step": int(ncells * 4),
+                        "ms_per_step": ms / args.steps, "note": "same measurement as value: this path starts at the files"},
+                "roofline": None, "cpu_baseline": None, "parity": None,
+                "result": {"N.pred_clusters": int(res["N.pred_clusters"]), "label_sha1_16": label_hash,
+                           "ranks_agree": True if comm else None}}
+        print(json.dumps(line))
+    if comm:
+        comm.close()
+
+
 def run_ours(args):
     if workload(args.workload).get("single"):
         return run_single(args, workload(args.workload))
+    if workload(args.workload).get("streamed"):
+        return run_streamed(args, workload(args.workload))
     import torch
     import sharp_b200
     from sharp_b200 import api

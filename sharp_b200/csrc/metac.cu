@@ -466,7 +466,7 @@ sm_codes_kernel(WmArgs A, const int *coloff, int *code, int *corder, int *coff) 
 }
 
 // colMeans(sE1[cluster, ]) in ascending row order: one CTA per cluster, threads over the p columns
-__global__ void __launch_bounds__(MT)
+__global__ void __launch_bounds__(MT, 2)
 sm_centroids_kernel(const double *__restrict__ E1, int p, const int *__restrict__ corder, const int *__restrict__ coff,
                     const int *nc_ptr, double *__restrict__ cen, int64_t *counts) {
     const int c = blockIdx.x;
@@ -475,7 +475,14 @@ sm_centroids_kernel(const double *__restrict__ E1, int p, const int *__restrict_
     for (int d = threadIdx.x; d < p; d += MT) {
         double s = 0.0;
         int q = q0;
-        for (; q + 8 <= q1; q += 8) { /* eight rows in flight; the adds stay in ascending row order */
+        for (; q + 32 <= q1; q += 32) { /* 32 rows in flight (part-level clusters hold thousands of cells); the adds stay in ascending row order */
+            double v[32];
+#pragma unroll
+            for (int u = 0; u < 32; u++) v[u] = E1[(size_t)corder[q + u] * p + d];
+#pragma unroll
+            for (int u = 0; u < 32; u++) s = __dadd_rn(s, v[u]);
+        }
+        for (; q + 8 <= q1; q += 8) {
             double v[8];
 #pragma unroll
             for (int u = 0; u < 8; u++) v[u] = E1[(size_t)corder[q + u] * p + d];

@@ -1910,10 +1910,15 @@ int sharp_rm_upload(sharp_ctx *c, int m, int p, int K, const int32_t *colptr, co
         }
         if (rv) {
             uint16_t *R0 = reinterpret_cast<uint16_t *>(H + o_rec);
-            memset(R0 + (size_t)g0 * rv * 8, 0, (size_t)(g1 - g0) * rv * 16);
             for (int i = g0; i < g1; i++) {
                 const uint32_t cn = rowptr[i + 1] - rowptr[i];
                 uint16_t *R = R0 + (size_t)i * rv * 8;
+                /* unused slots point at one of the 32 dummy words behind the + counts (never read back), spread over the
+                   banks: a kernel may scatter all seven slots of a vector without looking at the count */
+                for (int v = 0; v < rv; v++) {
+                    R[v * 8] = 0;
+                    for (int sl = 1; sl < 8; sl++) R[v * 8 + sl] = (uint16_t)((kpr + ((i * rv + v + 5 * sl) & 31)) << 2);
+                }
                 if ((int)cn > 7 * rv) { R[0] = 0xffffu; continue; }
                 for (uint32_t q = 0; q < cn; q++) {
                     const uint32_t en = ent[rowptr[i] + q];

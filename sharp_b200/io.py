@@ -104,6 +104,40 @@ class PartSlot:
             self.buf.close()
 
 
+# Page-locking memory costs about a second per 2 GB, far more than reading a part: the slots of a finished run are kept
+# for the next one (up to _POOL_BYTES) instead of being released, like the library's device workspaces.
+_POOL_BYTES = 24 << 30
+_pool: list = []
+_pool_lock = threading.Lock()
+
+
+def _acquire_slot(n_max, nnz_max, pinned) -> PartSlot:
+    with _pool_lock:
+        for k, s in enumerate(_pool):
+            if (s.buf is not None) == bool(pinned) and s.n_max >= n_max and s.nnz_max >= nnz_max and s.nnz_max <= 2 * max(nnz_max, 1):
+                return _pool.pop(k)
+    # 6 % slack, so that parts of slightly different sizes reuse the same slots
+    return PartSlot(n_max + n_max // 16 + 64, nnz_max + nnz_max // 16 + 1024, pinned)
+
+
+def _release_slot(slot: PartSlot) -> None:
+    with _pool_lock:
+        held = sum(s.o_v + s.nnz_max * 8 for s in _pool)
+        if held + slot.o_v + slot.nnz_max * 8 <= _POOL_BYTES:
+            _pool.append(slot)
+            return
+    slot.close()
+
+
+def release_pool() -> None:
+    """give the pooled page-locked slots back to the system"""
+    with _pool_lock:
+        slots = list(_pool)
+        _pool.clear()
+    for s in slots:
+        s.close()
+
+
 class BatchReader:
     """Reads the files of batch b + 1 on a host thread (the native reader releases the GIL) while batch b is in the GPU
     pipeline: two sets of ``batch`` pinned slots."""
@@ -112,7 +146,7 @@ class BatchReader:
         self.paths, self.infos, self.batch, self.threads = list(paths), list(infos), max(1, int(batch)), threads
         n_max = max(i[1] for i in infos)
         nnz_max = max(i[2] for i in infos)
-        self.sets = [[PartSlot(n_max, nnz_max, pinned) for _ in range(min(self.batch, len(paths)))] for _ in range(2)]
+        self.sets = [[_acquire_slot(n_max, nnz_max, pinned) for _ in range(min(self.batch, len(paths)))] for _ in range(2)]
         self.nb = (len(paths) + self.batch - 1) // self.batch
         self._thread = None
         self._result = None
@@ -148,4 +182,5 @@ class BatchReader:
             self._thread.join()
         for s in self.sets:
             for slot in s:
-                slot.close()
+                _release_slot(slot)
+        self.sets = []
