@@ -2308,11 +2308,16 @@ int sharp_run(sharp_ctx *c, int m, int64_t n, const double *dense, const int64_t
 
 // group boundaries of a run over `nparts` parts (shared by sharp_run_parts and sharp_parts_prefetch)
 static std::vector<int> plan_groups(int nparts, bool host_first, int &group, int &lanes) {
-    if (lanes <= 0) lanes = 2;
+    /* parts in host memory, many of them: three groups of two in flight hide the uploads best (B200, r2, 26 parts of
+       50 000 cells: 709 ms per run against 750 for two groups of four; device-resident parts: 668 vs 665) */
+    const bool many_host = host_first && nparts > 8;
+    if (lanes <= 0) lanes = many_host && group <= 0 ? 3 : 2;
     /* default group size: 4 parts share the block-clustering launches when there are many parts; with few parts (a rank
        of a multi-GPU job) smaller groups keep both lanes busy -- a group running alone leaves the device half idle
        during its latency-bound stages */
-    if (group <= 0) group = nparts <= 8 ? 2 : 4; /* measured on B200: 4 parts 160 ms as 2+2 vs 187 ms as 1+1+1+1 */
+    /* measured on B200 (r2, 50 000-cell parts): 4 resident parts 107 ms as 2+2 vs 111 ms as 1+1+1+1; 4 parts in host
+       memory 141 ms as 1+2+1 vs 123 ms as 1+1+1+1 (a part's upload hides behind ONE part's clustering) */
+    if (group <= 0) group = nparts <= 8 ? (host_first ? 1 : 2) : (many_host ? 2 : 4);
     group = std::min(group, nparts);
     // the parts are split as evenly as the group size allows, the smaller groups first and last (the first group's start
     // and the last group's tail are the stretches of the run nothing else overlaps with).  With host data the first

@@ -216,14 +216,14 @@ def test_plan_groups_covers_every_part_once():
                 if group:
                     assert g == min(group, nparts)
                 else:
-                    assert g == min(nparts, 2 if nparts <= 8 else 4)
+                    assert g == min(nparts, (1 if host else 2) if nparts <= 8 else (2 if host else 4))
                 if host and g >= 2 and nparts > g:
                     assert sizes[0] == g // 2
                 rest = sizes[1:] if (host and g >= 2 and nparts > g) else sizes
                 assert max(rest) - min(rest) <= 1                       # evenly split
     assert _lib.plan_groups(26, False)["gstart"] == [0, 3, 7, 11, 15, 19, 23, 26]      # the benchmark, parts in HBM
-    assert _lib.plan_groups(26, True)["gstart"] == [0, 2, 6, 10, 14, 18, 22, 26]       # the benchmark, host buffers
-    assert _lib.plan_groups(13, True)["gstart"] == [0, 2, 6, 10, 13]                   # one of two ranks
+    assert _lib.plan_groups(26, True)["gstart"] == [0, 1] + list(range(3, 26, 2)) + [26]   # the benchmark, host buffers: 3 lanes x 2 parts
+    assert _lib.plan_groups(13, True)["gstart"] == [0, 1, 3, 5, 7, 9, 11, 13]          # one of two ranks
 
 
 def test_sharp_unlimited2_is_two_level_like_the_reference():
