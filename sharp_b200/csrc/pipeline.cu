@@ -2311,7 +2311,7 @@ static std::vector<int> plan_groups(int nparts, bool host_first, int &group, int
     /* parts in host memory, many of them: three groups of two in flight hide the uploads best (B200, r2, 26 parts of
        50 000 cells: 709 ms per run against 750 for two groups of four; device-resident parts: 668 vs 665) */
     const bool many_host = host_first && nparts > 8;
-    if (lanes <= 0) lanes = many_host && group <= 0 ? 3 : 2;
+    if (lanes <= 0) lanes = (nparts > 8 && group <= 0) ? 3 : 2; /* device-resident, 26 parts: 655 ms with 3 lanes of 4 vs 664 with 2 */
     /* default group size: 4 parts share the block-clustering launches when there are many parts; with few parts (a rank
        of a multi-GPU job) smaller groups keep both lanes busy -- a group running alone leaves the device half idle
        during its latency-bound stages */
