@@ -9,8 +9,13 @@ Workload (BASELINE.json configs[3], the one the metric is quoted on; it fits one
 synthetic 27 998 genes x 1 306 127 cells UMI matrix given as 26 sparse parts (25 x 50 000 + 56 127, the 10x-brain
 layout of the reference's README), exp.type = "UMI" (CPM normalisation fused into the projection load), K = 5,
 p = 508, rN.seed = 2103, viewflag = FALSE.  A "step" is one complete SHARP_unlimited call over all parts.
-With N GPUs the parts are dealt round-robin to the ranks (strong scaling: the job is always the 1.3 M cells);
-the only exchange is the allgather of part-level centroids and labels before the global sMetaC.
+With N GPUs whole parts are dealt round-robin to the ranks while they divide evenly and the left-over parts are
+block-sharded over all ranks (strong scaling: the job is always the 1.3 M cells); the communicator is NCCL behind the
+C ABI (sharp_comm_*), torch.distributed.run is only the process launcher.  Exchanges: the ranM members a rank drew,
+block-level labels + enE rows of the sharded parts, part-level centroids and labels before the global sMetaC.
+
+Other workloads (--workload): cfg2 / cfg3 = BASELINE.json configs[1] / [2] through SHARP() (one matrix; cfg3 deals the
+cell blocks over the ranks), cfg5 = config 5's shape bounded to 1e6 cells, SHARP_unlimited3 streaming SHCSC001 files.
 
   value : whole-job cells/sec with every part already resident in HBM (sharp_expr_upload before the timed region)
   e2e   : the same call on HOST buffers (pinned dgCMatrix slots): per-part H2D copies and the D2H of labels and
@@ -673,6 +678,9 @@ def run_ours(args):
     # N > 1: the communicator is NCCL behind the C ABI (sharp_comm_*); torch is only used to generate the synthetic data
     comm = sharp_comm.init_from_env(ctx)
     rank, world = (comm.rank, comm.world) if comm else (0, 1)
+    # one process per GPU: keep this rank's host buffers on the GPU's NUMA node (what numactl would do for a launcher
+    # that knows the topology); at N = 1 the process keeps all cores (the CPU baseline uses them)
+    affinity = ctx.bind_host() if (world > 1 and not args.no_bind) else ""
     wl = workload(args.workload)
     if args.parts:
         wl["parts"] = wl["parts"][:args.parts]
@@ -896,7 +904,7 @@ def run_ours(args):
                                      + (f", the cell blocks of the other {len(shared)} dealt over all ranks (NCCL allgather of block-level labels and enE rows)" if shared else "")
                                      + f"; fused loop over parts (sharp_run_parts), group={args.group or 'default'}, lanes={args.lanes or 'default'}"),
                        "l2": "inputs larger than L2 (CSC input %.1f GB per step)" % (sum(nnz_all) * 12 / 1e9),
-                       "generation_s": t_gen},
+                       "generation_s": t_gen, "host_affinity_rank0": affinity or None},
             "step_wall_ms": walls_dev, "clocks": clocks, "gpu_launches": int(launches / args.steps),
             "e2e": {"value": e2e_value, "unit": "cells/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": ms_e2e / e2e_steps, "labels_equal_device_resident_run": same, "step_wall_ms": walls_e2e,
@@ -913,6 +921,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg4")
+    ap.add_argument("--no-bind", action="store_true", help="N > 1: do not bind the ranks to the CPUs next to their GPUs")
     ap.add_argument("--streams", type=int, default=8, help="contexts (CUDA streams) per GPU working on different parts")
     ap.add_argument("--parts", type=int, default=0, help="development: only the first PARTS parts")
     ap.add_argument("--group", type=int, default=0, help="parts per group of the fused loop over parts (0 = library default)")

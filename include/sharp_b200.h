@@ -303,6 +303,12 @@ void sharp_host_free(void *ptr);
 int sharp_csc_file_info(const char *path, int *m, int64_t *n, int64_t *nnz);
 int sharp_csc_file_read(const char *path, int64_t *colptr, int32_t *rowidx, double *val, int threads);
 
+/* Binds the calling thread (and threads created after) to the CPUs next to the context's GPU, read from
+ * /sys/bus/pci/devices/<bus id>/local_cpulist -- what `numactl --cpunodebind` does for a launcher that knows the
+ * topology; host buffers first touched afterwards live on the GPU's NUMA node.  One process per GPU calls it once,
+ * before allocating its input buffers.  cpulist (optional) receives the list applied ("" = topology not exposed, no-op). */
+int sharp_ctx_bind_host(sharp_ctx *ctx, char *cpulist, int cpulist_len);
+
 /* ---- multi-GPU: one process -- or one host thread -- per GPU, NCCL over NVLink behind this ABI -----------
  * Replaces the gather side of foreach / doParallel (`.combine`, R/SHARP.R:554, 627-635, 692; R/SHARP_unlimited3.R:137-147)
  * across GPUs.  The path shards by parts and cell blocks with no data-path collective; what is exchanged are block-level

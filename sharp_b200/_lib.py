@@ -62,7 +62,7 @@ EXPORTS = [
     "sharp_hclust", "sharp_opt_hclust", "sharp_getrowcolor", "sharp_wmetac", "sharp_smetac", "sharp_run",
     "sharp_expr_upload", "sharp_expr_free", "sharp_run_dev", "sharp_centroids", "sharp_smetac_centroids",
     "sharp_last_member", "sharp_last_vie", "sharp_prof_enable", "sharp_prof_reset", "sharp_prof_kernels", "sharp_prof_name",
-    "sharp_prof_get", "sharp_ctx_set_rp_variant", "sharp_r_ranm", "sharp_r_sample_perm", "sharp_labels_combine", "sharp_run_parts",
+    "sharp_prof_get", "sharp_ctx_set_rp_variant", "sharp_r_ranm", "sharp_r_sample_perm", "sharp_labels_combine", "sharp_ctx_bind_host", "sharp_run_parts",
     "sharp_ctx_set_block_budget", "sharp_ctx_set_serial", "sharp_parts_prefetch", "sharp_plan_groups",
     "sharp_comm_unique_id", "sharp_comm_init", "sharp_comm_destroy", "sharp_comm_info", "sharp_comm_allgatherv",
     "sharp_comm_bcast", "sharp_comm_barrier", "sharp_host_alloc", "sharp_host_free", "sharp_csc_file_info",
@@ -412,6 +412,12 @@ class Context:
         _check(load().sharp_smetac(self._h, C.c_int64(ncells), p, _ptr(lab, C.c_int32), _ptr(se1, C.c_double),
                                    C.byref(prm), _ptr(fc, C.c_int32), _ptr(tf, C.c_int32), C.byref(nc)))
         return {"finalColor": fc, "tf": tf[:nc.value]}
+
+    def bind_host(self) -> str:
+        """bind this thread to the CPUs next to the GPU (sharp_ctx_bind_host); returns the cpulist applied ("" = no-op)"""
+        buf = C.create_string_buffer(4096)
+        _check(load().sharp_ctx_bind_host(self._h, buf, 4096))
+        return buf.value.decode()
 
     def smetac_centroids(self, cen, ncells_total, prm: HcParams) -> np.ndarray:
         cen = _f64(cen)

@@ -164,10 +164,18 @@ int sharp_comm_allgatherv(sharp_ctx *c, const void *send, const int64_t *bytes, 
     }
     const int64_t mine = bytes[c->comm_rank];
     if (mine > 0 && !send) return set_error(SHARP_E_ARG, "comm_allgatherv: null send buffer");
-    SHARP_TRY(c->ws[WS_COMM_SLOT].reserve((size_t)std::max<int64_t>(total + mine, 16)));
+    const int64_t total4 = (total + 3) & ~(int64_t)3, mine4 = (mine + 3) & ~(int64_t)3;
+    SHARP_TRY(c->ws[WS_COMM_SLOT].reserve((size_t)std::max<int64_t>(total4 + mine4, 16)));
     unsigned char *dev = c->ws[WS_COMM_SLOT].as<unsigned char>();
-    unsigned char *dsend = dev + total;
-    if (mine > 0) SHARP_CUDA(cudaMemcpyAsync(dsend, send, (size_t)mine, cudaMemcpyHostToDevice, c->stream));
+    unsigned char *dsend = dev + total4;
+    if (mine > 0) {
+        /* host -> device through the page-locked arena and a copy KERNEL (up to 8 MB): the copy engine may be busy with a
+           look-ahead upload of expression data queued earlier, and would make every rank wait for it */
+        if (mine4 <= ((int64_t)8 << 20) && c->reserve_pinned((size_t)mine4) == 0) {
+            memcpy(c->pinned, send, (size_t)mine);
+            SHARP_TRY(h2d_by_kernel(c->stream, dsend, c->pinned, (size_t)mine4));
+        } else SHARP_CUDA(cudaMemcpyAsync(dsend, send, (size_t)mine, cudaMemcpyHostToDevice, c->stream));
+    }
     SHARP_TRY(comm_allgatherv_dev(c, dsend, dev, bytes, c->stream));
     if (total > 0) SHARP_CUDA(cudaMemcpyAsync(recv, dev, (size_t)total, cudaMemcpyDeviceToHost, c->stream));
     SHARP_CUDA(cudaStreamSynchronize(c->stream));

@@ -253,6 +253,7 @@ int launch_hclust(sharp_ctx *c, HcProb *probs_dev, int nprob, int max_n, int met
 // write the working copy Dw (round 1 reads the pristine D)
 bool hclust_fast_ok(int max_n, int method);
 // sweep.cu
+int h2d_by_kernel(cudaStream_t st, void *dst, const void *src, size_t bytes); /* pipeline.cu: copy engine bypass for small page-locked sources */
 size_t sweep_nested_scratch_bytes(int max_n, int max_p, HcParamsDev prm);
 int launch_sweep_nested(sharp_ctx *c, HcProb *probs_dev, SweepOut *outs_dev, int nprob, int max_n, int max_p,
                         HcParamsDev prm, double *scratch, size_t scratch_per_prob);

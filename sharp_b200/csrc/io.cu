@@ -12,10 +12,14 @@
 // The reader fills CALLER buffers (pinned host memory from sharp_host_alloc, so the following H2D copy is asynchronous)
 // with pread() from several threads; nothing here touches the GPU except the pinned allocator.
 #include <fcntl.h>
+#include <sched.h>
 #include <sys/stat.h>
 #include <unistd.h>
 
+#include <cctype>
 #include <cerrno>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <thread>
 #include <vector>
@@ -112,6 +116,50 @@ int sharp_csc_file_read(const char *path, int64_t *colptr, int32_t *rowidx, doub
     close(fd);
     if (e) return set_error(SHARP_E_ARG, "reading %s: %s", path, strerror(e));
     if (colptr[0] != 0 || colptr[n] != nnz) return set_error(SHARP_E_ARG, "%s: colptr does not match nnz", path);
+    return 0;
+}
+
+
+// Binds the CALLING thread (and the threads it creates later) to the CPUs next to the context's GPU
+// (/sys/bus/pci/devices/<bus id>/local_cpulist), so that host buffers allocated and first touched afterwards live on the
+// GPU's NUMA node: with one process per GPU on a two-socket host the uploads of all ranks otherwise cross the socket
+// link.  What `numactl --cpunodebind` does for a launcher that knows the topology.  cpulist (optional) receives the
+// list that was applied ("" when the topology is not exposed: the call is then a no-op).
+int sharp_ctx_bind_host(sharp_ctx *c, char *cpulist, int cpulist_len) {
+    if (!c) return set_error(SHARP_E_ARG, "null context");
+    if (cpulist && cpulist_len > 0) cpulist[0] = 0;
+    char bus[64] = {0};
+    if (cudaDeviceGetPCIBusId(bus, sizeof bus, c->device) != cudaSuccess) { cudaGetLastError(); return 0; }
+    for (char *q = bus; *q; q++) *q = (char)tolower(*q);
+    char path[160];
+    snprintf(path, sizeof path, "/sys/bus/pci/devices/%s/local_cpulist", bus);
+    FILE *f = fopen(path, "r");
+    if (!f) return 0;
+    char line[4096] = {0};
+    const bool got = fgets(line, sizeof line, f) != nullptr;
+    fclose(f);
+    if (!got) return 0;
+    cpu_set_t set;
+    CPU_ZERO(&set);
+    int ncpu = 0;
+    for (char *q = line; *q && *q != '\n';) { /* "0-31,64-95" */
+        char *end;
+        long a = strtol(q, &end, 10);
+        if (end == q) break;
+        long b = a;
+        if (*end == '-') { q = end + 1; b = strtol(q, &end, 10); }
+        for (long v = a; v <= b && v < CPU_SETSIZE; v++) { CPU_SET((int)v, &set); ncpu++; }
+        q = (*end == ',') ? end + 1 : end;
+        if (*end != ',' ) break;
+    }
+    if (ncpu == 0) return 0;
+    if (sched_setaffinity(0, sizeof set, &set) != 0) return 0;
+    if (cpulist && cpulist_len > 0) {
+        size_t n = strcspn(line, "\n");
+        if (n >= (size_t)cpulist_len) n = (size_t)cpulist_len - 1;
+        memcpy(cpulist, line, n);
+        cpulist[n] = 0;
+    }
     return 0;
 }
 

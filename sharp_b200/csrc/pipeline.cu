@@ -333,6 +333,16 @@ static int h2d(sharp_ctx *c, void *dst, const void *src, size_t bytes) {
 __global__ void stage_copy_kernel(uint32_t *__restrict__ dst, const uint32_t *__restrict__ src, size_t nwords) {
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nwords; i += (size_t)gridDim.x * blockDim.x) dst[i] = src[i];
 }
+// the same copy on an explicit stream, any size (multiple of 4 bytes, 4-byte aligned): `src` is page-locked host memory
+int h2d_by_kernel(cudaStream_t st, void *dst, const void *src, size_t bytes) {
+    if (bytes == 0) return 0;
+    if ((bytes & 3) || ((uintptr_t)dst & 3) || ((uintptr_t)src & 3)) return set_error(SHARP_E_ARG, "h2d_by_kernel: unaligned");
+    const size_t nw = bytes / 4;
+    const int grid = (int)std::min<size_t>(148, (nw + 255) / 256);
+    stage_copy_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<uint32_t *>(dst), reinterpret_cast<const uint32_t *>(src), nw);
+    SHARP_CUDA(cudaGetLastError());
+    return 0;
+}
 static int h2d_staged(sharp_ctx *c, void *dst, const void *src, size_t bytes) {
     if (bytes == 0) return 0;
     if ((bytes & 3) || ((uintptr_t)dst & 3) || ((uintptr_t)src & 3) || bytes > ((size_t)16 << 20)) return h2d(c, dst, src, bytes);
@@ -1933,7 +1943,9 @@ int sharp_rm_upload(sharp_ctx *c, int m, int p, int K, const int32_t *colptr, co
     unsigned char *dev = nullptr;
     cudaError_t e1 = rm_alloc(c->device, (void **)&dev, total);
     if (e1 == cudaSuccess && !c->rm_stream) e1 = cudaStreamCreateWithFlags(&c->rm_stream, cudaStreamNonBlocking);
-    if (e1 == cudaSuccess) e1 = cudaMemcpyAsync(dev, H, total, cudaMemcpyHostToDevice, c->rm_stream);
+    /* copied by a kernel that reads the page-locked blob, not by the copy engine: the engine serves copies in submission
+       order, and a look-ahead upload of expression data (a GB per part) may already be queued */
+    if (e1 == cudaSuccess && h2d_by_kernel(c->rm_stream, dev, H, total) != 0) e1 = cudaErrorUnknown;
     if (e1 == cudaSuccess) e1 = cudaStreamSynchronize(c->rm_stream);
     tr.mark("rm_copy");
     if (e1 != cudaSuccess) {
