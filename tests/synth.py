@@ -51,10 +51,10 @@ def ari(a, b):
     ct = np.zeros((ai.max() + 1, bi.max() + 1), dtype=np.int64)
     np.add.at(ct, (ai, bi), 1)
     comb = lambda x: x * (x - 1) // 2
-    sij = comb(ct).sum()
-    sa = comb(ct.sum(1)).sum()
-    sb = comb(ct.sum(0)).sum()
-    tot = comb(len(a))
+    sij = int(comb(ct).sum())                # Python integers: sa * sb exceeds 2^63 beyond ~1e5 cells
+    sa = int(comb(ct.sum(1)).sum())
+    sb = int(comb(ct.sum(0)).sum())
+    tot = int(comb(len(a)))
     exp = sa * sb / tot
     mx = (sa + sb) / 2
     if mx == exp:
