@@ -292,6 +292,11 @@ int sharp_smetac_centroids(sharp_ctx *ctx, int nC, int p, const double *cen, int
 int sharp_labels_combine(int nparts, const int64_t *part_start, const int32_t *part_off, const int32_t *pred,
                          const int32_t *tf, int ntf, int merge_thre, int32_t *out, int64_t *counts, int *n_labels);
 
+/* clusterID = match(y, unique(y)) (R/SHARP.R:429-432, 828-832) for ids in 0..nvals-1, pure host code: codes 1.. in order
+ * of first appearance; uniq (optional, nvals entries) receives unique(y).  Returns the number of distinct ids, -1 for an
+ * id out of range. */
+int sharp_first_appearance_codes(const int32_t *y, int64_t n, int nvals, int32_t *codes, int32_t *uniq);
+
 /* ---- streaming ingestion for SHARP_unlimited3 -------------------------------------------------------
  * Replaces  mat = readRDS(allfiles[i])  (R/SHARP_unlimited3.R:105, freed at :124-125) for parts kept in the raw dgCMatrix
  * container SHCSC001 (64-byte header: "SHCSC001", int32 m, int32 0, int64 n, int64 nnz; then the slots p (int64[n+1]),

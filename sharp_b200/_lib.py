@@ -62,7 +62,7 @@ EXPORTS = [
     "sharp_hclust", "sharp_opt_hclust", "sharp_getrowcolor", "sharp_wmetac", "sharp_smetac", "sharp_run",
     "sharp_expr_upload", "sharp_expr_free", "sharp_run_dev", "sharp_centroids", "sharp_smetac_centroids",
     "sharp_last_member", "sharp_last_vie", "sharp_prof_enable", "sharp_prof_reset", "sharp_prof_kernels", "sharp_prof_name",
-    "sharp_prof_get", "sharp_ctx_set_rp_variant", "sharp_r_ranm", "sharp_r_sample_perm", "sharp_labels_combine", "sharp_ctx_bind_host", "sharp_run_parts",
+    "sharp_prof_get", "sharp_ctx_set_rp_variant", "sharp_r_ranm", "sharp_r_sample_perm", "sharp_labels_combine", "sharp_first_appearance_codes", "sharp_ctx_bind_host", "sharp_run_parts",
     "sharp_ctx_set_block_budget", "sharp_ctx_set_serial", "sharp_parts_prefetch", "sharp_plan_groups",
     "sharp_comm_unique_id", "sharp_comm_init", "sharp_comm_destroy", "sharp_comm_info", "sharp_comm_allgatherv",
     "sharp_comm_bcast", "sharp_comm_barrier", "sharp_host_alloc", "sharp_host_free", "sharp_csc_file_info",
@@ -180,6 +180,18 @@ def r_sample_perm_native(n: int, seed: int) -> np.ndarray:
     if rc != 0:
         raise SharpError(rc, "sharp_r_sample_perm failed")
     return out
+
+
+def first_appearance_codes(y: np.ndarray, nvals: int) -> tuple[np.ndarray, np.ndarray]:
+    """match(y, unique(y)) for int32 ids in 0..nvals-1 (sharp_first_appearance_codes, pure host) -> (codes, unique(y))"""
+    y = np.ascontiguousarray(y, dtype=np.int32)
+    codes = np.empty(len(y), dtype=np.int32)
+    uniq = np.empty(int(nvals), dtype=np.int32)
+    k = load().sharp_first_appearance_codes(_ptr(y, C.c_int32), C.c_int64(len(y)), int(nvals), _ptr(codes, C.c_int32),
+                                            _ptr(uniq, C.c_int32))
+    if k < 0:
+        raise SharpError(E_ARG, "sharp_first_appearance_codes: id out of range")
+    return codes, uniq[:k]
 
 
 def labels_combine(preds: list, counts_per_part: list, tf: np.ndarray, merge_thre: int) -> tuple[np.ndarray, np.ndarray]:

@@ -207,15 +207,10 @@ def _first_appearance_codes(y) -> tuple[np.ndarray, np.ndarray]:
     """match(y, unique(y)) -> (codes 1.., unique values in first-appearance order)"""
     y = np.asarray(y)
     n = len(y)
-    if n and y.dtype.kind in "iu" and 0 <= int(y.min()) and int(y.max()) <= 4 * n + 1024:
-        # small non-negative integers (cluster ids): O(n) with a lookup table instead of a sort
-        first = np.full(int(y.max()) + 1, n, dtype=np.int64)
-        np.minimum.at(first, y, np.arange(n, dtype=np.int64))   # first occurrence of every id (defined for repeats)
-        present = np.flatnonzero(first < n)
-        order = present[np.argsort(first[present], kind="stable")]
-        rank = np.zeros(len(first), dtype=np.int32)
-        rank[order] = np.arange(1, len(order) + 1, dtype=np.int32)
-        return rank[y], order.astype(y.dtype)
+    if n and y.dtype.kind in "iu" and 0 <= int(y.min()) and int(y.max()) <= min(4 * n + 1024, 2 ** 31 - 2):
+        # small non-negative integers (cluster ids): one native pass with a lookup table instead of a sort
+        codes, uniq = _lib.first_appearance_codes(y, int(y.max()) + 1)
+        return codes, uniq.astype(y.dtype)
     vals, first, inv = np.unique(y, return_index=True, return_inverse=True)
     order = np.argsort(first, kind="stable")
     rank = np.empty(len(vals), dtype=np.int64)

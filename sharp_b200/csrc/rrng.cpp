@@ -318,4 +318,25 @@ int sharp_labels_combine(int nparts, const int64_t *part_start, const int32_t *p
     return SHARP_OK;
 }
 
+
+// clusterID = match(y, unique(y)) (R/SHARP.R:429-432, 828-832) for non-negative integer ids below `nvals`: codes 1.. in
+// order of first appearance, one pass.  uniq (optional, nvals entries) receives unique(y); returns the number of
+// distinct ids, or -1 for an id out of range.
+int sharp_first_appearance_codes(const int32_t *y, int64_t n, int nvals, int32_t *codes, int32_t *uniq) {
+    if (!y || !codes || nvals < 1) return -1;
+    std::vector<int32_t> code((size_t)nvals, 0);
+    int next = 0;
+    for (int64_t i = 0; i < n; i++) {
+        const int32_t v = y[i];
+        if (v < 0 || v >= nvals) return -1;
+        int32_t &c = code[v];
+        if (!c) {
+            c = ++next;
+            if (uniq) uniq[next - 1] = v;
+        }
+        codes[i] = c;
+    }
+    return next;
+}
+
 }  // extern "C"
