@@ -129,26 +129,55 @@ __global__ void __launch_bounds__(MT) wm_enumerate_kernel(WmArgs A) {
 // ---------------------------------------------------------------------------------------------------
 // wm_weights: grid (ceil(maxN / MT), T); one thread per cell
 // ---------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(MT) wm_weights_kernel(WmArgs A) {
+__global__ void __launch_bounds__(MT) wm_weights_kernel(WmArgs A, int packed_cap) {
+    extern __shared__ unsigned long long wpk[]; /* [packed_cap]: the K <= 8 labels of every cell of the block, one byte each */
     const int t = blockIdx.y;
     const int64_t s0 = A.start[t];
     const int N = (int)(A.start[t + 1] - s0);
     const int i = blockIdx.x * MT + threadIdx.x;
     const int K = A.K;
     __shared__ double term[WM_MAXK + 1]; /* x (1 - x) for x = cnt / K: the K + 1 values an entry of AA can take */
+    __shared__ int s_wide;
     if (threadIdx.x <= K) {
         const double x = __ddiv_rn((double)threadIdx.x, (double)K);
         term[threadIdx.x] = __dmul_rn(x, __dsub_rn(1.0, x));
     }
+    if (threadIdx.x == 0) s_wide = (K > 8 || N > packed_cap) ? 1 : 0;
+    __syncthreads();
+    const int wide0 = s_wide;
+    __syncthreads();
+    if (!wide0) { /* labels 1..256 as bytes: one 64-bit word per cell, compared four bytes at a time */
+        for (int j = threadIdx.x; j < N; j += MT) {
+            unsigned long long w = 0ull;
+            for (int k = 0; k < K; k++) {
+                const int l = A.labels[(size_t)k * A.ncells + s0 + j];
+                if (l < 1 || l > 256) s_wide = 1;
+                w |= (unsigned long long)((unsigned)(l - 1) & 255u) << (8 * k);
+            }
+            wpk[j] = w;
+        }
+    }
     __syncthreads();
     if (i >= N) return;
-    int mine[WM_MAXK];
-    for (int k = 0; k < K; k++) mine[k] = A.labels[(size_t)k * A.ncells + s0 + i];
     double rs = 0.0;
-    for (int j = 0; j < N; j++) {
-        int cnt = 0;
-        for (int k = 0; k < K; k++) cnt += (A.labels[(size_t)k * A.ncells + s0 + j] == mine[k]);
-        rs = __dadd_rn(rs, term[cnt]); /* term[0] = +0: the sum is the one over the pairs that share a cluster */
+    if (!s_wide) {
+        const unsigned long long me = wpk[i];
+        const unsigned mlo = K >= 4 ? 0xffffffffu : ((1u << (8 * K)) - 1u);
+        const unsigned mhi = K <= 4 ? 0u : (K >= 8 ? 0xffffffffu : ((1u << (8 * (K - 4))) - 1u));
+        const unsigned melo = (unsigned)me, mehi = (unsigned)(me >> 32);
+        for (int j = 0; j < N; j++) {
+            const unsigned long long o = wpk[j];
+            const int cnt = (__popc(__vcmpeq4((unsigned)o, melo) & mlo) + __popc(__vcmpeq4((unsigned)(o >> 32), mehi) & mhi)) >> 3;
+            rs = __dadd_rn(rs, term[cnt]); /* term[0] = +0: the sum is the one over the pairs that share a cluster */
+        }
+    } else {
+        int mine[WM_MAXK];
+        for (int k = 0; k < K; k++) mine[k] = A.labels[(size_t)k * A.ncells + s0 + i];
+        for (int j = 0; j < N; j++) {
+            int cnt = 0;
+            for (int k = 0; k < K; k++) cnt += (A.labels[(size_t)k * A.ncells + s0 + j] == mine[k]);
+            rs = __dadd_rn(rs, term[cnt]);
+        }
     }
     double w0 = __dmul_rn(__ddiv_rn(4.0, (double)N), rs);
     A.w1[s0 + i] = __ddiv_rn(__dadd_rn(w0, 0.01), __dadd_rn(1.0, 0.01));
@@ -374,7 +403,8 @@ int launch_wmetac_front(sharp_ctx *c, const WmArgs &A, int T, int max_block_n) {
     prof_end(c);
     dim3 g1((max_block_n + MT - 1) / MT, T);
     prof_begin(c, KID_WM_WEIGHTS);
-    wm_weights_kernel<<<g1, MT, 0, c->stream>>>(A);
+    const int packed_cap = std::min(max_block_n, 5000); /* 40 KB of dynamic shared memory at most; larger blocks take the plain loop */
+    wm_weights_kernel<<<g1, MT, (size_t)packed_cap * 8, c->stream>>>(A, packed_cap);
     prof_end(c);
     dim3 g2(((size_t)A.capC * A.capC + MT - 1) / MT, T);
     prof_begin(c, KID_WM_SIMILARITY);

@@ -177,7 +177,7 @@ __device__ __forceinline__ double sil_unkey(unsigned long long k) {
 // stats::median of a[0..n) by one warp: radix selection of the element of rank (n + 1) / 2 - 1, eight 8-bit passes over
 // the (L2-resident) values with a 256-bin histogram in shared memory; for even n the next element is either the same
 // value or the smallest larger one.  Returns the same bits as median_sorted() on the sorted array.
-__device__ double warp_median_select(const double *__restrict__ a, int n, int *hist, int lane) {
+__device__ double warp_median_select(const double *a, int n, int *hist, int lane) /* a[] was written by this block: plain loads, no read-only path */ {
     const int r0 = (n + 1) / 2 - 1;
     int r = r0, less = 0, eq = 0;
     unsigned long long prefix = 0ull, mask = 0ull;
@@ -185,11 +185,17 @@ __device__ double warp_median_select(const double *__restrict__ a, int n, int *h
     for (int b = 7; b >= 0; b--) {
         for (int i = lane; i < 256; i += 32) hist[i] = 0;
         __syncwarp();
-        for (int i = lane; i < n; i += 32) {
-            const double v = a[i];
-            if (v != v) { nan = true; continue; }
-            const unsigned long long k = sil_key(v);
-            if ((k & mask) == prefix) atomicAdd(&hist[(int)((k >> (8 * b)) & 255ull)], 1);
+        for (int i0 = lane; i0 < n; i0 += 32 * 8) { /* eight loads in flight per lane: the values live in L2, not in registers */
+            double v[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) v[u] = (i0 + 32 * u < n) ? a[i0 + 32 * u] : 0.0;
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                if (i0 + 32 * u >= n) continue;
+                if (v[u] != v[u]) { nan = true; continue; }
+                const unsigned long long k = sil_key(v[u]);
+                if ((k & mask) == prefix) atomicAdd(&hist[(int)((k >> (8 * b)) & 255ull)], 1);
+            }
         }
         __syncwarp();
         if (__any_sync(0xffffffffu, nan)) return __longlong_as_double(0x7ff8000000000000ll);
@@ -229,9 +235,15 @@ __device__ double warp_median_select(const double *__restrict__ a, int n, int *h
     double y = x;
     if (less + eq <= r0 + 1) { /* the next element in sorted order is the smallest value above x */
         unsigned long long best = ~0ull;
-        for (int i = lane; i < n; i += 32) {
-            const unsigned long long k = sil_key(a[i]);
-            if (k > prefix && k < best) best = k;
+        for (int i0 = lane; i0 < n; i0 += 32 * 8) {
+            double v[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) v[u] = (i0 + 32 * u < n) ? a[i0 + 32 * u] : 0.0;
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                const unsigned long long k = sil_key(v[u]);
+                if (i0 + 32 * u < n && k > prefix && k < best) best = k;
+            }
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
