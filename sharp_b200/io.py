@@ -114,7 +114,7 @@ _pool_lock = threading.Lock()
 def _acquire_slot(n_max, nnz_max, pinned) -> PartSlot:
     with _pool_lock:
         for k, s in enumerate(_pool):
-            if (s.buf is not None) == bool(pinned) and s.n_max >= n_max and s.nnz_max >= nnz_max and s.nnz_max <= 2 * max(nnz_max, 1):
+            if (s.buf is not None) == bool(pinned) and s.n_max >= n_max and s.nnz_max >= nnz_max and s.nnz_max <= 2 * nnz_max + 4096:
                 return _pool.pop(k)
     # 6 % slack, so that parts of slightly different sizes reuse the same slots
     return PartSlot(n_max + n_max // 16 + 64, nnz_max + nnz_max // 16 + 1024, pinned)

@@ -352,3 +352,46 @@ def test_labels_combine_native_equals_numpy_tail():
     assert got.tolist() == [2, 1, 3, 2, 1, 3]
     with pytest.raises(Exception):
         _lib.labels_combine([np.array([4], dtype=np.int32)], [3], tf, 0)
+
+
+def test_first_appearance_codes_native():
+    """match(y, unique(y)) (R/SHARP.R:429-432): the native pass against a direct transcription"""
+    from sharp_b200 import _lib
+    rng = np.random.default_rng(11)
+    for n, hi in ((1, 1), (17, 3), (5000, 40), (30000, 700)):
+        y = rng.integers(0, hi + 1, size=n).astype(np.int32)
+        codes, uniq = _lib.first_appearance_codes(y, hi + 1)
+        seen = list(dict.fromkeys(y.tolist()))
+        assert uniq.tolist() == seen
+        assert codes.tolist() == [seen.index(v) + 1 for v in y.tolist()]
+        c2, u2 = api._first_appearance_codes(y)                      # the API helper routes small ids through it
+        assert np.array_equal(c2, codes) and np.array_equal(u2, uniq)
+    with pytest.raises(Exception):
+        _lib.first_appearance_codes(np.array([0, 5], dtype=np.int32), 5)
+    s = np.array(["b", "a", "b", "c"])                                # non-integer ids keep the sort-based path
+    c3, u3 = api._first_appearance_codes(s)
+    assert c3.tolist() == [1, 2, 1, 3] and u3.tolist() == ["b", "a", "c"]
+
+
+def test_read_slots_are_pooled_between_runs(tmp_path):
+    """page-locking memory costs more than reading a part: a finished BatchReader hands its slots to the next one"""
+    from sharp_b200 import io as sio
+    rng = np.random.default_rng(3)
+    paths = []
+    for i in range(3):
+        x = (rng.random((30, 20 + i)) < 0.3) * rng.integers(1, 9, size=(30, 20 + i))
+        cp, ri, v = synth.to_csc(x.astype(np.float64))
+        p = tmp_path / f"part{i + 1}.csc"
+        sio.write_csc(p, 30, x.shape[1], cp, ri, v)
+        paths.append(str(p))
+    infos = [sio.file_info(p) for p in paths]
+    sio.release_pool()
+    rd = sio.BatchReader(paths, infos, batch=2, pinned=False)
+    first = {id(s) for st in rd.sets for s in st}
+    got = [(m, n, int(cp[-1])) for _, batch in rd for (m, n, (cp, ri, v)) in batch]
+    rd.close()
+    assert got == [(30, inf[1], inf[2]) for inf in infos]
+    rd2 = sio.BatchReader(paths, infos, batch=2, pinned=False)
+    assert {id(s) for st in rd2.sets for s in st} == first           # the same slot objects came back from the pool
+    rd2.close()
+    sio.release_pool()
