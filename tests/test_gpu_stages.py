@@ -294,6 +294,22 @@ def test_opt_hclust_round_parallel(ctx, n, p, g, sep, method):
     assert np.array_equal(got["f"], ref["f"])
 
 
+@pytest.mark.parametrize("n,max_n", [(1100, 60), (901, 64), (500, 41)])
+def test_opt_hclust_wide_k_range(ctx, n, max_n):
+    """maxN.cluster above 40 (R/SHARP.R:216-223 for parts over 200 000 cells): the nested sweep runs its 256-thread
+    layout (the cached means of 60+ clusters do not fit beside 512 threads); every level against the oracle"""
+    X, _ = _blobs(n, 36, 7, seed=n + max_n, sep=1.2)
+    prm = hc_params(max_n=max_n)
+    got = ctx.opt_hclust(X, False, prm)
+    ref = orc.opt_hclust(X, 0, orc_prm(prm))
+    assert got["v"].shape == ref["v"].shape == (n, max_n - 1)
+    assert np.array_equal(got["v"], ref["v"])
+    assert np.allclose(got["msil"], ref["msil"], rtol=0, atol=1e-12)
+    assert np.allclose(got["CHind"], ref["CHind"], rtol=1e-8)
+    assert got["oind"] == ref["oind"] and got["optN.cluster"] == ref["optN.cluster"]
+    assert np.array_equal(got["f"], ref["f"])
+
+
 def test_opt_hclust_round_parallel_ties_fall_back(ctx):
     """duplicated cells give exact ties (d = 0, equal rows): the round-parallel kernel must hand the problem to the
     exact kernel, and the result is still hclust.f's"""
