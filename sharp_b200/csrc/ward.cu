@@ -730,6 +730,7 @@ constexpr u16 TRI_MERGING = 0x8000u; /* flag in the column map: the old cluster 
 template <int TRI_THREADS, int TRI_MINB, int METHOD>
 __global__ void __launch_bounds__(TRI_THREADS, TRI_MINB) hclust_tri_kernel(HcProb *probs, int method) {
     constexpr int TRI_NW = TRI_THREADS / 32;
+    constexpr bool TRI_PIPE = (TRI_THREADS == 768); /* experiment: fewer warps, software-pipelined row streams */
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ int s_tie, s_nm;
     __shared__ int tmp_scan[TRI_THREADS];
@@ -877,7 +878,37 @@ __global__ void __launch_bounds__(TRI_THREADS, TRI_MINB) hclust_tri_kernel(HcPro
                 best.d = SHARP_INF; best.i = INT_MAX; best.tie = 0;
                 int flag = 0;
                 const int jstart = (a + 1) & ~31; /* aligned start: full sectors */
-                if (!im) {
+                if (!im && TRI_PIPE) {
+                    /* 24 warps, 85 registers: the next batch of the row is requested before this one is worked on */
+                    double x[RNN_UC];
+                    unsigned cm[RNN_UC];
+#pragma unroll
+                    for (int u = 0; u < RNN_UC; u++) {
+                        const int j = jstart + u * 32 + lane;
+                        const bool in = j > a && j < nr;
+                        x[u] = in ? rowa[j] : 0.0;
+                        cm[u] = in ? (unsigned)cmap[j] : (unsigned)TRI_MERGING;
+                    }
+                    for (int jb = jstart; jb < nr; jb += 32 * RNN_UC) {
+                        double xn[RNN_UC];
+                        unsigned cmn[RNN_UC];
+#pragma unroll
+                        for (int u = 0; u < RNN_UC; u++) {
+                            const int j = jb + 32 * RNN_UC + u * 32 + lane;
+                            const bool in = j < nr; /* j > a holds: this is a later batch */
+                            xn[u] = in ? rowa[j] : 0.0;
+                            cmn[u] = in ? (unsigned)cmap[j] : (unsigned)TRI_MERGING;
+                        }
+#pragma unroll
+                        for (int u = 0; u < RNN_UC; u++) {
+                            const double v = sq ? __dmul_rn(x[u], x[u]) : x[u];
+                            tri_elem(!(cm[u] & TRI_MERGING), v, (int)(cm[u] & 0x7fffu), out, best, cmin2, flag);
+                        }
+#pragma unroll
+                        for (int u = 0; u < RNN_UC; u++) { x[u] = xn[u]; cm[u] = cmn[u]; }
+                    }
+                }
+                if (!im && !TRI_PIPE) {
                     for (int jb = jstart; jb < nr; jb += 32 * RNN_UC) {
                         double x[RNN_UC];
                         unsigned cm[RNN_UC];
@@ -894,6 +925,8 @@ __global__ void __launch_bounds__(TRI_THREADS, TRI_MINB) hclust_tri_kernel(HcPro
                             tri_elem(!(cm[u] & TRI_MERGING), v, (int)(cm[u] & 0x7fffu), out, best, cmin2, flag);
                         }
                     }
+                }
+                if (!im) {
                     for (int q0 = 0; q0 < m; q0 += 32) { /* this row's cluster a against the new cluster (d, c), d < c: I2 = d, J2 = c, K = a */
                         const int q = q0 + lane;
                         const int c = q < m ? (int)pl[q] : 0;
@@ -1077,6 +1110,11 @@ int launch_hclust(sharp_ctx *c, HcProb *probs_dev, int nprob, int max_n, int met
             } else if (tri_threads == 1024) {
                 SHARP_SMEM_OPTIN_ONCE((hclust_tri_kernel<1024, 1, 0>), c->device);
                 hclust_tri_kernel<1024, 1, 0><<<nprob, 1024, tsm, c->stream>>>(probs_dev, method);
+            } else if (tri_threads == 768) {
+                SHARP_SMEM_OPTIN_ONCE((hclust_tri_kernel<768, 1, SHARP_WARD_D>), c->device);
+                SHARP_SMEM_OPTIN_ONCE((hclust_tri_kernel<768, 1, 0>), c->device);
+                if (method == SHARP_WARD_D) hclust_tri_kernel<768, 1, SHARP_WARD_D><<<nprob, 768, tsm, c->stream>>>(probs_dev, method);
+                else hclust_tri_kernel<768, 1, 0><<<nprob, 768, tsm, c->stream>>>(probs_dev, method);
             } else if (method == SHARP_WARD_D) {
                 SHARP_SMEM_OPTIN_ONCE((hclust_tri_kernel<512, 2, SHARP_WARD_D>), c->device);
                 hclust_tri_kernel<512, 2, SHARP_WARD_D><<<nprob, 512, tsm, c->stream>>>(probs_dev, method);
