@@ -218,8 +218,6 @@ def init_from_env(ctx=None) -> NcclComm | None:
         from . import api
         api.set_devices(local)
         ctx = api.get_context(local)
-    # whatever NCCL_DEBUG asks for (the version banner included) goes to stderr: stdout belongs to the caller's results
-    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     addr = os.environ.get("MASTER_ADDR", "127.0.0.1")
     port = int(os.environ.get("MASTER_PORT", "29500")) + 1
     uid = None
