@@ -21,6 +21,7 @@ cell blocks over the ranks), cfg5 = config 5's shape bounded to 1e6 cells, SHARP
   e2e   : the same call on HOST buffers (pinned dgCMatrix slots): per-part H2D copies and the D2H of labels and
           centroids are inside the timed region
 Both are timed on the device (CUDA events on the library's stream around the K steps), max over ranks.
+Rank 0 prints ONE JSON line, the last line of stdout (with N > 1 NCCL itself prints its version banner before it).
 
 Only the cpu_baseline leg and --impl reference execute anything under oracle/ (the CPU restatement of the reference,
 OpenMP over (member, block) tasks like the reference's foreach), on a bounded sample of the same workload.
