@@ -337,13 +337,24 @@ def _rm_list(m, p, K, rN_seed, comm=None):
             got = dict(zip(mine, ex.map(draw, mine)))
     if world == 1:
         return [got[k] for k in range(K)]
+    # the slots travel as (p, i, sign bytes, magnitude): a ranM matrix is ternary, x = +-sqrt(sqrt(m)) (R/ranM.R:20-29)
     payload = {}
     for k, r in got.items():
-        payload[3 * k] = np.ascontiguousarray(r["p"], dtype=np.int32)
-        payload[3 * k + 1] = np.ascontiguousarray(r["i"], dtype=np.int32)
-        payload[3 * k + 2] = np.ascontiguousarray(r["x"], dtype=np.float64)
-    allv = comm.allgather_parts(payload, 3 * K)
-    return [{"Dim": (m, p), "p": allv[3 * k], "i": allv[3 * k + 1], "x": allv[3 * k + 2]} for k in range(K)]
+        x = np.asarray(r["x"], dtype=np.float64)
+        mag = float(np.abs(x[0])) if len(x) else 0.0
+        if len(x) and not np.array_equal(np.abs(x), np.full(len(x), mag)):
+            raise ValueError("ranM produced a matrix that is not ternary")
+        payload[4 * k] = np.ascontiguousarray(r["p"], dtype=np.int32)
+        payload[4 * k + 1] = np.ascontiguousarray(r["i"], dtype=np.int32)
+        payload[4 * k + 2] = (x < 0).astype(np.uint8)
+        payload[4 * k + 3] = np.array([mag], dtype=np.float64)
+    allv = comm.allgather_parts(payload, 4 * K)
+    out = []
+    for k in range(K):
+        mag = float(allv[4 * k + 3][0])
+        x = np.where(allv[4 * k + 2] != 0, -mag, mag)
+        out.append({"Dim": (m, p), "p": allv[4 * k], "i": allv[4 * k + 1], "x": x})
+    return out
 
 
 def _as_rmdev(ctx: Context, rM, m, p, K, rN_seed) -> tuple[RmDev, bool]:
