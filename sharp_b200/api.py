@@ -307,6 +307,28 @@ def _reind(n: int, rN_seed) -> np.ndarray:
     return _lib.r_sample_perm_native(n, 50)
 
 
+def _reinds_for(sizes: list, rN_seed) -> list:
+    """the shuffles of several parts of ONE call (None for parts of 1e5 cells or more, R/SHARP.R:493-498).  A seeded run
+    draws `set.seed(50); sample(n)` for every part: a pure function of n, so parts of equal size share one draw (the
+    result is read-only); distinct sizes are drawn on separate host threads (the native generator releases the GIL)"""
+    need = [n for n in sizes if n < 1e5]
+    if not need:
+        return [None] * len(sizes)
+    if rN_seed == 0.5:       # unseeded: every part has its own stream
+        from concurrent.futures import ThreadPoolExecutor
+        with ThreadPoolExecutor(max_workers=min(8, len(need))) as ex:
+            drawn = iter(list(ex.map(lambda n: _reind(n, rN_seed), need)))
+        return [next(drawn) if n < 1e5 else None for n in sizes]
+    distinct = sorted(set(need))
+    if len(distinct) == 1:
+        table = {distinct[0]: _reind(distinct[0], rN_seed)}
+    else:
+        from concurrent.futures import ThreadPoolExecutor
+        with ThreadPoolExecutor(max_workers=min(8, len(distinct))) as ex:
+            table = dict(zip(distinct, ex.map(lambda n: _reind(n, rN_seed), distinct)))
+    return [table[n] if n < 1e5 else None for n in sizes]
+
+
 def _member_seeds(K, rN_seed, comm=None):
     """the integer seeds of the K ranM draws; an unseeded run (rN.seed = 0.5) takes them from the OS entropy -- ONCE:
     with several ranks, rank 0 draws and everybody uses its seeds (the reference builds rM once for all partitions,
@@ -845,17 +867,20 @@ def _fused_inputs(parts, mine):
     return ins
 
 
-def _run_parts_fused(ctx, parts, mine, rM, p, K, rN_seed, a, n_cores, shared=frozenset()):
+def _run_parts_fused(ctx, parts, mine, rM, p, K, rN_seed, a, n_cores, shared=frozenset(), reinds=None):
     """What the loop `y[[i]] = SHARP(scExp[[i]], reduced.ndim = p, prep = FALSE, logflag = FALSE, rM = rM, ...)` returns
     for the parts in ``mine`` (R/SHARP_unlimited.R:125-149), computed by ONE sharp_run_parts call."""
     normalize = a["exp_type"] is not None and a["exp_type"] not in ("CPM", "TPM")
     hc = _hc(a["hmethod"], None, 2, a["maxN_cluster"], a["sil_thre"], a["height_Ntimes"], a["flashmark"])
     prm = RunParams(1, 1, 2, -1, int(a["partition_ncells"]), 0, _ncl(a["enpN_cluster"]), _ncl(a["indN_cluster"]), hc,
                     2 if normalize else 0, 1e6)
-    ins, reinds = _fused_inputs(parts, mine), []
+    ins = _fused_inputs(parts, mine)
     for i in mine:
         _cat("Processing Partition", i + 1, "of the scRNA-seq data...")
-        reinds.append(_reind(parts[i].n, rN_seed) if parts[i].n < 1e5 else None)
+    if reinds is None:
+        reinds = _reinds_for([parts[i].n for i in mine], rN_seed)
+    elif callable(reinds):   # a future started earlier (drawn while the ranM matrices were)
+        reinds = reinds()
     start = time.time()
     outs = ctx.run_parts(rM, prm, parts[mine[0]].m, ins, reinds, small_thre=10, cen_cap=max(64, a["maxN_cluster"] + 1),
                          group=_fused_group, lanes=_fused_lanes, sharded=[i in shared for i in mine])
@@ -944,6 +969,25 @@ def SHARP_unlimited(scExp, viewflag=True, n_cores=None, ensize_K=None, N_cluster
     if fast is not None and mine and parts[mine[0]].dev is None:
         _pf_keep = ctx.parts_prefetch(parts[mine[0]].m, _fused_inputs(parts, mine), _fused_group, _fused_lanes,
                                       sharded=[i in shared for i in mine])
+    _reind_job = None
+    if fast is not None and mine:   # the parts' shuffles are drawn on a host thread while the ranM matrices are
+        import threading
+        _box: dict = {}
+
+        def _draw():
+            try:
+                _box["v"] = _reinds_for([parts[i].n for i in mine], rN_seed)
+            except BaseException as ex:  # surfaced by the consumer
+                _box["e"] = ex
+
+        _th = threading.Thread(target=_draw, daemon=True)
+        _th.start()
+
+        def _reind_job():
+            _th.join()
+            if "e" in _box:
+                raise _box["e"]
+            return _box["v"]
     rms_host = _rm_list(parts[0].m, p, ensize_K, rN_seed, comm)
     _mark("ranM")
     rM = ctx.upload_rm(rms_host)
@@ -976,7 +1020,7 @@ def SHARP_unlimited(scExp, viewflag=True, n_cores=None, ensize_K=None, N_cluster
     try:
         if fast is not None:  # every part takes the SHARP_large path with the same parameters: one fused device call
             t0 = time.time()
-            outs = _run_parts_fused(ctx, parts, mine, rM, p, ensize_K, rN_seed, fast, n_cores, set(shared))
+            outs = _run_parts_fused(ctx, parts, mine, rM, p, ensize_K, rN_seed, fast, n_cores, set(shared), reinds=_reind_job)
             for i, o in zip(mine, outs):
                 y[i], cens[i], viEs[i] = o, o.pop("cen"), None
             if _TRACE:
