@@ -251,7 +251,7 @@ typedef struct {
 } sharp_part;
 int sharp_run_parts(sharp_ctx *ctx, int m, int nparts, sharp_part *parts, const sharp_rm_dev *rm,
                     const sharp_run_params *prm, int small_thre, int cen_cap, int group, int lanes);
-/* Optional head start for sharp_run_parts on HOST buffers: enqueues the uploads of the first group of the same `parts`
+/* Optional head start for sharp_run_parts on HOST buffers: enqueues the upload of the FIRST PART of the same `parts`
  * array (same group / lanes arguments) and returns at once, so that the copy overlaps host work the caller still has
  * to do before sharp_run_parts (SHARP_unlimited generates its ranM matrices there, R/SHARP_unlimited.R:97-104).  Takes
  * effect from the second call on a context (the staging buffers must already have their size); otherwise a no-op.
